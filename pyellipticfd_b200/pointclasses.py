@@ -1,0 +1,489 @@
+"""Point classes consumed by the operators: a fast ``FDRegularGrid`` and the
+plain ``FDPointCloud`` container.
+
+Mirrors the constructor signatures and attributes of the reference
+(/root/reference/pointclasses.py:123-285 ``FDPointCloud``, :473-622
+``FDRegularGrid``) but builds the regular-grid stencil data in O(points near
+the wall) instead of the reference's O(N^2) Delaunay + sparse-power search, so
+that the benchmark grids (4097^2 ... 32768^2) can be created at all.
+
+Structure of a pairs grid (``interpolation=False``):
+
+* *deep interior* -- lattice points at least ``stencil_radius`` cells from every
+  wall.  Their stencil is translation invariant: one table of antipodal offset
+  pairs (``stencil_pairs``, shape (D, 4) = (a0, b0, a1, b1)).  Never
+  materialised per point; the CUDA stencil kernel bakes the table in.
+* *band* -- the remaining interior points.  Their neighbour sets include the
+  fractional wall points the reference generates (pointclasses.py:523-540) and
+  are irregular; they are stored explicitly (``band_pairs`` rows ``(I, J0,
+  J1)`` grouped by ascending ``I``).
+
+Membership rules follow the reference exactly (checked per point against
+golden pair sets generated from the reference, ``tests/test_grid.py``):
+neighbours = points at l-inf distance in (0, r] on the *unscaled* coordinates
+(pointclasses.py:443-447), colinear pruning with tolerance 1e-3 keeping the
+closer neighbour and re-admitting wall points that only lost to other wall
+points (:37-103, :576-578), antipodal pairing ``cos < -1 + 1e-3`` (:12-35).
+The ORDER of rows inside one centre point's group is this module's own
+(lattice neighbours by (a, b), then wall points by index; pairs in upper-
+triangular order) -- the reference's order is an artefact of a joggled
+Delaunay triangulation and only matters for exact ties.
+"""
+import itertools
+
+import numpy as np
+
+from . import stencils
+
+COLINEAR_TOL = 1e-3          # pointclasses.py:577
+
+
+class FDPointCloud(object):
+    """Base container (pointclasses.py:123-285): interior points first."""
+
+    def __repr__(self):
+        return "FDPointCloud in {0.dim}D with {0.num_points} points".format(self)
+
+    def __init__(self, points, angular_resolution=None, num_interior=None,
+                 spatial_resolution=None, neighbours=None, bdry_resolution=None,
+                 dist_to_bdry=None, bdry_normals=None):
+        if num_interior is None:
+            raise TypeError("Please provide the number of interior points")
+        if angular_resolution is None:
+            self.angular_resolution = angular_resolution
+        elif 0 < angular_resolution <= np.pi:
+            self.angular_resolution = angular_resolution
+        else:
+            raise TypeError("angular_resolution must be strictly greater than 0 and less than pi")
+        self.spatial_resolution = spatial_resolution
+        self.bdry_resolution = bdry_resolution
+        self.dist_to_bdry = dist_to_bdry
+        self.neighbours = neighbours
+        self.simplices = None
+        self.pairs = None
+        self.bdry_normals = bdry_normals
+        self._d1cache = None
+        self._d2cache = None
+        self.num_interior = num_interior
+        self.num_bdry = points.shape[0] - num_interior
+        self.points = points
+
+    # -- index / geometry helpers (pointclasses.py:183-213) -----------------
+    @property
+    def num_points(self):
+        return self.num_interior + self.num_bdry
+
+    @property
+    def dim(self):
+        return self.points.shape[1]
+
+    @property
+    def indices(self):
+        return np.arange(self.num_points)
+
+    @property
+    def interior(self):
+        return np.arange(self.num_interior)
+
+    @property
+    def bdry(self):
+        return np.arange(self.num_interior, self.num_interior + self.num_bdry)
+
+    @property
+    def interior_points(self):
+        return self.points[:self.num_interior]
+
+    @property
+    def bdry_points(self):
+        return self.points[self.num_interior:]
+
+    @property
+    def bbox(self):
+        return np.array([np.amin(self.points, 0), np.amax(self.points, 0)])
+
+    @property
+    def Cd(self):
+        if self.dim == 2:
+            return 2
+        elif self.dim == 3:
+            return 1 + 2 / np.sqrt(3)
+        raise TypeError("Dimensions other than two and three not supported")
+
+    @property
+    def max_radius(self):
+        h, th = self.spatial_resolution, self.angular_resolution
+        return h * (1 + self.Cd / np.sin(th / 2))
+
+    @property
+    def min_radius(self):
+        h, th = self.spatial_resolution, self.angular_resolution
+        return h * (-1 + self.Cd / np.sin(th / 2))
+
+    @property
+    def min_interior_nb_dist(self):
+        nb = np.asarray(self.neighbours)
+        m = nb[:, 0] < self.num_interior
+        V = self.points[nb[m, 1]] - self.points[nb[m, 0]]
+        return np.linalg.norm(V, axis=1).min()
+
+
+# ---------------------------------------------------------------------------
+# stencil rules, restated for a batch of centre points
+# ---------------------------------------------------------------------------
+
+def _prune_and_pair(V, valid, is_bdry, tol=COLINEAR_TOL):
+    """Apply the reference's colinear pruning and antipodal pairing to a batch.
+
+    V       (B, K, 2) scaled stencil vectors (garbage where ``valid`` is False)
+    valid   (B, K) candidate mask
+    is_bdry (B, K) candidate is a wall point
+    Returns (keep (B, K) bool, pair_mask (B, K, K) bool upper-triangular over kept).
+    """
+    B, K, _ = V.shape
+    D = np.sqrt(V[..., 0] * V[..., 0] + V[..., 1] * V[..., 1])
+    D = np.where(valid, D, 1.0)
+    dot = V[:, :, None, 0] * V[:, None, :, 0] + V[:, :, None, 1] * V[:, None, :, 1]
+    cosv = dot / (D[:, :, None] * D[:, None, :])
+    np.clip(cosv, -1.0, 1.0, out=cosv)
+    both = valid[:, :, None] & valid[:, None, :]
+    upper = np.triu(np.ones((K, K), dtype=bool), 1)[None]
+    col = ((1.0 - cosv) < tol) & both & upper          # doubles (k<l) failing the test
+    # of each double discard the farther one; ties discard the first (np.argmax)
+    first_far = D[:, :, None] >= D[:, None, :]          # True -> discard k (row index)
+    disc_k = col & first_far
+    disc_l = col & ~first_far
+    discarded = disc_k.any(axis=2) | disc_l.any(axis=1)
+    # wall points are only really lost when they lose against/with an interior point
+    mixed = is_bdry[:, :, None] ^ is_bdry[:, None, :]
+    disc_mixed = (disc_k & mixed).any(axis=2) | (disc_l & mixed).any(axis=1)
+    keep = valid & (~discarded | (is_bdry & ~disc_mixed))
+    # antipodal pairing on normalised vectors (pointclasses.py:18-33)
+    Vs = V / D[..., None]
+    cs = Vs[:, :, None, 0] * Vs[:, None, :, 0] + Vs[:, :, None, 1] * Vs[:, None, :, 1]
+    pair = (cs < -1 + tol) & keep[:, :, None] & keep[:, None, :] & upper
+    return keep, pair
+
+
+class FDRegularGrid(FDPointCloud):
+    """Fast drop-in for pointclasses.FDRegularGrid (pointclasses.py:473-622)."""
+
+    def __repr__(self):
+        return ("FDRegularGrid in {0.dim}D with {0.num_points} points, "
+                "spatial resolution {0.spatial_resolution:.3g}, "
+                "and angular resolution {0.angular_resolution:.3g}").format(self)
+
+    def __init__(self, interior_shape, bounds, stencil_radius, interpolation=True):
+        if interpolation:
+            raise NotImplementedError(
+                "pyellipticfd_b200.FDRegularGrid builds antipodal pairs only "
+                "(interpolation=False); simplices on regular grids are not on the hot path")
+        dim = len(interior_shape)
+        if dim != 2:
+            raise NotImplementedError("only 2-D regular grids are implemented")
+        self._interp = interpolation
+        self.stencil_radius = r = int(stencil_radius)
+        shape = np.array(interior_shape)
+        bounds = np.array(bounds)
+        self.interior_shape = tuple(int(s) for s in shape)
+        self.bounds = bounds
+        nx, ny = self.interior_shape
+        self.scaling = (bounds[1] - bounds[0]) / (shape + 1)             # :508
+        self.spatial_resolution = np.linalg.norm(bounds / (shape + 1)) / 2   # :510-511 (quirk Q11)
+        self.num_interior = nx * ny
+        self._points = None
+        self._pairs = None
+        self.simplices = None
+        self._d1cache = None
+        self._d2cache = None
+        self.bdry_normals = None
+
+        stcl = stencils.create(r, dim)
+        self._make_wall_points(stcl)
+        self._make_metadata(stcl)
+        self._make_deep_table()
+        self._make_band()
+
+    # -- geometry -------------------------------------------------------------
+    def _make_wall_points(self, stcl):
+        """Wall points with the reference's literal arithmetic (:520-540)."""
+        nx, ny = self.interior_shape
+        shape = np.array(self.interior_shape)
+        bounds = self.bounds
+        stcl_l1 = stcl / np.max(np.abs(stcl), axis=1)[:, None]
+        # interior points adjacent to a wall, as lattice coordinates
+        edge = []
+        ix = np.arange(1, nx + 1)
+        iy = np.arange(1, ny + 1)
+        edge.append(np.stack([np.full(ny, 1), iy], 1))
+        edge.append(np.stack([np.full(ny, nx), iy], 1))
+        edge.append(np.stack([ix, np.full(nx, 1)], 1))
+        edge.append(np.stack([ix, np.full(nx, ny)], 1))
+        edge = np.unique(np.concatenate(edge), axis=0)
+        X = edge[:, :, None] + stcl_l1.T[None, :, :]
+        X = np.moveaxis(X, 2, 0).reshape(-1, 2)
+        on_wall = ((X[:, 0] == 0) | (X[:, 0] == nx + 1) |
+                   (X[:, 1] == 0) | (X[:, 1] == ny + 1))
+        X = X[on_wall]
+        h = (bounds[1] - bounds[0]) / (shape + 1)
+        self._wall_unscaled = (np.unique(h * X + bounds[0], axis=0) - bounds[0]) / h
+        self.num_bdry = self._wall_unscaled.shape[0]
+        # outward normals (pointclasses.py:401-418), stored as in the reference
+        Xb = self._wall_unscaled
+        nrm = np.zeros(Xb.shape)
+        M = Xb.max(0)
+        for i in range(2):
+            nrm[Xb[:, i] == 0, i] = -1.0
+            nrm[Xb[:, i] == M[i], i] = 1.0
+        self.normals = nrm / np.linalg.norm(nrm, axis=1)[:, None]
+
+    def _make_metadata(self, stcl):
+        """angular / boundary resolutions (:555-574)."""
+        r = self.stencil_radius
+        s = stcl * self.scaling
+        s = s[np.logical_not(s == 0).all(axis=1)]
+        vs = s / np.linalg.norm(s, axis=1)[:, None]
+
+        def dtheta(i):
+            e = np.zeros(2)
+            e[i] = 1
+            th = np.arccos(vs.dot(e))
+            return th[th > 0].min()
+
+        self.angular_resolution = max(dtheta(i) for i in range(2))
+        self.dist_to_bdry = self.scaling.min()
+        b_rect = np.full(2, 1 / r) * self.scaling
+        self.bdry_resolution = max(np.linalg.norm(v) / 2
+                                   for v in itertools.combinations(b_rect, 1))
+
+    def _scaled(self, P):
+        """Lattice coordinates -> physical coordinates, as :551."""
+        return P * self.scaling + self.bounds[0]
+
+    def _make_deep_table(self):
+        """The translation-invariant pair table of deep-interior points."""
+        r = self.stencil_radius
+        offs = np.array([(a, b) for a in range(-r, r + 1) for b in range(-r, r + 1)
+                         if (a, b) != (0, 0)])
+        # scaled vectors as seen from a generic lattice point (exact when the
+        # spacing is dyadic; otherwise positions differ only by roundoff)
+        c = np.array([r + 1.0, r + 1.0])
+        V = self._scaled(c + offs) - self._scaled(c)
+        keep, pair = _prune_and_pair(V[None], np.ones((1, len(offs)), bool),
+                                     np.zeros((1, len(offs)), bool))
+        k, l = np.nonzero(pair[0])
+        self.stencil_offsets = offs[keep[0]]
+        self.stencil_pairs = np.concatenate([offs[k], offs[l]], axis=1).astype(np.int32)
+        self.halo = int(np.abs(self.stencil_pairs).max()) if len(k) else 0
+
+    def _band_mask_1d(self, n):
+        r = self.stencil_radius
+        i = np.arange(1, n + 1)
+        return (i <= r) | (i >= n - r + 1)
+
+    def _make_band(self, batch=256):
+        nx, ny = self.interior_shape
+        r = self.stencil_radius
+        N = self.num_interior
+        bx = self._band_mask_1d(nx)
+        by = self._band_mask_1d(ny)
+        band2d = bx[:, None] | by[None, :]
+        bi, bj = np.nonzero(band2d)                      # C order == ascending point id
+        self.band_index = (bi * ny + bj).astype(np.int64)
+        cx = (bi + 1).astype(np.float64)
+        cy = (bj + 1).astype(np.float64)
+        nb = len(cx)
+
+        offs = np.array([(a, b) for a in range(-r, r + 1) for b in range(-r, r + 1)
+                         if (a, b) != (0, 0)])
+        W = self._wall_unscaled
+        # split the wall points into four lists sorted along the wall
+        wid = np.arange(self.num_bdry)
+        lists = []
+        for axis, val, excl in ((0, 0.0, False), (0, nx + 1.0, False),
+                                (1, 0.0, True), (1, ny + 1.0, True)):
+            m = W[:, axis] == val
+            if excl:
+                m &= ~((W[:, 0] == 0) | (W[:, 0] == nx + 1))
+            ids = wid[m]
+            t = W[ids, 1 - axis]
+            o = np.argsort(t, kind="stable")
+            lists.append((axis, val, ids[o], t[o]))
+
+        rows_I, rows_J0, rows_J1 = [], [], []
+        min_nb = np.inf
+        sx, sy = self.scaling
+        b0 = self.bounds[0]
+        for s in range(0, nb, batch):
+            e = min(nb, s + batch)
+            B = e - s
+            pcx, pcy = cx[s:e], cy[s:e]
+            # lattice candidates
+            lx = pcx[:, None] + offs[None, :, 0]
+            ly = pcy[:, None] + offs[None, :, 1]
+            lvalid = (lx >= 1) & (lx <= nx) & (ly >= 1) & (ly <= ny)
+            lid = ((lx - 1) * ny + (ly - 1)).astype(np.int64)
+            cand_x, cand_y, cand_id, cand_ok = [lx], [ly], [lid], [lvalid]
+            # wall candidates: a window of each sorted wall list
+            for axis, val, ids, t in lists:
+                c_al = pcy if axis == 0 else pcx          # coordinate along the wall
+                c_ac = pcx if axis == 0 else pcy          # coordinate across
+                near = np.abs(c_ac - val) <= r
+                if not near.any() or ids.size == 0:
+                    continue
+                lo = np.searchsorted(t, c_al - r - 1e-9, side="left")
+                hi = np.searchsorted(t, c_al + r + 1e-9, side="right")
+                lo = np.where(near, lo, 0)
+                hi = np.where(near, hi, 0)
+                width = int((hi - lo).max())
+                if width == 0:
+                    continue
+                k = lo[:, None] + np.arange(width)[None, :]
+                ok = k < hi[:, None]
+                k = np.minimum(k, ids.size - 1)
+                wx = W[ids[k], 0]
+                wy = W[ids[k], 1]
+                cand_x.append(wx)
+                cand_y.append(wy)
+                cand_id.append(N + ids[k])
+                cand_ok.append(ok)
+            n_lat = offs.shape[0]
+            PX = np.concatenate(cand_x, 1)
+            PY = np.concatenate(cand_y, 1)
+            ID = np.concatenate(cand_id, 1)
+            OK = np.concatenate(cand_ok, 1)
+            isb = np.zeros(PX.shape, bool)
+            isb[:, n_lat:] = True
+            # l-inf window on the unscaled coordinates (:443-447)
+            dinf = np.maximum(np.abs(PX - pcx[:, None]), np.abs(PY - pcy[:, None]))
+            OK &= (dinf <= r) & (dinf > 0)
+            # drop columns unused by the whole batch to keep K small
+            used = OK.any(axis=0)
+            PX, PY, ID, OK, isb = PX[:, used], PY[:, used], ID[:, used], OK[:, used], isb[:, used]
+            # scaled stencil vectors (:551, :226-228)
+            VX = (PX * sx + b0[0]) - (pcx * sx + b0[0])[:, None]
+            VY = (PY * sy + b0[1]) - (pcy * sy + b0[1])[:, None]
+            V = np.stack([VX, VY], axis=2)
+            keep, pair = _prune_and_pair(V, OK, isb)
+            Dk = np.sqrt(VX * VX + VY * VY)
+            min_nb = min(min_nb, np.where(keep, Dk, np.inf).min())
+            b, k, l = np.nonzero(pair)
+            rows_I.append(self.band_index[s + b])
+            rows_J0.append(ID[b, k])
+            rows_J1.append(ID[b, l])
+            has = np.zeros(B, bool)
+            has[b] = True
+            if not has.all():
+                bad = self.band_index[s + np.flatnonzero(~has)[0]]
+                raise TypeError("Point {0} has no pairs".format(bad))   # :26-27
+        if nb:
+            self.band_pairs = np.stack([np.concatenate(rows_I), np.concatenate(rows_J0),
+                                        np.concatenate(rows_J1)], axis=1).astype(np.int64)
+        else:
+            self.band_pairs = np.zeros((0, 3), np.int64)
+        counts = np.bincount(np.searchsorted(self.band_index, self.band_pairs[:, 0]),
+                             minlength=nb)
+        self.band_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        self._band2d = band2d
+        n_deep = N - nb
+        if n_deep > 0:
+            offs_k = self.stencil_offsets * self.scaling
+            min_nb = min(min_nb, np.sqrt((offs_k ** 2).sum(1)).min())
+        self._min_interior_nb_dist = float(min_nb)
+
+    # -- lazily materialised reference attributes --------------------------------
+    @property
+    def points(self):
+        """(num_points, 2) physical coordinates, interior first in C order with
+        y fastest (:513-515, :540, :551).  Materialised on first access."""
+        if self._points is None:
+            nx, ny = self.interior_shape
+            ix, iy = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), indexing="ij")
+            Xint = np.stack([ix.ravel(), iy.ravel()], axis=1)
+            P = np.concatenate([Xint, self._wall_unscaled])
+            self._points = P * self.scaling + self.bounds[0]
+        return self._points
+
+    @points.setter
+    def points(self, value):
+        self._points = value
+
+    @property
+    def dim(self):
+        return 2
+
+    @property
+    def bdry_points(self):
+        return self._wall_unscaled * self.scaling + self.bounds[0]
+
+    @property
+    def num_deep(self):
+        return self.num_interior - self.band_index.size
+
+    @property
+    def num_pairs(self):
+        return self.num_deep * self.stencil_pairs.shape[0] + self.band_pairs.shape[0]
+
+    @property
+    def pairs(self):
+        """Explicit (P, 3) ``(I, J0, J1)`` rows grouped by ascending I, the array
+        the reference operators consume (pointclasses.py:35).  Materialised on
+        demand -- ~24 bytes per pair, so only sensible up to a few 1000^2."""
+        if self._pairs is None:
+            self._pairs = self._materialise_pairs()
+        return self._pairs
+
+    @pairs.setter
+    def pairs(self, value):
+        self._pairs = value
+
+    def _materialise_pairs(self, max_rows=2 ** 31):
+        nx, ny = self.interior_shape
+        D = self.stencil_pairs.shape[0]
+        if self.num_pairs > max_rows:
+            raise MemoryError("refusing to materialise %d pair rows" % self.num_pairs)
+        deep = np.flatnonzero(~self._band2d.ravel())
+        di, dj = deep // ny, deep % ny
+        sp = self.stencil_pairs
+        J0 = ((di[:, None] + sp[None, :, 0]) * ny + dj[:, None] + sp[None, :, 1])
+        J1 = ((di[:, None] + sp[None, :, 2]) * ny + dj[:, None] + sp[None, :, 3])
+        I = np.broadcast_to(deep[:, None], J0.shape)
+        deep_rows = np.stack([I.ravel(), J0.ravel(), J1.ravel()], axis=1)
+        allrows = np.concatenate([deep_rows, self.band_pairs])
+        order = np.argsort(allrows[:, 0], kind="stable")
+        return allrows[order]
+
+    # -- radii (pointclasses.py:590-622) -------------------------------------------
+    @property
+    def max_radius(self):
+        return self.spatial_resolution * self.stencil_radius
+
+    @property
+    def min_radius(self):
+        return np.max([0, self.scaling.min()])
+
+    @property
+    def maximum_bdry_res(self):
+        return self.bdry_resolution
+
+    @property
+    def min_interior_nb_dist(self):
+        return self._min_interior_nb_dist
+
+    def uniform_weights(self):
+        """True when the physical coordinates are exact multiples of a power-of-
+        two-friendly spacing, i.e. every deep-interior stencil vector has
+        bit-identical length wherever it is applied.  Then 1/h and 2/(h0+h1)
+        are per-direction constants and the structured kernel is bit-exact
+        against the per-pair arithmetic of the reference (ddg.py:276-281)."""
+        nx, ny = self.interior_shape
+        r = self.halo
+        ok = True
+        for n, s, b in ((nx, self.scaling[0], self.bounds[0][0]),
+                        (ny, self.scaling[1], self.bounds[0][1])):
+            c = np.arange(1, n + 1) * s + b
+            for a in range(1, r + 1):
+                if n - a <= 0:
+                    continue
+                d = c[a:] - c[:-a]
+                ok &= bool((d == d[0]).all())
+        return ok
