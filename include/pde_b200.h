@@ -1,0 +1,213 @@
+/*
+ * pde_b200.h -- C ABI of the B200-native (sm_100a) pyellipticfd hot path.
+ *
+ * The reference (cfinlay/pyellipticfd) is pure Python and has no FFI layer; the
+ * boundary it offers is the set of module-level functions ddg/ddi/ddf.d2eigs,
+ * convex_envelope/pucci.operator+solve and solvers.euler/NewtonEulerLS.  This
+ * header is the C-level contract those functions are re-implemented on: plain
+ * pointers and sizes, no torch / Python types.  Every entry point cites the
+ * reference code it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure; the message of
+ *    the last failure on the calling thread is pde_last_error().
+ *  - all `double*`, `uint16_t*`, `int32_t*` arguments named d_* are DEVICE
+ *    pointers on the context's device; h_* are HOST pointers.
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream).
+ *    Calls are asynchronous on that stream unless stated otherwise.
+ *
+ * State layout ("state vector", length pde_grid_state_len()):
+ *    [ rows x pitch doubles : lattice rows (halo rows, owned rows, halo rows),
+ *                             y fastest, pitch = ny rounded up to 16, padding = 0 ]
+ *    [ nb doubles           : wall (boundary) points in the grid's order ]
+ *  EVERY per-point array of this ABI (values, residuals, policies, Krylov
+ *  vectors) uses this one layout, so one offset addresses them all.
+ *  The reference's flat vector u (pointclasses.py:513-515,540: interior points
+ *  first in C order, then boundary points) maps to it by pde_grid_pack/unpack.
+ */
+#ifndef PDE_B200_H
+#define PDE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDE_B200_ABI_VERSION 1
+#define PDE_MAX_DIRS 64          /* antipodal pairs per deep-interior point  */
+#define PDE_POLICY_IDENTITY 0xFFFFu /* policy value meaning "identity row"   */
+
+typedef struct pde_grid pde_grid;    /* regular pairs grid (ddg)            */
+typedef struct pde_ell pde_ell;      /* point-cloud ELL operator (ddi, ddf) */
+
+int pde_abi_version(void);
+const char *pde_last_error(void);
+/* number of CUDA kernels this library has launched since load (bench.py's
+ * gpu_launches claim is read from here). */
+int64_t pde_kernel_launches(void);
+
+/* ------------------------------------------------------------------------
+ * Regular-grid context.  Replaces the per-call geometry work of
+ * ddg.d2eigs (ddg.py:274-280: X, h, w, w0 recomputed from coordinates on
+ * every call) by one device-resident description of the grid:
+ *   - deep interior: D antipodal offset pairs (a0,b0,a1,b1) with per-direction
+ *     weights (w_0, w_1, w0) -- valid when the spacing makes them position
+ *     independent (FDRegularGrid.uniform_weights());
+ *   - band: explicit pair rows (I, J0, J1) with per-row weights, grouped by
+ *     band point (CSR); I/J are given as offsets into the state layout below
+ *     (the host converts the reference's global point ids).
+ * h_* arrays are copied; the caller may free them after the call.
+ * ---------------------------------------------------------------------- */
+int pde_grid_create(pde_grid **out, int device,
+                    int64_t nx_global, int64_t ny, int64_t nb, int stencil_radius,
+                    /* slab owned by this context: rows [x_offset, x_offset+nx_local)
+                     * of the global lattice plus halo_rows extra rows on each side
+                     * (single GPU: 0, nx_global, 0) */
+                    int64_t x_offset, int64_t nx_local, int64_t halo_rows,
+                    int D, const int32_t *h_stencil_pairs /* D x 4 */,
+                    const double *h_stencil_w /* D x 3 : w_0, w_1, w0 */,
+                    const double *h_stencil_X /* D x 2 : physical vector of (a0,b0) */,
+                    int64_t n_band,
+                    const int64_t *h_band_center /* n_band : state offset of I */,
+                    const int64_t *h_band_ptr /* n_band+1 */,
+                    const int64_t *h_band_j /* P x 2 : state offsets of J0, J1 */,
+                    const double *h_band_w /* P x 3 : w_0, w_1, w0 */,
+                    const double *h_band_X /* P x 2 : points[J0]-points[I] */);
+int pde_grid_destroy(pde_grid *g);
+int64_t pde_grid_pitch(const pde_grid *g);      /* doubles per lattice row        */
+int64_t pde_grid_rows(const pde_grid *g);       /* nx_local + 2*halo_rows         */
+int64_t pde_grid_state_len(const pde_grid *g);  /* rows*pitch + nb                */
+int64_t pde_grid_policy_len(const pde_grid *g); /* rows*pitch (uint16 entries)    */
+
+/* flat reference vector (N + nb) <-> state layout.  Both on device. */
+int pde_grid_pack(pde_grid *g, const double *d_u_flat, double *d_state, void *stream);
+int pde_grid_unpack(pde_grid *g, const double *d_state, double *d_u_flat, void *stream);
+/* interior part of a state-layout array -> flat (N) interior order */
+int pde_grid_unpad(pde_grid *g, const double *d_padded, double *d_flat, void *stream);
+int pde_grid_unpad_u16(pde_grid *g, const uint16_t *d_padded, int32_t *d_flat, void *stream);
+
+/* ddg.d2eigs (ddg.py:251-327) values + policy.  Any output may be NULL.
+ * d_lmin/d_lmax: state layout.  d_pmin/d_pmax (state layout, uint16): selected
+ * pair per interior point: deep points -> row of the stencil table, band
+ * points -> position inside the point's band_pairs group.  Tie rule as
+ * ddg.py:283-292: min = last pair attaining it, max = first.
+ * mode 0 = reference arithmetic order (bit-exact), 1 = fast re-associated. */
+int pde_ddg_d2eigs(pde_grid *g, const double *d_state,
+                   double *d_lmin, double *d_lmax,
+                   uint16_t *d_pmin, uint16_t *d_pmax, int mode, void *stream);
+
+/* Selected-pair finite-difference rows applied matrix-free
+ * (replaces the CSR assembly ddg.py:304-323):
+ *   y[i] = sum over the policy's pair at i of  w0*w_0*x[J0] + w0*w_1*x[J1]
+ *          - w0*(w_0+w_1)*x[i]            for interior i;  y = x on the wall. */
+int pde_ddg_apply_policy(pde_grid *g, const uint16_t *d_policy,
+                         const double *d_x, double *d_y, void *stream);
+/* control directions of ddg.py:297-300 (quirk: both scaled by the min pair's
+ * 1/h): d_vmin, d_vmax are (N,2) flat. */
+int pde_ddg_control(pde_grid *g, const uint16_t *d_pmin, const uint16_t *d_pmax,
+                    double *d_vmin, double *d_vmax, void *stream);
+/* ------------------------------------------------------------------------
+ * Jacobian of a policy, matrix-free.  Replaces convex_envelope.py:48-54
+ * (Jac = I; Jac[active] = -M_min[active]) and pucci.py:50-54,136-139
+ * (Jac[interior] = A0*M_max + A1*M_min).
+ *   interior row i : y = cmax_i * (M_pmax x)_i + cmin_i * (M_pmin x)_i,
+ *                    or y = x_i when d_pmin[i] == PDE_POLICY_IDENTITY
+ *   wall rows      : y = x
+ * cmin/cmax are scalars when d_cmin/d_cmax are NULL (then cmin_s/cmax_s are
+ * used), otherwise per-interior-point arrays in padded layout.
+ * x, y: state layout.  transpose != 0 applies the transposed operator
+ * (solvers.py:192, Jac.transpose().dot). */
+typedef struct pde_jac {
+    const uint16_t *d_pmin;   /* padded layout, may hold PDE_POLICY_IDENTITY */
+    const uint16_t *d_pmax;   /* NULL when cmax == 0 (convex envelope)       */
+    double cmin_s, cmax_s;
+    const double *d_cmin, *d_cmax;
+} pde_jac;
+int pde_jac_matvec(pde_grid *g, const pde_jac *J, const double *d_x, double *d_y,
+                   int transpose, void *stream);
+int pde_jac_diagonal(pde_grid *g, const pde_jac *J, double *d_diag, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Convex envelope, convex_envelope.py:8-56 / :58-123.
+ * residual: F = W-g everywhere; interior rows with -lambda_min > W-g are
+ * replaced by -lambda_min and marked active (policy = selected pair, else
+ * PDE_POLICY_IDENTITY).  d_F: state layout.  d_policy may be NULL.
+ * d_red (2 doubles, device): [max|F|, unused] accumulated with max. */
+int pde_ce_residual(pde_grid *g, const double *d_W, const double *d_g,
+                    double *d_F, uint16_t *d_policy, double *d_red, void *stream);
+
+/* Device-resident explicit Euler loop (solvers.py:13-93 specialised to the
+ * convex-envelope operator): runs up to max_iters iterations of
+ * U <- U - dt*F(U) without host round trips, stopping at the first iteration
+ * where max|U_new-U| < solution_tol and max|F(U)| < operator_tol.
+ * d_U0/d_U1: two state buffers (ping-pong), d_U0 holds the initial iterate.
+ * h_out: [iterations, which buffer holds the result (0/1), diff, max|F|,
+ *         stop reason (1 converged, 2 max_iters)] -- synchronises the stream. */
+int pde_ce_euler(pde_grid *g, double *d_U0, double *d_U1, const double *d_g,
+                 double dt, double solution_tol, double operator_tol,
+                 int64_t max_iters, int64_t check_every, double *h_out, void *stream);
+
+/* Pucci, pucci.py:7-58 / :123-141:  F = A0*lambda_max + A1*lambda_min - f on
+ * the interior, W - dirichlet on the wall.  d_f: state layout (interior f,
+ * wall g).  A0/A1 scalar, or arrays when d_A0/d_A1 non-NULL (padded). */
+int pde_pucci_residual(pde_grid *g, const double *d_W, const double *d_f,
+                       double A0, double A1, const double *d_A0, const double *d_A1,
+                       double *d_F, uint16_t *d_pmin, uint16_t *d_pmax,
+                       double *d_red, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Jacobi-preconditioned BiCGStab, matrix-free on a pde_jac.  Replaces
+ * solvers.py:179-181 (P = diags(1/Jac.diagonal()); bicgstab(Jac, -Gu, M=P,
+ * tol=...)) and follows SciPy 1.18.1 scipy/sparse/linalg/_isolve/iterative.py
+ * `bicgstab` step for step: x0 = 0, stop when ||r||_2 < max(atol, rtol*||b||),
+ * tested at the top of each iteration and after the half step; breakdown
+ * exits -10 (rho) / -11 (omega, <rtilde,v> == 0); maxiter default 10*n.
+ * d_b, d_x: state layout.  d_work: 8 * state_len doubles of scratch.
+ * h_info[0] = SciPy's `info` (0 ok, >0 = maxiter reached, <0 breakdown),
+ * h_info[1] = iterations performed.  Synchronises the stream. */
+int pde_bicgstab(pde_grid *g, const pde_jac *J, const double *d_b, double *d_x,
+                 double rtol, double atol, int64_t maxiter, int64_t check_every,
+                 double *d_work, int64_t *h_info, void *stream);
+
+/* small fused vector helpers used by the Newton loop (solvers.py:189-199) */
+int pde_vec_newton_update(pde_grid *g, const double *d_U, const double *d_d,
+                          const double *d_F, const double *d_Jd, double *d_Unew,
+                          double *h_out /* [max|U-Unew|, F.(J d), ||d||^2] */, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Point-cloud operators (ddi.py:304-414 cached path, ddf.py:137-252): the Nds
+ * cached CSR matrices (5 nnz/row) stored as one ELL table:
+ *   idx (n, nds, 4) int32, w (n, nds, 4) double, centre weight = -sum(w).
+ * ---------------------------------------------------------------------- */
+int pde_ell_create(pde_ell **out, int device, int64_t n_interior, int64_t n_points,
+                   int nds, const int32_t *d_idx, const double *d_w);
+int pde_ell_destroy(pde_ell *e);
+/* d2u[i,k] = sum_j w[i,k,j]*(u[idx[i,k,j]] - u[i]); min/max over k.
+ * argmin/argmax: lowest k among exact ties (np.argsort tie order is
+ * unspecified in the reference, ddi.py:363). Outputs may be NULL. */
+int pde_ell_d2eigs(pde_ell *e, const double *d_u, double *d_lmin, double *d_lmax,
+                   int32_t *d_kmin, int32_t *d_kmax, void *stream);
+/* y[i] = row (i, k[i]) of the table applied to x (selected-direction rows). */
+int pde_ell_apply_policy(pde_ell *e, const int32_t *d_k, const double *d_x,
+                         double *d_y, void *stream);
+/* Build the ddi table on the device (ddi.py:253-299): for every interior point
+ * and direction V[k], the first simplex (row order) whose cone contains +v and
+ * the first containing -v, barycentric weights, 2/(hf+hb) scaling.
+ * simplices: (S,3) int64 rows (i, s1, s2) grouped by ascending i, with
+ * simp_ptr (n_interior+1).  eps_over_h = 1e-15/spatial_resolution (ddi.py:267).
+ * froese != 0 builds the ddf weights instead (ddf.py:46-116). */
+int pde_ell_build(int device, int64_t n_interior, const double *d_points /* (n,2) */,
+                  const int64_t *d_simplices, const int64_t *d_simp_ptr,
+                  int nds, const double *d_V /* (nds,2) */, double eps_over_h,
+                  int froese, int32_t *d_idx, double *d_w, int32_t *d_fail, void *stream);
+
+/* fp64 FMA-chain microbenchmark: returns achieved DFMA/s of the device in
+ * *h_dfma_per_s (synchronous).  Used by bench.py to evidence which roof
+ * (HBM or the fp64 pipe) binds the stencil kernel. */
+int pde_fp64_peak(int device, double *h_dfma_per_s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PDE_B200_H */

@@ -1,0 +1,397 @@
+"""Device context of a pairs grid: the host side of ``pde_grid`` (C ABI).
+
+A context owns the device copy of the grid description (direction table with
+its weights, band pair rows) and offers the raw operations on *state-layout*
+tensors that ``ddg`` / ``convex_envelope`` / ``pucci`` / ``solvers`` are written
+on.  It is cached on the grid object, the same place the reference caches its
+finite-difference matrices (``G._d2cache``, ddi.py:355-356).
+
+PyTorch is used only for device memory and streams; every kernel is reached
+through ``libpde_b200.so``.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import pde_jac, check, vp
+
+POLICY_IDENTITY = 0xFFFF
+
+
+def _ptr(t):
+    return vp(0) if t is None else vp(t.data_ptr())
+
+
+def _stream():
+    return vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _np_ptr(a):
+    return vp(a.ctypes.data)
+
+
+def require_cuda(device=None):
+    if not torch.cuda.is_available():
+        raise _lib.PdeError("pyellipticfd_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _lib.PdeError("pyellipticfd_b200 computes on CUDA devices only")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def to_device(u, device, dtype=torch.float64):
+    """numpy / torch (any device) -> contiguous tensor on ``device``."""
+    if isinstance(u, torch.Tensor):
+        return u.to(device=device, dtype=dtype).contiguous()
+    a = np.ascontiguousarray(np.asarray(u), dtype={torch.float64: np.float64}[dtype])
+    return torch.from_numpy(a).to(device)
+
+
+def like_input(u, t):
+    """Return device tensor ``t`` in the container type of the user's input ``u``."""
+    if isinstance(u, torch.Tensor):
+        return t if u.is_cuda else t.cpu()
+    return t.cpu().numpy()
+
+
+def pair_weights(PI, PJ0, PJ1):
+    """(w_0, w_1, w0) and X0 with the reference's arithmetic (ddg.py:276-280)."""
+    X0 = PJ0 - PI
+    X1 = PJ1 - PI
+    h0 = np.sqrt(X0[:, 0] * X0[:, 0] + X0[:, 1] * X0[:, 1])
+    h1 = np.sqrt(X1[:, 0] * X1[:, 0] + X1[:, 1] * X1[:, 1])
+    w = np.stack([1 / h0, 1 / h1, 2 / (h0 + h1)], axis=1)
+    return np.ascontiguousarray(w), np.ascontiguousarray(X0)
+
+
+class Slab(object):
+    """Rows [x_offset, x_offset + nx_local) of the lattice plus ``halo`` rows each side."""
+
+    def __init__(self, x_offset, nx_local, halo):
+        self.x_offset, self.nx_local, self.halo = int(x_offset), int(nx_local), int(halo)
+
+
+class GridContext(object):
+    """Host handle of one ``pde_grid``."""
+
+    def __init__(self, G, device=None, slab=None):
+        self.lib = _lib.lib()
+        self.device = require_cuda(device)
+        self.G = G
+        structured = hasattr(G, "stencil_pairs") and hasattr(G, "band_pairs")
+        if structured and G.uniform_weights():
+            self._init_structured(G, slab)
+        else:
+            if slab is not None:
+                raise _lib.PdeError("slab decomposition needs a structured, uniformly weighted grid")
+            self._init_generic(G)
+        self.pitch = int(self.lib.pde_grid_pitch(self.h))
+        self.rows = int(self.lib.pde_grid_rows(self.h))
+        self.n_state = int(self.lib.pde_grid_state_len(self.h))
+        self.n_lattice = self.rows * self.pitch
+
+    # ---- construction --------------------------------------------------------------
+    def _create(self, nx_global, ny, nb, radius, x_offset, nx_local, halo, sp, sw, sX,
+                band_center, band_ptr, band_j, band_w, band_X):
+        sp = np.ascontiguousarray(sp, dtype=np.int32).reshape(-1, 4)
+        sw = np.ascontiguousarray(sw, dtype=np.float64).reshape(-1, 3)
+        sX = np.ascontiguousarray(sX, dtype=np.float64).reshape(-1, 2)
+        band_center = np.ascontiguousarray(band_center, dtype=np.int64)
+        band_ptr = np.ascontiguousarray(band_ptr, dtype=np.int64)
+        band_j = np.ascontiguousarray(band_j, dtype=np.int64).reshape(-1, 2)
+        band_w = np.ascontiguousarray(band_w, dtype=np.float64).reshape(-1, 3)
+        band_X = np.ascontiguousarray(band_X, dtype=np.float64).reshape(-1, 2)
+        h = vp()
+        check(self.lib.pde_grid_create(
+            C.byref(h), self.device.index, nx_global, ny, nb, radius, x_offset, nx_local, halo,
+            sp.shape[0], _np_ptr(sp), _np_ptr(sw), _np_ptr(sX),
+            band_center.shape[0], _np_ptr(band_center), _np_ptr(band_ptr), _np_ptr(band_j),
+            _np_ptr(band_w), _np_ptr(band_X)))
+        self.h = h
+        self.nx_global, self.ny, self.nb = int(nx_global), int(ny), int(nb)
+        self.x_offset, self.nx_local, self.halo_rows = int(x_offset), int(nx_local), int(halo)
+        self.radius = int(radius)
+        self.n_interior_local = self.nx_local * self.ny
+        self.stencil_pairs = sp
+        self.band_ptr = band_ptr
+        self.n_band = band_center.shape[0]
+
+    def _init_structured(self, G, slab):
+        nx, ny = G.interior_shape
+        r = G.stencil_radius
+        if slab is None:
+            slab = Slab(0, nx, 0)
+        self.slab = slab
+        pitch = (ny + 15) // 16 * 16
+        rows = slab.nx_local + 2 * slab.halo
+        N = G.num_interior
+        sp = G.stencil_pairs
+        # per-direction weights at a generic deep point (position independent here)
+        c = np.array([[r + 1.0, r + 1.0]])
+        PI = G._scaled(c)
+        w, X0 = pair_weights(np.repeat(PI, len(sp), 0), G._scaled(c + sp[:, 0:2]),
+                             G._scaled(c + sp[:, 2:4]))
+        # band rows owned by this slab
+        bi = G.band_index
+        brow = bi // ny
+        own = (brow >= slab.x_offset) & (brow < slab.x_offset + slab.nx_local)
+        sel = np.flatnonzero(own)
+        self.band_sel = sel
+        ptr = G.band_ptr
+        counts = (ptr[1:] - ptr[:-1])[sel]
+        lptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        take = (np.repeat(ptr[sel] - lptr[:-1], counts) + np.arange(lptr[-1])).astype(np.int64)
+        bp = G.band_pairs[take]
+
+        def offs(ids):
+            ids = np.asarray(ids, dtype=np.int64)
+            lat = ids < N
+            o = np.empty(ids.shape, np.int64)
+            rr = ids[lat] // ny - slab.x_offset + slab.halo
+            if lat.any() and ((rr < 0).any() or (rr >= rows).any()):
+                raise _lib.PdeError("slab halo too small for the band stencil")
+            o[lat] = rr * pitch + ids[lat] % ny
+            o[~lat] = rows * pitch + (ids[~lat] - N)
+            return o
+
+        bw, bX = pair_weights(G.coords(bp[:, 0]), G.coords(bp[:, 1]), G.coords(bp[:, 2]))
+        self.band_global = bi[sel]
+        self._create(nx, ny, G.num_bdry, r, slab.x_offset, slab.nx_local, slab.halo,
+                     sp, w, X0, offs(bi[sel]), lptr,
+                     np.stack([offs(bp[:, 1]), offs(bp[:, 2])], 1) if len(bp) else np.zeros((0, 2)),
+                     bw, bX)
+        self.band_pairs = bp
+        self.structured = True
+
+    def _init_generic(self, G):
+        """Any object with ``pairs``, ``points``, ``num_interior`` (e.g. a grid built
+        by the reference constructor, or a non-dyadic grid): every interior point is
+        handled by the explicit pair-row kernel."""
+        pairs = np.asarray(G.pairs, dtype=np.int64)
+        points = np.asarray(G.points, dtype=np.float64)
+        N = int(G.num_interior)
+        nb = points.shape[0] - N
+        order = np.argsort(pairs[:, 0], kind="stable")
+        pairs = pairs[order]
+        counts = np.bincount(pairs[:, 0], minlength=N)
+        if (counts == 0).any():
+            raise TypeError("Point {0} has no pairs".format(int(np.flatnonzero(counts == 0)[0])))
+        ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        pitch = (N + 15) // 16 * 16
+
+        def offs(ids):
+            ids = np.asarray(ids, dtype=np.int64)
+            return np.where(ids < N, ids, pitch + (ids - N))
+
+        bw, bX = pair_weights(points[pairs[:, 0]], points[pairs[:, 1]], points[pairs[:, 2]])
+        self.slab = Slab(0, 1, 0)
+        self._create(1, N, nb, N + 1, 0, 1, 0, np.zeros((0, 4)), np.zeros((0, 3)), np.zeros((0, 2)),
+                     offs(np.arange(N)), ptr, np.stack([offs(pairs[:, 1]), offs(pairs[:, 2])], 1),
+                     bw, bX)
+        self.band_pairs = pairs
+        self.band_global = np.arange(N)
+        self.pair_order = order
+        self.structured = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "h", None):
+                self.lib.pde_grid_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+    # ---- cache on the grid object ----------------------------------------------------------
+    @staticmethod
+    def get(G, device=None):
+        device = require_cuda(device)
+        cache = getattr(G, "_b200ctx", None)
+        if cache is None:
+            cache = {}
+            try:
+                G._b200ctx = cache
+            except AttributeError:
+                pass
+        key = device.index
+        if key not in cache:
+            cache[key] = GridContext(G, device)
+        return cache[key]
+
+    # ---- buffers ---------------------------------------------------------------------------------
+    def zeros(self):
+        return torch.zeros(self.n_state, dtype=torch.float64, device=self.device)
+
+    def empty_policy(self):
+        return torch.empty(self.n_lattice, dtype=torch.uint16, device=self.device)
+
+    def n_flat(self):
+        return self.n_interior_local + self.nb
+
+    def pack(self, u_flat, out=None):
+        u_flat = to_device(u_flat, self.device)
+        if u_flat.numel() != self.n_flat():
+            raise ValueError("expected a vector over all %d points, got %d"
+                             % (self.n_flat(), u_flat.numel()))
+        S = out if out is not None else torch.empty(self.n_state, dtype=torch.float64,
+                                                    device=self.device)
+        check(self.lib.pde_grid_pack(self.h, _ptr(u_flat), _ptr(S), _stream()))
+        return S
+
+    def unpack(self, S):
+        out = torch.empty(self.n_flat(), dtype=torch.float64, device=self.device)
+        check(self.lib.pde_grid_unpack(self.h, _ptr(S), _ptr(out), _stream()))
+        return out
+
+    def unpad(self, S):
+        out = torch.empty(self.n_interior_local, dtype=torch.float64, device=self.device)
+        check(self.lib.pde_grid_unpad(self.h, _ptr(S), _ptr(out), _stream()))
+        return out
+
+    def unpad_policy(self, P):
+        out = torch.empty(self.n_interior_local, dtype=torch.int32, device=self.device)
+        check(self.lib.pde_grid_unpad_u16(self.h, _ptr(P), _ptr(out), _stream()))
+        return out
+
+    # ---- operators --------------------------------------------------------------------------------
+    def d2eigs(self, S, want_min=True, want_max=True, policy=False, mode=0, out=None):
+        """Raw ddg.d2eigs on a state tensor -> (lmin, lmax, pmin, pmax) state-layout."""
+        if out is not None:
+            lmin, lmax, pmin, pmax = out
+        else:
+            lmin = self.zeros() if want_min else None
+            lmax = self.zeros() if want_max else None
+            pmin = self.empty_policy() if policy else None
+            pmax = self.empty_policy() if policy else None
+        check(self.lib.pde_ddg_d2eigs(self.h, _ptr(S), _ptr(lmin), _ptr(lmax), _ptr(pmin),
+                                      _ptr(pmax), int(mode), _stream()))
+        return lmin, lmax, pmin, pmax
+
+    def apply_policy(self, policy, X):
+        Y = self.zeros()
+        check(self.lib.pde_ddg_apply_policy(self.h, _ptr(policy), _ptr(X), _ptr(Y), _stream()))
+        return Y
+
+    def control(self, pmin, pmax):
+        vmin = torch.empty((self.n_interior_local, 2), dtype=torch.float64, device=self.device)
+        vmax = torch.empty_like(vmin)
+        check(self.lib.pde_ddg_control(self.h, _ptr(pmin), _ptr(pmax), _ptr(vmin), _ptr(vmax),
+                                       _stream()))
+        return vmin, vmax
+
+    def jac_struct(self, pmin, pmax=None, cmin=1.0, cmax=0.0):
+        J = pde_jac()
+        J.d_pmin = pmin.data_ptr()
+        J.d_pmax = pmax.data_ptr() if pmax is not None else None
+        if isinstance(cmin, torch.Tensor):
+            J.d_cmin, J.cmin_s = cmin.data_ptr(), 0.0
+        else:
+            J.d_cmin, J.cmin_s = None, float(cmin)
+        if isinstance(cmax, torch.Tensor):
+            J.d_cmax, J.cmax_s = cmax.data_ptr(), 0.0
+        else:
+            J.d_cmax, J.cmax_s = None, float(cmax)
+        return J
+
+    def jac_matvec(self, J, X, transpose=False, out=None):
+        Y = out if out is not None else self.zeros()
+        check(self.lib.pde_jac_matvec(self.h, C.byref(J), _ptr(X), _ptr(Y), int(transpose),
+                                      _stream()))
+        return Y
+
+    def jac_diagonal(self, J):
+        Dg = self.zeros()
+        check(self.lib.pde_jac_diagonal(self.h, C.byref(J), _ptr(Dg), _stream()))
+        return Dg
+
+    def ce_residual(self, W, g, policy=True):
+        F = self.zeros()
+        P = self.empty_policy() if policy else None
+        red = torch.zeros(2, dtype=torch.float64, device=self.device)
+        check(self.lib.pde_ce_residual(self.h, _ptr(W), _ptr(g), _ptr(F), _ptr(P), _ptr(red),
+                                       _stream()))
+        return F, P, red
+
+    def pucci_residual(self, W, f, A0, A1, policy=True):
+        F = self.zeros()
+        pmin = self.empty_policy() if policy else None
+        pmax = self.empty_policy() if policy else None
+        red = torch.zeros(2, dtype=torch.float64, device=self.device)
+        a0 = A0 if isinstance(A0, torch.Tensor) else None
+        a1 = A1 if isinstance(A1, torch.Tensor) else None
+        check(self.lib.pde_pucci_residual(
+            self.h, _ptr(W), _ptr(f), 0.0 if a0 is not None else float(A0),
+            0.0 if a1 is not None else float(A1), _ptr(a0), _ptr(a1), _ptr(F), _ptr(pmin),
+            _ptr(pmax), _ptr(red), _stream()))
+        return F, pmin, pmax, red
+
+    def ce_euler(self, U0, g, dt, solution_tol, operator_tol, max_iters, check_every=64):
+        """Device-resident Euler loop.  Returns (U, diff, iters, max|F|, reason)."""
+        U1 = self.zeros()
+        out = (C.c_double * 5)()
+        check(self.lib.pde_ce_euler(self.h, _ptr(U0), _ptr(U1), _ptr(g), float(dt),
+                                    float(solution_tol), float(operator_tol), int(max_iters),
+                                    int(check_every), out, _stream()))
+        iters = int(out[0])
+        U = U1 if int(out[1]) == 1 else U0
+        return U, float(out[2]), iters, float(out[3]), int(out[4])
+
+    def bicgstab(self, J, b, rtol, atol=0.0, maxiter=0, check_every=32, work=None):
+        x = self.zeros()
+        if work is None:
+            work = torch.empty(8 * self.n_state, dtype=torch.float64, device=self.device)
+        info = (C.c_int64 * 2)()
+        check(self.lib.pde_bicgstab(self.h, C.byref(J), _ptr(b), _ptr(x), float(rtol), float(atol),
+                                    int(maxiter), int(check_every), _ptr(work), info, _stream()))
+        return x, int(info[0]), int(info[1])
+
+    def newton_update(self, U, d, F, Jd):
+        Unew = torch.empty_like(U)
+        out = (C.c_double * 3)()
+        check(self.lib.pde_vec_newton_update(self.h, _ptr(U), _ptr(d), _ptr(F), _ptr(Jd),
+                                             _ptr(Unew), out, _stream()))
+        return Unew, float(out[0]), float(out[1]), float(out[2])
+
+    # ---- policy -> explicit rows (small grids; the `.tocsr()` escape hatch) ------------------------
+    def policy_rows(self, policy_flat):
+        """(J0, J1, w_0, w_1, w0) global ids / weights of the selected pair of every
+        interior point, from a flat int policy (host numpy)."""
+        pol = np.asarray(policy_flat, dtype=np.int64)
+        N = self.n_interior_local
+        J0 = np.empty(N, np.int64)
+        J1 = np.empty(N, np.int64)
+        W = np.empty((N, 3))
+        if self.structured:
+            G = self.G
+            ny = self.ny
+            isband = np.zeros(N, bool)
+            isband[self.band_global - self.x_offset * ny] = True
+            deep = np.flatnonzero(~isband)
+            gid = deep + self.x_offset * ny
+            sp = self.stencil_pairs[pol[deep]]
+            di, dj = gid // ny, gid % ny
+            J0[deep] = (di + sp[:, 0]) * ny + dj + sp[:, 1]
+            J1[deep] = (di + sp[:, 2]) * ny + dj + sp[:, 3]
+            c = np.array([[self.radius + 1.0] * 2])
+            w, _ = pair_weights(np.repeat(G._scaled(c), len(self.stencil_pairs), 0),
+                                G._scaled(c + self.stencil_pairs[:, 0:2]),
+                                G._scaled(c + self.stencil_pairs[:, 2:4]))
+            W[deep] = w[pol[deep]]
+            bl = self.band_global - self.x_offset * ny
+            rows = self.band_ptr[:-1] + pol[bl]
+            bp = self.band_pairs[rows]
+            J0[bl], J1[bl] = bp[:, 1], bp[:, 2]
+            bw, _ = pair_weights(G.coords(bp[:, 0]), G.coords(bp[:, 1]), G.coords(bp[:, 2]))
+            W[bl] = bw
+        else:
+            rows = self.band_ptr[:-1] + pol
+            bp = self.band_pairs[rows]
+            J0, J1 = bp[:, 1], bp[:, 2]
+            P = np.asarray(self.G.points)
+            W, _ = pair_weights(P[bp[:, 0]], P[bp[:, 1]], P[bp[:, 2]])
+        return J0, J1, W

@@ -1,0 +1,298 @@
+// ddg operators on the regular grid: structured deep-interior kernel (K1,
+// stencil_deep.cuh) + CSR band kernel, with the convex-envelope / Pucci
+// epilogues fused in.  C ABI in include/pde_b200.h.
+#include <algorithm>
+#include "stencil_deep.cuh"
+
+using namespace pde;
+
+namespace pde {
+
+// ---- band kernel: one thread per band point, explicit pair rows -----------------
+// Scans the point's rows in the given order with `<=` (min keeps the LAST minimal
+// row) and `>` (max keeps the FIRST maximal row): ddg.py:283-292.
+template <int MODE, class Epi>
+__global__ void __launch_bounds__(128)
+k_band(int64_t n_band, const int64_t *__restrict__ center, const int64_t *__restrict__ ptr,
+       const int64_t *__restrict__ jj, const double *__restrict__ ww,
+       const double *__restrict__ S, const Epi epi, double *red_out,
+       const unsigned long long *done_flag) {
+    if (done_flag && *done_flag) return;
+    BlockMax2 red{0.0, 0.0};
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < n_band) {
+        int64_t o = center[i];
+        double uc = S[o];
+        double mn = __longlong_as_double(0x7ff0000000000000LL);
+        double mx = __longlong_as_double(0xfff0000000000000LL);
+        int kmn = 0, kmx = 0;
+        int64_t b = ptr[i], e = ptr[i + 1];
+        for (int64_t k = b; k < e; ++k) {
+            double u0 = S[jj[2 * k]], u1 = S[jj[2 * k + 1]];
+            double w_0 = ww[3 * k], w_1 = ww[3 * k + 1], w0 = ww[3 * k + 2];
+            double d;
+            if (MODE == 0)
+                d = pair_value_exact(uc, u0, u1, w_0, w_1, w0);
+            else
+                d = (fma(w_1, u1 - uc, w_0 * (u0 - uc))) * w0;
+            if (Epi::kMin && d <= mn) {
+                mn = d;
+                kmn = (int)(k - b);
+            }
+            if (Epi::kMax && d > mx) {
+                mx = d;
+                kmx = (int)(k - b);
+            }
+        }
+        epi(o, uc, mn, mx, kmn, kmx, red);
+    }
+    if (Epi::kRed) {
+        double a = warp_max(red.a), bb = warp_max(red.b);
+        if ((threadIdx.x & 31) == 0) {
+            atomic_max_nonneg(&red_out[0], a);
+            atomic_max_nonneg(&red_out[1], bb);
+        }
+    }
+}
+
+// ---- wall rows of the residual / Euler step -------------------------------------------
+// mode 0: F = W - g  (convex_envelope.py:44; pucci.py:130,141), red[0] = max|F|
+// mode 1: Unew = U - dt*(U - g), red[0] = max|F|, red[1] = max|U-Unew|
+__global__ void k_wall(int64_t nb, int64_t off, const double *__restrict__ W,
+                       const double *__restrict__ g, double *__restrict__ out, double dt, int mode,
+                       double *red_out, const unsigned long long *done_flag) {
+    if (done_flag && *done_flag) return;
+    double ra = 0.0, rb = 0.0;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < nb;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double u = W[off + i];
+        double f = __dsub_rn(u, g[off + i]);
+        ra = fmax(ra, fabs(f));
+        if (mode == 0) {
+            out[off + i] = f;
+        } else {
+            double un = __dsub_rn(u, __dmul_rn(dt, f));
+            out[off + i] = un;
+            rb = fmax(rb, fabs(__dsub_rn(u, un)));
+        }
+    }
+    ra = warp_max(ra);
+    rb = warp_max(rb);
+    if ((threadIdx.x & 31) == 0) {
+        atomic_max_nonneg(&red_out[0], ra);
+        atomic_max_nonneg(&red_out[1], rb);
+    }
+}
+
+// ---- host-side launch helpers ----------------------------------------------------------
+struct DeepRegion {
+    int row0, col0, nrows, ncols;   // buffer coordinates
+};
+
+static DeepRegion deep_region(const pde_grid *g) {
+    int64_t r = g->radius;
+    int64_t gx0 = std::max<int64_t>(r, g->x_offset);
+    int64_t gx1 = std::min<int64_t>(g->nx_global - r, g->x_offset + g->nx_local);
+    DeepRegion d;
+    d.row0 = (int)(gx0 - g->x_offset + g->halo_rows);
+    d.nrows = (int)std::max<int64_t>(0, gx1 - gx0);
+    d.col0 = (int)r;
+    d.ncols = (int)std::max<int64_t>(0, g->ny - 2 * r);
+    return d;
+}
+
+static int make_tmap(const pde_grid *g, const double *S, int boxy, int boxx, CUtensorMap *out) {
+    PDE_REQUIRE((reinterpret_cast<uintptr_t>(S) & 15) == 0, "state buffer must be 16-byte aligned");
+    cuuint64_t gdim[2] = {(cuuint64_t)g->ny, (cuuint64_t)g->rows};
+    cuuint64_t gstr[1] = {(cuuint64_t)g->pitch * 8};
+    cuuint32_t box[2] = {(cuuint32_t)boxy, (cuuint32_t)boxx};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g->encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(S), gdim,
+                           gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char buf[128];
+        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return pde::fail(buf, __FILE__, __LINE__);
+    }
+    return 0;
+}
+
+template <int H, int P, int MODE, class Epi>
+static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *red,
+                          const unsigned long long *done, cudaStream_t st) {
+    DeepRegion dr = deep_region(g);
+    if (dr.nrows <= 0 || dr.ncols <= 0) return 0;
+    constexpr int TX = 2 * P;
+    DeepGeom geo;
+    geo.pitch = g->pitch;
+    geo.row0 = dr.row0;
+    geo.col0 = dr.col0;
+    geo.nrows = dr.nrows;
+    geo.ncols = dr.ncols;
+    geo.tiles_x = (dr.nrows + TX - 1) / TX;
+    geo.tiles_y = (dr.ncols + K1_TY - 1) / K1_TY;
+    CUtensorMap tmap;
+    int rc = make_tmap(g, S, K1_TY + 2 * H + 2, TX + 2 * H, &tmap);
+    if (rc) return rc;
+    constexpr int smem = k_deep_smem_bytes<H, P>();
+    auto kern = k_deep<H, P, MODE, Epi>;
+    static bool attr_set = false;   // per template instantiation
+    if (!attr_set) {
+        PDE_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    int ntiles = geo.tiles_x * geo.tiles_y;
+    int grid = std::min(ntiles, g->num_sms * 2);
+    kern<<<grid, K1_THREADS, smem, st>>>(tmap, g->tab, geo, epi, S, red, done);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int MODE, class Epi>
+static int launch_deep(pde_grid *g, const double *S, const Epi &epi, double *red,
+                       const unsigned long long *done, cudaStream_t st) {
+    if (g->tab.D == 0) return 0;
+    switch (g->tab.H) {
+        case 1: return launch_deep_hp<1, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 2: return launch_deep_hp<2, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 3: return launch_deep_hp<3, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 4: return launch_deep_hp<4, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 5: return launch_deep_hp<5, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 6: return launch_deep_hp<6, 8, MODE, Epi>(g, S, epi, red, done, st);
+    }
+    return pde::fail("unsupported stencil halo", __FILE__, __LINE__);
+}
+
+template <int MODE, class Epi>
+static int launch_band(pde_grid *g, const double *S, const Epi &epi, double *red,
+                       const unsigned long long *done, cudaStream_t st) {
+    if (g->n_band == 0) return 0;
+    int grid = (int)((g->n_band + 127) / 128);
+    k_band<MODE, Epi><<<grid, 128, 0, st>>>(g->n_band, g->d_band_center, g->d_band_ptr,
+                                             g->d_band_j, g->d_band_w, S, epi, red, done);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <class Epi>
+static int launch_both(pde_grid *g, const double *S, const Epi &epi, int mode, double *red,
+                       const unsigned long long *done, cudaStream_t st) {
+    int rc;
+    if (mode == 0) {
+        if ((rc = launch_deep<0, Epi>(g, S, epi, red, done, st))) return rc;
+        return launch_band<0, Epi>(g, S, epi, red, done, st);
+    }
+    if ((rc = launch_deep<1, Epi>(g, S, epi, red, done, st))) return rc;
+    return launch_band<1, Epi>(g, S, epi, red, done, st);
+}
+
+static int launch_wall(pde_grid *g, const double *W, const double *gg, double *out, double dt,
+                       int mode, double *red, const unsigned long long *done, cudaStream_t st) {
+    if (g->nb == 0) return 0;
+    int grid = (int)std::min<int64_t>((g->nb + 255) / 256, 1024);
+    k_wall<<<grid, 256, 0, st>>>(g->nb, g->rows * g->pitch, W, gg, out, dt, mode, red, done);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+// ---- Euler loop control ------------------------------------------------------------------
+// ctrl[0] = stop reason (0 running), ctrl[1] = iterations completed,
+// red[0] = max|F|, red[1] = max|dU| of the iteration in flight; red[2], red[3] keep the
+// values of the last completed iteration.
+__global__ void k_euler_finalize(double *red, unsigned long long *ctrl, double sol_tol,
+                                 double op_tol, unsigned long long max_iters) {
+    if (ctrl[0]) return;
+    double fmx = red[0], diff = red[1];
+    red[2] = fmx;
+    red[3] = diff;
+    red[0] = 0.0;
+    red[1] = 0.0;
+    unsigned long long it = ctrl[1] + 1;
+    ctrl[1] = it;
+    if (diff < sol_tol && fmx < op_tol)      // solvers.py:84
+        ctrl[0] = 1;
+    else if (it >= max_iters)                // solvers.py:86
+        ctrl[0] = 2;
+}
+
+}  // namespace pde
+
+extern "C" {
+
+int pde_ddg_d2eigs(pde_grid *g, const double *d_state, double *d_lmin, double *d_lmax,
+                   uint16_t *d_pmin, uint16_t *d_pmax, int mode, void *stream) {
+    PDE_REQUIRE(g && d_state, "null argument");
+    DeviceGuard guard(g->device);
+    EpiEigs epi{d_lmin, d_lmax, d_pmin, d_pmax};
+    return launch_both(g, d_state, epi, mode, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+int pde_ce_residual(pde_grid *g, const double *d_W, const double *d_g, double *d_F,
+                    uint16_t *d_policy, double *d_red, void *stream) {
+    PDE_REQUIRE(g && d_W && d_g && d_F, "null argument");
+    DeviceGuard guard(g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    double *red = d_red ? d_red : g->d_red + 8;
+    EpiCeResidual epi{d_g, d_F, d_policy};
+    int rc = launch_both(g, d_W, epi, 0, red, nullptr, st);
+    if (rc) return rc;
+    return launch_wall(g, d_W, d_g, d_F, 0.0, 0, red, nullptr, st);
+}
+
+int pde_pucci_residual(pde_grid *g, const double *d_W, const double *d_f, double A0, double A1,
+                       const double *d_A0, const double *d_A1, double *d_F, uint16_t *d_pmin,
+                       uint16_t *d_pmax, double *d_red, void *stream) {
+    PDE_REQUIRE(g && d_W && d_f && d_F, "null argument");
+    DeviceGuard guard(g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    double *red = d_red ? d_red : g->d_red + 8;
+    EpiPucciResidual epi{d_f, d_F, d_pmin, d_pmax, A0, A1, d_A0, d_A1};
+    int rc = launch_both(g, d_W, epi, 0, red, nullptr, st);
+    if (rc) return rc;
+    return launch_wall(g, d_W, d_f, d_F, 0.0, 0, red, nullptr, st);
+}
+
+int pde_ce_euler(pde_grid *g, double *d_U0, double *d_U1, const double *d_g, double dt,
+                 double solution_tol, double operator_tol, int64_t max_iters, int64_t check_every,
+                 double *h_out, void *stream) {
+    PDE_REQUIRE(g && d_U0 && d_U1 && d_g && h_out, "null argument");
+    PDE_REQUIRE(max_iters >= 1, "max_iters must be >= 1");
+    DeviceGuard guard(g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (check_every < 1) check_every = 64;
+    PDE_CHECK(cudaMemsetAsync(g->d_red, 0, 4 * sizeof(double), st));
+    PDE_CHECK(cudaMemsetAsync(g->d_ctrl, 0, 2 * sizeof(unsigned long long), st));
+    unsigned long long h_ctrl[2] = {0, 0};
+    double *buf[2] = {d_U0, d_U1};
+    int64_t launched = 0;
+    while (true) {
+        int64_t n = std::min<int64_t>(check_every, max_iters - launched);
+        for (int64_t i = 0; i < n; ++i, ++launched) {
+            const double *Uin = buf[launched & 1];
+            double *Uout = buf[(launched + 1) & 1];
+            EpiCeEuler epi{d_g, Uout, dt};
+            int rc = launch_both(g, Uin, epi, 0, g->d_red, g->d_ctrl, st);
+            if (rc) return rc;
+            if ((rc = launch_wall(g, Uin, d_g, Uout, dt, 1, g->d_red, g->d_ctrl, st))) return rc;
+            k_euler_finalize<<<1, 1, 0, st>>>(g->d_red, g->d_ctrl, solution_tol, operator_tol,
+                                              (unsigned long long)max_iters);
+            PDE_LAUNCH_CHECK();
+        }
+        PDE_CHECK(cudaMemcpyAsync(h_ctrl, g->d_ctrl, sizeof h_ctrl, cudaMemcpyDeviceToHost, st));
+        PDE_CHECK(cudaStreamSynchronize(st));
+        if (h_ctrl[0] != 0 || launched >= max_iters) break;
+    }
+    double h_red[4];
+    PDE_CHECK(cudaMemcpyAsync(h_red, g->d_red, sizeof h_red, cudaMemcpyDeviceToHost, st));
+    PDE_CHECK(cudaStreamSynchronize(st));
+    h_out[0] = (double)h_ctrl[1];
+    h_out[1] = (double)(h_ctrl[1] & 1);
+    h_out[2] = h_red[3];
+    h_out[3] = h_red[2];
+    h_out[4] = (double)h_ctrl[0];
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,245 @@
+// Context management, layout conversion and error plumbing for the C ABI
+// declared in include/pde_b200.h.
+#include <atomic>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+
+namespace pde {
+
+static thread_local std::string g_last_error;
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const std::string &msg) { g_last_error = msg; }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+
+int fail(const char *what, const char *file, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s (%s:%d)", what, file, line);
+    g_last_error = buf;
+    return 1;
+}
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line) {
+    char buf[768];
+    snprintf(buf, sizeof buf, "CUDA error %d (%s) in %s (%s:%d)", (int)e, cudaGetErrorString(e),
+             what, file, line);
+    g_last_error = buf;
+    return (int)e ? (int)e : 1;
+}
+
+// ---- layout kernels ------------------------------------------------------------
+__global__ void k_pack(const double *__restrict__ flat, double *__restrict__ state, int64_t nloc,
+                       int64_t ny, int64_t pitch, int64_t halo_rows, int64_t flat_row0,
+                       int64_t n_interior_global, int64_t nb, int64_t rows) {
+    // one thread per state entry; padding and halo rows are zeroed
+    int64_t total = rows * pitch + nb;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        double v = 0.0;
+        if (i >= rows * pitch) {
+            v = flat[n_interior_global + (i - rows * pitch)];
+        } else {
+            int64_t r = i / pitch, cidx = i - r * pitch;
+            int64_t lr = r - halo_rows;
+            if (cidx < ny && lr >= 0 && lr < nloc) v = flat[(flat_row0 + lr) * ny + cidx];
+        }
+        state[i] = v;
+    }
+}
+
+__global__ void k_unpack(const double *__restrict__ state, double *__restrict__ flat, int64_t nloc,
+                         int64_t ny, int64_t pitch, int64_t halo_rows, int64_t flat_row0,
+                         int64_t n_interior_global, int64_t nb, int64_t rows, int with_wall) {
+    int64_t total = nloc * ny + (with_wall ? nb : 0);
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < nloc * ny) {
+            int64_t r = i / ny, cidx = i - r * ny;
+            flat[(flat_row0 + r) * ny + cidx] = state[(r + halo_rows) * pitch + cidx];
+        } else {
+            int64_t j = i - nloc * ny;
+            flat[n_interior_global + j] = state[rows * pitch + j];
+        }
+    }
+}
+
+__global__ void k_unpad_u16(const uint16_t *__restrict__ padded, int32_t *__restrict__ flat,
+                            int64_t nloc, int64_t ny, int64_t pitch, int64_t halo_rows,
+                            int64_t flat_row0) {
+    int64_t total = nloc * ny;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ny, cidx = i - r * ny;
+        flat[(flat_row0 + r) * ny + cidx] = padded[(r + halo_rows) * pitch + cidx];
+    }
+}
+
+template <class T>
+static int upload(T **dst, const T *src, size_t n) {
+    *dst = nullptr;
+    if (n == 0) n = 1;      // keep pointers valid
+    PDE_CHECK(cudaMalloc((void **)dst, n * sizeof(T)));
+    if (src) PDE_CHECK(cudaMemcpy(*dst, src, n * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+}  // namespace pde
+
+using namespace pde;
+
+extern "C" {
+
+int pde_abi_version(void) { return PDE_B200_ABI_VERSION; }
+const char *pde_last_error(void) { return pde::g_last_error.c_str(); }
+int64_t pde_kernel_launches(void) { return pde::g_launches.load(); }
+
+int pde_grid_create(pde_grid **out, int device, int64_t nx_global, int64_t ny, int64_t nb,
+                    int stencil_radius, int64_t x_offset, int64_t nx_local, int64_t halo_rows,
+                    int D, const int32_t *h_stencil_pairs, const double *h_stencil_w,
+                    const double *h_stencil_X, int64_t n_band, const int64_t *h_band_center,
+                    const int64_t *h_band_ptr, const int64_t *h_band_j, const double *h_band_w,
+                    const double *h_band_X) {
+    PDE_REQUIRE(out != nullptr, "out is NULL");
+    PDE_REQUIRE(D >= 0 && D <= PDE_MAX_DIRS, "D out of range");
+    PDE_REQUIRE(nx_local >= 0 && ny > 0 && x_offset >= 0 && x_offset + nx_local <= nx_global,
+                "bad slab extents");
+    PDE_REQUIRE(halo_rows >= 0, "bad halo_rows");
+    int ndev = 0;
+    PDE_CHECK(cudaGetDeviceCount(&ndev));
+    PDE_REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
+    DeviceGuard guard(device);
+
+    pde_grid *g = new pde_grid();
+    memset(g, 0, sizeof(*g));
+    g->device = device;
+    g->nx_global = nx_global;
+    g->ny = ny;
+    g->x_offset = x_offset;
+    g->nx_local = nx_local;
+    g->halo_rows = halo_rows;
+    g->rows = nx_local + 2 * halo_rows;
+    g->pitch = (ny + 15) / 16 * 16;
+    g->nb = nb;
+    g->radius = stencil_radius;
+    g->tab.D = D;
+    int H = 0;
+    for (int k = 0; k < D; ++k) {
+        g->tab.a0[k] = h_stencil_pairs[4 * k + 0];
+        g->tab.b0[k] = h_stencil_pairs[4 * k + 1];
+        g->tab.a1[k] = h_stencil_pairs[4 * k + 2];
+        g->tab.b1[k] = h_stencil_pairs[4 * k + 3];
+        for (int j = 0; j < 4; ++j) H = max(H, abs(h_stencil_pairs[4 * k + j]));
+        g->tab.w_0[k] = h_stencil_w[3 * k + 0];
+        g->tab.w_1[k] = h_stencil_w[3 * k + 1];
+        g->tab.w0[k] = h_stencil_w[3 * k + 2];
+        g->stencil_X[k][0] = h_stencil_X ? h_stencil_X[2 * k + 0] : 0.0;
+        g->stencil_X[k][1] = h_stencil_X ? h_stencil_X[2 * k + 1] : 0.0;
+    }
+    g->tab.H = H;
+    if (H > 6 || H > stencil_radius) {
+        delete g;
+        return pde::fail("stencil halo larger than supported (6) or than the radius", __FILE__,
+                         __LINE__);
+    }
+    g->n_band = n_band;
+    g->n_band_pairs = n_band ? h_band_ptr[n_band] : 0;
+    int rc = 0;
+    rc |= upload(&g->d_band_center, h_band_center, (size_t)n_band);
+    rc |= upload(&g->d_band_ptr, h_band_ptr, (size_t)n_band + 1);
+    rc |= upload(&g->d_band_j, h_band_j, (size_t)g->n_band_pairs * 2);
+    rc |= upload(&g->d_band_w, h_band_w, (size_t)g->n_band_pairs * 3);
+    rc |= upload(&g->d_band_X, h_band_X, (size_t)g->n_band_pairs * 2);
+    rc |= upload<double>(&g->d_red, nullptr, 16);
+    rc |= upload<unsigned long long>(&g->d_ctrl, nullptr, 16);
+    if (rc) {
+        pde_grid_destroy(g);
+        return rc;
+    }
+    PDE_CHECK(cudaMemset(g->d_red, 0, 16 * sizeof(double)));
+    PDE_CHECK(cudaMemset(g->d_ctrl, 0, 16 * sizeof(unsigned long long)));
+
+    cudaDeviceProp prop;
+    PDE_CHECK(cudaGetDeviceProperties(&prop, device));
+    g->num_sms = prop.multiProcessorCount;
+    if (prop.major != 10) {
+        pde_grid_destroy(g);
+        return pde::fail("pde_b200 requires an sm_100-class (Blackwell) device", __FILE__, __LINE__);
+    }
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    PDE_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (qres != cudaDriverEntryPointSuccess || !fn) {
+        pde_grid_destroy(g);
+        return pde::fail("cuTensorMapEncodeTiled not available", __FILE__, __LINE__);
+    }
+    g->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
+    *out = g;
+    return 0;
+}
+
+int pde_grid_destroy(pde_grid *g) {
+    if (!g) return 0;
+    DeviceGuard guard(g->device);
+    cudaFree(g->d_band_center);
+    cudaFree(g->d_band_ptr);
+    cudaFree(g->d_band_j);
+    cudaFree(g->d_band_w);
+    cudaFree(g->d_band_X);
+    cudaFree(g->d_red);
+    cudaFree(g->d_ctrl);
+    delete g;
+    return 0;
+}
+
+int64_t pde_grid_pitch(const pde_grid *g) { return g->pitch; }
+int64_t pde_grid_rows(const pde_grid *g) { return g->rows; }
+int64_t pde_grid_state_len(const pde_grid *g) { return g->rows * g->pitch + g->nb; }
+int64_t pde_grid_policy_len(const pde_grid *g) { return g->rows * g->pitch; }
+
+static inline int grid_for(int64_t n, int num_sms) {
+    int64_t b = (n + 255) / 256;
+    int64_t cap = (int64_t)num_sms * 16;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+int pde_grid_pack(pde_grid *g, const double *d_u_flat, double *d_state, void *stream) {
+    DeviceGuard guard(g->device);
+    int64_t total = pde_grid_state_len(g);
+    k_pack<<<grid_for(total, g->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        d_u_flat, d_state, g->nx_local, g->ny, g->pitch, g->halo_rows, 0,
+        g->nx_local * g->ny, g->nb, g->rows);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pde_grid_unpack(pde_grid *g, const double *d_state, double *d_u_flat, void *stream) {
+    DeviceGuard guard(g->device);
+    int64_t total = g->nx_local * g->ny + g->nb;
+    k_unpack<<<grid_for(total, g->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        d_state, d_u_flat, g->nx_local, g->ny, g->pitch, g->halo_rows, 0,
+        g->nx_local * g->ny, g->nb, g->rows, 1);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pde_grid_unpad(pde_grid *g, const double *d_padded, double *d_flat, void *stream) {
+    DeviceGuard guard(g->device);
+    int64_t total = g->nx_local * g->ny;
+    k_unpack<<<grid_for(total, g->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        d_padded, d_flat, g->nx_local, g->ny, g->pitch, g->halo_rows, 0,
+        g->nx_local * g->ny, g->nb, g->rows, 0);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pde_grid_unpad_u16(pde_grid *g, const uint16_t *d_padded, int32_t *d_flat, void *stream) {
+    DeviceGuard guard(g->device);
+    int64_t total = g->nx_local * g->ny;
+    k_unpad_u16<<<grid_for(total, g->num_sms), 256, 0, (cudaStream_t)stream>>>(
+        d_padded, d_flat, g->nx_local, g->ny, g->pitch, g->halo_rows, 0);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

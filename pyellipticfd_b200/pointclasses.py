@@ -259,6 +259,19 @@ class FDRegularGrid(FDPointCloud):
         """Lattice coordinates -> physical coordinates, as :551."""
         return P * self.scaling + self.bounds[0]
 
+    def coords(self, ids):
+        """Physical coordinates of the given point ids, with the arithmetic of
+        ``points`` (:551) but without materialising the whole array."""
+        ids = np.asarray(ids, dtype=np.int64)
+        nx, ny = self.interior_shape
+        N = self.num_interior
+        P = np.empty((ids.size, 2))
+        lat = ids < N
+        P[lat, 0] = ids[lat] // ny + 1
+        P[lat, 1] = ids[lat] % ny + 1
+        P[~lat] = self._wall_unscaled[ids[~lat] - N]
+        return P * self.scaling + self.bounds[0]
+
     def _make_deep_table(self):
         """The translation-invariant pair table of deep-interior points."""
         r = self.stencil_radius
