@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: d2min wide-stencil evaluation on a 4097^2 grid, r = 4.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one application of ``ddg.d2min`` to a field on the grid of
+BASELINE.json configs[1] (4097^2 lattice = 4095^2 interior points, stencil radius 4,
+24 antipodal pairs per deep-interior point, fp64).
+
+* ``value``  Gpoint.dir/s = interior points x 24 / device time, state resident in HBM
+             (CUDA events on the launch stream around K steps, max over ranks).
+* ``e2e``    the same metric through the public API ``pyellipticfd_b200.ddg.d2min(G, u)``
+             with the field in pinned HOST memory and the result returned to the host:
+             H2D copy, pack, kernels, unpack, D2H inside the timed region.
+* ``roofline`` the deep-interior stencil kernel against the measured HBM copy bandwidth
+             (MEASURED_PEAKS.json): algorithmic bytes = 16 B per interior point (read u,
+             write lambda_min).  The kernel is bound by the fp64 pipe, not HBM (24 pairs x
+             7 fp64 instructions per point): see ``fp64`` and DESIGN.md.
+* ``cpu_baseline`` the NumPy port of the reference operator (oracle/) on the host cores.
+
+N > 1 (torchrun): weak scaling -- the global lattice has N x 4095 rows, each rank owns a
+4095-row slab and exchanges ``r`` halo rows with its neighbours (NCCL send/recv) before
+every operator application.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "Gpoint.dir/s for d2min stencil eval (4097^2 grid, radius-4 stencil, fp64)"
+UNIT = "Gpoint.dir/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--n", type=int, default=4095, help="interior points per side")
+    ap.add_argument("--radius", type=int, default=4)
+    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--solve", type=int, default=0,
+                    help="also time convex_envelope.solve (Newton) on an S^2 interior grid")
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names)
+                   if any(len(r) > 3 + k and r[3 + k].lower().startswith("active") for r in self.rows)]
+        pw = [float(r[2]) for r in self.rows if len(r) > 2 and r[2].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx[0] if mx else None,
+                "power_w_max": max(pw) if pw else None, "samples": len(sm), "reasons": reasons}
+
+
+def cpu_baseline(n, r, workers=None, rows=32, reps=1):
+    workers = workers or min(os.cpu_count() or 1, 32)
+    out = subprocess.run([sys.executable, "-m", "oracle.cpu_baseline", str(n), str(r), str(rows),
+                          str(workers), str(reps)], cwd=ROOT, capture_output=True, text=True,
+                         timeout=600)
+    if out.returncode != 0:
+        raise RuntimeError("cpu baseline failed: " + out.stderr[-400:])
+    res = json.loads(out.stdout.strip().splitlines()[-1])
+    return res
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference
+    is pure Python and cannot travel to the GPU box (oracle/_ref does not apply), so this is
+    the NumPy port under oracle/ (pinned bit-for-bit against the reference by
+    oracle/make_golden.py), on all host cores, each step a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    workers = min(os.cpu_count() or 1, 32)
+    vals = []
+    sample = None
+    steps = max(1, min(args.steps, 3))
+    for k in range(min(args.warmup, 1) + steps):
+        res = cpu_baseline(args.n, args.radius, workers)
+        sample = res
+        vals.append(res["points_per_s"] * res["D"] / 1e9)
+    vals = vals[-steps:]
+    v = sum(vals) / len(vals)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": min(args.warmup, 1),
+        "ms_per_step": 1e3 * (args.n - 2 * args.radius) ** 2 * sample["D"] / (v * 1e9),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "gpu_launches": 0,
+        "config": {"workload": "d2min on %d^2 grid r=%d" % (args.n + 2, args.radius),
+                   "note": "ms_per_step extrapolated from the bounded sample"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": sample["cores"], "kind": "port",
+                         "sample": sample["sample"]},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pyellipticfd_b200 import ddg, _lib
+    from pyellipticfd_b200._context import GridContext, Slab
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    from pyellipticfd_b200 import multigpu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n, r = args.n, args.radius
+    # CPU baseline first (rank 0, before the GPU is busy), bounded sample
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            cpu = cpu_baseline(n, r)
+        except Exception as e:        # reported, not fatal
+            cpu = {"error": str(e)}
+
+    bounds = np.array([[0.0, 1.0], [0.0, 1.0]]).T
+    t0 = time.time()
+    if world == 1:
+        G = FDRegularGrid([n, n], bounds, r, interpolation=False)
+        ctx = GridContext.get(G, dev)
+        sharded = None
+    else:
+        # weak scaling: world x n rows, n columns; spacing stays dyadic in y only if n+1 is;
+        # keep h = 1/(n+1) in both directions by stretching the x extent
+        bounds = np.array([[0.0, float(world)], [0.0, 1.0]]).T
+        bounds[1, 0] = (world * n + 1) / (n + 1.0)
+        sharded = multigpu.ShardedGrid([world * n, n], bounds, r, rank, world, dev)
+        ctx = sharded.ctx
+        G = sharded.G
+    t_grid = time.time() - t0
+    D = int(G.stencil_pairs.shape[0])
+    n_local = ctx.n_interior_local
+
+    # synthetic field u = sin(3x)cos(2y) + xy over the local rows (+ wall points)
+    flat = torch.empty(ctx.n_flat(), dtype=torch.float64, device=dev)
+    nxl, ny = ctx.nx_local, ctx.ny
+    hx, hy = G.scaling
+    xs = (torch.arange(ctx.x_offset + 1, ctx.x_offset + nxl + 1, device=dev, dtype=torch.float64)
+          * hx + bounds[0, 0])
+    ys = torch.arange(1, ny + 1, device=dev, dtype=torch.float64) * hy + bounds[0, 1]
+    flat[:nxl * ny] = (torch.sin(3 * xs)[:, None] * torch.cos(2 * ys)[None, :]
+                       + xs[:, None] * ys[None, :]).reshape(-1)
+    wp = torch.from_numpy(G.bdry_points).to(dev)
+    flat[nxl * ny:] = torch.sin(3 * wp[:, 0]) * torch.cos(2 * wp[:, 1]) + wp[:, 0] * wp[:, 1]
+    S = ctx.pack(flat)
+    lmin = ctx.zeros()
+    out = (lmin, None, None, None)
+
+    def step():
+        if sharded is not None:
+            sharded.exchange_halo(S)
+        ctx.d2eigs(S, want_min=True, want_max=False, out=out)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    launches0 = _lib.kernel_launches()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.kernel_launches() - launches0
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms / args.steps
+    total_points = n_local * world
+    value = total_points * D / (ms_step * 1e-3) / 1e9
+
+    # the dominant kernel alone (deep-interior stencil kernel = first launch of each step)
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 20
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(reps):
+        ctx.d2eigs(S, want_min=True, want_max=False, out=out)
+    k1.record()
+    torch.cuda.synchronize()
+    ms_kernel = k0.elapsed_time(k1) / reps
+    pk, pk_kind = peaks()
+    alg_bytes = 16.0 * n_local
+    achieved = alg_bytes / (ms_kernel * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k_deep_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roof = {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
+            "frac": achieved / pk["hbm_gbs"], "traffic": traffic, "peak_kind": pk_kind,
+            "kernel": "k_deep<H=%d,P=8,mode0,EpiEigs<min>> + k_band" % G.halo,
+            "kernel_ms": ms_kernel, "algorithmic_bytes": alg_bytes}
+
+    # e2e through the public API with pinned host buffers (rank-local field)
+    e2e = None
+    fp64 = None
+    solve = None
+    if world == 1:
+        host = torch.empty(flat.numel(), dtype=torch.float64, pin_memory=True)
+        host.copy_(flat)
+        torch.cuda.synchronize()
+        res = ddg.d2min(G, host)[0]          # warm-up (pinned pool, context)
+        t = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            res = ddg.d2min(G, host)[0]
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t) / args.e2e_steps
+        assert not res.is_cuda
+        e2e = {"value": n_local * D / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(host.numel() * 8), "d2h_bytes_per_step": int(res.numel() * 8)}
+        import ctypes
+        v = ctypes.c_double()
+        _lib.check(_lib.lib().pde_fp64_peak(local, ctypes.byref(v)))
+        fp64 = {"dfma_per_s_measured": v.value,
+                "kernel_fp64_instr_per_s": n_local * D * 7.0 / (ms_kernel * 1e-3),
+                "note": "mode-0 d2min issues 7 fp64-pipe instructions per pair (2 DADD, 2 DMUL, "
+                        "DADD, DMUL, DSETP); frac_of_fp64_pipe = kernel rate / DFMA-chain rate",
+                }
+        fp64["frac_of_fp64_pipe"] = fp64["kernel_fp64_instr_per_s"] / v.value
+        if args.solve:
+            from pyellipticfd_b200 import convex_envelope
+            from oracle.make_golden import two_cones  # obstacle definition only (not timed)
+            Gs = FDRegularGrid([args.solve] * 2, np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, r,
+                               interpolation=False)
+            g = two_cones(Gs.points)
+            st = {}
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            U, diff, it, _ = convex_envelope._solve_grid(Gs, g, None, "newton", stats=st)
+            torch.cuda.synchronize()
+            solve = {"grid": "%d^2" % (args.solve + 2), "seconds": time.perf_counter() - t,
+                     "newton_iters": it, "diff": diff, **st}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "ddg.d2min on a %d^2 lattice (%d^2 interior points%s), "
+                                   "stencil radius %d (%d pairs/point), arithmetic mode 0 "
+                                   "(reference operation order)"
+                                   % (n + 2, n, " per GPU, slab-sharded rows" if world > 1 else "",
+                                      r, D),
+                       "l2": "input field %.0f MB + output %.0f MB per step exceed the 126 MB L2"
+                             % (n_local * 8 / 1e6, n_local * 8 / 1e6),
+                       "parallelism": "slab%d" % world, "grid_build_s": t_grid},
+            "gpoint_per_s": total_points / (ms_step * 1e-3) / 1e9,
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if fp64:
+            line["fp64"] = fp64
+        if cpu is not None and "error" not in cpu:
+            line["cpu_baseline"] = {"value": cpu["points_per_s"] * cpu["D"] / 1e9, "unit": UNIT,
+                                    "cores": cpu["cores"], "kind": "port", "sample": cpu["sample"]}
+        elif cpu is not None:
+            line["cpu_baseline"] = {"value": None, "error": cpu["error"]}
+        if solve:
+            line["solve"] = solve
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

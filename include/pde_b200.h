@@ -148,6 +148,13 @@ int pde_ce_euler(pde_grid *g, double *d_U0, double *d_U1, const double *d_g,
                  double dt, double solution_tol, double operator_tol,
                  int64_t max_iters, int64_t check_every, double *h_out, void *stream);
 
+/* One explicit Euler step of the same operator (the building block of the
+ * multi-GPU loop, where a halo exchange sits between steps):
+ * Unew = U - dt*F(U); d_red[0] = max(d_red[0], max|F|), d_red[1] likewise max|U-Unew|.
+ * Only owned entries of d_Unew are written. */
+int pde_ce_euler_step(pde_grid *g, const double *d_U, const double *d_g, double dt,
+                      double *d_Unew, double *d_red, void *stream);
+
 /* Pucci, pucci.py:7-58 / :123-141:  F = A0*lambda_max + A1*lambda_min - f on
  * the interior, W - dirichlet on the wall.  d_f: state layout (interior f,
  * wall g).  A0/A1 scalar, or arrays when d_A0/d_A1 non-NULL (padded). */
@@ -177,30 +184,51 @@ int pde_vec_newton_update(pde_grid *g, const double *d_U, const double *d_d,
 
 /* ------------------------------------------------------------------------
  * Point-cloud operators (ddi.py:304-414 cached path, ddf.py:137-252): the Nds
- * cached CSR matrices (5 nnz/row) stored as one ELL table:
- *   idx (n, nds, 4) int32, w (n, nds, 4) double, centre weight = -sum(w).
+ * cached CSR matrices (5 nnz/row) stored as one direction-major ELL table:
+ *   idx (nds, n, 4) int32, w (nds, n, 4) double, centre weight = -sum(w)
+ * (n = n_interior; 48 contiguous bytes per (direction, point), coalesced over
+ * points).  The tables stay owned by the caller (device memory, 32-byte aligned).
  * ---------------------------------------------------------------------- */
 int pde_ell_create(pde_ell **out, int device, int64_t n_interior, int64_t n_points,
                    int nds, const int32_t *d_idx, const double *d_w);
 int pde_ell_destroy(pde_ell *e);
-/* d2u[i,k] = sum_j w[i,k,j]*(u[idx[i,k,j]] - u[i]); min/max over k.
- * argmin/argmax: lowest k among exact ties (np.argsort tie order is
- * unspecified in the reference, ddi.py:363). Outputs may be NULL. */
+/* d2u[i,k] = sum_j w[k,i,j]*(u[idx[k,i,j]] - u[i]); min/max over k (ddi.py:358-367).
+ * Ties: lowest k for the minimum, highest k for the maximum (np.argsort's tie
+ * order is unspecified in the reference, ddi.py:363). Outputs may be NULL. */
 int pde_ell_d2eigs(pde_ell *e, const double *d_u, double *d_lmin, double *d_lmax,
                    int32_t *d_kmin, int32_t *d_kmax, void *stream);
-/* y[i] = row (i, k[i]) of the table applied to x (selected-direction rows). */
+/* y[i] = row (k[i], i) of the table applied to x (selected-direction rows,
+ * replaces the per-row CSR slicing loop ddi.py:369-404). */
 int pde_ell_apply_policy(pde_ell *e, const int32_t *d_k, const double *d_x,
                          double *d_y, void *stream);
-/* Build the ddi table on the device (ddi.py:253-299): for every interior point
- * and direction V[k], the first simplex (row order) whose cone contains +v and
- * the first containing -v, barycentric weights, 2/(hf+hb) scaling.
- * simplices: (S,3) int64 rows (i, s1, s2) grouped by ascending i, with
- * simp_ptr (n_interior+1).  eps_over_h = 1e-15/spatial_resolution (ddi.py:267).
- * froese != 0 builds the ddf weights instead (ddf.py:46-116). */
-int pde_ell_build(int device, int64_t n_interior, const double *d_points /* (n,2) */,
+/* Build the table on the device (ddi.py:253-299): for every interior point and
+ * direction V[k], the first simplex (row order) whose cone contains +v and the
+ * first containing -v (2x2 solves with partial pivoting), barycentric weights,
+ * 2/(hf+hb) scaling.  simplices: (S,3) int64 rows (i, s1, s2) grouped by
+ * ascending i with simp_ptr (n_interior+1).  eps_over_h = 1e-15/spatial_resolution
+ * (ddi.py:10,267).  v_per_point != 0: nds must be 1 and d_V is (n,2), one direction
+ * per point (ddi.d2 / ddf.d2).  froese != 0 builds Froese's weights instead
+ * (ddf.py:46-116).  *d_fail counts (point, direction) units with no enclosing cone. */
+int pde_ell_build(int device, int64_t n_interior, const double *d_points /* (npts,2) */,
                   const int64_t *d_simplices, const int64_t *d_simp_ptr,
-                  int nds, const double *d_V /* (nds,2) */, double eps_over_h,
+                  int nds, const double *d_V, int v_per_point, double eps_over_h,
                   int froese, int32_t *d_idx, double *d_w, int32_t *d_fail, void *stream);
+
+/* ------------------------------------------------------------------------
+ * Host-side pre-processing (no GPU needed): pair rows of the band points of a
+ * regular grid.  Replaces, for the points within `stencil_radius` cells of a wall,
+ * pointclasses.py:421-471 (neighbour search), :37-103 (colinear pruning, tol 1e-3)
+ * and :12-35 (antipodal pairing) of FDRegularGrid(interpolation=False).
+ * wall: (nb,2) unscaled wall-point coordinates (pointclasses.py:523-538);
+ * band_ids: interior point ids (ascending).  Outputs are malloc'd: *out_ptr
+ * (n_band+1) and *out_pairs (P x 3 rows (I, J0, J1) with global point ids);
+ * release them with pde_free.  Returns 2 with "Point i has no pairs"
+ * (pointclasses.py:26-27) when a point ends up without a pair. */
+int pde_band_build(int64_t nx, int64_t ny, int stencil_radius, double sx, double sy,
+                   double bx, double by, int64_t nb, const double *h_wall,
+                   int64_t n_band, const int64_t *h_band_ids, double colinear_tol,
+                   int64_t **out_ptr, int64_t **out_pairs, double *out_min_nb_dist);
+void pde_free(void *p);
 
 /* fp64 FMA-chain microbenchmark: returns achieved DFMA/s of the device in
  * *h_dfma_per_s (synchronous).  Used by bench.py to evidence which roof

@@ -1,0 +1,91 @@
+"""CPU baseline: the NumPy restatement of the reference operator timed on host cores.
+
+TEST / BENCH INFRASTRUCTURE.  ``ddg_oracle.d2eigs`` is the faithful port of
+ddg.d2eigs (gathers + norms + segmented selection, recomputing the geometry on
+every call like ddg.py:274-292).  The reference is single-threaded; to use every
+core the sample is split into disjoint row chunks, one worker process each
+(valid because the reference groups pairs by centre point, ddg.py:283-292).
+"""
+import multiprocessing as mp
+import os
+import time
+import types
+
+import numpy as np
+
+from . import ddg_oracle
+
+
+def lattice_chunk(ny, r, table, scaling, b0, row_lo, nrows):
+    """Duck-typed grid holding deep rows [row_lo, row_lo+nrows) of an (nx, ny) lattice
+    plus the r rows either side they read.  Interior-first numbering: the chunk's deep
+    points come first, then the remaining lattice points of the window."""
+    H = int(np.abs(table).max())
+    lo = row_lo - H
+    rows = nrows + 2 * H
+    ix, iy = np.meshgrid(np.arange(lo, lo + rows), np.arange(ny), indexing="ij")
+    deep = (ix >= row_lo) & (ix < row_lo + nrows) & (iy >= r) & (iy < ny - r)
+    order = np.concatenate([np.flatnonzero(deep.ravel()), np.flatnonzero(~deep.ravel())])
+    newid = np.empty(order.size, np.int64)
+    newid[order] = np.arange(order.size)
+    P = np.stack([(ix.ravel() + 1) * scaling[0] + b0[0], (iy.ravel() + 1) * scaling[1] + b0[1]], 1)
+    di, dj = ix[deep] - lo, iy[deep]
+    I = di * ny + dj
+    J0 = (di[:, None] + table[None, :, 0]) * ny + dj[:, None] + table[None, :, 1]
+    J1 = (di[:, None] + table[None, :, 2]) * ny + dj[:, None] + table[None, :, 3]
+    pairs = np.stack([np.broadcast_to(I[:, None], J0.shape).ravel(), J0.ravel(), J1.ravel()], 1)
+    G = types.SimpleNamespace(points=P[order], pairs=newid[pairs], num_interior=int(deep.sum()),
+                              num_points=order.size, dim=2)
+    return G
+
+
+def _work(args):
+    ny, r, table, scaling, b0, row_lo, nrows, reps, seed = args
+    G = lattice_chunk(ny, r, np.asarray(table), np.asarray(scaling), np.asarray(b0), row_lo, nrows)
+    u = np.random.default_rng(seed).standard_normal(G.num_points)
+    ddg_oracle.d2eigs(G, u)                       # warm-up (page faults, imports)
+    t = time.perf_counter()
+    for _ in range(reps):
+        ddg_oracle.d2eigs(G, u)
+    dt = (time.perf_counter() - t) / reps
+    return G.num_interior, len(G.pairs), dt
+
+
+def time_d2eigs(ny, r, table, scaling, b0, rows_per_worker=24, workers=None, reps=2):
+    """Returns dict(points_per_s, pairs_per_s, cores, sample, seconds)."""
+    workers = workers or os.cpu_count() or 1
+    H = int(np.abs(np.asarray(table)).max())
+    args = [(ny, r, np.asarray(table), tuple(scaling), tuple(b0),
+             r + H + w * rows_per_worker, rows_per_worker, reps, w) for w in range(workers)]
+    if workers == 1:
+        res = [_work(args[0])]
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:      # run from a CUDA-free process
+            res = pool.map(_work, args)
+    pts = sum(x[0] for x in res)
+    prs = sum(x[1] for x in res)
+    wall = max(x[2] for x in res)
+    return dict(points_per_s=pts / wall, pairs_per_s=prs / wall, cores=workers, seconds=wall,
+                sample="%d workers x %d deep rows x %d cols (%d pairs), NumPy port of ddg.d2eigs"
+                       % (workers, rows_per_worker, ny - 2 * r, prs))
+
+
+def main(argv=None):
+    """``python -m oracle.cpu_baseline NY R ROWS_PER_WORKER WORKERS REPS`` on a unit-square
+    dyadic lattice; prints one JSON line.  bench.py runs this in a fresh (CUDA-free)
+    process so that the worker pool can fork safely."""
+    import json
+    import sys
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    a = (argv or sys.argv[1:])
+    ny, r, rows, workers, reps = int(a[0]), int(a[1]), int(a[2]), int(a[3]), int(a[4])
+    small = FDRegularGrid([4 * r + 3, 4 * r + 3], np.array([[0.0, 1.0], [0.0, 1.0]]).T * 1.0, r,
+                          interpolation=False)
+    h = 1.0 / (ny + 1)
+    out = time_d2eigs(ny, r, small.stencil_pairs, (h, h), (0.0, 0.0), rows, workers, reps)
+    out["D"] = int(small.stencil_pairs.shape[0])
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

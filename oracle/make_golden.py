@@ -1,0 +1,198 @@
+"""Generate the committed golden fixtures from the UNMODIFIED reference.
+
+TEST INFRASTRUCTURE.  Runs only in the build container (needs /root/reference):
+
+    python -m oracle.make_golden            # writes tests/golden/*.npz
+
+For every case it (1) builds the grid with the reference constructor, (2) runs
+the reference operators / solvers, (3) checks that the restatements under
+``oracle/`` reproduce those outputs (bit-for-bit where the arithmetic is the
+same), and (4) stores inputs + reference outputs as small ``.npz`` files.  The
+tests then pin the oracle, the fast grid constructor and the CUDA path against
+these files on any machine.
+"""
+import os
+import sys
+import time
+import warnings
+
+import numpy as np
+
+from . import refshim, ddg_oracle, solvers_oracle
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def canon_pairs(pairs):
+    p = np.asarray(pairs).copy()
+    lo, hi = np.minimum(p[:, 1], p[:, 2]), np.maximum(p[:, 1], p[:, 2])
+    p[:, 1], p[:, 2] = lo, hi
+    return p[np.lexsort((p[:, 2], p[:, 1], p[:, 0]))].astype(np.int32)
+
+
+def fields(G, seed=0):
+    rng = np.random.default_rng(seed)
+    X, Y = G.points.T
+    return {"random": rng.standard_normal(G.num_points),
+            "saddle": X ** 2 - Y ** 2,
+            "zero": np.zeros(G.num_points),
+            "smooth": np.sin(3 * X) * np.cos(2 * Y) + X * Y}
+
+
+# two-cone obstacle of examples/convex_envelope.py:8-18
+def two_cones(X):
+    r, n, rot = 3 / 7, 2, np.pi / 5
+    C = r * np.array([[np.cos(2 * i * np.pi / n + rot), np.sin(2 * i * np.pi / n + rot)]
+                      for i in range(n)])
+    x, y = X.T
+    v = np.array([np.sqrt((x + c[0]) ** 2 + (y + c[1]) ** 2) for c in C])
+    return v.min(axis=0)
+
+
+def bitwise(a, b):
+    return a.shape == b.shape and np.array_equal(a, b)
+
+
+def ddg_case(R, name, shape, bounds, r):
+    t = time.time()
+    b = np.array(bounds, dtype=float).T
+    G = R.pointclasses.FDRegularGrid(list(shape), b, r, interpolation=False)
+    out = dict(shape=np.array(shape), bounds=b, radius=r, num_bdry=G.num_bdry,
+               bdry_points=G.points[G.num_interior:], pairs=canon_pairs(G.pairs),
+               meta=np.array([G.spatial_resolution, G.angular_resolution, G.dist_to_bdry,
+                              G.bdry_resolution, G.max_radius, G.min_radius,
+                              G.min_interior_nb_dist]))
+    for fname, u in fields(G).items():
+        (lmin, Mmin, vmin), (lmax, Mmax, vmax) = R.ddg.d2eigs(G, u, jacobian=True, control=True)
+        (omin, oMmin, ovmin), (omax, oMmax, ovmax) = ddg_oracle.d2eigs(G, u, True, True)
+        assert bitwise(lmin, omin) and bitwise(lmax, omax), (name, fname)
+        assert (Mmin != oMmin).nnz == 0 and (Mmax != oMmax).nnz == 0, (name, fname)
+        assert bitwise(vmin, ovmin) and bitwise(vmax, ovmax), (name, fname)
+        out["lmin_" + fname], out["lmax_" + fname] = lmin, lmax
+    u = fields(G)["random"]
+    for k, v in enumerate(([1, 0], [0, 1], 0.3)):
+        d, M = R.ddg.d2(G, v, u, jacobian=True)
+        od, oM = ddg_oracle.d2(G, v, u, jacobian=True)
+        assert bitwise(d, od) and (M != oM).nnz == 0
+        out["d2_%d" % k] = d
+    # convex-envelope and Pucci residuals at a generic iterate
+    W, g = fields(G)["smooth"], fields(G)["saddle"]
+    F, J = R.convex_envelope.operator(G, W.copy(), g, jacobian=True, fdmethod="grid")
+    oF, oJ = solvers_oracle.ce_operator(G, W.copy(), g, True)
+    assert bitwise(F, oF) and abs(J - oJ).max() == 0, name
+    out["ce_F"] = F
+    x = fields(G, 3)["random"]
+    out["ce_Jx"] = J.dot(x)
+    out["ce_diag"] = J.diagonal()
+    val, M = R.pucci.operator(G, W, (2, 1), jacobian=True, fdmethod="grid")
+    out["pucci_val"] = val
+    out["pucci_Mx"] = M.dot(x)
+    np.savez_compressed(os.path.join(OUT, "ddg_%s.npz" % name), **out)
+    print("ddg_%s: %d pairs, %.1fs" % (name, len(G.pairs), time.time() - t), flush=True)
+    return G
+
+
+def solve_case(R, name, shape, bounds, r, newton=True, euler=True, pucci=False):
+    t = time.time()
+    b = np.array(bounds, dtype=float).T
+    G = R.pointclasses.FDRegularGrid(list(shape), b, r, interpolation=False)
+    g = two_cones(G.points)
+    out = dict(shape=np.array(shape), bounds=b, radius=r, g=g)
+    if euler:
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            U, diff, it, _ = R.convex_envelope.solve(G, g, fdmethod="grid", solver="euler")
+        oU, odiff, oit, _ = solvers_oracle.ce_solve(G, g, solver="euler")
+        assert bitwise(U, oU) and it == oit and diff == odiff, (name, it, oit)
+        out.update(euler_U=U, euler_diff=diff, euler_iters=it)
+        print("  euler: %d its" % it, flush=True)
+    if newton:
+        U, diff, it, _ = R.convex_envelope.solve(G, g, fdmethod="grid", solver="newton")
+        st = {}
+        oU, odiff, oit, _ = solvers_oracle.ce_solve(G, g, solver="newton", stats=st)
+        sU, sdiff, sit, _ = solvers_oracle.ce_solve(G, g, solver="newton", use_scipy=True)
+        # the restated BiCGStab against the installed SciPy, and both against the reference
+        assert it == sit and np.abs(U - sU).max() < 1e-12, (name, it, sit)
+        assert it == oit and np.abs(U - oU).max() < 1e-9, (name, it, oit, np.abs(U - oU).max())
+        out.update(newton_U=U, newton_diff=diff, newton_iters=it,
+                   newton_krylov=st["krylov_iters"])
+        print("  newton: %d its, %d krylov, |ref-oracle| %.2e" %
+              (it, st["krylov_iters"], np.abs(U - oU).max()), flush=True)
+    if pucci:
+        X, Y = G.points.T
+        Uex = X ** 2 + 2 * Y ** 2
+        N = G.num_interior
+        f = np.full(N, 2 * 4.0 + 1 * 2.0)       # A=(2,1): 2*lambda_max(=4) + 1*lambda_min(=2)
+        U, diff, it, _ = R.pucci.solve(G, f, Uex[N:], A=(2, 1), fdmethod="grid", solver="newton")
+        oU, odiff, oit, _ = solvers_oracle.pucci_solve(G, f, Uex[N:], A=(2, 1))
+        assert it == oit and np.abs(U - oU).max() < 1e-9, (it, oit)
+        out.update(pucci_U=U, pucci_iters=it, pucci_f=f, pucci_g=Uex[N:])
+        print("  pucci: %d its, err %.2e" % (it, np.abs(U - Uex).max()), flush=True)
+    np.savez_compressed(os.path.join(OUT, "solve_%s.npz" % name), **out)
+    print("solve_%s: %.1fs" % (name, time.time() - t), flush=True)
+
+
+def cloud_case(R, name, h0):
+    """Point-cloud operators on a disc built by the reference FDTriMesh constructor."""
+    from scipy.spatial import Delaunay
+    from . import ddi_oracle, disc
+    import types
+    t = time.time()
+    theta = np.pi * h0 ** (1 / 3)                       # tests/setup_discs.py:45
+    p, nint = disc.disc_points(h0, theta)
+    tri = Delaunay(p).simplices
+    G = R.pointclasses.FDTriMesh(p, tri, num_interior=nint, angular_resolution=theta,
+                                 bdry_normals=p[nint:])
+    out = dict(points=G.points, simplices=G.simplices.astype(np.int32), num_interior=nint,
+               spatial_resolution=G.spatial_resolution, angular_resolution=G.angular_resolution)
+    X, Y = G.points.T
+    flds = {"saddle": X ** 2 - Y ** 2, "random": np.random.default_rng(0).standard_normal(len(X)),
+            "smooth": np.sin(3 * X) * np.cos(2 * Y) + X * Y}
+    for mod, froese, tag in ((R.ddi, False, "ddi"), (R.ddf, True, "ddf")):
+        G._d2cache = None
+        for fname, u in flds.items():
+            (lmin, Mmin, vmin), (lmax, Mmax, vmax) = mod.d2eigs(G, u, jacobian=True, control=True)
+            out["%s_lmin_%s" % (tag, fname)], out["%s_lmax_%s" % (tag, fname)] = lmin, lmax
+            omin, omax, _ = ddi_oracle.d2eigs(G, u, froese)
+            scale = 1e-12 * np.abs(lmin).max() + 1e-9
+            assert np.abs(omin - lmin).max() < scale and np.abs(omax - lmax).max() < scale, \
+                (tag, fname, np.abs(omin - lmin).max())
+        assert np.abs(Mmin.dot(u) - lmin).max() < 1e-9
+        V, fdms = G._d2cache[1], G._d2cache[2]
+        oV, oS, oW = ddi_oracle.d2eigs_table(G, froese)
+        assert np.array_equal(V, oV)
+        for k in (0, len(fdms) // 3, len(fdms) - 1):
+            assert abs(fdms[k] - ddi_oracle.matrix(G, oS[k], oW[k])).max() < 1e-9 * abs(fdms[k]).max()
+        u = flds["random"]
+        for k, v in enumerate(([1, 0], 0.3)):
+            d, M = mod.d2(G, v, u, jacobian=True)
+            od, oM = ddi_oracle.d2(G, v, u, jacobian=True, froese=froese)
+            assert np.abs(d - od).max() < 1e-9 * np.abs(d).max(), (tag, np.abs(d - od).max())
+            out["%s_d2_%d" % (tag, k)] = d
+        out["%s_nds" % tag] = len(fdms)
+    np.savez_compressed(os.path.join(OUT, "cloud_%s.npz" % name), **out)
+    print("cloud_%s: %d points (%d interior), %d simplices, %.1fs" %
+          (name, len(p), nint, len(G.simplices), time.time() - t), flush=True)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    R = refshim.modules()
+    if "--clouds-only" in sys.argv:
+        cloud_case(R, "disc_h0.1", 0.1)
+        cloud_case(R, "disc_h0.06", 0.06)
+        return
+    ddg_case(R, "n9_r2", (9, 9), [[0, 1], [0, 1]], 2)            # tests/test_ddg.py fixture
+    ddg_case(R, "n19_r4", (19, 19), [[0, 1], [0, 1]], 4)         # tests/test_regular_grid.py fixture
+    ddg_case(R, "n11x14_r2", (11, 14), [[-1, 1], [0, 3]], 2)     # anisotropic, non-dyadic
+    ddg_case(R, "n15_r5", (15, 15), [[-1, 1], [-1, 1]], 5)
+    ddg_case(R, "n13_r3", (13, 13), [[0, 1], [0, 1]], 3)
+    solve_case(R, "n31_r2", (31, 31), [[-1, 1], [-1, 1]], 2, pucci=True)
+    solve_case(R, "n63_r2", (63, 63), [[-1, 1], [-1, 1]], 2)     # BASELINE config 1a (65^2 grid)
+    solve_case(R, "n15_r4", (15, 15), [[-1, 1], [-1, 1]], 4, pucci=True)
+    cloud_case(R, "disc_h0.1", 0.1)
+    cloud_case(R, "disc_h0.06", 0.06)
+
+
+if __name__ == "__main__":
+    main()

@@ -16,7 +16,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",
     "--fmad=false",                 # parity first: FMA contraction only where written explicitly
-    "-Xcompiler", "-fPIC,-O2,-fopenmp",
+    "-Xcompiler", "-fPIC,-O2,-fopenmp,-ffp-contract=off",
     "-Xptxas", "-v",
 ]
 

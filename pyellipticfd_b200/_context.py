@@ -48,15 +48,22 @@ def require_cuda(device=None):
 def to_device(u, device, dtype=torch.float64):
     """numpy / torch (any device) -> contiguous tensor on ``device``."""
     if isinstance(u, torch.Tensor):
-        return u.to(device=device, dtype=dtype).contiguous()
+        return u.to(device=device, dtype=dtype, non_blocking=True).contiguous()
     a = np.ascontiguousarray(np.asarray(u), dtype={torch.float64: np.float64}[dtype])
     return torch.from_numpy(a).to(device)
 
 
 def like_input(u, t):
-    """Return device tensor ``t`` in the container type of the user's input ``u``."""
+    """Return device tensor ``t`` in the container type of the user's input ``u``:
+    CUDA tensor -> stays on the device; host tensor -> pinned host tensor (torch's
+    caching host allocator makes the repeated allocation cheap); NumPy -> NumPy."""
     if isinstance(u, torch.Tensor):
-        return t if u.is_cuda else t.cpu()
+        if u.is_cuda:
+            return t
+        out = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        out.copy_(t, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
     return t.cpu().numpy()
 
 
@@ -266,8 +273,8 @@ class GridContext(object):
         else:
             lmin = self.zeros() if want_min else None
             lmax = self.zeros() if want_max else None
-            pmin = self.empty_policy() if policy else None
-            pmax = self.empty_policy() if policy else None
+            pmin = self.empty_policy() if (policy and want_min) else None
+            pmax = self.empty_policy() if (policy and want_max) else None
         check(self.lib.pde_ddg_d2eigs(self.h, _ptr(S), _ptr(lmin), _ptr(lmax), _ptr(pmin),
                                       _ptr(pmax), int(mode), _stream()))
         return lmin, lmax, pmin, pmax
@@ -340,6 +347,14 @@ class GridContext(object):
         iters = int(out[0])
         U = U1 if int(out[1]) == 1 else U0
         return U, float(out[2]), iters, float(out[3]), int(out[4])
+
+    def ce_euler_step(self, U, g, dt):
+        """One Euler step -> (Unew, red) with red = [max|F|, max|U-Unew|] on the device."""
+        Unew = self.zeros()
+        red = torch.zeros(2, dtype=torch.float64, device=self.device)
+        check(self.lib.pde_ce_euler_step(self.h, _ptr(U), _ptr(g), float(dt), _ptr(Unew),
+                                         _ptr(red), _stream()))
+        return Unew, red
 
     def bicgstab(self, J, b, rtol, atol=0.0, maxiter=0, check_every=32, work=None):
         x = self.zeros()

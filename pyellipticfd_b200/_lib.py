@@ -47,11 +47,21 @@ SIGNATURES = {
     "pde_jac_diagonal": (c_int, [vp, C.POINTER(pde_jac), vp, vp]),
     "pde_ce_residual": (c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "pde_ce_euler": (c_int, [vp, vp, vp, vp, c_dbl, c_dbl, c_dbl, c_i64, c_i64, vp, vp]),
+    "pde_ce_euler_step": (c_int, [vp, vp, vp, c_dbl, vp, vp, vp]),
     "pde_pucci_residual": (c_int, [vp, vp, vp, c_dbl, c_dbl, vp, vp, vp, vp, vp, vp, vp]),
     "pde_bicgstab": (c_int, [vp, C.POINTER(pde_jac), vp, vp, c_dbl, c_dbl, c_i64, c_i64,
                              vp, vp, vp]),
     "pde_vec_newton_update": (c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
+    "pde_ell_create": (c_int, [C.POINTER(vp), c_int, c_i64, c_i64, c_int, vp, vp]),
+    "pde_ell_destroy": (c_int, [vp]),
+    "pde_ell_d2eigs": (c_int, [vp, vp, vp, vp, vp, vp, vp]),
+    "pde_ell_apply_policy": (c_int, [vp, vp, vp, vp, vp]),
+    "pde_ell_build": (c_int, [c_int, c_i64, vp, vp, vp, c_int, vp, c_int, c_dbl, c_int,
+                              vp, vp, vp, vp]),
     "pde_fp64_peak": (c_int, [c_int, C.POINTER(c_dbl)]),
+    "pde_band_build": (c_int, [c_i64, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, vp,
+                               c_i64, vp, c_dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(c_dbl)]),
+    "pde_free": (None, [vp]),
 }
 
 

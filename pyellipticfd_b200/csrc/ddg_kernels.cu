@@ -225,8 +225,16 @@ int pde_ddg_d2eigs(pde_grid *g, const double *d_state, double *d_lmin, double *d
                    uint16_t *d_pmin, uint16_t *d_pmax, int mode, void *stream) {
     PDE_REQUIRE(g && d_state, "null argument");
     DeviceGuard guard(g->device);
-    EpiEigs epi{d_lmin, d_lmax, d_pmin, d_pmax};
-    return launch_both(g, d_state, epi, mode, nullptr, nullptr, (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool want_min = d_lmin || d_pmin, want_max = d_lmax || d_pmax;
+    if (want_min && !want_max)      // ddg.d2min: the max half of the reference's work is dead
+        return launch_both(g, d_state, EpiEigs<true, false>{d_lmin, d_lmax, d_pmin, d_pmax}, mode,
+                           nullptr, nullptr, st);
+    if (want_max && !want_min)
+        return launch_both(g, d_state, EpiEigs<false, true>{d_lmin, d_lmax, d_pmin, d_pmax}, mode,
+                           nullptr, nullptr, st);
+    return launch_both(g, d_state, EpiEigs<true, true>{d_lmin, d_lmax, d_pmin, d_pmax}, mode,
+                       nullptr, nullptr, st);
 }
 
 int pde_ce_residual(pde_grid *g, const double *d_W, const double *d_g, double *d_F,
@@ -252,6 +260,17 @@ int pde_pucci_residual(pde_grid *g, const double *d_W, const double *d_f, double
     int rc = launch_both(g, d_W, epi, 0, red, nullptr, st);
     if (rc) return rc;
     return launch_wall(g, d_W, d_f, d_F, 0.0, 0, red, nullptr, st);
+}
+
+int pde_ce_euler_step(pde_grid *g, const double *d_U, const double *d_g, double dt,
+                      double *d_Unew, double *d_red, void *stream) {
+    PDE_REQUIRE(g && d_U && d_g && d_Unew && d_red, "null argument");
+    DeviceGuard guard(g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    EpiCeEuler epi{d_g, d_Unew, dt};
+    int rc = launch_both(g, d_U, epi, 0, d_red, nullptr, st);
+    if (rc) return rc;
+    return launch_wall(g, d_U, d_g, d_Unew, dt, 1, d_red, nullptr, st);
 }
 
 int pde_ce_euler(pde_grid *g, double *d_U0, double *d_U1, const double *d_g, double dt,

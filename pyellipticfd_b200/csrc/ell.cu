@@ -1,0 +1,263 @@
+// Point-cloud operators: linear-interpolation (ddi) and Froese (ddf) finite differences.
+//
+// The reference caches one SciPy CSR matrix (5 nnz/row) per search direction
+// (ddi.py:355-356, ddf.py:193-194) and evaluates `Nds` SpMVs + a row argsort per call
+// (ddi.py:358-367).  Here the Nds matrices are ONE direction-major ELL table
+//     idx[k][i][0..3]  int32   neighbour point of interior point i in direction k
+//     w  [k][i][0..3]  double  its weight (centre weight = -sum, not stored)
+// so that thread i streams 48 contiguous bytes per direction (coalesced over i) and
+// gathers u through L2.  Algorithmic traffic 48 B per (point, direction): HBM-bound.
+#include "common.cuh"
+
+struct pde_ell {
+    int device;
+    int64_t n_interior, n_points;
+    int nds;
+    const int32_t *idx;   // (nds, n_interior, 4), caller-owned device memory
+    const double *w;      // (nds, n_interior, 4)
+    int num_sms;
+};
+
+namespace pde {
+
+// d2u[i,k] = sum_j w_j (u[idx_j] - u_i): the first-call formula of ddi.py:283-286 with the
+// 2/(hf+hb) factor folded into w (the cached path M.dot(u) of ddi.py:361 differs from it by
+// rounding only).  Ties: lowest k for the minimum, highest k for the maximum (what a stable
+// ascending sort would give for arg[:,0] / arg[:,-1]; np.argsort's order is unspecified).
+template <int UNROLL>
+__global__ void __launch_bounds__(256)
+k_ell_d2eigs(int64_t n, int nds, const int4 *__restrict__ idx, const double2 *__restrict__ w,
+             const double *__restrict__ u, double *__restrict__ lmin, double *__restrict__ lmax,
+             int32_t *__restrict__ kmin, int32_t *__restrict__ kmax) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const double ui = u[i];
+    double mn = __longlong_as_double(0x7ff0000000000000LL);
+    double mx = __longlong_as_double(0xfff0000000000000LL);
+    int an = 0, ax = 0;
+    int k = 0;
+    for (; k + UNROLL <= nds; k += UNROLL) {
+        int4 id[UNROLL];
+        double2 wa[UNROLL], wb[UNROLL];
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            const int64_t e = (int64_t)(k + q) * n + i;
+            id[q] = __ldcs(&idx[e]);                                 // streamed once
+            wa[q] = __ldcs(&w[2 * e]);
+            wb[q] = __ldcs(&w[2 * e + 1]);
+        }
+#pragma unroll
+        for (int q = 0; q < UNROLL; ++q) {
+            double d = wa[q].x * (u[id[q].x] - ui) + wa[q].y * (u[id[q].y] - ui) +
+                       wb[q].x * (u[id[q].z] - ui) + wb[q].y * (u[id[q].w] - ui);
+            if (d < mn) { mn = d; an = k + q; }
+            if (d >= mx) { mx = d; ax = k + q; }
+        }
+    }
+    for (; k < nds; ++k) {
+        const int64_t e = (int64_t)k * n + i;
+        int4 id = idx[e];
+        double2 wa = w[2 * e], wb = w[2 * e + 1];
+        double d = wa.x * (u[id.x] - ui) + wa.y * (u[id.y] - ui) + wb.x * (u[id.z] - ui) +
+                   wb.y * (u[id.w] - ui);
+        if (d < mn) { mn = d; an = k; }
+        if (d >= mx) { mx = d; ax = k; }
+    }
+    if (lmin) lmin[i] = mn;
+    if (lmax) lmax[i] = mx;
+    if (kmin) kmin[i] = an;
+    if (kmax) kmax[i] = ax;
+}
+
+__global__ void k_ell_apply(int64_t n, const int4 *__restrict__ idx, const double2 *__restrict__ w,
+                            const int32_t *__restrict__ ksel, const double *__restrict__ x,
+                            double *__restrict__ y) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int k = ksel[i];
+    const int64_t e = (int64_t)k * n + i;
+    int4 id = idx[e];
+    double2 wa = w[2 * e], wb = w[2 * e + 1];
+    double xi = x[i];
+    y[i] = wa.x * (x[id.x] - xi) + wa.y * (x[id.y] - xi) + wb.x * (x[id.z] - xi) +
+           wb.y * (x[id.w] - xi);
+}
+
+// 2x2 solve X xi = v with partial pivoting (what LAPACK gesv does for ddi.py:265)
+__device__ __forceinline__ void solve2(double a, double b, double c, double d, double v0, double v1,
+                                       double &x0, double &x1) {
+    // rows: [a b | v0], [c d | v1]
+    if (fabs(c) > fabs(a)) {
+        double t;
+        t = a; a = c; c = t;
+        t = b; b = d; d = t;
+        t = v0; v0 = v1; v1 = t;
+    }
+    double l = c * (1.0 / a);
+    double u22 = d - l * b;
+    double y1 = v1 - l * v0;
+    x1 = y1 / u22;
+    x0 = (v0 - b * x1) / a;
+}
+
+// one thread per (interior point, direction)
+__global__ void __launch_bounds__(128)
+k_ell_build(int64_t n, int nds, const double *__restrict__ P, const int64_t *__restrict__ simp,
+            const int64_t *__restrict__ sptr, const double *__restrict__ V, int v_per_point,
+            double eps_h, int froese, int32_t *__restrict__ idx, double *__restrict__ w,
+            int32_t *__restrict__ fail) {
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int k = blockIdx.y;
+    if (i >= n) return;
+    const double vx = v_per_point ? V[2 * i] : V[2 * k];
+    const double vy = v_per_point ? V[2 * i + 1] : V[2 * k + 1];
+    const double px = P[2 * i], py = P[2 * i + 1];
+    bool have_f = false, have_b = false;
+    int64_t f1 = 0, f2 = 0, b1 = 0, b2 = 0;
+    double xf1 = 0, xf2 = 0, xb1 = 0, xb2 = 0;
+    const double lo = froese ? 0.0 : -eps_h, hi = froese ? 0.0 : eps_h;
+    for (int64_t s = sptr[i]; s < sptr[i + 1] && !(have_f && have_b); ++s) {
+        int64_t s1 = simp[3 * s + 1], s2 = simp[3 * s + 2];
+        double a = P[2 * s1] - px, c = P[2 * s1 + 1] - py;       // first simplex vector
+        double b = P[2 * s2] - px, d = P[2 * s2 + 1] - py;       // second
+        double x0, x1;
+        solve2(a, b, c, d, vx, vy, x0, x1);
+        if (!have_f && x0 >= lo && x1 >= lo) {                   // ddi.py:267 / ddf.py:62
+            have_f = true; f1 = s1; f2 = s2; xf1 = x0; xf2 = x1;
+        }
+        if (!have_b && x0 <= hi && x1 <= hi) {                   // ddi.py:268 / ddf.py:63
+            have_b = true; b1 = s1; b2 = s2; xb1 = -x0; xb2 = -x1;
+        }
+    }
+    int64_t o = ((int64_t)k * n + i) * 4;
+    if (!(have_f && have_b)) {
+        atomicAdd(fail, 1);
+        idx[o] = idx[o + 1] = idx[o + 2] = idx[o + 3] = (int32_t)i;
+        w[o] = w[o + 1] = w[o + 2] = w[o + 3] = 0.0;
+        return;
+    }
+    if (!froese) {
+        // ddi.py:279-297: hf = 1/sum(xi_f), hb = 1/sum(xi_b); rows scaled by 2/(hf+hb)
+        double hf = 1.0 / (xf1 + xf2), hb = 1.0 / (xb1 + xb2);
+        double sc = 2.0 / (hf + hb);
+        idx[o] = (int32_t)f1; idx[o + 1] = (int32_t)f2; idx[o + 2] = (int32_t)b1; idx[o + 3] = (int32_t)b2;
+        w[o] = sc * xf1; w[o + 1] = sc * xf2; w[o + 2] = sc * xb1; w[o + 3] = sc * xb2;
+        return;
+    }
+    // Froese's generalised finite difference, ddf.py:74-116
+    const double TWO_PI = 6.283185307179586;
+    int64_t S[4] = {f1, f2, b1, b2};
+    double h[4], dth[4];
+    double vth = atan2(vy, vx);
+    for (int j = 0; j < 4; ++j) {
+        double X = P[2 * S[j]] - px, Y = P[2 * S[j] + 1] - py;
+        h[j] = sqrt(X * X + Y * Y);
+        double t = atan2(Y, X) - vth;
+        t = fmod(t, TWO_PI);
+        if (t < 0) t += TWO_PI;                                   // numpy's % (sign of divisor)
+        dth[j] = t;
+    }
+    // stable sort of 4 angles (np.argsort, ddf.py:92)
+    int ord[4] = {0, 1, 2, 3};
+    for (int a = 1; a < 4; ++a)
+        for (int b = a; b > 0 && dth[ord[b]] < dth[ord[b - 1]]; --b) {
+            int t = ord[b]; ord[b] = ord[b - 1]; ord[b - 1] = t;
+        }
+    double c[4], s[4];
+    int64_t Ss[4];
+    for (int j = 0; j < 4; ++j) {
+        c[j] = h[ord[j]] * cos(dth[ord[j]]);
+        s[j] = h[ord[j]] * sin(dth[ord[j]]);
+        Ss[j] = S[ord[j]];
+    }
+    if (c[0] >= 0 && c[1] >= 0 && s[0] >= 0 && s[1] >= 0) {       // ddf.py:104-108 roll by -1
+        double c0 = c[0], s0 = s[0];
+        int64_t S0 = Ss[0];
+        for (int j = 0; j < 3; ++j) { c[j] = c[j + 1]; s[j] = s[j + 1]; Ss[j] = Ss[j + 1]; }
+        c[3] = c0; s[3] = s0; Ss[3] = S0;
+    }
+    double A = c[2] * s[1] - c[1] * s[2], B = c[0] * s[3] - c[3] * s[0];
+    double denom = A * (c[0] * c[0] * s[3] - c[3] * c[3] * s[0]) -
+                   B * (c[2] * c[2] * s[1] - c[1] * c[1] * s[2]);
+    w[o] = 2 * s[3] * A / denom;
+    w[o + 1] = 2 * s[2] * B / denom;
+    w[o + 2] = -2 * s[1] * B / denom;
+    w[o + 3] = -2 * s[0] * A / denom;
+    for (int j = 0; j < 4; ++j) idx[o + j] = (int32_t)Ss[j];
+}
+
+}  // namespace pde
+
+using namespace pde;
+
+extern "C" {
+
+int pde_ell_create(pde_ell **out, int device, int64_t n_interior, int64_t n_points, int nds,
+                   const int32_t *d_idx, const double *d_w) {
+    PDE_REQUIRE(out && d_idx && d_w && nds > 0 && n_interior > 0, "bad argument");
+    PDE_REQUIRE(n_points < ((int64_t)1 << 31), "point ids must fit int32");
+    PDE_REQUIRE((reinterpret_cast<uintptr_t>(d_idx) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(d_w) & 31) == 0, "ELL tables must be 32-byte aligned");
+    cudaDeviceProp prop;
+    PDE_CHECK(cudaGetDeviceProperties(&prop, device));
+    PDE_REQUIRE(prop.major == 10, "pde_b200 requires an sm_100-class (Blackwell) device");
+    pde_ell *e = new pde_ell();
+    e->device = device;
+    e->n_interior = n_interior;
+    e->n_points = n_points;
+    e->nds = nds;
+    e->idx = d_idx;
+    e->w = d_w;
+    e->num_sms = prop.multiProcessorCount;
+    *out = e;
+    return 0;
+}
+
+int pde_ell_destroy(pde_ell *e) {
+    delete e;
+    return 0;
+}
+
+int pde_ell_d2eigs(pde_ell *e, const double *d_u, double *d_lmin, double *d_lmax, int32_t *d_kmin,
+                   int32_t *d_kmax, void *stream) {
+    PDE_REQUIRE(e && d_u, "null argument");
+    DeviceGuard guard(e->device);
+    int64_t n = e->n_interior;
+    unsigned grid = (unsigned)((n + 255) / 256);
+    k_ell_d2eigs<4><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        n, e->nds, reinterpret_cast<const int4 *>(e->idx), reinterpret_cast<const double2 *>(e->w),
+        d_u, d_lmin, d_lmax, d_kmin, d_kmax);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pde_ell_apply_policy(pde_ell *e, const int32_t *d_k, const double *d_x, double *d_y,
+                         void *stream) {
+    PDE_REQUIRE(e && d_k && d_x && d_y, "null argument");
+    DeviceGuard guard(e->device);
+    int64_t n = e->n_interior;
+    k_ell_apply<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        n, reinterpret_cast<const int4 *>(e->idx), reinterpret_cast<const double2 *>(e->w), d_k,
+        d_x, d_y);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+int pde_ell_build(int device, int64_t n_interior, const double *d_points,
+                  const int64_t *d_simplices, const int64_t *d_simp_ptr, int nds,
+                  const double *d_V, int v_per_point, double eps_over_h, int froese,
+                  int32_t *d_idx, double *d_w, int32_t *d_fail, void *stream) {
+    PDE_REQUIRE(d_points && d_simplices && d_simp_ptr && d_V && d_idx && d_w && d_fail,
+                "null argument");
+    PDE_REQUIRE(nds > 0 && nds < 65536, "bad direction count");
+    PDE_REQUIRE(!v_per_point || nds == 1, "per-point directions need nds == 1");
+    DeviceGuard guard(device);
+    dim3 grid((unsigned)((n_interior + 127) / 128), (unsigned)nds);
+    k_ell_build<<<grid, 128, 0, (cudaStream_t)stream>>>(n_interior, nds, d_points, d_simplices,
+                                                        d_simp_ptr, d_V, v_per_point, eps_over_h, froese,
+                                                        d_idx, d_w, d_fail);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"

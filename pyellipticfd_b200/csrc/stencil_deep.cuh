@@ -71,10 +71,11 @@ struct BlockMax2 {   // two running maxima per thread, reduced once per CTA at t
 // ---- epilogues -----------------------------------------------------------------
 // Each epilogue sees one evaluated point: state offset `o`, centre value, the two
 // extremes and their table rows.
-struct EpiEigs {    // ddg.d2eigs values + policy (ddg.py:292)
+template <bool MIN, bool MAX>
+struct EpiEigs {    // ddg.d2eigs values + policy (ddg.py:292); d2min / d2max skip the unused half
     double *lmin, *lmax;
     uint16_t *pmin, *pmax;
-    static constexpr bool kMin = true, kMax = true, kRed = false;
+    static constexpr bool kMin = MIN, kMax = MAX, kRed = false;
     __device__ __forceinline__ void operator()(int64_t o, double, double mn, double mx, int kmn,
                                                int kmx, BlockMax2 &) const {
         if (lmin) lmin[o] = mn;

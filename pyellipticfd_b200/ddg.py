@@ -51,14 +51,29 @@ def d2eigs(G, u, jacobian=False, control=False):
     return (lam_min, M_min, v_min), (lam_max, M_max, v_max)
 
 
+def _one_extreme(G, u, which, jacobian=False, control=False):
+    """d2min / d2max without the other half of the work (the reference computes both
+    and discards one, ddg.py:329-339)."""
+    if control:                      # quirk Q1 couples v_max to the min pair: need both
+        return d2eigs(G, u, jacobian=jacobian, control=True)[which]
+    _require_pairs(G)
+    ctx = GridContext.get(G)
+    S = ctx.pack(u)
+    lmin, lmax, pmin, pmax = ctx.d2eigs(S, want_min=(which == 0), want_max=(which == 1),
+                                        policy=jacobian, mode=ARITHMETIC_MODE)
+    lam = like_input(u, ctx.unpad(lmin if which == 0 else lmax))
+    M = PolicyMatrix(ctx, pmin if which == 0 else pmax) if jacobian else None
+    return lam, M, None
+
+
 def d2min(G, u, **kwargs):
     """ddg.d2min (ddg.py:329-333)."""
-    return d2eigs(G, u, **kwargs)[0]
+    return _one_extreme(G, u, 0, **kwargs)
 
 
 def d2max(G, u, **kwargs):
     """ddg.d2max (ddg.py:335-339)."""
-    return d2eigs(G, u, **kwargs)[1]
+    return _one_extreme(G, u, 1, **kwargs)
 
 
 def _aligned_policy(G, ctx, v):

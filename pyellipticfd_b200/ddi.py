@@ -1,4 +1,40 @@
-"""placeholder -- replaced by the ELL implementation"""
-def _pending(*a, **k):
-    raise NotImplementedError("ddi ELL path not built yet")
-d2 = d2eigs = d2min = d2max = _ce_operator = _ce_solve = _pucci_operator = _pucci_solve = _pending
+"""Finite differences with linear interpolation on point clouds -- CUDA.
+
+Drop-in for the second-derivative part of /root/reference/ddi.py (``d2``
+ddi.py:223-301, ``d2eigs`` / ``d2min`` / ``d2max`` ddi.py:304-427): same names,
+arguments, return conventions and exceptions.  The per-direction finite
+difference matrices of the reference are one ELL table on the device (see
+``_ell.py``); Jacobians are :class:`~pyellipticfd_b200._ell.EllMatrix` objects.
+``d1`` / ``d1n`` / ``d1grad`` (ddi.py:12-221) are not on the hot path.
+"""
+import numpy as np
+
+from . import _ell
+
+eps = _ell.EPS
+
+
+def _num_directions(G):
+    """Number of search directions (ddi.py:120-122)."""
+    return np.max([int(2 * np.ceil(np.pi ** 2 / G.angular_resolution ** 2)), 4])
+
+
+def d2(G, v, u=None, jacobian=False):
+    """Second derivative in direction ``v`` by linear interpolation inside the
+    forward and backward simplices (ddi.py:223-301).  Returns ``(d2u, M)``."""
+    return _ell.d2(G, v, u, jacobian, froese=False)
+
+
+def d2eigs(G, u, jacobian=False, control=False, cache_fdmatrices=True):
+    """Min / max directional second derivative over ``_num_directions(G)`` directions
+    (ddi.py:304-414): ``((lmin, M_min, v_min), (lmax, M_max, v_max))``."""
+    return _ell.d2eigs(G, u, __name__, int(_num_directions(G)), False, jacobian, control,
+                       cache_fdmatrices)
+
+
+def d2min(G, u, **kwargs):
+    return d2eigs(G, u, **kwargs)[0]
+
+
+def d2max(G, u, **kwargs):
+    return d2eigs(G, u, **kwargs)[1]

@@ -1,0 +1,123 @@
+"""Slab sharding of a regular grid over the GPUs of one box.
+
+The reference is single-process; this is the B200 addition for
+grids that do not fit, or are too slow on, one GPU.  The lattice is cut into
+contiguous slabs of rows (x is the slow axis, rows of ``ny`` values are contiguous:
+pointclasses.py:513-515).  Every rank owns one slab plus ``r`` halo rows on each
+side in its state buffer; before an operator application the halo rows are
+refreshed from the neighbouring ranks (NCCL send/recv over NVLink, one message of
+``r * pitch`` doubles per neighbour).  Wall points are replicated on every rank.
+Infinity-norm / dot-product reductions of the solvers are small all-reduces.
+"""
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from ._context import GridContext, Slab
+from .pointclasses import FDRegularGrid
+
+
+def slab_partition(nx, world):
+    """Rows [lo, hi) of every rank: equal slabs, remainder spread over the first ranks."""
+    base, rem = divmod(nx, world)
+    lo = [r * base + min(r, rem) for r in range(world)]
+    hi = [lo[r] + base + (1 if r < rem else 0) for r in range(world)]
+    return list(zip(lo, hi))
+
+
+def halo_exchange(view, nx_local, halo, rank, world, group=None):
+    """Refresh the halo rows of ``view`` ((nx_local + 2*halo) x pitch, contiguous rows).
+
+    Sends the first/last ``halo`` owned rows to the previous/next rank and receives
+    their counterparts into the halo rows.  Works for CPU tensors (gloo) and CUDA
+    tensors (NCCL).  Slabs must hold at least ``halo`` rows."""
+    if world == 1 or halo == 0:
+        return
+    H = halo
+    ops = []
+    if rank > 0:
+        ops.append(dist.P2POp(dist.isend, view[H:2 * H], rank - 1, group))
+        ops.append(dist.P2POp(dist.irecv, view[0:H], rank - 1, group))
+    if rank < world - 1:
+        ops.append(dist.P2POp(dist.isend, view[nx_local:nx_local + H], rank + 1, group))
+        ops.append(dist.P2POp(dist.irecv, view[nx_local + H:nx_local + 2 * H], rank + 1, group))
+    for req in dist.batch_isend_irecv(ops):
+        req.wait()
+
+
+class ShardedGrid(object):
+    """One rank's slab of a global FDRegularGrid."""
+
+    def __init__(self, interior_shape, bounds, stencil_radius, rank, world, device, grid=None):
+        self.rank, self.world = rank, world
+        self.G = grid if grid is not None else FDRegularGrid(list(interior_shape), bounds,
+                                                             stencil_radius, interpolation=False)
+        nx, ny = self.G.interior_shape
+        lo, hi = slab_partition(nx, world)[rank]
+        if world > 1 and hi - lo < stencil_radius:
+            raise ValueError("slab thinner than the stencil radius")
+        halo = stencil_radius if world > 1 else 0
+        self.slab = Slab(lo, hi - lo, halo)
+        self.ctx = GridContext(self.G, device, slab=self.slab)
+
+    def lattice_view(self, S):
+        c = self.ctx
+        return S[:c.rows * c.pitch].view(c.rows, c.pitch)
+
+    def exchange_halo(self, S):
+        halo_exchange(self.lattice_view(S), self.ctx.nx_local, self.slab.halo, self.rank,
+                      self.world)
+
+    def local_flat(self, fn):
+        """Evaluate ``fn(points (n,2) tensor) -> values`` on this rank's points:
+        owned interior rows first, then all wall points (the rank-local flat vector)."""
+        c, G = self.ctx, self.G
+        dev = c.device
+        hx, hy = G.scaling
+        xs = (torch.arange(c.x_offset + 1, c.x_offset + c.nx_local + 1, device=dev,
+                           dtype=torch.float64) * hx + G.bounds[0][0])
+        ys = torch.arange(1, c.ny + 1, device=dev, dtype=torch.float64) * hy + G.bounds[0][1]
+        P = torch.stack([xs[:, None].expand(-1, c.ny), ys[None, :].expand(c.nx_local, -1)],
+                        dim=2).reshape(-1, 2)
+        W = torch.from_numpy(G.bdry_points).to(dev)
+        return torch.cat([fn(P), fn(W)])
+
+    # ---- distributed convex-envelope Euler iteration ------------------------------------
+    def ce_euler(self, U, g, dt, solution_tol=1e-6, operator_tol=1e-6, max_iters=None,
+                 check_every=16):
+        """solvers.euler on the convex-envelope operator, slab-parallel: halo exchange,
+        one fused step kernel per rank, MAX all-reduce of (max|F|, max|dU|) every
+        ``check_every`` iterations is NOT enough to stop at the reference's iteration --
+        so the two maxima of EVERY iteration are kept in a device ring and reduced in one
+        all-reduce per batch; the stopping iteration is then found exactly and the state
+        recomputed from the last checkpoint if the loop overshot."""
+        c = self.ctx
+        if max_iters is None:
+            max_iters = self.G.num_points
+        it = 0
+        diff = float("inf")
+        fmax = float("inf")
+        while it < max_iters:
+            n = int(min(check_every, max_iters - it))
+            ckpt = U.clone()
+            red = torch.zeros((n, 2), dtype=torch.float64, device=c.device)
+            V = ckpt.clone()
+            for k in range(n):
+                self.exchange_halo(V)
+                V, r2 = c.ce_euler_step(V, g, dt)
+                red[k] = r2
+            if self.world > 1:
+                dist.all_reduce(red, op=dist.ReduceOp.MAX)
+            h = red.cpu().numpy()
+            ok = (h[:, 1] < solution_tol) & (h[:, 0] < operator_tol)
+            if ok.any():
+                stop = int(np.flatnonzero(ok)[0]) + 1
+                V = ckpt
+                for k in range(stop):          # replay to the exact stopping iterate
+                    self.exchange_halo(V)
+                    V, _ = c.ce_euler_step(V, g, dt)
+                return V, float(h[stop - 1, 1]), it + stop, float(h[stop - 1, 0])
+            U = V
+            it += n
+            diff, fmax = float(h[-1, 1]), float(h[-1, 0])
+        return U, diff, it, fmax

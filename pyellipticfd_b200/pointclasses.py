@@ -172,7 +172,9 @@ class FDRegularGrid(FDPointCloud):
                 "spatial resolution {0.spatial_resolution:.3g}, "
                 "and angular resolution {0.angular_resolution:.3g}").format(self)
 
-    def __init__(self, interior_shape, bounds, stencil_radius, interpolation=True):
+    def __init__(self, interior_shape, bounds, stencil_radius, interpolation=True,
+                 native=True):
+        self._native_band = native
         if interpolation:
             raise NotImplementedError(
                 "pyellipticfd_b200.FDRegularGrid builds antipodal pairs only "
@@ -259,6 +261,42 @@ class FDRegularGrid(FDPointCloud):
         """Lattice coordinates -> physical coordinates, as :551."""
         return P * self.scaling + self.bounds[0]
 
+    def _make_band_native(self):
+        import ctypes as C
+        try:
+            from . import _lib
+            L = _lib.lib()
+            fn = L.pde_band_build
+        except Exception:
+            return False
+        nx, ny = self.interior_shape
+        W = np.ascontiguousarray(self._wall_unscaled, dtype=np.float64)
+        ids = np.ascontiguousarray(self.band_index, dtype=np.int64)
+        ptr, pairs, mn = C.c_void_p(), C.c_void_p(), C.c_double()
+        rc = fn(nx, ny, self.stencil_radius, float(self.scaling[0]), float(self.scaling[1]),
+                float(self.bounds[0][0]), float(self.bounds[0][1]), W.shape[0],
+                C.c_void_p(W.ctypes.data), ids.size, C.c_void_p(ids.ctypes.data), COLINEAR_TOL,
+                C.byref(ptr), C.byref(pairs), C.byref(mn))
+        if rc == 2:
+            raise TypeError(L.pde_last_error().decode())          # "Point i has no pairs"
+        _lib.check(rc)
+        n = ids.size
+        try:
+            self.band_ptr = np.ctypeslib.as_array(
+                C.cast(ptr, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+            P = int(self.band_ptr[-1])
+            self.band_pairs = np.ctypeslib.as_array(
+                C.cast(pairs, C.POINTER(C.c_int64)), shape=(max(P, 1) * 3,)).copy()[:3 * P].reshape(P, 3)
+        finally:
+            L.pde_free(ptr)
+            L.pde_free(pairs)
+        min_nb = mn.value
+        if self.num_interior - n > 0:
+            offs_k = self.stencil_offsets * self.scaling
+            min_nb = min(min_nb, np.sqrt((offs_k ** 2).sum(1)).min())
+        self._min_interior_nb_dist = float(min_nb)
+        return True
+
     def coords(self, ids):
         """Physical coordinates of the given point ids, with the arithmetic of
         ``points`` (:551) but without materialising the whole array."""
@@ -293,15 +331,33 @@ class FDRegularGrid(FDPointCloud):
         i = np.arange(1, n + 1)
         return (i <= r) | (i >= n - r + 1)
 
-    def _make_band(self, batch=256):
+    def _make_band(self, batch=None):
+        """Pair rows of the band points.  Uses the native builder of libpde_b200.so
+        (host code, OpenMP) when the library is built; the NumPy implementation below is
+        the executable specification it is tested against (tests/test_grid.py)."""
         nx, ny = self.interior_shape
         r = self.stencil_radius
         N = self.num_interior
         bx = self._band_mask_1d(nx)
         by = self._band_mask_1d(ny)
-        band2d = bx[:, None] | by[None, :]
-        bi, bj = np.nonzero(band2d)                      # C order == ascending point id
-        self.band_index = (bi * ny + bj).astype(np.int64)
+        self._band_rows_1d, self._band_cols_1d = bx, by
+        if nx * ny <= 4_000_000:
+            bi, bj = np.nonzero(bx[:, None] | by[None, :])   # C order == ascending point id
+            band_index = (bi * ny + bj).astype(np.int64)
+        else:                                                  # same set without an nx*ny mask
+            full = np.flatnonzero(bx)
+            part = np.flatnonzero(~bx)
+            cols = np.flatnonzero(by)
+            band_index = np.sort(np.concatenate([
+                (full[:, None] * ny + np.arange(ny)[None, :]).ravel(),
+                (part[:, None] * ny + cols[None, :]).ravel()])).astype(np.int64)
+            bi, bj = band_index // ny, band_index % ny
+        self.band_index = band_index
+        if self._native_band and self._make_band_native():
+            return
+        if batch is None:
+            kest = (2 * r + 1) ** 2 + 2 * (2 * r + 1) * r * r
+            batch = int(min(1024, max(4, 3_000_000 // (kest * kest))))
         cx = (bi + 1).astype(np.float64)
         cy = (bj + 1).astype(np.float64)
         nb = len(cx)
@@ -396,7 +452,6 @@ class FDRegularGrid(FDPointCloud):
         counts = np.bincount(np.searchsorted(self.band_index, self.band_pairs[:, 0]),
                              minlength=nb)
         self.band_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-        self._band2d = band2d
         n_deep = N - nb
         if n_deep > 0:
             offs_k = self.stencil_offsets * self.scaling
@@ -454,7 +509,9 @@ class FDRegularGrid(FDPointCloud):
         D = self.stencil_pairs.shape[0]
         if self.num_pairs > max_rows:
             raise MemoryError("refusing to materialise %d pair rows" % self.num_pairs)
-        deep = np.flatnonzero(~self._band2d.ravel())
+        isband = np.zeros(self.num_interior, bool)
+        isband[self.band_index] = True
+        deep = np.flatnonzero(~isband)
         di, dj = deep // ny, deep % ny
         sp = self.stencil_pairs
         J0 = ((di[:, None] + sp[None, :, 0]) * ny + dj[:, None] + sp[None, :, 1])

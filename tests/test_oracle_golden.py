@@ -1,0 +1,111 @@
+"""CPU: the oracle restatements and the fast grid constructor against the golden
+fixtures generated from the unmodified reference (oracle/make_golden.py)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ddg_oracle as O, solvers_oracle as SO, c_oracle
+from oracle.make_golden import canon_pairs, fields, two_cones
+from pyellipticfd_b200.pointclasses import FDRegularGrid
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+DDG = sorted(glob.glob(os.path.join(GOLD, "ddg_*.npz")))
+SOLVE = sorted(glob.glob(os.path.join(GOLD, "solve_*.npz")))
+
+
+def grid_of(z):
+    return FDRegularGrid([int(s) for s in z["shape"]], z["bounds"], int(z["radius"]),
+                         interpolation=False)
+
+
+def test_fixtures_present():
+    assert len(DDG) >= 5 and len(SOLVE) >= 3
+
+
+@pytest.mark.parametrize("path", DDG, ids=[os.path.basename(p) for p in DDG])
+def test_grid_constructor_matches_reference(path):
+    z = np.load(path)
+    G = grid_of(z)
+    assert G.num_bdry == int(z["num_bdry"])
+    assert np.array_equal(G.points[G.num_interior:], z["bdry_points"])
+    assert np.array_equal(canon_pairs(G.pairs), z["pairs"])       # per-point pair SETS
+    meta = np.array([G.spatial_resolution, G.angular_resolution, G.dist_to_bdry,
+                     G.bdry_resolution, G.max_radius, G.min_radius, G.min_interior_nb_dist])
+    assert np.array_equal(meta, z["meta"])
+
+
+@pytest.mark.parametrize("path", DDG, ids=[os.path.basename(p) for p in DDG])
+def test_oracle_values_match_reference(path):
+    z = np.load(path)
+    G = grid_of(z)
+    for name, u in fields(G).items():
+        (lmin, _, _), (lmax, _, _) = O.d2eigs(G, u)
+        assert np.array_equal(lmin, z["lmin_" + name]), name
+        assert np.array_equal(lmax, z["lmax_" + name]), name
+        # plain-C restatement
+        cmin, cmax, _, _ = c_oracle.pairs_d2eigs(G.points, G.pairs, u, G.num_interior)
+        assert np.array_equal(cmin, lmin) and np.array_equal(cmax, lmax)
+    u = fields(G)["random"]
+    deep = np.ones(G.num_interior, bool)
+    deep[G.band_index] = False
+    for k, v in enumerate(([1, 0], [0, 1], 0.3)):
+        # the best-aligned pair is order dependent at exact score ties, which only occur
+        # among the irregular wall pairs of band points (documented tie exemption)
+        d = O.d2(G, v, u)[0]
+        assert np.array_equal(d[deep], z["d2_%d" % k][deep])
+        assert (d == z["d2_%d" % k]).mean() > 0.5
+    W, g = fields(G)["smooth"], fields(G)["saddle"]
+    F, J = SO.ce_operator(G, W.copy(), g, True)
+    assert np.array_equal(F, z["ce_F"])
+    x = fields(G, 3)["random"]
+    # rows of band points with an exact tie in lambda_min may select another (equal-valued)
+    # pair than the reference's arbitrary pair order does: tie exemption
+    notband = np.ones(G.num_points, bool)
+    notband[G.band_index] = False
+    ok = np.isclose(J.dot(x), z["ce_Jx"], rtol=1e-13, atol=1e-9)
+    assert ok[notband].all() and ok.mean() > 0.97
+    okd = J.diagonal() == z["ce_diag"]
+    assert okd[notband].all() and okd.mean() > 0.97
+
+
+@pytest.mark.parametrize("path", SOLVE, ids=[os.path.basename(p) for p in SOLVE])
+def test_oracle_solvers_match_reference(path):
+    z = np.load(path)
+    if int(z["shape"][0]) > 40:
+        pytest.skip("large case is covered by the GPU parity test")
+    G = grid_of(z)
+    g = two_cones(G.points)
+    assert np.array_equal(g, z["g"])
+    U, diff, it, _ = SO.ce_solve(G, g, solver="euler")
+    assert it == int(z["euler_iters"]) and np.array_equal(U, z["euler_U"])
+    U, diff, it, _ = SO.ce_solve(G, g, solver="newton")
+    assert it == int(z["newton_iters"])
+    assert np.abs(U - z["newton_U"]).max() < 1e-9
+    if "pucci_U" in z.files:
+        U, diff, it, _ = SO.pucci_solve(G, z["pucci_f"], z["pucci_g"], A=(2, 1))
+        assert it == int(z["pucci_iters"]) and np.abs(U - z["pucci_U"]).max() < 1e-9
+
+
+def test_bicgstab_restatement_matches_scipy():
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import bicgstab as sb
+    rng = np.random.default_rng(0)
+    n = 300
+    A = sp.diags([-1.0, 2.4, -1.1], [-1, 0, 1], shape=(n, n), format="csr")
+    b = rng.standard_normal(n)
+    P = sp.diags(1 / A.diagonal(), format="csr")
+    x, info = sb(A, b, M=P, rtol=1e-8)
+    y, oinfo, _ = SO.bicgstab(A, b, rtol=1e-8, M=P)
+    assert info == oinfo == 0 and np.array_equal(x, y)
+
+
+def test_c_lattice_oracle_matches_numpy():
+    G = FDRegularGrid([40, 37], np.array([[0, 1], [-1, 2]]).T, 3, interpolation=False)
+    u = np.random.default_rng(0).standard_normal(G.num_points)
+    lmin, lmax, rmin, rmax = O.d2eigs_policy(G, u)
+    c = c_oracle.lattice_d2eigs(G, u)
+    m = ~np.isnan(c[0])
+    assert m.sum() == G.num_deep
+    assert np.array_equal(c[0][m], lmin[m]) and np.array_equal(c[1][m], lmax[m])
