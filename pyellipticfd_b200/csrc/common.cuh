@@ -66,6 +66,7 @@ struct pde_grid {
     int64_t nb;                  // wall points
     int radius;                  // stencil radius r: deep = [r, n-r) on both axes
     pde::DeepTable tab;
+    int ct_id;                   // index of the matching compile-time table, or -1
     double stencil_X[PDE_MAX_DIRS][2];  // physical vector of (a0,b0)
     // band (CSR over band points owned by this context)
     int64_t n_band, n_band_pairs;
@@ -78,6 +79,8 @@ struct pde_grid {
     // scratch for reductions / control words
     double *d_red;               // 16 doubles
     unsigned long long *d_ctrl;  // 16 words
+    cudaStream_t side;           // band kernel runs here, concurrently with the deep kernel
+    cudaEvent_t ev_fork, ev_join;
     PFN_cuTensorMapEncodeTiled_v12000 encode;
     int num_sms;
 };

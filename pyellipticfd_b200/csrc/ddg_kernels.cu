@@ -2,6 +2,8 @@
 // stencil_deep.cuh) + CSR band kernel, with the convex-envelope / Pucci
 // epilogues fused in.  C ABI in include/pde_b200.h.
 #include <algorithm>
+#include <cstdlib>
+#include <type_traits>
 #include "stencil_deep.cuh"
 
 using namespace pde;
@@ -17,17 +19,21 @@ k_band(int64_t n_band, const int64_t *__restrict__ center, const int64_t *__rest
        const int64_t *__restrict__ jj, const double *__restrict__ ww,
        const double *__restrict__ S, const Epi epi, double *red_out,
        const unsigned long long *done_flag) {
+    // one WARP per band point: lanes stride over the point's pair rows (coalesced reads of
+    // the row tables), then a warp reduction that keeps the tie rule: among equal values
+    // the minimum keeps the highest row number, the maximum the lowest.
     if (done_flag && *done_flag) return;
     BlockMax2 red{0.0, 0.0};
-    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     if (i < n_band) {
         int64_t o = center[i];
         double uc = S[o];
         double mn = __longlong_as_double(0x7ff0000000000000LL);
         double mx = __longlong_as_double(0xfff0000000000000LL);
-        int kmn = 0, kmx = 0;
+        int kmn = -1, kmx = 0x7fffffff;
         int64_t b = ptr[i], e = ptr[i + 1];
-        for (int64_t k = b; k < e; ++k) {
+        for (int64_t k = b + lane; k < e; k += 32) {
             double u0 = S[jj[2 * k]], u1 = S[jj[2 * k + 1]];
             double w_0 = ww[3 * k], w_1 = ww[3 * k + 1], w0 = ww[3 * k + 2];
             double d;
@@ -35,20 +41,35 @@ k_band(int64_t n_band, const int64_t *__restrict__ center, const int64_t *__rest
                 d = pair_value_exact(uc, u0, u1, w_0, w_1, w0);
             else
                 d = (fma(w_1, u1 - uc, w_0 * (u0 - uc))) * w0;
-            if (Epi::kMin && d <= mn) {
+            if (Epi::kMin && d <= mn) {        // rows ascend within a lane: keeps the last
                 mn = d;
                 kmn = (int)(k - b);
             }
-            if (Epi::kMax && d > mx) {
+            if (Epi::kMax && d > mx) {         // keeps the first
                 mx = d;
                 kmx = (int)(k - b);
             }
         }
-        epi(o, uc, mn, mx, kmn, kmx, red);
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            double omn = __shfl_xor_sync(0xffffffffu, mn, s);
+            int okn = __shfl_xor_sync(0xffffffffu, kmn, s);
+            double omx = __shfl_xor_sync(0xffffffffu, mx, s);
+            int okx = __shfl_xor_sync(0xffffffffu, kmx, s);
+            if (Epi::kMin && (omn < mn || (omn == mn && okn > kmn))) {
+                mn = omn;
+                kmn = okn;
+            }
+            if (Epi::kMax && (omx > mx || (omx == mx && okx < kmx))) {
+                mx = omx;
+                kmx = okx;
+            }
+        }
+        if (lane == 0) epi(o, uc, mn, mx, kmn, kmx, red);
     }
     if (Epi::kRed) {
         double a = warp_max(red.a), bb = warp_max(red.b);
-        if ((threadIdx.x & 31) == 0) {
+        if (lane == 0) {
             atomic_max_nonneg(&red_out[0], a);
             atomic_max_nonneg(&red_out[1], bb);
         }
@@ -119,7 +140,7 @@ static int make_tmap(const pde_grid *g, const double *S, int boxy, int boxx, CUt
     return 0;
 }
 
-template <int H, int P, int MODE, class Epi>
+template <class Eval, int H, int P, int MODE, class Epi, int MINB = 2>
 static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *red,
                           const unsigned long long *done, cudaStream_t st) {
     DeepRegion dr = deep_region(g);
@@ -137,15 +158,15 @@ static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *
     int rc = make_tmap(g, S, K1_TY + 2 * H + 2, TX + 2 * H, &tmap);
     if (rc) return rc;
     constexpr int smem = k_deep_smem_bytes<H, P>();
-    auto kern = k_deep<H, P, MODE, Epi>;
+    auto kern = k_deep<Eval, H, P, MODE, Epi, MINB>;
     static bool attr_set = false;   // per template instantiation
     if (!attr_set) {
         PDE_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set = true;
     }
     int ntiles = geo.tiles_x * geo.tiles_y;
-    int grid = std::min(ntiles, g->num_sms * 2);
-    kern<<<grid, K1_THREADS, smem, st>>>(tmap, g->tab, geo, epi, S, red, done);
+    int grid = std::min(ntiles, g->num_sms * MINB);
+    kern<<<grid, K1_THREADS, smem, st>>>(tmap, g->tab, geo, epi, red, done);
     PDE_LAUNCH_CHECK();
     return 0;
 }
@@ -154,13 +175,36 @@ template <int MODE, class Epi>
 static int launch_deep(pde_grid *g, const double *S, const Epi &epi, double *red,
                        const unsigned long long *done, cudaStream_t st) {
     if (g->tab.D == 0) return 0;
-    switch (g->tab.H) {
-        case 1: return launch_deep_hp<1, 8, MODE, Epi>(g, S, epi, red, done, st);
-        case 2: return launch_deep_hp<2, 8, MODE, Epi>(g, S, epi, red, done, st);
-        case 3: return launch_deep_hp<3, 8, MODE, Epi>(g, S, epi, red, done, st);
-        case 4: return launch_deep_hp<4, 8, MODE, Epi>(g, S, epi, red, done, st);
-        case 5: return launch_deep_hp<5, 8, MODE, Epi>(g, S, epi, red, done, st);
-        case 6: return launch_deep_hp<6, 8, MODE, Epi>(g, S, epi, red, done, st);
+    if constexpr (std::is_same<Epi, EpiEigs<true, false, false>>::value && MODE == 0) {
+        // tuning switch for the benchmark kernel (r = 4, d2min values): PDE_K1_VARIANT
+        static const int variant = getenv("PDE_K1_VARIANT") ? atoi(getenv("PDE_K1_VARIANT")) : 0;
+        if (g->ct_id == 3 && variant == 1)
+            return launch_deep_hp<EvalCt<3>, 4, 4, MODE, Epi, 3>(g, S, epi, red, done, st);
+        if (g->ct_id == 3 && variant == 2)
+            return launch_deep_hp<EvalCt<3>, 4, 4, MODE, Epi, 4>(g, S, epi, red, done, st);
+        if (g->ct_id == 3 && variant == 3)
+            return launch_deep_hp<EvalCt<3>, 4, 8, MODE, Epi, 1>(g, S, epi, red, done, st);
+        if (g->ct_id == 3 && variant == 4)
+            return launch_deep_hp<EvalCt<3>, 4, 16, MODE, Epi, 1>(g, S, epi, red, done, st);
+        if (g->ct_id == 3 && variant == 5)
+            return launch_deep_hp<EvalCt<3>, 4, 6, MODE, Epi, 3>(g, S, epi, red, done, st);
+    }
+    // compile-time table (square cells): fully unrolled evaluator with register windows
+    switch (g->ct_id) {
+        case 0: return launch_deep_hp<EvalCt<0>, 1, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 1: return launch_deep_hp<EvalCt<1>, 2, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 2: return launch_deep_hp<EvalCt<2>, 3, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 3: return launch_deep_hp<EvalCt<3>, 4, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 4: return launch_deep_hp<EvalCt<4>, 5, 8, MODE, Epi>(g, S, epi, red, done, st);
+        default: break;
+    }
+    switch (g->tab.H) {      // run-time table (anisotropic cells, user tables)
+        case 1: return launch_deep_hp<EvalRuntime, 1, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 2: return launch_deep_hp<EvalRuntime, 2, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 3: return launch_deep_hp<EvalRuntime, 3, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 4: return launch_deep_hp<EvalRuntime, 4, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 5: return launch_deep_hp<EvalRuntime, 5, 8, MODE, Epi>(g, S, epi, red, done, st);
+        case 6: return launch_deep_hp<EvalRuntime, 6, 8, MODE, Epi>(g, S, epi, red, done, st);
     }
     return pde::fail("unsupported stencil halo", __FILE__, __LINE__);
 }
@@ -169,7 +213,7 @@ template <int MODE, class Epi>
 static int launch_band(pde_grid *g, const double *S, const Epi &epi, double *red,
                        const unsigned long long *done, cudaStream_t st) {
     if (g->n_band == 0) return 0;
-    int grid = (int)((g->n_band + 127) / 128);
+    int grid = (int)((g->n_band + 3) / 4);           // one warp per band point
     k_band<MODE, Epi><<<grid, 128, 0, st>>>(g->n_band, g->d_band_center, g->d_band_ptr,
                                              g->d_band_j, g->d_band_w, S, epi, red, done);
     PDE_LAUNCH_CHECK();
@@ -179,13 +223,28 @@ static int launch_band(pde_grid *g, const double *S, const Epi &epi, double *red
 template <class Epi>
 static int launch_both(pde_grid *g, const double *S, const Epi &epi, int mode, double *red,
                        const unsigned long long *done, cudaStream_t st) {
+    // The band kernel (explicit pair rows: latency / bandwidth bound, few registers) is
+    // forked onto the context's side stream so that it shares the SMs with the fp64-bound
+    // deep kernel instead of running after it; the two write disjoint points.
     int rc;
-    if (mode == 0) {
-        if ((rc = launch_deep<0, Epi>(g, S, epi, red, done, st))) return rc;
-        return launch_band<0, Epi>(g, S, epi, red, done, st);
+    const bool fork = g->n_band > 0 && g->tab.D > 0;
+    cudaStream_t sb = fork ? g->side : st;
+    if (fork) {
+        PDE_CHECK(cudaEventRecord(g->ev_fork, st));
+        PDE_CHECK(cudaStreamWaitEvent(sb, g->ev_fork, 0));
     }
-    if ((rc = launch_deep<1, Epi>(g, S, epi, red, done, st))) return rc;
-    return launch_band<1, Epi>(g, S, epi, red, done, st);
+    if (mode == 0) {
+        if ((rc = launch_band<0, Epi>(g, S, epi, red, done, sb))) return rc;
+        if ((rc = launch_deep<0, Epi>(g, S, epi, red, done, st))) return rc;
+    } else {
+        if ((rc = launch_band<1, Epi>(g, S, epi, red, done, sb))) return rc;
+        if ((rc = launch_deep<1, Epi>(g, S, epi, red, done, st))) return rc;
+    }
+    if (fork) {
+        PDE_CHECK(cudaEventRecord(g->ev_join, sb));
+        PDE_CHECK(cudaStreamWaitEvent(st, g->ev_join, 0));
+    }
+    return 0;
 }
 
 static int launch_wall(pde_grid *g, const double *W, const double *gg, double *out, double dt,
@@ -227,14 +286,21 @@ int pde_ddg_d2eigs(pde_grid *g, const double *d_state, double *d_lmin, double *d
     DeviceGuard guard(g->device);
     cudaStream_t st = (cudaStream_t)stream;
     const bool want_min = d_lmin || d_pmin, want_max = d_lmax || d_pmax;
-    if (want_min && !want_max)      // ddg.d2min: the max half of the reference's work is dead
-        return launch_both(g, d_state, EpiEigs<true, false>{d_lmin, d_lmax, d_pmin, d_pmax}, mode,
-                           nullptr, nullptr, st);
-    if (want_max && !want_min)
-        return launch_both(g, d_state, EpiEigs<false, true>{d_lmin, d_lmax, d_pmin, d_pmax}, mode,
-                           nullptr, nullptr, st);
-    return launch_both(g, d_state, EpiEigs<true, true>{d_lmin, d_lmax, d_pmin, d_pmax}, mode,
-                       nullptr, nullptr, st);
+    const bool pol = d_pmin || d_pmax;
+#define PDE_EIGS(MIN, MAX, POL)                                                              \
+    return launch_both(g, d_state, EpiEigs<MIN, MAX, POL>{d_lmin, d_lmax, d_pmin, d_pmax}, mode, \
+                       nullptr, nullptr, st)
+    if (want_min && !want_max) {    // ddg.d2min: the max half of the reference's work is dead
+        if (pol) PDE_EIGS(true, false, true);
+        PDE_EIGS(true, false, false);
+    }
+    if (want_max && !want_min) {
+        if (pol) PDE_EIGS(false, true, true);
+        PDE_EIGS(false, true, false);
+    }
+    if (pol) PDE_EIGS(true, true, true);
+    PDE_EIGS(true, true, false);
+#undef PDE_EIGS
 }
 
 int pde_ce_residual(pde_grid *g, const double *d_W, const double *d_g, double *d_F,
@@ -243,8 +309,8 @@ int pde_ce_residual(pde_grid *g, const double *d_W, const double *d_g, double *d
     DeviceGuard guard(g->device);
     cudaStream_t st = (cudaStream_t)stream;
     double *red = d_red ? d_red : g->d_red + 8;
-    EpiCeResidual epi{d_g, d_F, d_policy};
-    int rc = launch_both(g, d_W, epi, 0, red, nullptr, st);
+    int rc = d_policy ? launch_both(g, d_W, EpiCeResidual<true>{d_g, d_F, d_policy}, 0, red, nullptr, st)
+                      : launch_both(g, d_W, EpiCeResidual<false>{d_g, d_F, d_policy}, 0, red, nullptr, st);
     if (rc) return rc;
     return launch_wall(g, d_W, d_g, d_F, 0.0, 0, red, nullptr, st);
 }
@@ -256,8 +322,11 @@ int pde_pucci_residual(pde_grid *g, const double *d_W, const double *d_f, double
     DeviceGuard guard(g->device);
     cudaStream_t st = (cudaStream_t)stream;
     double *red = d_red ? d_red : g->d_red + 8;
-    EpiPucciResidual epi{d_f, d_F, d_pmin, d_pmax, A0, A1, d_A0, d_A1};
-    int rc = launch_both(g, d_W, epi, 0, red, nullptr, st);
+    int rc = (d_pmin || d_pmax)
+                 ? launch_both(g, d_W, EpiPucciResidual<true>{d_f, d_F, d_pmin, d_pmax, A0, A1, d_A0, d_A1},
+                               0, red, nullptr, st)
+                 : launch_both(g, d_W, EpiPucciResidual<false>{d_f, d_F, d_pmin, d_pmax, A0, A1, d_A0, d_A1},
+                               0, red, nullptr, st);
     if (rc) return rc;
     return launch_wall(g, d_W, d_f, d_F, 0.0, 0, red, nullptr, st);
 }

@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "stencil_ct.cuh"
 
 namespace pde {
 
@@ -137,6 +138,14 @@ int pde_grid_create(pde_grid **out, int device, int64_t nx_global, int64_t ny, i
         g->stencil_X[k][1] = h_stencil_X ? h_stencil_X[2 * k + 1] : 0.0;
     }
     g->tab.H = H;
+    g->ct_id = -1;
+    for (int t = 0; t < pde::CT_NUM_TABLES && g->ct_id < 0; ++t) {
+        if (pde::CT_TABLE_D[t] != D) continue;
+        bool same = true;
+        for (int k = 0; k < D && same; ++k)
+            for (int j = 0; j < 4; ++j) same = same && pde::CT_TABLES[t][k][j] == h_stencil_pairs[4 * k + j];
+        if (same) g->ct_id = t;
+    }
     if (H > 6 || H > stencil_radius) {
         delete g;
         return pde::fail("stencil halo larger than supported (6) or than the radius", __FILE__,
@@ -158,6 +167,9 @@ int pde_grid_create(pde_grid **out, int device, int64_t nx_global, int64_t ny, i
     }
     PDE_CHECK(cudaMemset(g->d_red, 0, 16 * sizeof(double)));
     PDE_CHECK(cudaMemset(g->d_ctrl, 0, 16 * sizeof(unsigned long long)));
+    PDE_CHECK(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking));
+    PDE_CHECK(cudaEventCreateWithFlags(&g->ev_fork, cudaEventDisableTiming));
+    PDE_CHECK(cudaEventCreateWithFlags(&g->ev_join, cudaEventDisableTiming));
 
     cudaDeviceProp prop;
     PDE_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -188,6 +200,9 @@ int pde_grid_destroy(pde_grid *g) {
     cudaFree(g->d_band_X);
     cudaFree(g->d_red);
     cudaFree(g->d_ctrl);
+    if (g->side) cudaStreamDestroy(g->side);
+    if (g->ev_fork) cudaEventDestroy(g->ev_fork);
+    if (g->ev_join) cudaEventDestroy(g->ev_join);
     delete g;
     return 0;
 }

@@ -16,6 +16,7 @@
 // `<=` keeps the LAST minimal pair, `>` keeps the FIRST maximal pair.
 #pragma once
 #include "common.cuh"
+#include "stencil_ct.cuh"
 
 namespace pde {
 
@@ -71,11 +72,11 @@ struct BlockMax2 {   // two running maxima per thread, reduced once per CTA at t
 // ---- epilogues -----------------------------------------------------------------
 // Each epilogue sees one evaluated point: state offset `o`, centre value, the two
 // extremes and their table rows.
-template <bool MIN, bool MAX>
+template <bool MIN, bool MAX, bool POL>
 struct EpiEigs {    // ddg.d2eigs values + policy (ddg.py:292); d2min / d2max skip the unused half
     double *lmin, *lmax;
     uint16_t *pmin, *pmax;
-    static constexpr bool kMin = MIN, kMax = MAX, kRed = false;
+    static constexpr bool kMin = MIN, kMax = MAX, kRed = false, kPol = POL;
     __device__ __forceinline__ void operator()(int64_t o, double, double mn, double mx, int kmn,
                                                int kmx, BlockMax2 &) const {
         if (lmin) lmin[o] = mn;
@@ -85,11 +86,12 @@ struct EpiEigs {    // ddg.d2eigs values + policy (ddg.py:292); d2min / d2max sk
     }
 };
 
+template <bool POL>
 struct EpiCeResidual {   // convex_envelope.operator (convex_envelope.py:44-46)
     const double *g;
     double *F;
     uint16_t *policy;
-    static constexpr bool kMin = true, kMax = false, kRed = true;
+    static constexpr bool kMin = true, kMax = false, kRed = true, kPol = POL;
     __device__ __forceinline__ void operator()(int64_t o, double uc, double mn, double, int kmn,
                                                int, BlockMax2 &red) const {
         double f = __dsub_rn(uc, g[o]);
@@ -106,7 +108,7 @@ struct EpiCeEuler {   // one explicit Euler step (solvers.py:65-74 on convex_env
     const double *g;
     double *Unew;
     double dt;
-    static constexpr bool kMin = true, kMax = false, kRed = true;
+    static constexpr bool kMin = true, kMax = false, kRed = true, kPol = false;
     __device__ __forceinline__ void operator()(int64_t o, double uc, double mn, double, int, int,
                                                BlockMax2 &red) const {
         double f = __dsub_rn(uc, g[o]);
@@ -119,13 +121,14 @@ struct EpiCeEuler {   // one explicit Euler step (solvers.py:65-74 on convex_env
     }
 };
 
+template <bool POL>
 struct EpiPucciResidual {   // pucci.py:48, :127-141
     const double *f;
     double *F;
     uint16_t *pmin, *pmax;
     double A0, A1;
     const double *dA0, *dA1;
-    static constexpr bool kMin = true, kMax = true, kRed = true;
+    static constexpr bool kMin = true, kMax = true, kRed = true, kPol = POL;
     __device__ __forceinline__ void operator()(int64_t o, double, double mn, double mx, int kmn,
                                                int kmx, BlockMax2 &red) const {
         double a0 = dA0 ? dA0[o] : A0;
@@ -139,11 +142,48 @@ struct EpiPucciResidual {   // pucci.py:48, :127-141
     }
 };
 
+// ---- direction-table evaluators -----------------------------------------------------
+// Run-time table (any grid whose weights are position independent, e.g. hx != hy): the
+// offsets come from the kernel-parameter constant bank.
+struct EvalRuntime {
+    template <int P, int TYH, int MODE, bool WMIN, bool WMAX, bool WPOL>
+    static __device__ __forceinline__ void run(const double *__restrict__ ctr, const DeepTable &tab,
+                                               const double (&uc)[P], double (&mn)[P],
+                                               double (&mx)[P], int (&kmn)[P], int (&kmx)[P]) {
+        const int D = tab.D;
+#pragma unroll 2
+        for (int k = 0; k < D; ++k) {
+            const double *q0 = ctr + tab.a0[k] * TYH + tab.b0[k];
+            const double *q1 = ctr + tab.a1[k] * TYH + tab.b1[k];
+            const double w_0 = tab.w_0[k], w_1 = tab.w_1[k], w0 = tab.w0[k];
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                double u0 = q0[p * TYH], u1 = q1[p * TYH];
+                double d;
+                if (MODE == 0)
+                    d = pair_value_exact(uc[p], u0, u1, w_0, w_1, w0);
+                else
+                    d = (fma(w_1, u1 - uc[p], w_0 * (u0 - uc[p]))) * w0;   // fewer fp64 ops, not bit-exact
+                if (WMIN) {
+                    bool le = d <= mn[p];
+                    mn[p] = le ? d : mn[p];
+                    if (WPOL) kmn[p] = le ? k : kmn[p];
+                }
+                if (WMAX) {
+                    bool gt = d > mx[p];
+                    mx[p] = gt ? d : mx[p];
+                    if (WPOL) kmx[p] = gt ? k : kmx[p];
+                }
+            }
+        }
+    }
+};
+
 // ---- the kernel ------------------------------------------------------------------
-template <int H, int P, int MODE, class Epi>
-__global__ void __launch_bounds__(K1_THREADS, 2)
+template <class Eval, int H, int P, int MODE, class Epi, int MINB = 2>
+__global__ void __launch_bounds__(K1_THREADS, MINB)
 k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTable tab,
-       const DeepGeom geo, const Epi epi, const double *__restrict__ U, double *red_out,
+       const DeepGeom geo, const Epi epi, double *red_out,
        const unsigned long long *done_flag) {
     constexpr int TX = 2 * P;                 // 256 threads = 128 columns x 2 row groups
     // +2 columns: the TMA box must start on a 16-byte boundary of the row, so when the
@@ -208,34 +248,7 @@ k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTab
             kmn[p] = 0;
             kmx[p] = 0;
         }
-        const int D = tab.D;
-#pragma unroll 2
-        for (int k = 0; k < D; ++k) {
-            const double *q0 = ctr + tab.a0[k] * TYH + tab.b0[k];
-            const double *q1 = ctr + tab.a1[k] * TYH + tab.b1[k];
-            const double w_0 = tab.w_0[k], w_1 = tab.w_1[k], w0 = tab.w0[k];
-#pragma unroll
-            for (int p = 0; p < P; ++p) {
-                double u0 = q0[p * TYH], u1 = q1[p * TYH];
-                double d;
-                if (MODE == 0) {
-                    d = pair_value_exact(uc[p], u0, u1, w_0, w_1, w0);
-                } else {
-                    // re-associated: fewer fp64 ops, not bit-exact
-                    d = (fma(w_1, u1 - uc[p], w_0 * (u0 - uc[p]))) * w0;
-                }
-                if (Epi::kMin) {
-                    bool le = d <= mn[p];
-                    mn[p] = le ? d : mn[p];
-                    kmn[p] = le ? k : kmn[p];
-                }
-                if (Epi::kMax) {
-                    bool gt = d > mx[p];
-                    mx[p] = gt ? d : mx[p];
-                    kmx[p] = gt ? k : kmx[p];
-                }
-            }
-        }
+        Eval::template run<P, TYH, MODE, Epi::kMin, Epi::kMax, Epi::kPol>(ctr, tab, uc, mn, mx, kmn, kmx);
         if (ly < geo.ncols) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {

@@ -323,7 +323,15 @@ class FDRegularGrid(FDPointCloud):
                                      np.zeros((1, len(offs)), bool))
         k, l = np.nonzero(pair[0])
         self.stencil_offsets = offs[keep[0]]
-        self.stencil_pairs = np.concatenate([offs[k], offs[l]], axis=1).astype(np.int32)
+        sp = np.concatenate([offs[k], offs[l]], axis=1).astype(np.int32)
+        # canonical row order of the table (this module's own; it only matters for exact
+        # ties): orient every pair so that its first vector has b > 0 (or b == 0, a > 0)
+        # and sort by (|b|, a).  Pairs that share a column offset are then adjacent, which
+        # lets the stencil kernel reuse one register window of column +b / -b for all of them.
+        flip = (sp[:, 1] < 0) | ((sp[:, 1] == 0) & (sp[:, 0] < 0))
+        sp[flip] = sp[flip][:, [2, 3, 0, 1]]
+        order = np.lexsort((sp[:, 0], np.abs(sp[:, 1])))
+        self.stencil_pairs = np.ascontiguousarray(sp[order])
         self.halo = int(np.abs(self.stencil_pairs).max()) if len(k) else 0
 
     def _band_mask_1d(self, n):

@@ -1,0 +1,22 @@
+"""Time convex_envelope.solve (Newton / policy iteration) on growing grids (GPU)."""
+import sys, os, time, json
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from pyellipticfd_b200 import convex_envelope
+from pyellipticfd_b200.pointclasses import FDRegularGrid
+from oracle.make_golden import two_cones
+
+r = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+sizes = [int(s) for s in sys.argv[2:]] or [63, 127, 255, 511]
+for n in sizes:
+    t = time.time()
+    G = FDRegularGrid([n, n], np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, r, interpolation=False)
+    tg = time.time() - t
+    g = two_cones(G.points)
+    st = {}
+    torch.cuda.synchronize()
+    t = time.time()
+    U, diff, it, _ = convex_envelope._solve_grid(G, g, None, "newton", stats=st)
+    torch.cuda.synchronize()
+    dt = time.time() - t
+    print(json.dumps(dict(n=n, r=r, grid_s=round(tg, 2), solve_s=round(dt, 3), newton=it, diff=diff, **st)), flush=True)
