@@ -41,12 +41,12 @@ UNIT = "Gpoint.dir/s"
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--n", type=int, default=4095, help="interior points per side")
     ap.add_argument("--radius", type=int, default=4)
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--solve", type=int, default=0,
                     help="also time convex_envelope.solve (Newton) on an S^2 interior grid")
@@ -226,6 +226,9 @@ def main():
     launches0 = _lib.kernel_launches()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()          # all ranks enter the timed region together
+        torch.cuda.synchronize()
     e0.record()
     for _ in range(args.steps):
         step()
@@ -277,7 +280,8 @@ def main():
         host = torch.empty(flat.numel(), dtype=torch.float64, pin_memory=True)
         host.copy_(flat)
         torch.cuda.synchronize()
-        res = ddg.d2min(G, host)[0]          # warm-up (pinned pool, context)
+        for _ in range(3):                   # warm-up (pinned host pool, context)
+            res = ddg.d2min(G, host)[0]
         t = time.perf_counter()
         for _ in range(args.e2e_steps):
             res = ddg.d2min(G, host)[0]

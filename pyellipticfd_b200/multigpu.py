@@ -25,7 +25,7 @@ def slab_partition(nx, world):
     return list(zip(lo, hi))
 
 
-def halo_exchange(view, nx_local, halo, rank, world, group=None):
+def halo_exchange(view, nx_local, halo, rank, world, group=None, method="auto"):
     """Refresh the halo rows of ``view`` ((nx_local + 2*halo) x pitch, contiguous rows).
 
     Sends the first/last ``halo`` owned rows to the previous/next rank and receives
@@ -34,6 +34,18 @@ def halo_exchange(view, nx_local, halo, rank, world, group=None):
     if world == 1 or halo == 0:
         return
     H = halo
+    if view.is_cuda and method != "p2p":
+        # One small all-gather of every rank's first/last H owned rows (2*H*pitch doubles per
+        # rank; 262 kB at ny = 4095, r = 4) instead of four point-to-point operations: a
+        # single NCCL kernel over NVLink, no per-peer send/recv matching.
+        send = torch.cat([view[H:2 * H], view[nx_local:nx_local + H]])
+        got = torch.empty((world,) + tuple(send.shape), dtype=send.dtype, device=send.device)
+        dist.all_gather_into_tensor(got, send, group=group)
+        if rank > 0:
+            view[0:H].copy_(got[rank - 1, H:2 * H])
+        if rank < world - 1:
+            view[nx_local + H:nx_local + 2 * H].copy_(got[rank + 1, 0:H])
+        return
     ops = []
     if rank > 0:
         ops.append(dist.P2POp(dist.isend, view[H:2 * H], rank - 1, group))

@@ -1,0 +1,74 @@
+"""CPU (gloo, world_size 2 and 3): the slab partition and the halo exchange of
+pyellipticfd_b200.multigpu -- the host-side logic of the N > 1 path."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from pyellipticfd_b200.multigpu import slab_partition, halo_exchange
+
+
+def test_slab_partition_covers_rows():
+    for nx, world in ((4095, 1), (4095, 2), (32766, 8), (17, 3)):
+        parts = slab_partition(nx, world)
+        assert parts[0][0] == 0 and parts[-1][1] == nx
+        assert all(a[1] == b[0] for a, b in zip(parts, parts[1:]))
+        sizes = [hi - lo for lo, hi in parts]
+        assert max(sizes) - min(sizes) <= 1
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, nx, pitch, halo, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        lo, hi = slab_partition(nx, world)[rank]
+        nloc = hi - lo
+        # global field value = 1000*row + col ; halo rows start as -1
+        view = torch.full((nloc + 2 * halo, pitch), -1.0, dtype=torch.float64)
+        rows = torch.arange(lo, hi, dtype=torch.float64)[:, None]
+        view[halo:halo + nloc] = 1000 * rows + torch.arange(pitch, dtype=torch.float64)[None, :]
+        halo_exchange(view, nloc, halo, rank, world)
+        ok = True
+        glob = lambda r: 1000.0 * r + torch.arange(pitch, dtype=torch.float64)
+        for k in range(halo):
+            top = lo - halo + k
+            bot = hi + k
+            exp_top = glob(top) if top >= 0 and rank > 0 else torch.full((pitch,), -1.0, dtype=torch.float64)
+            exp_bot = glob(bot) if bot < nx and rank < world - 1 else torch.full((pitch,), -1.0, dtype=torch.float64)
+            ok &= bool(torch.equal(view[k], exp_top)) and bool(torch.equal(view[halo + nloc + k], exp_bot))
+        # allreduce(max) of a per-rank pair, as the solvers do for (max|F|, max|dU|)
+        red = torch.tensor([float(rank), float(world - rank)], dtype=torch.float64)
+        dist.all_reduce(red, op=dist.ReduceOp.MAX)
+        ok &= red.tolist() == [float(world - 1), float(world)]
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.timeout(120)
+def test_halo_exchange_gloo(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, 37, 48, 4, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(100)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert all(res.values()) and len(res) == world

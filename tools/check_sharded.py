@@ -1,0 +1,68 @@
+"""torchrun worker: slab-sharded ddg.d2eigs and Euler solve against the oracle / one GPU.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port 29533 tools/check_sharded.py
+Prints one line per check on rank 0; exit code 1 on any mismatch."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch, torch.distributed as dist
+from pyellipticfd_b200.pointclasses import FDRegularGrid
+from pyellipticfd_b200.multigpu import ShardedGrid
+from pyellipticfd_b200._context import GridContext
+from pyellipticfd_b200 import convex_envelope
+from oracle import c_oracle
+from oracle.make_golden import two_cones
+
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+local = int(os.environ.get("LOCAL_RANK", rank))
+torch.cuda.set_device(local)
+dev = torch.device("cuda", local)
+dist.init_process_group("nccl", device_id=dev)
+ok_all = True
+
+def report(name, ok):
+    global ok_all
+    t = torch.tensor([1.0 if ok else 0.0], device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    ok_all &= bool(t.item() == 1.0)
+    if rank == 0:
+        print("%-50s %s" % (name, "OK" if t.item() == 1.0 else "MISMATCH"), flush=True)
+
+for shape, bounds, r in (((515, 300), [[0, 129.0 / 64], [0, 301.0 / 256]], 4),
+                         ((255, 255), [[-1, 1], [-1, 1]], 2),
+                         ((300, 200), [[0, 301.0 / 64], [0, 201.0 / 64]], 6)):
+    G = FDRegularGrid(list(shape), np.array(bounds, dtype=float).T, r, interpolation=False)
+    assert G.uniform_weights()
+    sh = ShardedGrid(shape, None, r, rank, world, dev, grid=G)
+    c = sh.ctx
+    u = np.random.default_rng(0).standard_normal(G.num_points)
+    N, ny = G.num_interior, shape[1]
+    lo, hi = c.x_offset, c.x_offset + c.nx_local
+    flat = np.concatenate([u[lo * ny:hi * ny], u[N:]])
+    S = c.pack(flat)
+    sh.exchange_halo(S)
+    lmin, lmax, pmin, pmax = c.d2eigs(S, policy=True)
+    omin, omax, rmin, rmax = c_oracle.pairs_d2eigs(G.points, G.pairs, u, N)
+    a, b = c.unpad(lmin).cpu().numpy(), c.unpad(lmax).cpu().numpy()
+    report("d2eigs %sx%s r=%d on %d ranks (bit-exact)" % (shape[0], shape[1], r, world),
+           np.array_equal(a, omin[lo * ny:hi * ny]) and np.array_equal(b, omax[lo * ny:hi * ny]))
+
+# Euler solve: sharded loop vs the single-GPU device loop (every rank runs the latter too)
+G = FDRegularGrid([127, 127], np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, 2, interpolation=False)
+g = two_cones(G.points)
+import warnings
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    Uref, dref, itref, _ = convex_envelope.solve(G, g, fdmethod="grid", solver="euler", max_iters=3000)
+sh = ShardedGrid((127, 127), None, 2, rank, world, dev, grid=G)
+c = sh.ctx
+N, ny = G.num_interior, 127
+lo, hi = c.x_offset, c.x_offset + c.nx_local
+gs = c.pack(np.concatenate([g[lo * ny:hi * ny], g[N:]]))
+U, diff, it, fmax = sh.ce_euler(gs.clone(), gs, convex_envelope.cfl_dt(G), max_iters=3000, check_every=64)
+mine = c.unpack(U).cpu().numpy()
+ref_local = np.concatenate([Uref[lo * ny:hi * ny], Uref[N:]])
+report("Euler 127^2 r=2: %d its (1 GPU %d), bit-exact U" % (it, itref),
+       it == itref and diff == dref and np.array_equal(mine, ref_local))
+dist.destroy_process_group()
+sys.exit(0 if ok_all else 1)
