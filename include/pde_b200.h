@@ -75,6 +75,12 @@ int pde_grid_create(pde_grid **out, int device,
                     const double *h_band_w /* P x 3 : w_0, w_1, w0 */,
                     const double *h_band_X /* P x 2 : points[J0]-points[I] */);
 int pde_grid_destroy(pde_grid *g);
+/* Restrict the following stencil launches (pde_ddg_d2eigs, pde_ce_residual,
+ * pde_ce_euler_step, pde_pucci_residual) to owned rows [row_lo, row_hi); wall entries
+ * are handled by the window that starts at row 0.  (0, nx_local) restores the full
+ * slab.  Used to overlap the halo exchange (edge rows last) and host<->device copies
+ * (row chunks) with the arithmetic. */
+int pde_grid_set_row_window(pde_grid *g, int64_t row_lo, int64_t row_hi);
 int64_t pde_grid_pitch(const pde_grid *g);      /* doubles per lattice row        */
 int64_t pde_grid_rows(const pde_grid *g);       /* nx_local + 2*halo_rows         */
 int64_t pde_grid_state_len(const pde_grid *g);  /* rows*pitch + nb                */

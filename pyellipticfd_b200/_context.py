@@ -265,6 +265,10 @@ class GridContext(object):
         check(self.lib.pde_grid_unpad_u16(self.h, _ptr(P), _ptr(out), _stream()))
         return out
 
+    def set_row_window(self, lo=0, hi=None):
+        """Restrict the stencil launches to owned rows [lo, hi) (None = all rows)."""
+        check(self.lib.pde_grid_set_row_window(self.h, int(lo), int(self.nx_local if hi is None else hi)))
+
     # ---- operators --------------------------------------------------------------------------------
     def d2eigs(self, S, want_min=True, want_max=True, policy=False, mode=0, out=None):
         """Raw ddg.d2eigs on a state tensor -> (lmin, lmax, pmin, pmax) state-layout."""
@@ -348,10 +352,13 @@ class GridContext(object):
         U = U1 if int(out[1]) == 1 else U0
         return U, float(out[2]), iters, float(out[3]), int(out[4])
 
-    def ce_euler_step(self, U, g, dt):
+    def ce_euler_step(self, U, g, dt, out=None):
         """One Euler step -> (Unew, red) with red = [max|F|, max|U-Unew|] on the device."""
-        Unew = self.zeros()
-        red = torch.zeros(2, dtype=torch.float64, device=self.device)
+        if out is not None:
+            Unew, red = out
+        else:
+            Unew = self.zeros()
+            red = torch.zeros(2, dtype=torch.float64, device=self.device)
         check(self.lib.pde_ce_euler_step(self.h, _ptr(U), _ptr(g), float(dt), _ptr(Unew),
                                          _ptr(red), _stream()))
         return Unew, red

@@ -32,6 +32,7 @@ SIGNATURES = {
                                 c_i64, c_i64, c_i64, c_int, vp, vp, vp,
                                 c_i64, vp, vp, vp, vp, vp]),
     "pde_grid_destroy": (c_int, [vp]),
+    "pde_grid_set_row_window": (c_int, [vp, c_i64, c_i64]),
     "pde_grid_pitch": (c_i64, [vp]),
     "pde_grid_rows": (c_i64, [vp]),
     "pde_grid_state_len": (c_i64, [vp]),

@@ -70,6 +70,8 @@ struct pde_grid {
     double stencil_X[PDE_MAX_DIRS][2];  // physical vector of (a0,b0)
     // band (CSR over band points owned by this context)
     int64_t n_band, n_band_pairs;
+    int64_t win_lo, win_hi;      // owned rows [win_lo, win_hi) the stencil launches act on
+    int64_t *h_band_row;         // host: owned-row number of every band point (ascending)
     int64_t *d_band_center;      // n_band: state offset of the centre
     int64_t *d_band_pcenter;     // n_band: padded-layout offset (policy / per-point outputs)
     int64_t *d_band_ptr;         // n_band+1

@@ -112,8 +112,8 @@ struct DeepRegion {
 
 static DeepRegion deep_region(const pde_grid *g) {
     int64_t r = g->radius;
-    int64_t gx0 = std::max<int64_t>(r, g->x_offset);
-    int64_t gx1 = std::min<int64_t>(g->nx_global - r, g->x_offset + g->nx_local);
+    int64_t gx0 = std::max<int64_t>(r, g->x_offset + g->win_lo);
+    int64_t gx1 = std::min<int64_t>(g->nx_global - r, g->x_offset + g->win_hi);
     DeepRegion d;
     d.row0 = (int)(gx0 - g->x_offset + g->halo_rows);
     d.nrows = (int)std::max<int64_t>(0, gx1 - gx0);
@@ -213,8 +213,14 @@ template <int MODE, class Epi>
 static int launch_band(pde_grid *g, const double *S, const Epi &epi, double *red,
                        const unsigned long long *done, cudaStream_t st) {
     if (g->n_band == 0) return 0;
-    int grid = (int)((g->n_band + 3) / 4);           // one warp per band point
-    k_band<MODE, Epi><<<grid, 128, 0, st>>>(g->n_band, g->d_band_center, g->d_band_ptr,
+    // band points of the active row window (band points are sorted by row)
+    const int64_t *rb = g->h_band_row, *re = g->h_band_row + g->n_band;
+    int64_t b_lo = std::lower_bound(rb, re, g->win_lo) - rb;
+    int64_t b_hi = std::lower_bound(rb, re, g->win_hi) - rb;
+    int64_t nbp = b_hi - b_lo;
+    if (nbp <= 0) return 0;
+    int grid = (int)((nbp + 3) / 4);                 // one warp per band point
+    k_band<MODE, Epi><<<grid, 128, 0, st>>>(nbp, g->d_band_center + b_lo, g->d_band_ptr + b_lo,
                                              g->d_band_j, g->d_band_w, S, epi, red, done);
     PDE_LAUNCH_CHECK();
     return 0;
@@ -227,7 +233,7 @@ static int launch_both(pde_grid *g, const double *S, const Epi &epi, int mode, d
     // forked onto the context's side stream so that it shares the SMs with the fp64-bound
     // deep kernel instead of running after it; the two write disjoint points.
     int rc;
-    const bool fork = g->n_band > 0 && g->tab.D > 0;
+    const bool fork = g->n_band > 0 && g->tab.D > 0 && g->win_hi - g->win_lo > 64;
     cudaStream_t sb = fork ? g->side : st;
     if (fork) {
         PDE_CHECK(cudaEventRecord(g->ev_fork, st));
@@ -249,7 +255,7 @@ static int launch_both(pde_grid *g, const double *S, const Epi &epi, int mode, d
 
 static int launch_wall(pde_grid *g, const double *W, const double *gg, double *out, double dt,
                        int mode, double *red, const unsigned long long *done, cudaStream_t st) {
-    if (g->nb == 0) return 0;
+    if (g->nb == 0 || g->win_lo != 0) return 0;      // wall entries go with the first window
     int grid = (int)std::min<int64_t>((g->nb + 255) / 256, 1024);
     k_wall<<<grid, 256, 0, st>>>(g->nb, g->rows * g->pitch, W, gg, out, dt, mode, red, done);
     PDE_LAUNCH_CHECK();

@@ -152,6 +152,10 @@ int pde_grid_create(pde_grid **out, int device, int64_t nx_global, int64_t ny, i
                          __LINE__);
     }
     g->n_band = n_band;
+    g->win_lo = 0;
+    g->win_hi = nx_local;
+    g->h_band_row = new int64_t[n_band > 0 ? n_band : 1];
+    for (int64_t i = 0; i < n_band; ++i) g->h_band_row[i] = h_band_center[i] / g->pitch - halo_rows;
     g->n_band_pairs = n_band ? h_band_ptr[n_band] : 0;
     int rc = 0;
     rc |= upload(&g->d_band_center, h_band_center, (size_t)n_band);
@@ -200,10 +204,21 @@ int pde_grid_destroy(pde_grid *g) {
     cudaFree(g->d_band_X);
     cudaFree(g->d_red);
     cudaFree(g->d_ctrl);
+    delete[] g->h_band_row;
     if (g->side) cudaStreamDestroy(g->side);
     if (g->ev_fork) cudaEventDestroy(g->ev_fork);
     if (g->ev_join) cudaEventDestroy(g->ev_join);
     delete g;
+    return 0;
+}
+
+int pde_grid_set_row_window(pde_grid *g, int64_t row_lo, int64_t row_hi) {
+    PDE_REQUIRE(g, "null argument");
+    if (row_lo < 0) row_lo = 0;
+    if (row_hi > g->nx_local) row_hi = g->nx_local;
+    if (row_hi < row_lo) row_hi = row_lo;
+    g->win_lo = row_lo;
+    g->win_hi = row_hi;
     return 0;
 }
 

@@ -80,6 +80,42 @@ class ShardedGrid(object):
         halo_exchange(self.lattice_view(S), self.ctx.nx_local, self.slab.halo, self.rank,
                       self.world)
 
+    def overlapped(self, S, launch):
+        """Run ``launch()`` (stencil launches that read the state ``S``) with the halo
+        exchange of ``S`` hidden behind the rows that do not need it: the exchange goes to a
+        communication stream, the interior rows [r, nx_local - r) are computed meanwhile on
+        the current stream, the 2*r edge rows afterwards."""
+        c, H = self.ctx, self.slab.halo
+        if self.world == 1 or H == 0:
+            return launch()
+        if c.nx_local <= 4 * H:
+            self.exchange_halo(S)
+            return launch()
+        if not hasattr(self, "_comm"):
+            self._comm = torch.cuda.Stream(device=c.device)
+        main = torch.cuda.current_stream()
+        self._comm.wait_stream(main)
+        with torch.cuda.stream(self._comm):
+            self.exchange_halo(S)
+        try:
+            c.set_row_window(H, c.nx_local - H)
+            res = launch()
+            main.wait_stream(self._comm)
+            c.set_row_window(0, H)
+            launch()
+            c.set_row_window(c.nx_local - H, c.nx_local)
+            launch()
+        finally:
+            c.set_row_window()
+        return res
+
+    def d2eigs(self, S, out, **kw):
+        """Slab-parallel ddg.d2eigs on the state ``S`` (halo refreshed inside); ``out`` is the
+        (lmin, lmax, pmin, pmax) tuple of preallocated state-layout outputs (None to skip)."""
+        return self.overlapped(S, lambda: self.ctx.d2eigs(S, want_min=out[0] is not None or out[2] is not None,
+                                                           want_max=out[1] is not None or out[3] is not None,
+                                                           out=out, **kw))
+
     def local_flat(self, fn):
         """Evaluate ``fn(points (n,2) tensor) -> values`` on this rank's points:
         owned interior rows first, then all wall points (the rank-local flat vector)."""
@@ -93,6 +129,12 @@ class ShardedGrid(object):
                         dim=2).reshape(-1, 2)
         W = torch.from_numpy(G.bdry_points).to(dev)
         return torch.cat([fn(P), fn(W)])
+
+    def _step(self, V, g, dt, red):
+        """One overlapped Euler step; ``red`` (2 doubles, device) accumulates the maxima."""
+        Vn = self.ctx.zeros()
+        self.overlapped(V, lambda: self.ctx.ce_euler_step(V, g, dt, out=(Vn, red)))
+        return Vn
 
     # ---- distributed convex-envelope Euler iteration ------------------------------------
     def ce_euler(self, U, g, dt, solution_tol=1e-6, operator_tol=1e-6, max_iters=None,
@@ -115,9 +157,7 @@ class ShardedGrid(object):
             red = torch.zeros((n, 2), dtype=torch.float64, device=c.device)
             V = ckpt.clone()
             for k in range(n):
-                self.exchange_halo(V)
-                V, r2 = c.ce_euler_step(V, g, dt)
-                red[k] = r2
+                V = self._step(V, g, dt, red[k])
             if self.world > 1:
                 dist.all_reduce(red, op=dist.ReduceOp.MAX)
             h = red.cpu().numpy()
@@ -125,9 +165,9 @@ class ShardedGrid(object):
             if ok.any():
                 stop = int(np.flatnonzero(ok)[0]) + 1
                 V = ckpt
+                scratch = torch.zeros(2, dtype=torch.float64, device=c.device)
                 for k in range(stop):          # replay to the exact stopping iterate
-                    self.exchange_halo(V)
-                    V, _ = c.ce_euler_step(V, g, dt)
+                    V = self._step(V, g, dt, scratch)
                 return V, float(h[stop - 1, 1]), it + stop, float(h[stop - 1, 0])
             U = V
             it += n

@@ -40,8 +40,8 @@ for shape, bounds, r in (((515, 300), [[0, 129.0 / 64], [0, 301.0 / 256]], 4),
     lo, hi = c.x_offset, c.x_offset + c.nx_local
     flat = np.concatenate([u[lo * ny:hi * ny], u[N:]])
     S = c.pack(flat)
-    sh.exchange_halo(S)
-    lmin, lmax, pmin, pmax = c.d2eigs(S, policy=True)
+    lmin, lmax, pmin, pmax = c.zeros(), c.zeros(), c.empty_policy(), c.empty_policy()
+    sh.d2eigs(S, (lmin, lmax, pmin, pmax))
     omin, omax, rmin, rmax = c_oracle.pairs_d2eigs(G.points, G.pairs, u, N)
     a, b = c.unpad(lmin).cpu().numpy(), c.unpad(lmax).cpu().numpy()
     report("d2eigs %sx%s r=%d on %d ranks (bit-exact)" % (shape[0], shape[1], r, world),
