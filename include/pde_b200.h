@@ -220,6 +220,35 @@ int pde_ell_build(int device, int64_t n_interior, const double *d_points /* (npt
                   int nds, const double *d_V, int v_per_point, double eps_over_h,
                   int froese, int32_t *d_idx, double *d_w, int32_t *d_fail, void *stream);
 
+/* Problems and the Newton linear solve on point clouds (fdmethod 'interpolate' /
+ * 'froese').  All vectors are the reference's flat vectors (n_points doubles,
+ * interior points first).
+ * pde_ell_residual mode 0: convex_envelope.py:44-46 (F = W-g; interior rows with
+ *   -lambda_min > W-g become -lambda_min; d_kmin = selected direction or -1 for an
+ *   identity row).  mode 1: pucci.py:48,127-141 (interior A0*lambda_max + A1*lambda_min
+ *   - f, boundary W - dirichlet; d_g holds f then the Dirichlet data).
+ * d_red[0] accumulates max|F|. */
+int pde_ell_residual(pde_ell *e, const double *d_W, const double *d_g, int mode,
+                     double A0, double A1, double *d_F, int32_t *d_kmin, int32_t *d_kmax,
+                     double *d_red, void *stream);
+/* Jacobian of a direction policy: interior row i = cmin*row(kmin[i]) (+ cmax*row(kmax[i])),
+ * identity when kmin[i] < 0; boundary rows identity (convex_envelope.py:48-54,
+ * pucci.py:50-54,136-139 with the rows of ddi.py:369-404). */
+typedef struct pde_ell_jac {
+    const int32_t *d_kmin;
+    const int32_t *d_kmax;   /* NULL when cmax == 0 */
+    double cmin, cmax;
+} pde_ell_jac;
+int pde_ell_jac_matvec(pde_ell *e, const pde_ell_jac *J, const double *d_x, double *d_y,
+                       void *stream);
+int pde_ell_jac_diagonal(pde_ell *e, const pde_ell_jac *J, double *d_diag, void *stream);
+/* same contract as pde_bicgstab (solvers.py:179-181); d_work: 8 * n_points doubles */
+int pde_ell_bicgstab(pde_ell *e, const pde_ell_jac *J, const double *d_b, double *d_x,
+                     double rtol, double atol, int64_t maxiter, int64_t check_every,
+                     double *d_work, int64_t *h_info, void *stream);
+int pde_ell_newton_update(pde_ell *e, const double *d_U, const double *d_d, const double *d_F,
+                          const double *d_Jd, double *d_Unew, double *h_out, void *stream);
+
 /* ------------------------------------------------------------------------
  * Host-side pre-processing (no GPU needed): pair rows of the band points of a
  * regular grid.  Replaces, for the points within `stencil_radius` cells of a wall,

@@ -170,6 +170,23 @@ def cloud_case(R, name, h0):
             assert np.abs(d - od).max() < 1e-9 * np.abs(d).max(), (tag, np.abs(d - od).max())
             out["%s_d2_%d" % (tag, k)] = d
         out["%s_nds" % tag] = len(fdms)
+    # the example's solve (examples/convex_envelope.py:38-42): two-cone obstacle, Newton,
+    # fdmethod='interpolate', solution_tol=1e-10 -- and the same with Froese's scheme
+    out["min_interior_nb_dist"] = G.min_interior_nb_dist
+    out["min_radius"] = G.min_radius
+    g = two_cones(G.points)
+    for tag, fd in (("ddi", "interpolate"), ("ddf", "froese")):
+        G._d2cache = None
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            U, diff, it, _ = R.convex_envelope.solve(G, g, solver="newton", fdmethod=fd,
+                                                     solution_tol=1e-10)
+            F, J = R.convex_envelope.operator(G, g - 0.01 * (1 - X ** 2 - Y ** 2), g,
+                                              jacobian=True, fdmethod=fd)
+        out["%s_ce_U" % tag], out["%s_ce_iters" % tag] = U, it
+        out["%s_ce_F" % tag] = F
+        out["%s_ce_Jx" % tag] = J.dot(flds["random"])
+        print("  %s convex envelope: %d Newton its, diff %.2e" % (tag, it, diff), flush=True)
     np.savez_compressed(os.path.join(OUT, "cloud_%s.npz" % name), **out)
     print("cloud_%s: %d points (%d interior), %d simplices, %.1fs" %
           (name, len(p), nint, len(G.simplices), time.time() - t), flush=True)

@@ -74,8 +74,8 @@ def install():
         return _solve(a, b)
 
     np.linalg.solve = solve
-    if not hasattr(np, "in1d"):
-        np.in1d = lambda a, b, **k: np.isin(a, b, **k).ravel()
+    # NumPy 2 deprecates in1d, and NewtonEulerLS promotes warnings to errors (solvers.py:174)
+    np.in1d = lambda a, b, **k: np.isin(a, b, **k).ravel()
     warnings.filterwarnings("ignore", category=DeprecationWarning)
     _installed = True
 

@@ -176,3 +176,224 @@ def d2(G, v, u, jacobian, froese):
     if u is not None:
         d2u = like_input(u, table.apply(k, to_device(u, table.device)))
     return d2u, (M if jacobian else None)
+
+
+# ---------------------------------------------------------------------------------------------
+# problems on point clouds: convex_envelope / pucci with fdmethod 'interpolate' | 'froese'
+# ---------------------------------------------------------------------------------------------
+
+class EllJacobian(object):
+    """Square Jacobian over all points of a direction policy (convex_envelope.py:48-54,
+    pucci.py:136-139): interior row i = cmin*row(kmin[i]) + cmax*row(kmax[i]), the identity
+    where kmin[i] < 0; boundary rows identity."""
+
+    def __init__(self, table, kmin, kmax=None, cmin=1.0, cmax=0.0):
+        self.table, self.kmin, self.kmax, self.cmin, self.cmax = table, kmin, kmax, cmin, cmax
+        self.ctx = table
+        J = _lib.pde_ell_jac()
+        J.d_kmin = kmin.data_ptr()
+        J.d_kmax = kmax.data_ptr() if kmax is not None else None
+        J.cmin, J.cmax = float(cmin), float(cmax)
+        self._J = J
+
+    @property
+    def shape(self):
+        return (self.table.n_points, self.table.n_points)
+
+    def matvec_state(self, X, out=None):
+        t = self.table
+        Y = out if out is not None else torch.empty(t.n_points, dtype=torch.float64, device=t.device)
+        check(t.lib.pde_ell_jac_matvec(t.h, C.byref(self._J), _ptr(X), _ptr(Y), _stream()))
+        return Y
+
+    def dot(self, x):
+        return like_input(x, self.matvec_state(to_device(x, self.table.device)))
+
+    __matmul__ = dot
+
+    def diagonal(self):
+        t = self.table
+        D = torch.empty(t.n_points, dtype=torch.float64, device=t.device)
+        check(t.lib.pde_ell_jac_diagonal(t.h, C.byref(self._J), _ptr(D), _stream()))
+        return D
+
+    def bicgstab_state(self, B, rtol, atol=0.0, maxiter=0, check_every=32):
+        t = self.table
+        x = torch.zeros(t.n_points, dtype=torch.float64, device=t.device)
+        work = torch.empty(8 * t.n_points, dtype=torch.float64, device=t.device)
+        info = (C.c_int64 * 2)()
+        check(t.lib.pde_ell_bicgstab(t.h, C.byref(self._J), _ptr(B), _ptr(x), float(rtol),
+                                     float(atol), int(maxiter), int(check_every), _ptr(work), info,
+                                     _stream()))
+        return x, int(info[0]), int(info[1])
+
+    def tocsr(self):
+        t = self.table
+        N, n = t.N, t.n_points
+        km = self.kmin.cpu().numpy()
+        active = km >= 0
+
+        def rows(k, c):
+            k = np.where(active, k, 0)
+            M = EllMatrix(t, torch.from_numpy(k.astype(np.int32)).to(t.device), c).tocsr()
+            sel = sp.diags(active.astype(float))
+            return sp.vstack([sel.dot(M), sp.csr_matrix((n - N, n))])
+
+        M = rows(km, self.cmin)
+        if self.kmax is not None:
+            M = M + rows(self.kmax.cpu().numpy(), self.cmax)
+        ident = np.ones(n)
+        ident[:N][active] = 0.0
+        return (M + sp.diags(ident)).tocsr()
+
+
+def _problem_table(G, module_name, nds, froese):
+    table = cached_table(G, module_name, nds, froese)
+    # duck-type the pieces of GridContext that solvers.newton_state / euler_state use
+    if not hasattr(table, "n_flat"):
+        table.n_flat = lambda: table.n_points
+
+        def newton_update(U, D, F, JD):
+            Unew = torch.empty_like(U)
+            out = (C.c_double * 3)()
+            check(table.lib.pde_ell_newton_update(table.h, _ptr(U), _ptr(D), _ptr(F), _ptr(JD),
+                                                  _ptr(Unew), out, _stream()))
+            return Unew, float(out[0]), float(out[1]), float(out[2])
+        table.newton_update = newton_update
+    return table
+
+
+def residual(table, W, g, mode, A=(0.0, 0.0), policy=True):
+    n, dev = table.n_points, table.device
+    F = torch.empty(n, dtype=torch.float64, device=dev)
+    kmin = torch.empty(table.N, dtype=torch.int32, device=dev) if policy else None
+    kmax = torch.empty(table.N, dtype=torch.int32, device=dev) if (policy and mode == 1) else None
+    red = torch.zeros(1, dtype=torch.float64, device=dev)
+    check(table.lib.pde_ell_residual(table.h, _ptr(W), _ptr(g), int(mode), float(A[0]), float(A[1]),
+                                     _ptr(F), _ptr(kmin), _ptr(kmax), _ptr(red), _stream()))
+    return F, kmin, kmax, red
+
+
+def ce_operator(G, W, g, jacobian, module_name, nds, froese):
+    """convex_envelope.operator for a point cloud (convex_envelope.py:37-56)."""
+    table = _problem_table(G, module_name, nds, froese)
+    F, kmin, _, _ = residual(table, to_device(W, table.device), to_device(g, table.device), 0,
+                             policy=jacobian)
+    Jac = EllJacobian(table, kmin, None, cmin=-1.0) if jacobian else None
+    return like_input(W, F), Jac
+
+
+def ce_solve(G, g, U0, solver, module_name, nds, froese, stats=None, **kwargs):
+    """convex_envelope.solve for a point cloud (convex_envelope.py:100-123)."""
+    import time
+    from . import solvers
+    table = _problem_table(G, module_name, nds, froese)
+    t0 = time.time()
+    dev = table.device
+    gs = to_device(g, dev)
+    Us = gs.clone() if U0 is None else to_device(U0, dev).clone()
+    proto = g if U0 is None else U0
+    dt = 1 / 2 * np.max([G.min_interior_nb_dist, G.min_radius]) ** 2      # convex_envelope.py:110
+    sol, opt = kwargs.get("solution_tol", 1e-6), kwargs.get("operator_tol", 1e-6)
+
+    def euler_res(U):
+        F, _, _, red = residual(table, U, gs, 0, policy=False)
+        return F, red[0]
+
+    if solver == "euler":
+        Us, diff, iters = solvers.euler_state(table, Us, euler_res, dt, sol, opt,
+                                              kwargs.get("max_iters"), kwargs.get("timeout"))
+        return like_input(proto, Us), diff, iters, time.time() - t0
+    for k in ("plotter", "max_euler_iters"):
+        kwargs.pop(k, None)
+
+    def res(U, jacobian):
+        F, kmin, _, red = residual(table, U, gs, 0, policy=jacobian)
+        return F, (EllJacobian(table, kmin, None, cmin=-1.0) if jacobian else None), red[0]
+
+    def fallback(U, timeout):
+        U, diff, _ = solvers.euler_state(table, U, euler_res, dt, sol, opt, 10 * table.n_points,
+                                         timeout)
+        return U, diff
+
+    Us, diff, iters = solvers.newton_state(table, Us, res, fallback, stats=stats, **kwargs)
+    return like_input(proto, Us), diff, iters, time.time() - t0
+
+
+def pucci_operator(G, W, A, jacobian, module_name, nds, froese):
+    """pucci.operator for a point cloud (pucci.py:40-58): returns (-val, -M)."""
+    if not (np.isscalar(A[0]) and np.isscalar(A[1])):
+        raise NotImplementedError("per-point Pucci coefficients on point clouds")
+    table = _problem_table(G, module_name, nds, froese)
+    Wd = to_device(W, table.device)
+    zero = torch.zeros(table.n_points, dtype=torch.float64, device=table.device)
+    F, kmin, kmax, _ = residual(table, Wd, zero, 1, A, policy=jacobian)
+    val = F[:table.N]
+    M = None
+    if jacobian:
+        J = EllJacobian(table, kmin, kmax, cmin=-float(A[1]), cmax=-float(A[0]))
+        M = _InteriorView(J)
+    return like_input(W, -val), M
+
+
+class _InteriorView(object):
+    def __init__(self, J):
+        self.J = J
+
+    @property
+    def shape(self):
+        return (self.J.table.N, self.J.table.n_points)
+
+    def dot(self, x):
+        return self.J.dot(x)[:self.J.table.N]
+
+    def tocsr(self):
+        return self.J.tocsr()[:self.J.table.N]
+
+
+def pucci_solve(G, f, g, A, U0, solver, module_name, nds, froese, stats=None, **kwargs):
+    """pucci.solve for a point cloud (pucci.py:105-160)."""
+    import time
+    from . import solvers
+    if not (np.isscalar(A[0]) and np.isscalar(A[1])):
+        raise NotImplementedError("per-point Pucci coefficients on point clouds")
+    table = _problem_table(G, module_name, nds, froese)
+    t0 = time.time()
+    dev, N, n = table.device, table.N, table.n_points
+    proto = f if not np.isscalar(f) else (g if not np.isscalar(g) else np.zeros(1))
+    Fv = torch.zeros(n, dtype=torch.float64, device=dev)
+    Fv[:N] = to_device(f, dev) if not np.isscalar(f) else float(f)
+    if g is not None:
+        Fv[N:] = to_device(g, dev) if not np.isscalar(g) else float(g)
+    dt = 1 / 2 * np.max([G.min_radius, G.min_interior_nb_dist]) ** 2
+    if U0 is None:
+        Us = torch.ones(n, dtype=torch.float64, device=dev)
+        if g is not None:
+            Us[N:] = Fv[N:]
+    else:
+        Us = to_device(U0, dev).clone()
+    sol, opt = kwargs.get("solution_tol", 1e-6), kwargs.get("operator_tol", 1e-6)
+
+    def res(U, jacobian):
+        R, kmin, kmax, red = residual(table, U, Fv, 1, A, policy=jacobian)
+        Jac = EllJacobian(table, kmin, kmax, cmin=float(A[1]), cmax=float(A[0])) if jacobian else None
+        return R, Jac, red[0]
+
+    def euler_res(U):
+        R, _, _, red = residual(table, U, Fv, 1, A, policy=False)
+        R[:N].neg_()                      # stable sign for explicit Euler (SURVEY Q3)
+        return R, red[0]
+
+    if solver == "euler":
+        Us, diff, iters = solvers.euler_state(table, Us, euler_res, dt, sol, opt,
+                                              kwargs.get("max_iters"), kwargs.get("timeout"))
+        return like_input(proto, Us), diff, iters, time.time() - t0
+    for k in ("plotter", "max_euler_iters"):
+        kwargs.pop(k, None)
+
+    def fallback(U, timeout):
+        U, diff, _ = solvers.euler_state(table, U, euler_res, dt, sol, opt, 10 * n, timeout)
+        return U, diff
+
+    Us, diff, iters = solvers.newton_state(table, Us, res, fallback, stats=stats, **kwargs)
+    return like_input(proto, Us), diff, iters, time.time() - t0

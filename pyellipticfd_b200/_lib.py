@@ -18,6 +18,10 @@ c_dbl = C.c_double
 vp = C.c_void_p
 
 
+class pde_ell_jac(C.Structure):
+    _fields_ = [("d_kmin", vp), ("d_kmax", vp), ("cmin", c_dbl), ("cmax", c_dbl)]
+
+
 class pde_jac(C.Structure):
     _fields_ = [("d_pmin", vp), ("d_pmax", vp), ("cmin_s", c_dbl), ("cmax_s", c_dbl),
                 ("d_cmin", vp), ("d_cmax", vp)]
@@ -59,6 +63,12 @@ SIGNATURES = {
     "pde_ell_apply_policy": (c_int, [vp, vp, vp, vp, vp]),
     "pde_ell_build": (c_int, [c_int, c_i64, vp, vp, vp, c_int, vp, c_int, c_dbl, c_int,
                               vp, vp, vp, vp]),
+    "pde_ell_residual": (c_int, [vp, vp, vp, c_int, c_dbl, c_dbl, vp, vp, vp, vp, vp]),
+    "pde_ell_jac_matvec": (c_int, [vp, C.POINTER(pde_ell_jac), vp, vp, vp]),
+    "pde_ell_jac_diagonal": (c_int, [vp, C.POINTER(pde_ell_jac), vp, vp]),
+    "pde_ell_bicgstab": (c_int, [vp, C.POINTER(pde_ell_jac), vp, vp, c_dbl, c_dbl, c_i64, c_i64,
+                                 vp, vp, vp]),
+    "pde_ell_newton_update": (c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "pde_fp64_peak": (c_int, [c_int, C.POINTER(c_dbl)]),
     "pde_band_build": (c_int, [c_i64, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, vp,
                                c_i64, vp, c_dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(c_dbl)]),

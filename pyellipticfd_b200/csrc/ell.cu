@@ -261,3 +261,209 @@ int pde_ell_build(int device, int64_t n_interior, const double *d_points,
 }
 
 }  // extern "C"
+
+// ===========================================================================================
+// Problems and the Newton linear solve on point clouds: convex_envelope / pucci with
+// fdmethod='interpolate' | 'froese' (convex_envelope.py:37-54, pucci.py:40-58,127-141) and
+// solvers.py:179-181 with the ELL Jacobian.  Vectors are the reference's flat vectors
+// (interior points first, then boundary points): no padding, no re-ordering.
+// ===========================================================================================
+#include "krylov.cuh"
+
+namespace pde {
+
+struct EllJacDev {
+    const int32_t *kmin, *kmax;     // selected direction per interior point; kmin < 0 = identity row
+    double cmin, cmax;
+};
+
+__device__ __forceinline__ double ell_row(const int4 *idx, const double2 *w, int64_t n, int k,
+                                          int64_t i, const double *x, double xi) {
+    const int64_t e = (int64_t)k * n + i;
+    int4 id = idx[e];
+    double2 wa = w[2 * e], wb = w[2 * e + 1];
+    return wa.x * (x[id.x] - xi) + wa.y * (x[id.y] - xi) + wb.x * (x[id.z] - xi) +
+           wb.y * (x[id.w] - xi);
+}
+__device__ __forceinline__ double ell_diag(const double2 *w, int64_t n, int k, int64_t i) {
+    const int64_t e = (int64_t)k * n + i;
+    double2 wa = w[2 * e], wb = w[2 * e + 1];
+    return -(wa.x + wa.y + wb.x + wb.y);
+}
+__device__ __forceinline__ double ell_jac_row(const int4 *idx, const double2 *w, int64_t n,
+                                              const EllJacDev &J, int64_t i, const double *x) {
+    double xi = x[i];
+    int k = J.kmin[i];
+    if (k < 0) return xi;
+    double y = J.cmin * ell_row(idx, w, n, k, i, x, xi);
+    if (J.kmax) y += J.cmax * ell_row(idx, w, n, J.kmax[i], i, x, xi);
+    return y;
+}
+
+// mode 0: y = J x   1: diag (or 1/diag when invert)   2: Av (partial <rt, y>)   3: At (<y,s>,<y,y>)
+template <int MODE, int NRED>
+__global__ void __launch_bounds__(PASS_THREADS)
+k_ell_rows(int64_t n, int64_t npts, const int4 *__restrict__ idx, const double2 *__restrict__ w,
+           EllJacDev J, const double *__restrict__ x, const double *__restrict__ aux,
+           double *__restrict__ y, int invert, double *partials, const BicgScal *scal) {
+    double acc[NRED > 0 ? NRED : 1] = {0.0};
+    bool skip = scal && (scal->done || (MODE == 3 && scal->half));
+    if (!skip) {
+        for (int64_t i = blockIdx.x * (int64_t)PASS_THREADS + threadIdx.x; i < npts;
+             i += (int64_t)gridDim.x * PASS_THREADS) {
+            double v;
+            if (MODE == 1) {
+                v = 1.0;
+                if (i < n && J.kmin[i] >= 0) {
+                    v = J.cmin * ell_diag(w, n, J.kmin[i], i);
+                    if (J.kmax) v += J.cmax * ell_diag(w, n, J.kmax[i], i);
+                }
+                if (invert) v = 1.0 / v;
+            } else {
+                v = i < n ? ell_jac_row(idx, w, n, J, i, x) : x[i];
+            }
+            y[i] = v;
+            if (MODE == 2) acc[0] += aux[i] * v;
+            if (MODE == 3) {
+                acc[0] += v * aux[i];
+                acc[1] += v * v;
+            }
+        }
+    }
+    if (NRED > 0) block_store_partials(acc, partials);
+}
+
+// residuals: mode 0 convex envelope, mode 1 Pucci
+__global__ void __launch_bounds__(256)
+k_ell_residual(int64_t n, int64_t npts, int nds, const int4 *__restrict__ idx,
+               const double2 *__restrict__ w, const double *__restrict__ W,
+               const double *__restrict__ g, double A0, double A1, int mode,
+               double *__restrict__ F, int32_t *__restrict__ kmin_out,
+               int32_t *__restrict__ kmax_out, double *red_out) {
+    double rmax = 0.0;
+    int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i < npts) {
+        double wi = W[i];
+        double f = wi - g[i];
+        if (i < n) {
+            double mn = __longlong_as_double(0x7ff0000000000000LL);
+            double mx = __longlong_as_double(0xfff0000000000000LL);
+            int an = 0, ax = 0;
+            for (int k = 0; k < nds; ++k) {
+                double d = ell_row(idx, w, n, k, i, W, wi);
+                if (d < mn) { mn = d; an = k; }
+                if (d >= mx) { mx = d; ax = k; }
+            }
+            if (mode == 0) {                       // convex_envelope.py:44-46
+                double nl = -mn;
+                bool active = nl > f;
+                if (active) f = nl;
+                if (kmin_out) kmin_out[i] = active ? an : -1;
+            } else {                               // pucci.py:48,128,141: A0*lmax + A1*lmin - f
+                f = (A0 * mx + A1 * mn) - g[i];
+                if (kmin_out) kmin_out[i] = an;
+                if (kmax_out) kmax_out[i] = ax;
+            }
+        }
+        F[i] = f;
+        rmax = fabs(f);
+    }
+    rmax = warp_max(rmax);
+    if ((threadIdx.x & 31) == 0 && red_out) atomic_max_nonneg(red_out, rmax);
+}
+
+}  // namespace pde
+
+extern "C" {
+
+int pde_ell_residual(pde_ell *e, const double *d_W, const double *d_g, int mode, double A0,
+                     double A1, double *d_F, int32_t *d_kmin, int32_t *d_kmax, double *d_red,
+                     void *stream) {
+    PDE_REQUIRE(e && d_W && d_g && d_F, "null argument");
+    DeviceGuard guard(e->device);
+    unsigned grid = (unsigned)((e->n_points + 255) / 256);
+    k_ell_residual<<<grid, 256, 0, (cudaStream_t)stream>>>(
+        e->n_interior, e->n_points, e->nds, reinterpret_cast<const int4 *>(e->idx),
+        reinterpret_cast<const double2 *>(e->w), d_W, d_g, A0, A1, mode, d_F, d_kmin, d_kmax, d_red);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+}  // extern "C"
+
+static pde::EllJacDev ell_jac_dev(const pde_ell_jac *J) {
+    pde::EllJacDev d;
+    d.kmin = J->d_kmin;
+    d.kmax = J->d_kmax;
+    d.cmin = J->cmin;
+    d.cmax = J->cmax;
+    return d;
+}
+
+template <int MODE, int NRED>
+static int ell_rows(pde_ell *e, const pde::EllJacDev &J, const double *x, const double *aux,
+                    double *y, int invert, double *partials, const pde::BicgScal *scal,
+                    cudaStream_t st, int *nb) {
+    int nblk = pde::elem_grid(e->n_points, e->num_sms);
+    pde::k_ell_rows<MODE, NRED><<<nblk, pde::PASS_THREADS, 0, st>>>(
+        e->n_interior, e->n_points, reinterpret_cast<const int4 *>(e->idx),
+        reinterpret_cast<const double2 *>(e->w), J, x, aux, y, invert, partials, scal);
+    PDE_LAUNCH_CHECK();
+    if (nb) *nb = nblk;
+    return 0;
+}
+
+extern "C" {
+
+int pde_ell_jac_matvec(pde_ell *e, const pde_ell_jac *J, const double *d_x, double *d_y,
+                       void *stream) {
+    PDE_REQUIRE(e && J && J->d_kmin && d_x && d_y, "null argument");
+    DeviceGuard guard(e->device);
+    return ell_rows<0, 0>(e, ell_jac_dev(J), d_x, nullptr, d_y, 0, nullptr, nullptr,
+                          (cudaStream_t)stream, nullptr);
+}
+
+int pde_ell_jac_diagonal(pde_ell *e, const pde_ell_jac *J, double *d_diag, void *stream) {
+    PDE_REQUIRE(e && J && J->d_kmin && d_diag, "null argument");
+    DeviceGuard guard(e->device);
+    return ell_rows<1, 0>(e, ell_jac_dev(J), nullptr, nullptr, d_diag, 0, nullptr, nullptr,
+                          (cudaStream_t)stream, nullptr);
+}
+
+int pde_ell_bicgstab(pde_ell *e, const pde_ell_jac *J, const double *d_b, double *d_x, double rtol,
+                     double atol, int64_t maxiter, int64_t check_every, double *d_work,
+                     int64_t *h_info, void *stream) {
+    PDE_REQUIRE(e && J && J->d_kmin && d_b && d_x && d_work && h_info, "null argument");
+    DeviceGuard guard(e->device);
+    struct EllBackend {
+        pde_ell *e;
+        pde::EllJacDev J;
+        int64_t n() const { return e->n_points; }
+        int64_t unknowns() const { return e->n_points; }
+        int64_t max_row_blocks() const { return pde::elem_grid(e->n_points, e->num_sms); }
+        int num_sms() const { return e->num_sms; }
+        int dinv(double *out, cudaStream_t st) {
+            return ell_rows<1, 0>(e, J, nullptr, nullptr, out, 1, nullptr, nullptr, st, nullptr);
+        }
+        int Av(const double *src, const double *rtilde, double *dst, double *partials,
+               const pde::BicgScal *scal, cudaStream_t st, int *nb) {
+            return ell_rows<2, 1>(e, J, src, rtilde, dst, 0, partials, scal, st, nb);
+        }
+        int At(const double *src, const double *s, double *dst, double *partials,
+               const pde::BicgScal *scal, cudaStream_t st, int *nb) {
+            return ell_rows<3, 2>(e, J, src, s, dst, 0, partials, scal, st, nb);
+        }
+    } backend{e, ell_jac_dev(J)};
+    return pde::bicgstab_run(backend, d_b, d_x, rtol, atol, maxiter, check_every, d_work, h_info,
+                             (cudaStream_t)stream);
+}
+
+int pde_ell_newton_update(pde_ell *e, const double *d_U, const double *d_d, const double *d_F,
+                          const double *d_Jd, double *d_Unew, double *h_out, void *stream) {
+    PDE_REQUIRE(e && d_U && d_d && d_F && d_Jd && d_Unew && h_out, "null argument");
+    DeviceGuard guard(e->device);
+    return pde::newton_update_launch(e->n_points, e->num_sms, d_U, d_d, d_F, d_Jd, d_Unew, h_out,
+                                     (cudaStream_t)stream);
+}
+
+}  // extern "C"

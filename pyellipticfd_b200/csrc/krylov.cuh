@@ -1,0 +1,352 @@
+// Backend-independent part of the Jacobi-preconditioned BiCGStab: device-resident
+// scalars, the fused vector passes, the one-block scalar stages and the driver loop.
+//
+// Follows SciPy 1.18.1 scipy/sparse/linalg/_isolve/iterative.py::bicgstab statement by
+// statement (the call the reference makes at solvers.py:179-181): x0 = 0,
+// atol_eff = max(atol, rtol*||b||), convergence tested at the loop head and after the
+// half step, breakdown exits -10 (|rho| < eps^2) and -11 (|omega| < eps^2 or
+// <rtilde,v> == 0), maxiter = 10 n, update order p -= omega*v; p *= beta; p += r.
+// A backend supplies the two operator passes (v = J phat with <rtilde,v>; t = J shat with
+// <t,s>, <t,t>) and 1/diag(J): the regular-grid policy Jacobian (bicgstab.cu) and the
+// point-cloud ELL Jacobian (ell.cu).
+#pragma once
+#include <cstddef>
+
+#include "common.cuh"
+
+namespace pde {
+
+constexpr int PASS_THREADS = 256;
+constexpr int MAX_RED = 3;
+
+struct BicgScal {
+    double bnrm2, atol, rho, rho_prev, alpha, omega, beta, rv, ss, ts, tt, rr, rtr;
+    double sums[MAX_RED];
+    long long iter, info, maxiter;
+    int done, half, first, pad;
+};
+
+template <int NRED>
+__device__ __forceinline__ void block_store_partials(double (&acc)[NRED], double *partials) {
+    __shared__ double sh[NRED][PASS_THREADS / 32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+    for (int j = 0; j < NRED; ++j) {
+        double v = warp_sum(acc[j]);
+        if (lane == 0) sh[j][wid] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NRED) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < PASS_THREADS / 32; ++w) s += sh[threadIdx.x][w];
+        partials[(int64_t)blockIdx.x * NRED + threadIdx.x] = s;
+    }
+}
+
+// elementwise passes over a whole vector (padding entries stay zero)
+template <class Op>
+__global__ void __launch_bounds__(PASS_THREADS)
+k_elem(int64_t n, Op op, double *partials, const BicgScal *scal) {
+    double acc[Op::NRED > 0 ? Op::NRED : 1] = {0.0};
+    if (!(scal && scal->done)) {
+        op.prepare(scal);
+        for (int64_t i = blockIdx.x * (int64_t)PASS_THREADS + threadIdx.x; i < n;
+             i += (int64_t)gridDim.x * PASS_THREADS)
+            op.at(i, acc);
+    }
+    if (Op::NRED > 0) block_store_partials(acc, partials);
+}
+
+// r = b (x0 = 0), rtilde = r, x = 0; partial <b,b>
+struct OpInit {
+    static constexpr int NRED = 1;
+    const double *b;
+    double *x, *r, *rtilde;
+    __device__ void prepare(const BicgScal *) {}
+    __device__ void at(int64_t i, double *acc) {
+        double v = b[i];
+        r[i] = v;
+        rtilde[i] = v;
+        x[i] = 0.0;
+        acc[0] += v * v;
+    }
+};
+
+// p = r + beta*(p - omega*v) in SciPy's order (p -= omega*v; p *= beta; p += r); phat = dinv*p
+struct OpP {
+    static constexpr int NRED = 0;
+    const double *r, *v, *dinv;
+    double *p, *phat;
+    double beta, omega;
+    int first;
+    __device__ void prepare(const BicgScal *s) {
+        beta = s->beta;
+        omega = s->omega;
+        first = s->first;
+    }
+    __device__ void at(int64_t i, double *) {
+        double pn;
+        if (first) {
+            pn = r[i];
+        } else {
+            pn = __dsub_rn(p[i], __dmul_rn(omega, v[i]));
+            pn = __dmul_rn(pn, beta);
+            pn = __dadd_rn(pn, r[i]);
+        }
+        p[i] = pn;
+        phat[i] = dinv[i] * pn;
+    }
+};
+
+// r -= alpha*v (this is s); shat = dinv*s; partial <s,s>
+struct OpS {
+    static constexpr int NRED = 1;
+    const double *v, *dinv;
+    double *r, *shat;
+    double alpha;
+    __device__ void prepare(const BicgScal *s) { alpha = s->alpha; }
+    __device__ void at(int64_t i, double *acc) {
+        double s = __dsub_rn(r[i], __dmul_rn(alpha, v[i]));
+        r[i] = s;
+        shat[i] = dinv[i] * s;
+        acc[0] += s * s;
+    }
+};
+
+// x += alpha*phat; x += omega*shat; r -= omega*t; partial <r,r>, <rtilde,r>
+struct OpX {
+    static constexpr int NRED = 2;
+    const double *phat, *shat, *t, *rtilde;
+    double *x, *r;
+    double alpha, omega;
+    int half;
+    __device__ void prepare(const BicgScal *s) {
+        alpha = s->alpha;
+        omega = s->omega;
+        half = s->half;
+    }
+    __device__ void at(int64_t i, double *acc) {
+        double xn = __dadd_rn(x[i], __dmul_rn(alpha, phat[i]));
+        if (half) {          // converged after the half step: x += alpha*phat only
+            x[i] = xn;
+            return;
+        }
+        xn = __dadd_rn(xn, __dmul_rn(omega, shat[i]));
+        x[i] = xn;
+        double rn = __dsub_rn(r[i], __dmul_rn(omega, t[i]));
+        r[i] = rn;
+        acc[0] += rn * rn;
+        acc[1] += rtilde[i] * rn;
+    }
+};
+
+// ---- scalar stages ------------------------------------------------------------------------
+enum Stage { ST_INIT = 0, ST_V = 1, ST_S = 2, ST_T = 3, ST_X = 4 };
+
+__device__ inline void top_of_loop(BicgScal *s) {
+    // iterative.py: loop head of `for iteration in range(maxiter)`
+    const double rhotol = 4.930380657631324e-32;      // eps**2 (iterative.py: rhotol)
+    if (s->iter >= s->maxiter) {
+        s->done = 1;
+        s->info = s->maxiter;
+        return;
+    }
+    if (sqrt(s->rr) < s->atol) {
+        s->done = 1;
+        s->info = 0;
+        return;
+    }
+    double rho = s->rtr;
+    if (fabs(rho) < rhotol) {
+        s->done = 1;
+        s->info = -10;
+        return;
+    }
+    if (s->iter > 0) {
+        if (fabs(s->omega) < rhotol) {
+            s->done = 1;
+            s->info = -11;
+            return;
+        }
+        s->beta = (rho / s->rho_prev) * (s->alpha / s->omega);
+    }
+    s->rho = rho;
+}
+
+template <int NRED>
+__global__ void k_stage(int stage, const double *partials, int nblocks, BicgScal *s, double rtol,
+                        double atol) {
+    __shared__ double sh[NRED][PASS_THREADS];
+    if (s->done) return;
+    if (stage == ST_T && s->half) return;
+    double acc[NRED];
+#pragma unroll
+    for (int j = 0; j < NRED; ++j) acc[j] = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += PASS_THREADS)
+#pragma unroll
+        for (int j = 0; j < NRED; ++j) acc[j] += partials[(int64_t)b * NRED + j];
+#pragma unroll
+    for (int j = 0; j < NRED; ++j) sh[j][threadIdx.x] = acc[j];
+    __syncthreads();
+    for (int o = PASS_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+#pragma unroll
+            for (int j = 0; j < NRED; ++j) sh[j][threadIdx.x] += sh[j][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x != 0) return;
+    double s0 = sh[0][0], s1 = NRED > 1 ? sh[NRED > 1 ? 1 : 0][0] : 0.0;
+    switch (stage) {
+        case ST_INIT:
+            s->bnrm2 = sqrt(s0);
+            s->atol = fmax(atol, rtol * s->bnrm2);
+            s->rr = s0;
+            s->rtr = s0;
+            s->iter = 0;
+            s->first = 1;
+            s->half = 0;
+            if (s->bnrm2 == 0.0) {
+                s->done = 1;
+                s->info = 0;
+                return;
+            }
+            top_of_loop(s);
+            break;
+        case ST_V:
+            s->rv = s0;
+            if (s0 == 0.0) {
+                s->done = 1;
+                s->info = -11;
+                return;
+            }
+            s->alpha = s->rho / s0;
+            break;
+        case ST_S:
+            s->ss = s0;
+            if (sqrt(s0) < s->atol) s->half = 1;
+            break;
+        case ST_T:
+            s->ts = s0;
+            s->tt = s1;
+            s->omega = s0 / s1;
+            break;
+        case ST_X:
+            if (s->half) {
+                s->done = 1;
+                s->info = 0;
+                return;
+            }
+            s->rr = s0;
+            s->rtr = s1;
+            s->rho_prev = s->rho;
+            s->iter += 1;
+            s->first = 0;
+            top_of_loop(s);
+            break;
+    }
+}
+
+static inline int elem_grid(int64_t n, int num_sms) {
+    int64_t b = (n + PASS_THREADS * 4 - 1) / (PASS_THREADS * 4);
+    int64_t cap = (int64_t)num_sms * 8;
+    return (int)(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+template <class Op>
+static int launch_elem(int64_t n, int num_sms, const Op &op, double *partials,
+                       const BicgScal *scal, cudaStream_t st, int *nblocks_out = nullptr) {
+    int nblk = elem_grid(n, num_sms);
+    k_elem<Op><<<nblk, PASS_THREADS, 0, st>>>(n, op, partials, scal);
+    PDE_LAUNCH_CHECK();
+    if (nblocks_out) *nblocks_out = nblk;
+    return 0;
+}
+
+// fused Newton update (solvers.py:189-199): Unew = U + d; h_out = [max|U - Unew|, F.(J d), d.d]
+// (defined in bicgstab.cu; synchronises the stream)
+int newton_update_launch(int64_t n, int num_sms, const double *U, const double *d, const double *F,
+                         const double *Jd, double *Unew, double *h_out, cudaStream_t st);
+
+// Backend concept:
+//   int64_t n() / unknowns() / max_row_blocks(); int num_sms();
+//   int dinv(double *out, cudaStream_t);                       out = 1/diag(J), 0 on padding
+//   int Av(src, rtilde, dst, partials, scal, st, &nblocks);    dst = J src, partial <rtilde,dst>
+//   int At(src, s, dst, partials, scal, st, &nblocks);         dst = J src, partial <dst,s>,<dst,dst>
+template <class Backend>
+static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol, double atol,
+                        int64_t maxiter, int64_t check_every, double *d_work, int64_t *h_info,
+                        cudaStream_t st) {
+    const int64_t n = B.n();
+    const int sms = B.num_sms();
+    if (maxiter <= 0) maxiter = 10 * B.unknowns();     // iterative.py: maxiter = n*10
+    if (check_every < 1) check_every = 32;
+    double *r = d_work, *rtilde = r + n, *p = rtilde + n, *v = p + n, *phat = v + n,
+           *shat = phat + n, *t = shat + n, *dinv = t + n;
+    int64_t max_blocks = B.max_row_blocks() + (int64_t)sms * 8;
+    double *partials = nullptr;
+    BicgScal *scal = nullptr;
+    PDE_CHECK(cudaMallocAsync((void **)&partials, sizeof(double) * MAX_RED * max_blocks, st));
+    PDE_CHECK(cudaMallocAsync((void **)&scal, sizeof(BicgScal), st));
+    struct Cleanup {
+        double *p;
+        BicgScal *s;
+        cudaStream_t st;
+        ~Cleanup() {
+            cudaFreeAsync(p, st);
+            cudaFreeAsync(s, st);
+        }
+    } cleanup{partials, scal, st};
+    {
+        BicgScal h{};
+        h.maxiter = maxiter;
+        PDE_CHECK(cudaMemcpyAsync(scal, &h, sizeof h, cudaMemcpyHostToDevice, st));
+    }
+    int rc, nb;
+    // dinv = 1/diag(J)   (solvers.py:179); zero on padding
+    PDE_CHECK(cudaMemsetAsync(dinv, 0, sizeof(double) * n, st));
+    if ((rc = B.dinv(dinv, st))) return rc;
+    PDE_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * n, st));
+    PDE_CHECK(cudaMemsetAsync(t, 0, sizeof(double) * n, st));
+    PDE_CHECK(cudaMemsetAsync(p, 0, sizeof(double) * n, st));
+    if ((rc = launch_elem(n, sms, OpInit{d_b, d_x, r, rtilde}, partials, nullptr, st, &nb))) return rc;
+    k_stage<1><<<1, PASS_THREADS, 0, st>>>(ST_INIT, partials, nb, scal, rtol, atol);
+    PDE_LAUNCH_CHECK();
+
+    struct {
+        long long iter, info, maxiter;
+        int done, half, first, pad;
+    } h_tail;
+    const size_t tail_off = offsetof(BicgScal, iter);
+    int64_t launched = 0;
+    while (true) {
+        for (int64_t k = 0; k < check_every; ++k, ++launched) {
+            if ((rc = launch_elem(n, sms, OpP{r, v, dinv, p, phat, 0, 0, 0}, nullptr, scal, st))) return rc;
+            if ((rc = B.Av(phat, rtilde, v, partials, scal, st, &nb))) return rc;
+            k_stage<1><<<1, PASS_THREADS, 0, st>>>(ST_V, partials, nb, scal, rtol, atol);
+            PDE_LAUNCH_CHECK();
+            if ((rc = launch_elem(n, sms, OpS{v, dinv, r, shat, 0}, partials, scal, st, &nb))) return rc;
+            k_stage<1><<<1, PASS_THREADS, 0, st>>>(ST_S, partials, nb, scal, rtol, atol);
+            PDE_LAUNCH_CHECK();
+            if ((rc = B.At(shat, r, t, partials, scal, st, &nb))) return rc;
+            k_stage<2><<<1, PASS_THREADS, 0, st>>>(ST_T, partials, nb, scal, rtol, atol);
+            PDE_LAUNCH_CHECK();
+            if ((rc = launch_elem(n, sms, OpX{phat, shat, t, rtilde, d_x, r, 0, 0, 0}, partials, scal,
+                                  st, &nb)))
+                return rc;
+            k_stage<2><<<1, PASS_THREADS, 0, st>>>(ST_X, partials, nb, scal, rtol, atol);
+            PDE_LAUNCH_CHECK();
+        }
+        PDE_CHECK(cudaMemcpyAsync(&h_tail, reinterpret_cast<char *>(scal) + tail_off,
+                                  sizeof h_tail, cudaMemcpyDeviceToHost, st));
+        PDE_CHECK(cudaStreamSynchronize(st));
+        if (h_tail.done) break;
+        if (launched > maxiter + check_every)
+            return pde::fail("bicgstab: device loop failed to terminate", __FILE__, __LINE__);
+    }
+    h_info[0] = h_tail.info;
+    h_info[1] = h_tail.iter;
+    return 0;
+}
+
+}  // namespace pde

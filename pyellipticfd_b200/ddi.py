@@ -38,3 +38,20 @@ def d2min(G, u, **kwargs):
 
 def d2max(G, u, **kwargs):
     return d2eigs(G, u, **kwargs)[1]
+
+
+# hooks used by convex_envelope / pucci for fdmethod='interpolate'
+def _ce_operator(G, W, g, jacobian):
+    return _ell.ce_operator(G, W, g, jacobian, __name__, int(_num_directions(G)), False)
+
+
+def _ce_solve(G, g, U0, solver, **kwargs):
+    return _ell.ce_solve(G, g, U0, solver, __name__, int(_num_directions(G)), False, **kwargs)
+
+
+def _pucci_operator(G, W, A, jacobian):
+    return _ell.pucci_operator(G, W, A, jacobian, __name__, int(_num_directions(G)), False)
+
+
+def _pucci_solve(G, f, g, A, U0, solver, **kwargs):
+    return _ell.pucci_solve(G, f, g, A, U0, solver, __name__, int(_num_directions(G)), False, **kwargs)

@@ -121,10 +121,23 @@ class FDPointCloud(object):
 
     @property
     def min_interior_nb_dist(self):
-        nb = np.asarray(self.neighbours)
+        """Minimum distance between an interior point and its stencil neighbours
+        (pointclasses.py:283-285); derived from ``neighbours`` (or, when only the
+        simplices were supplied, from their vertices) unless set explicitly."""
+        if getattr(self, "_min_nb", None) is not None:
+            return self._min_nb
+        if self.neighbours is not None:
+            nb = np.asarray(self.neighbours)
+        else:
+            S = np.asarray(self.simplices)
+            nb = np.concatenate([S[:, [0, 1]], S[:, [0, 2]]])
         m = nb[:, 0] < self.num_interior
         V = self.points[nb[m, 1]] - self.points[nb[m, 0]]
         return np.linalg.norm(V, axis=1).min()
+
+    @min_interior_nb_dist.setter
+    def min_interior_nb_dist(self, value):
+        self._min_nb = value
 
 
 # ---------------------------------------------------------------------------

@@ -188,7 +188,7 @@ def euler_state(ctx, U, residual, dt, solution_tol=1e-6, operator_tol=1e-6, max_
 
 def newton_state(ctx, U, residual, euler_fallback, solution_tol=1e-6, operator_tol=1e-6,
                  max_iters=1e2, euler_ratio=1, verbose=False, force_euler=False, stats=None,
-                 bicgstab_check_every=32):
+                 bicgstab_check_every=32, krylov_rtol=None, trace=None):
     """NewtonEulerLS (solvers.py:168-233) on state tensors.
 
     ``residual(U, jacobian) -> (F_state, PolicyJacobian|None, max|F|)``;
@@ -208,9 +208,14 @@ def newton_state(ctx, U, residual, euler_fallback, solution_tol=1e-6, operator_t
         tstart = time.time()
         F, Jac, fmax = residual(U, True)
         B = -F
-        D, info, kit = Jac.bicgstab_state(B, rtol=min(operator_tol, solution_tol),
-                                          check_every=bicgstab_check_every)
+        # reference: tol = min(operator_tol, solution_tol) (solvers.py:181); `krylov_rtol`
+        # is an extension for fine grids where a 1e-6 linear solve lets the active set chatter
+        D, info, kit = Jac.bicgstab_state(
+            B, rtol=min(operator_tol, solution_tol) if krylov_rtol is None else krylov_rtol,
+            check_every=bicgstab_check_every)
         krylov_total += kit
+        if trace is not None:
+            trace.append((i, float(fmax), kit, info))
         newtontime = time.time() - tstart
         timeout = euler_ratio * newtontime
         ok = info <= 0

@@ -75,3 +75,50 @@ def test_known_answers_on_disc():
         assert np.abs(d2min).max() < 4 and np.abs(d2max).max() < 4
         d2x, _ = mod.d2(G, [1, 0], U2)
         assert np.abs(d2x - 2).max() < 1.5
+
+
+@pytest.mark.parametrize("path", CLOUD, ids=[os.path.basename(p) for p in CLOUD])
+@pytest.mark.parametrize("tag,fd", [("ddi", "interpolate"), ("ddf", "froese")])
+def test_convex_envelope_on_cloud(path, tag, fd):
+    """examples/convex_envelope.py:38-42 (two cones, Newton, solution_tol=1e-10) and the
+    operator / Jacobian at a generic iterate, against the reference on the same cloud."""
+    from pyellipticfd_b200 import convex_envelope
+    from oracle.make_golden import two_cones
+    z = np.load(path)
+    G = cloud_of(z)
+    assert abs(G.min_interior_nb_dist - float(z["min_interior_nb_dist"])) < 1e-15
+    assert G.min_radius == float(z["min_radius"])
+    X, Y = G.points.T
+    g = two_cones(G.points)
+    W = g - 0.01 * (1 - X ** 2 - Y ** 2)
+    F, J = convex_envelope.operator(G, W, g, jacobian=True, fdmethod=fd)
+    refF = z[tag + "_ce_F"]
+    assert np.abs(F - refF).max() < 2e-9 * max(1.0, np.abs(refF).max())
+    x = fields(G)["random"]
+    refJx = z[tag + "_ce_Jx"]
+    ok = np.abs(J.dot(x) - refJx) < 1e-8 * np.abs(refJx).max()
+    assert ok.mean() > 0.98          # rows with a (near-)tie in lambda_min may pick another direction
+    assert np.abs(J.tocsr().dot(x) - J.dot(x)).max() < 1e-9 * np.abs(refJx).max()
+    U, diff, it, _ = convex_envelope.solve(G, g, solver="newton", fdmethod=fd, solution_tol=1e-10)
+    assert abs(it - int(z[tag + "_ce_iters"])) <= 2
+    assert np.abs(U - z[tag + "_ce_U"]).max() < 1e-8
+    # default arguments of the reference: fdmethod='interpolate', solver='newton'
+    if tag == "ddi":
+        U2, _, it2, _ = convex_envelope.solve(G, two_cones)
+        assert np.abs(U2 - z["ddi_ce_U"]).max() < 2e-6
+
+
+def test_pucci_on_cloud():
+    from pyellipticfd_b200 import pucci
+    z = np.load(CLOUD[0])
+    G = cloud_of(z)
+    X, Y = G.points.T
+    N = G.num_interior
+    Uex = X ** 2 + 2 * Y ** 2
+    val, M = pucci.operator(G, Uex, (2, 1), jacobian=True, fdmethod="interpolate")
+    assert val.shape == (N,) and M.shape == (N, len(X))
+    x = fields(G)["random"]
+    assert np.abs(M.tocsr().dot(x) - M.dot(x)).max() < 1e-9 * np.abs(M.dot(x)).max()
+    f = -val                                   # manufactured: Uex solves the discrete problem
+    U, diff, it, _ = pucci.solve(G, f, Uex[N:], A=(2, 1), fdmethod="interpolate", solver="newton")
+    assert np.abs(U - Uex).max() < 1e-5

@@ -7,6 +7,9 @@ from pyellipticfd_b200.pointclasses import FDRegularGrid
 from oracle.make_golden import two_cones
 
 r = int(sys.argv[1]) if len(sys.argv) > 1 else 2
+KW = {}
+if os.environ.get("KRYLOV_RTOL"):
+    KW["krylov_rtol"] = float(os.environ["KRYLOV_RTOL"])
 sizes = [int(s) for s in sys.argv[2:]] or [63, 127, 255, 511]
 for n in sizes:
     t = time.time()
@@ -16,7 +19,10 @@ for n in sizes:
     st = {}
     torch.cuda.synchronize()
     t = time.time()
-    U, diff, it, _ = convex_envelope._solve_grid(G, g, None, "newton", stats=st)
+    tr = []
+    U, diff, it, _ = convex_envelope._solve_grid(G, g, None, "newton", stats=st, trace=tr, **KW)
+    if os.environ.get("TRACE"):
+        print([(a, "%.2e" % b, c, d) for a, b, c, d in tr][:60])
     torch.cuda.synchronize()
     dt = time.time() - t
     print(json.dumps(dict(n=n, r=r, grid_s=round(tg, 2), solve_s=round(dt, 3), newton=it, diff=diff, **st)), flush=True)
