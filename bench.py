@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--radius", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--ell-points", type=int, default=1000000,
+                    help="points of the synthetic point-cloud table (164 directions)")
     ap.add_argument("--solve", type=int, default=0,
                     help="also time convex_envelope.solve (Newton) on an S^2 interior grid")
     return ap.parse_args()
@@ -144,6 +146,75 @@ def run_reference(args):
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line))
+
+
+def secondary_kernels(args, ctx, S, lmin, n_local, D, pk, dev):
+    """Roofline lines of the other kernels of the path (N = 1 only; not the headline):
+    d2eigs (both extremes), the fast re-associated mode, the fused Euler step, one
+    policy-Jacobian mat-vec, and the point-cloud ELL operator on a synthetic table of
+    BASELINE config 4's shape (164 directions)."""
+    import torch
+    out = {}
+
+    def timed(fn, reps=20):
+        for _ in range(3):
+            fn()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    def line(ms, bytes_, note):
+        ach = bytes_ / (ms * 1e-3) / 1e9
+        return {"ms": ms, "algorithmic_bytes": bytes_, "achieved_GBps": ach,
+                "hbm_frac": ach / pk["hbm_gbs"], "note": note}
+
+    lmax = ctx.zeros()
+    out["ddg.d2eigs_mode0"] = line(timed(lambda: ctx.d2eigs(S, out=(lmin, lmax, None, None))),
+                                   24.0 * n_local, "both extremes, 8 fp64 instr/pair; fp64-bound")
+    out["ddg.d2min_mode1_fast"] = line(
+        timed(lambda: ctx.d2eigs(S, want_min=True, want_max=False, mode=1, out=(lmin, None, None, None))),
+        16.0 * n_local, "opt-in re-associated arithmetic (FMA), not bit-exact; fp64-bound")
+    g = S.clone()
+    Un = ctx.zeros()
+    red = torch.zeros(2, dtype=torch.float64, device=dev)
+    out["ce_euler_step"] = line(timed(lambda: ctx.ce_euler_step(S, g, 1e-9, out=(Un, red))),
+                                24.0 * n_local, "fused residual + update + 2 max-reductions")
+    F, P, _ = ctx.ce_residual(S, g + 1.0, policy=True)
+    J = ctx.jac_struct(P, None, -1.0, 0.0)
+    Y = ctx.zeros()
+    out["policy_jacobian_matvec"] = line(timed(lambda: ctx.jac_matvec(J, S, out=Y)),
+                                         18.0 * n_local, "read x + 2 B policy, write y; HBM-bound")
+    del lmax, g, Un, F, P, Y
+    # point-cloud operator: synthetic direction-major ELL table, 164 directions
+    from pyellipticfd_b200 import _lib
+    import ctypes as C
+    npts, nds = args.ell_points, 164
+    try:
+        idx = torch.randint(0, 64, (nds, npts, 4), device=dev, dtype=torch.int32)
+        idx += (torch.arange(npts, device=dev, dtype=torch.int32) // 64 * 64)[None, :, None]
+        idx.clamp_(max=npts - 1)
+        w = torch.rand((nds, npts, 4), device=dev, dtype=torch.float64)
+        u = torch.randn(npts, device=dev, dtype=torch.float64)
+        lo, hi = torch.empty_like(u), torch.empty_like(u)
+        h = C.c_void_p()
+        L = _lib.lib()
+        _lib.check(L.pde_ell_create(C.byref(h), dev.index, npts, npts, nds, C.c_void_p(idx.data_ptr()),
+                                    C.c_void_p(w.data_ptr())))
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+        ms = timed(lambda: _lib.check(L.pde_ell_d2eigs(h, C.c_void_p(u.data_ptr()), C.c_void_p(lo.data_ptr()),
+                                                       C.c_void_p(hi.data_ptr()), None, None, st)), reps=5)
+        out["ddi.d2eigs_ell"] = line(ms, (48.0 * nds + 24.0) * npts,
+                                     "%d points x %d directions, synthetic table; HBM-bound; "
+                                     "%.1f Gpoint.dir/s" % (npts, nds, npts * nds / ms / 1e6))
+        L.pde_ell_destroy(h)
+    except Exception as e:             # reported, not fatal
+        out["ddi.d2eigs_ell"] = {"error": str(e)[:200]}
+    return out
 
 
 def main():
@@ -300,6 +371,7 @@ def main():
                         "DADD, DMUL, DSETP); frac_of_fp64_pipe = kernel rate / DFMA-chain rate",
                 }
         fp64["frac_of_fp64_pipe"] = fp64["kernel_fp64_instr_per_s"] / v.value
+        extra = secondary_kernels(args, ctx, S, lmin, n_local, D, pk, dev)
         if args.solve:
             from pyellipticfd_b200 import convex_envelope
             from oracle.make_golden import two_cones  # obstacle definition only (not timed)
@@ -341,6 +413,8 @@ def main():
             line["cpu_baseline"] = {"value": None, "error": cpu["error"]}
         if solve:
             line["solve"] = solve
+        if world == 1 and extra:
+            line["other_kernels"] = extra
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

@@ -8,6 +8,8 @@
 // tests -- with every scalar kept on the device so that a whole batch of
 // iterations runs without a host round trip.  Dot products are two-stage
 // (per-block partials, then one fixed-order pass), hence deterministic.
+#include <algorithm>
+
 #include "jacobian.cuh"
 #include "krylov.cuh"
 
@@ -19,24 +21,28 @@ namespace pde {
 template <class Op>
 __global__ void __launch_bounds__(PASS_THREADS)
 k_rows(const GridDev G, const __grid_constant__ DeepTable tab, Op op, double *partials,
-       const BicgScal *scal) {
+       const BicgScal *scal, const int nrb /* row blocks; the rest are tail blocks */) {
     double acc[Op::NRED > 0 ? Op::NRED : 1] = {0.0};
     bool skip = scal && (scal->done || (Op::kSkipOnHalf && scal->half));
     if (!skip) {
         op.prepare(scal);
-        if ((int64_t)blockIdx.x < G.rows) {
+        if ((int)blockIdx.x < nrb) {
+            // one block per lattice row: consecutive blocks sweep consecutive rows, so the
+            // +-r row gathers of a mat-vec hit L2 (measured faster than persistent row blocks)
             int64_t br = blockIdx.x;
             int64_t lr = br - G.halo_rows;
             if (lr >= 0 && lr < G.nx_local) {
                 int64_t gx = lr + G.x_offset;
                 bool deep_row = gx >= G.radius && gx < G.nx_global - G.radius;
-                for (int64_t c = threadIdx.x; c < G.ny; c += PASS_THREADS) {
-                    bool deep = deep_row && c >= G.radius && c < G.ny - G.radius;
-                    if (deep) op.deep(tab, G, br * G.pitch + c, acc);
+                if (deep_row) {
+                    const int64_t base = br * G.pitch;
+                    const int c1 = (int)G.ny - G.radius;
+                    for (int c = G.radius + threadIdx.x; c < c1; c += PASS_THREADS)
+                        op.deep(tab, G, base + c, acc);
                 }
             }
         } else {
-            int64_t i = ((int64_t)blockIdx.x - G.rows) * PASS_THREADS + threadIdx.x;
+            int64_t i = ((int64_t)blockIdx.x - nrb) * PASS_THREADS + threadIdx.x;
             if (i < G.n_band)
                 op.band(G, i, acc);
             else if (i < G.n_band + G.nb)
@@ -186,8 +192,9 @@ template <class Op>
 static int launch_rows(pde_grid *g, const Op &op, double *partials, const BicgScal *scal,
                        cudaStream_t st, int *nblocks_out = nullptr) {
     GridDev G = grid_dev(g);
-    int64_t nblk = g->rows + tail_blocks(g->n_band, g->nb);
-    k_rows<Op><<<(unsigned)nblk, PASS_THREADS, 0, st>>>(G, g->tab, op, partials, scal);
+    int nrb = (int)g->rows;
+    int64_t nblk = nrb + tail_blocks(g->n_band, g->nb);
+    k_rows<Op><<<(unsigned)nblk, PASS_THREADS, 0, st>>>(G, g->tab, op, partials, scal, nrb);
     PDE_LAUNCH_CHECK();
     if (nblocks_out) *nblocks_out = (int)nblk;
     return 0;

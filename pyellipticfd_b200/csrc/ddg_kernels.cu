@@ -65,7 +65,7 @@ k_band(int64_t n_band, const int64_t *__restrict__ center, const int64_t *__rest
                 kmx = okx;
             }
         }
-        if (lane == 0) epi(o, uc, mn, mx, kmn, kmx, red);
+        if (lane == 0) epi(o, uc, mn, mx, kmn, kmx, Epi::kPre ? epi.pre(o) : 0.0, red);
     }
     if (Epi::kRed) {
         double a = warp_max(red.a), bb = warp_max(red.b);

@@ -318,24 +318,59 @@ static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol,
         int done, half, first, pad;
     } h_tail;
     const size_t tail_off = offsetof(BicgScal, iter);
+    // one BiCGStab iteration = 9 launches whose arguments never change within a solve
+    auto iteration = [&]() -> int {
+        int rc2;
+        if ((rc2 = launch_elem(n, sms, OpP{r, v, dinv, p, phat, 0, 0, 0}, nullptr, scal, st))) return rc2;
+        if ((rc2 = B.Av(phat, rtilde, v, partials, scal, st, &nb))) return rc2;
+        k_stage<1><<<1, PASS_THREADS, 0, st>>>(ST_V, partials, nb, scal, rtol, atol);
+        PDE_LAUNCH_CHECK();
+        if ((rc2 = launch_elem(n, sms, OpS{v, dinv, r, shat, 0}, partials, scal, st, &nb))) return rc2;
+        k_stage<1><<<1, PASS_THREADS, 0, st>>>(ST_S, partials, nb, scal, rtol, atol);
+        PDE_LAUNCH_CHECK();
+        if ((rc2 = B.At(shat, r, t, partials, scal, st, &nb))) return rc2;
+        k_stage<2><<<1, PASS_THREADS, 0, st>>>(ST_T, partials, nb, scal, rtol, atol);
+        PDE_LAUNCH_CHECK();
+        if ((rc2 = launch_elem(n, sms, OpX{phat, shat, t, rtilde, d_x, r, 0, 0, 0}, partials, scal, st,
+                               &nb)))
+            return rc2;
+        k_stage<2><<<1, PASS_THREADS, 0, st>>>(ST_X, partials, nb, scal, rtol, atol);
+        PDE_LAUNCH_CHECK();
+        return 0;
+    };
+    // Small and medium grids are launch bound (9 launches of a few microseconds each per
+    // iteration): capture ONE iteration into a CUDA graph per solve (instantiating a graph of
+    // a whole batch cost ~30 ms, measured) and replay it; the device-side `done` flag turns
+    // surplus replays into no-ops.  Large grids gain nothing and skip the capture.
+    cudaGraphExec_t exec = nullptr;
+    if (B.unknowns() < (int64_t)4 << 20 &&
+        cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        int rcc = iteration();
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(st, &graph);
+        pde::count_launch(-9);                                 // captured, not executed
+        if (rcc == 0 && e == cudaSuccess && graph) {
+            if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+        if (!exec) cudaGetLastError();                         // fall back to plain launches
+    } else {
+        cudaGetLastError();
+    }
+    struct ExecGuard {
+        cudaGraphExec_t e;
+        ~ExecGuard() {
+            if (e) cudaGraphExecDestroy(e);
+        }
+    } exec_guard{exec};
     int64_t launched = 0;
     while (true) {
-        for (int64_t k = 0; k < check_every; ++k, ++launched) {
-            if ((rc = launch_elem(n, sms, OpP{r, v, dinv, p, phat, 0, 0, 0}, nullptr, scal, st))) return rc;
-            if ((rc = B.Av(phat, rtilde, v, partials, scal, st, &nb))) return rc;
-            k_stage<1><<<1, PASS_THREADS, 0, st>>>(ST_V, partials, nb, scal, rtol, atol);
-            PDE_LAUNCH_CHECK();
-            if ((rc = launch_elem(n, sms, OpS{v, dinv, r, shat, 0}, partials, scal, st, &nb))) return rc;
-            k_stage<1><<<1, PASS_THREADS, 0, st>>>(ST_S, partials, nb, scal, rtol, atol);
-            PDE_LAUNCH_CHECK();
-            if ((rc = B.At(shat, r, t, partials, scal, st, &nb))) return rc;
-            k_stage<2><<<1, PASS_THREADS, 0, st>>>(ST_T, partials, nb, scal, rtol, atol);
-            PDE_LAUNCH_CHECK();
-            if ((rc = launch_elem(n, sms, OpX{phat, shat, t, rtilde, d_x, r, 0, 0, 0}, partials, scal,
-                                  st, &nb)))
-                return rc;
-            k_stage<2><<<1, PASS_THREADS, 0, st>>>(ST_X, partials, nb, scal, rtol, atol);
-            PDE_LAUNCH_CHECK();
+        if (exec) {
+            for (int64_t k = 0; k < check_every; ++k, ++launched) PDE_CHECK(cudaGraphLaunch(exec, st));
+            pde::count_launch((int)(9 * check_every));
+        } else {
+            for (int64_t k = 0; k < check_every; ++k, ++launched)
+                if ((rc = iteration())) return rc;
         }
         PDE_CHECK(cudaMemcpyAsync(&h_tail, reinterpret_cast<char *>(scal) + tail_off,
                                   sizeof h_tail, cudaMemcpyDeviceToHost, st));

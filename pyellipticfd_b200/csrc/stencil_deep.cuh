@@ -76,9 +76,10 @@ template <bool MIN, bool MAX, bool POL>
 struct EpiEigs {    // ddg.d2eigs values + policy (ddg.py:292); d2min / d2max skip the unused half
     double *lmin, *lmax;
     uint16_t *pmin, *pmax;
-    static constexpr bool kMin = MIN, kMax = MAX, kRed = false, kPol = POL;
+    static constexpr bool kMin = MIN, kMax = MAX, kRed = false, kPol = POL, kPre = false;
+    __device__ __forceinline__ double pre(int64_t) const { return 0.0; }
     __device__ __forceinline__ void operator()(int64_t o, double, double mn, double mx, int kmn,
-                                               int kmx, BlockMax2 &) const {
+                                               int kmx, double, BlockMax2 &) const {
         if (lmin) lmin[o] = mn;
         if (lmax) lmax[o] = mx;
         if (pmin) pmin[o] = static_cast<uint16_t>(kmn);
@@ -91,10 +92,13 @@ struct EpiCeResidual {   // convex_envelope.operator (convex_envelope.py:44-46)
     const double *g;
     double *F;
     uint16_t *policy;
-    static constexpr bool kMin = true, kMax = false, kRed = true, kPol = POL;
+    static constexpr bool kMin = true, kMax = false, kRed = true, kPol = POL, kPre = true;
+    // the obstacle value is fetched before the direction loop so that its DRAM latency
+    // is hidden behind the arithmetic instead of stalling the tile's epilogue
+    __device__ __forceinline__ double pre(int64_t o) const { return g[o]; }
     __device__ __forceinline__ void operator()(int64_t o, double uc, double mn, double, int kmn,
-                                               int, BlockMax2 &red) const {
-        double f = __dsub_rn(uc, g[o]);
+                                               int, double go, BlockMax2 &red) const {
+        double f = __dsub_rn(uc, go);
         double nl = -mn;
         bool active = nl > f;            // strict '>' (convex_envelope.py:45)
         if (active) f = nl;
@@ -108,10 +112,11 @@ struct EpiCeEuler {   // one explicit Euler step (solvers.py:65-74 on convex_env
     const double *g;
     double *Unew;
     double dt;
-    static constexpr bool kMin = true, kMax = false, kRed = true, kPol = false;
+    static constexpr bool kMin = true, kMax = false, kRed = true, kPol = false, kPre = true;
+    __device__ __forceinline__ double pre(int64_t o) const { return g[o]; }
     __device__ __forceinline__ void operator()(int64_t o, double uc, double mn, double, int, int,
-                                               BlockMax2 &red) const {
-        double f = __dsub_rn(uc, g[o]);
+                                               double go, BlockMax2 &red) const {
+        double f = __dsub_rn(uc, go);
         double nl = -mn;
         if (nl > f) f = nl;
         double un = __dsub_rn(uc, __dmul_rn(dt, f));
@@ -128,13 +133,14 @@ struct EpiPucciResidual {   // pucci.py:48, :127-141
     uint16_t *pmin, *pmax;
     double A0, A1;
     const double *dA0, *dA1;
-    static constexpr bool kMin = true, kMax = true, kRed = true, kPol = POL;
+    static constexpr bool kMin = true, kMax = true, kRed = true, kPol = POL, kPre = true;
+    __device__ __forceinline__ double pre(int64_t o) const { return f[o]; }
     __device__ __forceinline__ void operator()(int64_t o, double, double mn, double mx, int kmn,
-                                               int kmx, BlockMax2 &red) const {
+                                               int kmx, double fo, BlockMax2 &red) const {
         double a0 = dA0 ? dA0[o] : A0;
         double a1 = dA1 ? dA1[o] : A1;
         double val = __dadd_rn(__dmul_rn(a0, mx), __dmul_rn(a1, mn));   // A[0]*lmax + A[1]*lmin
-        double r = __dsub_rn(val, f[o]);
+        double r = __dsub_rn(val, fo);
         F[o] = r;
         if (pmin) pmin[o] = static_cast<uint16_t>(kmn);
         if (pmax) pmax[o] = static_cast<uint16_t>(kmx);
@@ -230,12 +236,20 @@ k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTab
         const int slot = it & 1;
         const int next = tile + gridDim.x;
         if (next < ntiles && tid == 0) issue(next, slot ^ 1);
-        mbar_wait(&bars[slot], (it >> 1) & 1);
-
         const double *sm = slot ? buf1 : buf0;
         const int tx = tile / geo.tiles_y, ty = tile - tx * geo.tiles_y;
         const int lx0 = tx * TX + grp * P;                // row inside the deep region
         const int ly = ty * K1_TY + c;
+        double pre[Epi::kPre ? P : 1];
+        if (Epi::kPre) {      // epilogue operands (obstacle / forcing): loads issued before the wait
+#pragma unroll
+            for (int p = 0; p < P; ++p) {
+                bool in = ly < geo.ncols && lx0 + p < geo.nrows;
+                pre[p] = in ? epi.pre((int64_t)(geo.row0 + lx0 + p) * geo.pitch + (geo.col0 + ly)) : 0.0;
+            }
+        }
+        mbar_wait(&bars[slot], (it >> 1) & 1);
+
         const double *ctr = sm + (H + grp * P) * TYH + (H + c + ysh);
 
         double uc[P], mn[P], mx[P];
@@ -254,7 +268,7 @@ k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTab
             for (int p = 0; p < P; ++p) {
                 if (lx0 + p < geo.nrows) {
                     int64_t o = (int64_t)(geo.row0 + lx0 + p) * geo.pitch + (geo.col0 + ly);
-                    epi(o, uc[p], mn[p], mx[p], kmn[p], kmx[p], red);
+                    epi(o, uc[p], mn[p], mx[p], kmn[p], kmx[p], pre[Epi::kPre ? p : 0], red);
                 }
             }
         }
