@@ -89,6 +89,15 @@ int64_t pde_grid_policy_len(const pde_grid *g); /* rows*pitch (uint16 entries)  
 /* flat reference vector (N + nb) <-> state layout.  Both on device. */
 int pde_grid_pack(pde_grid *g, const double *d_u_flat, double *d_state, void *stream);
 int pde_grid_unpack(pde_grid *g, const double *d_state, double *d_u_flat, void *stream);
+/* The same conversion as one 2-D DMA copy between HOST memory (h_flat: the reference's
+ * flat vector, pinned for asynchronous copies) and the state layout, for owned rows
+ * [row_lo, row_hi) only; with_wall also copies the nb wall values.  Together with
+ * pde_grid_set_row_window this pipelines H2D / stencil / D2H over row chunks (the
+ * state buffer's padding columns must already be zero). */
+int pde_grid_h2d_rows(pde_grid *g, const double *h_flat, double *d_state,
+                      int64_t row_lo, int64_t row_hi, int with_wall, void *stream);
+int pde_grid_d2h_rows(pde_grid *g, const double *d_state, double *h_flat_interior,
+                      int64_t row_lo, int64_t row_hi, void *stream);
 /* interior part of a state-layout array -> flat (N) interior order */
 int pde_grid_unpad(pde_grid *g, const double *d_padded, double *d_flat, void *stream);
 int pde_grid_unpad_u16(pde_grid *g, const uint16_t *d_padded, int32_t *d_flat, void *stream);

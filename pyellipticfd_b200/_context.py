@@ -283,6 +283,50 @@ class GridContext(object):
                                       _ptr(pmax), int(mode), _stream()))
         return lmin, lmax, pmin, pmax
 
+    def d2eigs_host(self, u_host, want_min=True, want_max=True, mode=0, chunk_rows=256):
+        """ddg.d2eigs values for a field in PINNED host memory, results in pinned host
+        memory: the H2D copy, the stencil kernels and the D2H copy are pipelined over
+        chunks of rows on three streams (PCIe is full duplex), and the layout conversion
+        is done by the 2-D DMA copies themselves (no pack / unpack kernels)."""
+        nloc, ny, H = self.nx_local, self.ny, max(self.radius, 1)
+        if not hasattr(self, "_stage"):
+            self._stage = (self.zeros(), self.zeros(), self.zeros(),
+                           torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+        S, Lmin, Lmax, s_in, s_out = self._stage
+        main = torch.cuda.current_stream()
+        out_min = torch.empty(nloc * ny, dtype=torch.float64, pin_memory=True) if want_min else None
+        out_max = torch.empty(nloc * ny, dtype=torch.float64, pin_memory=True) if want_max else None
+        edges = list(range(0, nloc, chunk_rows)) + [nloc]
+        nchunk = len(edges) - 1
+        ev_in = [torch.cuda.Event() for _ in range(nchunk)]
+        s_in.wait_stream(main)
+        s_out.wait_stream(main)
+        with torch.cuda.stream(s_in):
+            for k in range(nchunk):
+                check(self.lib.pde_grid_h2d_rows(self.h, vp(u_host.data_ptr()), _ptr(S), edges[k],
+                                                 edges[k + 1], int(k == 0), _stream()))
+                ev_in[k].record()
+        outs = (Lmin if want_min else None, Lmax if want_max else None, None, None)
+        try:
+            for k in range(nchunk):
+                # rows of chunk k read up to H rows of chunk k+1
+                main.wait_event(ev_in[min(k + 1, nchunk - 1)])
+                self.set_row_window(edges[k], edges[k + 1])
+                self.d2eigs(S, want_min=want_min, want_max=want_max, mode=mode, out=outs)
+                ev = torch.cuda.Event()
+                ev.record(main)
+                s_out.wait_event(ev)
+                with torch.cuda.stream(s_out):
+                    for L, o in ((Lmin, out_min), (Lmax, out_max)):
+                        if o is not None:
+                            check(self.lib.pde_grid_d2h_rows(self.h, _ptr(L), vp(o.data_ptr()),
+                                                             edges[k], edges[k + 1], _stream()))
+        finally:
+            self.set_row_window()
+        main.wait_stream(s_out)
+        s_out.synchronize()
+        return out_min, out_max
+
     def apply_policy(self, policy, X):
         Y = self.zeros()
         check(self.lib.pde_ddg_apply_policy(self.h, _ptr(policy), _ptr(X), _ptr(Y), _stream()))

@@ -43,6 +43,8 @@ SIGNATURES = {
     "pde_grid_policy_len": (c_i64, [vp]),
     "pde_grid_pack": (c_int, [vp, vp, vp, vp]),
     "pde_grid_unpack": (c_int, [vp, vp, vp, vp]),
+    "pde_grid_h2d_rows": (c_int, [vp, vp, vp, c_i64, c_i64, c_int, vp]),
+    "pde_grid_d2h_rows": (c_int, [vp, vp, vp, c_i64, c_i64, vp]),
     "pde_grid_unpad": (c_int, [vp, vp, vp, vp]),
     "pde_grid_unpad_u16": (c_int, [vp, vp, vp, vp]),
     "pde_ddg_d2eigs": (c_int, [vp, vp, vp, vp, vp, vp, c_int, vp]),

@@ -272,4 +272,36 @@ int pde_grid_unpad_u16(pde_grid *g, const uint16_t *d_padded, int32_t *d_flat, v
     return 0;
 }
 
+// Host <-> state-layout copies of a range of owned rows, without a pack/unpack kernel:
+// one 2-D DMA copy converts between the reference's dense rows (ny doubles) and the
+// padded rows (pitch doubles).  Used to pipeline H2D / stencil / D2H over row chunks.
+int pde_grid_h2d_rows(pde_grid *g, const double *h_flat, double *d_state, int64_t row_lo,
+                      int64_t row_hi, int with_wall, void *stream) {
+    PDE_REQUIRE(g && h_flat && d_state, "null argument");
+    PDE_REQUIRE(row_lo >= 0 && row_hi <= g->nx_local && row_lo <= row_hi, "bad row range");
+    DeviceGuard guard(g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (row_hi > row_lo)
+        PDE_CHECK(cudaMemcpy2DAsync(d_state + (g->halo_rows + row_lo) * g->pitch, g->pitch * 8,
+                                    h_flat + row_lo * g->ny, g->ny * 8, g->ny * 8,
+                                    (size_t)(row_hi - row_lo), cudaMemcpyHostToDevice, st));
+    if (with_wall && g->nb > 0)
+        PDE_CHECK(cudaMemcpyAsync(d_state + g->rows * g->pitch, h_flat + g->nx_local * g->ny,
+                                  g->nb * 8, cudaMemcpyHostToDevice, st));
+    return 0;
+}
+
+int pde_grid_d2h_rows(pde_grid *g, const double *d_state, double *h_flat, int64_t row_lo,
+                      int64_t row_hi, void *stream) {
+    PDE_REQUIRE(g && h_flat && d_state, "null argument");
+    PDE_REQUIRE(row_lo >= 0 && row_hi <= g->nx_local && row_lo <= row_hi, "bad row range");
+    DeviceGuard guard(g->device);
+    if (row_hi > row_lo)
+        PDE_CHECK(cudaMemcpy2DAsync(h_flat + row_lo * g->ny, g->ny * 8,
+                                    d_state + (g->halo_rows + row_lo) * g->pitch, g->pitch * 8,
+                                    g->ny * 8, (size_t)(row_hi - row_lo), cudaMemcpyDeviceToHost,
+                                    (cudaStream_t)stream));
+    return 0;
+}
+
 }  // extern "C"

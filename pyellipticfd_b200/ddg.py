@@ -21,6 +21,11 @@ from .linop import PolicyMatrix
 ARITHMETIC_MODE = 0
 
 
+def _pinned_host(u):
+    return (isinstance(u, torch.Tensor) and not u.is_cuda and u.is_pinned()
+            and u.dtype == torch.float64 and u.is_contiguous())
+
+
 def _require_pairs(G):
     if getattr(G, "pairs", None) is None and not hasattr(G, "stencil_pairs"):
         raise TypeError('The grid was has no finite difference pairs. '
@@ -37,8 +42,11 @@ def d2eigs(G, u, jacobian=False, control=False):
     """
     _require_pairs(G)
     ctx = GridContext.get(G)
-    S = ctx.pack(u)
     need_policy = jacobian or control
+    if _pinned_host(u) and not need_policy and ctx.structured and ctx.nx_local >= 1024:
+        lo, hi = ctx.d2eigs_host(u, mode=ARITHMETIC_MODE)      # pipelined over row chunks
+        return (lo, None, None), (hi, None, None)
+    S = ctx.pack(u)
     lmin, lmax, pmin, pmax = ctx.d2eigs(S, policy=need_policy, mode=ARITHMETIC_MODE)
     lam_min = like_input(u, ctx.unpad(lmin))
     lam_max = like_input(u, ctx.unpad(lmax))
@@ -58,6 +66,10 @@ def _one_extreme(G, u, which, jacobian=False, control=False):
         return d2eigs(G, u, jacobian=jacobian, control=True)[which]
     _require_pairs(G)
     ctx = GridContext.get(G)
+    if _pinned_host(u) and not jacobian and ctx.structured and ctx.nx_local >= 1024:
+        lo, hi = ctx.d2eigs_host(u, want_min=(which == 0), want_max=(which == 1),
+                                 mode=ARITHMETIC_MODE)
+        return (lo if which == 0 else hi), None, None
     S = ctx.pack(u)
     lmin, lmax, pmin, pmax = ctx.d2eigs(S, want_min=(which == 0), want_max=(which == 1),
                                         policy=jacobian, mode=ARITHMETIC_MODE)

@@ -100,3 +100,25 @@ def test_torch_inputs_stay_on_device():
     assert lmin.is_cuda and lmax.is_cuda
     omin, omax = O.d2eigs(G, u.cpu().numpy())[0][0], O.d2eigs(G, u.cpu().numpy())[1][0]
     assert np.array_equal(lmin.cpu().numpy(), omin) and np.array_equal(lmax.cpu().numpy(), omax)
+
+
+def test_pinned_host_pipeline_bitexact():
+    """Pinned host tensors take the chunk-pipelined path (H2D / stencil / D2H over row
+    chunks, 2-D DMA layout conversion): same bits as the oracle."""
+    import torch
+    from oracle import c_oracle
+    from pyellipticfd_b200 import ddg
+    G = _grid((1100, 260), [[0, 1101.0 / 512], [0, 261.0 / 512]], 3)
+    assert G.uniform_weights()
+    u = np.random.default_rng(5).standard_normal(G.num_points)
+    omin, omax, _, _ = c_oracle.pairs_d2eigs(G.points, G.pairs, u, G.num_interior)
+    host = torch.from_numpy(u).pin_memory()
+    (lmin, _, _), (lmax, _, _) = ddg.d2eigs(G, host)
+    assert not lmin.is_cuda and lmin.is_pinned()
+    assert np.array_equal(lmin.numpy(), omin) and np.array_equal(lmax.numpy(), omax)
+    assert np.array_equal(ddg.d2min(G, host)[0].numpy(), omin)
+    assert np.array_equal(ddg.d2max(G, host)[0].numpy(), omax)
+    # repeated calls reuse the staging buffers
+    u2 = u[::-1].copy()
+    o2 = c_oracle.pairs_d2eigs(G.points, G.pairs, u2, G.num_interior)[0]
+    assert np.array_equal(ddg.d2min(G, torch.from_numpy(u2).pin_memory())[0].numpy(), o2)
