@@ -192,6 +192,23 @@ int pde_bicgstab(pde_grid *g, const pde_jac *J, const double *d_b, double *d_x,
                  double rtol, double atol, int64_t maxiter, int64_t check_every,
                  double *d_work, int64_t *h_info, void *stream);
 
+/* Slab-parallel variant of the same solver, one call per step so that the caller can
+ * place the NCCL traffic in between (pyellipticfd_b200/multigpu.py):
+ *   step 0 setup + init pass | 1 finalize | 2 p-update | 3 v = J phat (exchange the
+ *   halo of phat = d_work + 4n first) | 4 finalize | 5 s-update | 6 finalize |
+ *   7 t = J shat (halo of shat = d_work + 5n first) | 8 finalize | 9 x,r-update | 10 finalize.
+ * Every "pass" step leaves this rank's partial dot products in d_sums (3 doubles); the
+ * caller all-reduces them (SUM) before the following "finalize" step, which updates the
+ * device-resident scalars d_scal (pde_bicgstab_scal_bytes() bytes).  d_partials:
+ * 3 * (rows + tail blocks + 8*SMs) doubles of scratch.  pde_bicgstab_poll reads
+ * [done, info, iterations] (synchronises). */
+int64_t pde_bicgstab_scal_bytes(void);
+int pde_bicgstab_dist_step(pde_grid *g, const pde_jac *J, int step, const double *d_b,
+                           double *d_x, double *d_work, void *d_scal, double *d_partials,
+                           double *d_sums, double rtol, double atol, int64_t maxiter,
+                           void *stream);
+int pde_bicgstab_poll(const void *d_scal, int64_t *h_out, void *stream);
+
 /* small fused vector helpers used by the Newton loop (solvers.py:189-199) */
 int pde_vec_newton_update(pde_grid *g, const double *d_U, const double *d_d,
                           const double *d_F, const double *d_Jd, double *d_Unew,

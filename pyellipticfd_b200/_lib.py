@@ -58,6 +58,10 @@ SIGNATURES = {
     "pde_pucci_residual": (c_int, [vp, vp, vp, c_dbl, c_dbl, vp, vp, vp, vp, vp, vp, vp]),
     "pde_bicgstab": (c_int, [vp, C.POINTER(pde_jac), vp, vp, c_dbl, c_dbl, c_i64, c_i64,
                              vp, vp, vp]),
+    "pde_bicgstab_scal_bytes": (c_i64, []),
+    "pde_bicgstab_dist_step": (c_int, [vp, C.POINTER(pde_jac), c_int, vp, vp, vp, vp, vp, vp,
+                                       c_dbl, c_dbl, c_i64, vp]),
+    "pde_bicgstab_poll": (c_int, [vp, vp, vp]),
     "pde_vec_newton_update": (c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "pde_ell_create": (c_int, [C.POINTER(vp), c_int, c_i64, c_i64, c_int, vp, vp]),
     "pde_ell_destroy": (c_int, [vp]),

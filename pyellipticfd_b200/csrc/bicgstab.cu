@@ -281,6 +281,98 @@ int pde_bicgstab(pde_grid *g, const pde_jac *J, const double *d_b, double *d_x, 
                         (cudaStream_t)stream);
 }
 
+// ---- slab-parallel BiCGStab: the same passes, one call per step -----------------------------
+// The caller (pyellipticfd_b200/multigpu.py) puts the NCCL traffic between the steps: a halo
+// exchange of phat / shat before the two operator passes and a SUM all-reduce of d_sums
+// between every "pass" step and its "finalize" step.  Dot products need no masking: halo
+// rows of r, rtilde, v, t are identically zero, and the replicated wall entries are zero
+// whenever the iterate satisfies the Dirichlet data (F_wall = 0), which the caller checks.
+int64_t pde_bicgstab_scal_bytes(void) { return (int64_t)sizeof(BicgScal); }
+
+int pde_bicgstab_dist_step(pde_grid *g, const pde_jac *J, int step, const double *d_b, double *d_x,
+                           double *d_work, void *d_scal, double *d_partials, double *d_sums,
+                           double rtol, double atol, int64_t maxiter, void *stream) {
+    PDE_REQUIRE(g && J && d_b && d_x && d_work && d_scal && d_partials && d_sums && J->d_pmin,
+                "null argument");
+    DeviceGuard guard(g->device);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n = g->rows * g->pitch + g->nb;
+    const int sms = g->num_sms;
+    BicgScal *scal = static_cast<BicgScal *>(d_scal);
+    JacDev Jd = jac_dev(J);
+    double *r = d_work, *rtilde = r + n, *p = rtilde + n, *v = p + n, *phat = v + n,
+           *shat = phat + n, *t = shat + n, *dinv = t + n;
+    int rc = 0, nb = 0;
+    auto reduce = [&](int stage, int nred) {
+        if (nred == 1) k_stage<1><<<1, PASS_THREADS, 0, st>>>(stage, d_partials, nb, scal, rtol, atol, d_sums, 1);
+        else k_stage<2><<<1, PASS_THREADS, 0, st>>>(stage, d_partials, nb, scal, rtol, atol, d_sums, 1);
+    };
+    auto finalize = [&](int stage, int nred) {
+        if (nred == 1) k_stage<1><<<1, PASS_THREADS, 0, st>>>(stage, d_partials, 0, scal, rtol, atol, d_sums, 2);
+        else k_stage<2><<<1, PASS_THREADS, 0, st>>>(stage, d_partials, 0, scal, rtol, atol, d_sums, 2);
+    };
+    switch (step) {
+        case 0: {   // setup + init pass
+            BicgScal h{};
+            h.maxiter = maxiter > 0 ? maxiter : 10 * (g->nx_global * g->ny + g->nb);
+            PDE_CHECK(cudaMemcpyAsync(scal, &h, sizeof h, cudaMemcpyHostToDevice, st));
+            PDE_CHECK(cudaStreamSynchronize(st));     // h lives on this stack frame
+            PDE_CHECK(cudaMemsetAsync(dinv, 0, sizeof(double) * n, st));
+            if ((rc = launch_rows(g, OpDiag{Jd, dinv, 1}, nullptr, nullptr, st))) return rc;
+            PDE_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * n, st));
+            PDE_CHECK(cudaMemsetAsync(t, 0, sizeof(double) * n, st));
+            PDE_CHECK(cudaMemsetAsync(p, 0, sizeof(double) * n, st));
+            PDE_CHECK(cudaMemsetAsync(d_sums, 0, sizeof(double) * 3, st));
+            if ((rc = launch_elem(n, sms, OpInit{d_b, d_x, r, rtilde}, d_partials, nullptr, st, &nb))) return rc;
+            reduce(ST_INIT, 1);
+            break;
+        }
+        case 1: finalize(ST_INIT, 1); break;
+        case 2: rc = launch_elem(n, sms, OpP{r, v, dinv, p, phat, 0, 0, 0}, nullptr, scal, st); break;
+        case 3:
+            if ((rc = launch_rows(g, OpAv{Jd, phat, rtilde, v}, d_partials, scal, st, &nb))) return rc;
+            reduce(ST_V, 1);
+            break;
+        case 4: finalize(ST_V, 1); break;
+        case 5:
+            if ((rc = launch_elem(n, sms, OpS{v, dinv, r, shat, 0}, d_partials, scal, st, &nb))) return rc;
+            reduce(ST_S, 1);
+            break;
+        case 6: finalize(ST_S, 1); break;
+        case 7:
+            if ((rc = launch_rows(g, OpAt{Jd, shat, r, t}, d_partials, scal, st, &nb))) return rc;
+            reduce(ST_T, 2);
+            break;
+        case 8: finalize(ST_T, 2); break;
+        case 9:
+            if ((rc = launch_elem(n, sms, OpX{phat, shat, t, rtilde, d_x, r, 0, 0, 0}, d_partials, scal, st, &nb))) return rc;
+            reduce(ST_X, 2);
+            break;
+        case 10: finalize(ST_X, 2); break;
+        default: return pde::fail("bad step", __FILE__, __LINE__);
+    }
+    if (rc) return rc;
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+// h_out = [done, info, iterations]; synchronises the stream
+int pde_bicgstab_poll(const void *d_scal, int64_t *h_out, void *stream) {
+    PDE_REQUIRE(d_scal && h_out, "null argument");
+    struct {
+        long long iter, info, maxiter;
+        int done, half, first, pad;
+    } t;
+    cudaStream_t st = (cudaStream_t)stream;
+    PDE_CHECK(cudaMemcpyAsync(&t, static_cast<const char *>(d_scal) + offsetof(BicgScal, iter), sizeof t,
+                              cudaMemcpyDeviceToHost, st));
+    PDE_CHECK(cudaStreamSynchronize(st));
+    h_out[0] = t.done;
+    h_out[1] = t.info;
+    h_out[2] = t.iter;
+    return 0;
+}
+
 int pde_vec_newton_update(pde_grid *g, const double *d_U, const double *d_d, const double *d_F,
                           const double *d_Jd, double *d_Unew, double *h_out, void *stream) {
     PDE_REQUIRE(g && d_U && d_d && d_F && d_Jd && d_Unew && h_out, "null argument");

@@ -176,27 +176,41 @@ __device__ inline void top_of_loop(BicgScal *s) {
 
 template <int NRED>
 __global__ void k_stage(int stage, const double *partials, int nblocks, BicgScal *s, double rtol,
-                        double atol) {
+                        double atol, double *sums_io = nullptr, int phase = 0) {
+    // phase 0: reduce the per-block partials and update the scalars (single GPU)
+    // phase 1: reduce only, local sums -> sums_io   } multi-GPU: an all-reduce of sums_io
+    // phase 2: update the scalars from sums_io       } sits between the two
     __shared__ double sh[NRED][PASS_THREADS];
     if (s->done) return;
     if (stage == ST_T && s->half) return;
+    if (phase == 2) {
+        if (threadIdx.x == 0) sh[0][0] = sums_io[0];
+        if (threadIdx.x == 0 && NRED > 1) sh[NRED > 1 ? 1 : 0][0] = sums_io[1];
+    }
     double acc[NRED];
 #pragma unroll
     for (int j = 0; j < NRED; ++j) acc[j] = 0.0;
-    for (int b = threadIdx.x; b < nblocks; b += PASS_THREADS)
+    if (phase != 2) {
+        for (int b = threadIdx.x; b < nblocks; b += PASS_THREADS)
 #pragma unroll
-        for (int j = 0; j < NRED; ++j) acc[j] += partials[(int64_t)b * NRED + j];
+            for (int j = 0; j < NRED; ++j) acc[j] += partials[(int64_t)b * NRED + j];
 #pragma unroll
-    for (int j = 0; j < NRED; ++j) sh[j][threadIdx.x] = acc[j];
-    __syncthreads();
-    for (int o = PASS_THREADS / 2; o > 0; o >>= 1) {
-        if (threadIdx.x < o)
-#pragma unroll
-            for (int j = 0; j < NRED; ++j) sh[j][threadIdx.x] += sh[j][threadIdx.x + o];
+        for (int j = 0; j < NRED; ++j) sh[j][threadIdx.x] = acc[j];
         __syncthreads();
+        for (int o = PASS_THREADS / 2; o > 0; o >>= 1) {
+            if (threadIdx.x < o)
+#pragma unroll
+                for (int j = 0; j < NRED; ++j) sh[j][threadIdx.x] += sh[j][threadIdx.x + o];
+            __syncthreads();
+        }
     }
     if (threadIdx.x != 0) return;
     double s0 = sh[0][0], s1 = NRED > 1 ? sh[NRED > 1 ? 1 : 0][0] : 0.0;
+    if (phase == 1) {
+        sums_io[0] = s0;
+        if (NRED > 1) sums_io[1] = s1;
+        return;
+    }
     switch (stage) {
         case ST_INIT:
             s->bnrm2 = sqrt(s0);

@@ -136,6 +136,121 @@ class ShardedGrid(object):
         self.overlapped(V, lambda: self.ctx.ce_euler_step(V, g, dt, out=(Vn, red)))
         return Vn
 
+    # ---- distributed Newton / BiCGStab ------------------------------------------------------
+    def _allreduce(self, t, op=None):
+        if self.world > 1:
+            dist.all_reduce(t, op=op if op is not None else dist.ReduceOp.SUM)
+        return t
+
+    def bicgstab(self, Jac, B, rtol, atol=0.0, maxiter=0, check_every=16):
+        """Slab-parallel Jacobi-BiCGStab (solvers.py:179-181): the single-GPU passes, with a
+        halo exchange of phat / shat before the two operator passes and one SUM all-reduce
+        of <= 2 doubles after each of the four reduction passes.  Requires a
+        Dirichlet-consistent right-hand side (zero on the replicated wall entries), which
+        is what convex_envelope / pucci produce.  Returns (x, info, iterations)."""
+        import ctypes as C
+        from ._lib import check, vp
+        c = self.ctx
+        n = c.n_state
+        if float(B[c.n_lattice:].abs().max()) != 0.0:
+            raise ValueError("distributed solve needs a right-hand side that vanishes on the wall")
+        dev = c.device
+        work = torch.empty(8 * n, dtype=torch.float64, device=dev)
+        x = c.zeros()
+        scal = torch.zeros(int(c.lib.pde_bicgstab_scal_bytes()), dtype=torch.uint8, device=dev)
+        nblk = c.rows + (c.n_band + c.nb) // 256 + 8 * 256 + 2
+        partials = torch.zeros(3 * nblk, dtype=torch.float64, device=dev)
+        sums = torch.zeros(3, dtype=torch.float64, device=dev)
+        J = Jac._J
+        phat, shat = work[4 * n:5 * n], work[5 * n:6 * n]
+
+        def step(k):
+            check(c.lib.pde_bicgstab_dist_step(
+                c.h, C.byref(J), k, vp(B.data_ptr()), vp(x.data_ptr()), vp(work.data_ptr()),
+                vp(scal.data_ptr()), vp(partials.data_ptr()), vp(sums.data_ptr()), float(rtol),
+                float(atol), int(maxiter), vp(torch.cuda.current_stream().cuda_stream)))
+
+        step(0)
+        self._allreduce(sums)
+        step(1)
+        out = (C.c_int64 * 3)()
+        while True:
+            for _ in range(check_every):
+                step(2)
+                self.exchange_halo(phat)
+                step(3)
+                self._allreduce(sums)
+                step(4)
+                step(5)
+                self._allreduce(sums)
+                step(6)
+                self.exchange_halo(shat)
+                step(7)
+                self._allreduce(sums)
+                step(8)
+                step(9)
+                self._allreduce(sums)
+                step(10)
+            check(c.lib.pde_bicgstab_poll(vp(scal.data_ptr()), out,
+                                          vp(torch.cuda.current_stream().cuda_stream)))
+            if out[0]:
+                break
+        H = self.slab.halo
+        if H:
+            v = self.lattice_view(x)
+            v[:H].zero_()
+            v[H + c.nx_local:].zero_()
+        return x, int(out[1]), int(out[2])
+
+    def ce_newton(self, g, U0=None, solution_tol=1e-6, operator_tol=1e-6, max_iters=100,
+                  krylov_rtol=None, stats=None, check_every=16):
+        """convex_envelope.solve(..., fdmethod='grid', solver='newton') on the slabs: the
+        loop of solvers.NewtonEulerLS (solvers.py:168-233) with slab-parallel residual,
+        Krylov solve and reductions.  A failed solve / decrease test falls back to a bounded
+        number of Euler steps.  ``g``, ``U0``: this rank's state tensors."""
+        from .linop import PolicyJacobian
+        c = self.ctx
+        U = g.clone() if U0 is None else U0.clone()
+        rho, p = 0.5, 2
+        krylov = fallbacks = 0
+        diff = float("inf")
+        dt = None
+        for i in range(int(max_iters) + 1):
+            self.exchange_halo(U)
+            F, P, red = c.ce_residual(U, g, policy=True)
+            fmax = float(self._allreduce(red[:1].clone(), dist.ReduceOp.MAX))
+            Jac = PolicyJacobian(c, P, None, cmin=-1.0)
+            D, info, kit = self.bicgstab(Jac, -F, min(operator_tol, solution_tol)
+                                         if krylov_rtol is None else krylov_rtol,
+                                         check_every=check_every)
+            krylov += kit
+            ok = info <= 0
+            if ok:
+                self.exchange_halo(D)
+                JD = Jac.matvec_state(D)
+                Un, dmax, gtd, dd = c.newton_update(U, D, F, JD)
+                t = torch.tensor([gtd, dd], dtype=torch.float64, device=c.device)
+                self._allreduce(t)
+                m = self._allreduce(torch.tensor([dmax], dtype=torch.float64, device=c.device),
+                                    dist.ReduceOp.MAX)
+                gtd, dd, dmax = float(t[0]), float(t[1]), float(m[0])
+                if gtd > -rho * np.sqrt(dd) ** p:
+                    ok = False
+            if ok:
+                diff, U = dmax, Un
+            else:
+                fallbacks += 1
+                if dt is None:
+                    dt = 0.5 * max(self.G.min_interior_nb_dist, self.G.min_radius) ** 2
+                U, diff, _, _ = self.ce_euler(U, g, dt, solution_tol, operator_tol, max_iters=256,
+                                              check_every=64)
+            if diff < solution_tol and fmax < operator_tol:
+                break
+        if stats is not None:
+            stats.update(newton_iters=i + 1, krylov_iters=krylov, euler_fallbacks=fallbacks,
+                         residual=fmax)
+        return U, diff, i + 1
+
     # ---- distributed convex-envelope Euler iteration ------------------------------------
     def ce_euler(self, U, g, dt, solution_tol=1e-6, operator_tol=1e-6, max_iters=None,
                  check_every=16):

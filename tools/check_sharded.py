@@ -64,5 +64,14 @@ mine = c.unpack(U).cpu().numpy()
 ref_local = np.concatenate([Uref[lo * ny:hi * ny], Uref[N:]])
 report("Euler 127^2 r=2: %d its (1 GPU %d), bit-exact U" % (it, itref),
        it == itref and diff == dref and np.array_equal(mine, ref_local))
+# Newton / policy iteration with the slab-parallel BiCGStab vs the single-GPU solve
+Uref, dref, itref, _ = convex_envelope.solve(G, g, fdmethod="grid", solver="newton")
+st = {}
+U, diff, it = sh.ce_newton(gs, stats=st)
+mine = c.unpack(U).cpu().numpy()
+ref_local = np.concatenate([Uref[lo * ny:hi * ny], Uref[N:]])
+err = float(np.abs(mine - ref_local).max())
+report("Newton 127^2 r=2: %d its / %d Krylov (1 GPU %d its), |dU| %.1e" %
+       (it, st["krylov_iters"], itref, err), err < 2e-6 and abs(it - itref) <= 6)
 dist.destroy_process_group()
 sys.exit(0 if ok_all else 1)
