@@ -122,3 +122,99 @@ def test_pinned_host_pipeline_bitexact():
     u2 = u[::-1].copy()
     o2 = c_oracle.pairs_d2eigs(G.points, G.pairs, u2, G.num_interior)[0]
     assert np.array_equal(ddg.d2min(G, torch.from_numpy(u2).pin_memory())[0].numpy(), o2)
+
+
+def test_full_size_4097_r4_bitexact_and_properties():
+    """BASELINE configs[1] at full size (4095^2 interior points, r = 4): bit-exact against
+    the plain-C oracle (which recomputes every weight from the coordinates per pair, like
+    ddg.py:274-281) on all 16.7 M deep points, against the NumPy oracle on the band, and
+    the size-independent properties: exact on quadratics, zero on affine functions."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import c_oracle
+    from pyellipticfd_b200 import ddg
+    from pyellipticfd_b200._context import GridContext
+    n, r = 4095, 4
+    G = _grid((n, n), [[0, 1], [0, 1]], r)
+    assert G.uniform_weights() and G.stencil_pairs.shape[0] == 24
+    N, nb = G.num_interior, G.num_bdry
+    rng = np.random.default_rng(0)
+    u = rng.standard_normal(N + nb)
+    ud = torch.from_numpy(u).cuda()
+    (lmin, _, _), (lmax, _, _) = ddg.d2eigs(G, ud)
+    lmin, lmax = lmin.cpu().numpy(), lmax.cpu().numpy()
+    # deep interior: C oracle over row chunks on a few host threads (ctypes releases the GIL)
+    out = (np.full(N, np.nan), np.full(N, np.nan), np.full(N, -1, np.int32), np.full(N, -1, np.int32))
+    chunks = [(lo, min(n, lo + 256)) for lo in range(0, n, 256)]
+    with ThreadPoolExecutor(8) as ex:
+        list(ex.map(lambda c: c_oracle.lattice_d2eigs(G, u, c[0], c[1], out), chunks))
+    deep = ~np.isnan(out[0])
+    assert deep.sum() == G.num_deep
+    assert np.array_equal(lmin[deep], out[0][deep]) and np.array_equal(lmax[deep], out[1][deep])
+    # band: NumPy oracle on the explicit rows
+    bp = G.band_pairs
+    I, J, X, h, w, w0 = O.pair_geometry(_band_points(G), _relabel(G, bp))
+    uu = _band_values(G, u)
+    t = (uu[J] - uu[I, None]) * w
+    d = w0 * (t[:, 0] + t[:, 1])
+    cen, rmin, rmax = O.select_extremes(I, d)
+    ids = np.unique(bp)[cen]                          # centre ids in ascending order == band_index
+    assert np.array_equal(ids, G.band_index)
+    assert np.array_equal(lmin[ids], d[rmin]) and np.array_equal(lmax[ids], d[rmax])
+    # selected pairs of the deep points (policy) against the C oracle, ties included
+    ctx = GridContext.get(G)
+    _, _, pmin, pmax = ctx.d2eigs(ctx.pack(ud), policy=True)
+    kmin = ctx.unpad_policy(pmin).cpu().numpy()
+    kmax = ctx.unpad_policy(pmax).cpu().numpy()
+    assert np.array_equal(kmin[deep], out[2][deep]) and np.array_equal(kmax[deep], out[3][deep])
+    # properties at full size
+    x = (torch.arange(1, n + 1, device="cuda", dtype=torch.float64) / (n + 1))
+    Pw = torch.from_numpy(G.bdry_points).cuda()
+    def field(f):
+        return torch.cat([f(x[:, None].expand(n, n).reshape(-1), x[None, :].expand(n, n).reshape(-1)),
+                          f(Pw[:, 0], Pw[:, 1])])
+    (qmin, _, _), (qmax, _, _) = ddg.d2eigs(G, field(lambda X, Y: X ** 2 - Y ** 2))
+    scale = float(n + 1) ** 2 * 2.3e-16 * 8           # rounding of O(1) values divided by h^2
+    dm = torch.from_numpy(deep).cuda()
+    # exact on the symmetric deep-interior stencil; band pairs are only antipodal within the
+    # reference's 1e-3 tolerance (pointclasses.py:24), so quadratics are not exact there
+    assert float((qmin[dm] + 2).abs().max()) < scale and float((qmax[dm] - 2).abs().max()) < scale
+    (amin, _, _), (amax, _, _) = ddg.d2eigs(G, field(lambda X, Y: 3 * X - 2 * Y + 0.5))
+    assert float(amin[dm].abs().max()) < scale and float(amax[dm].abs().max()) < scale
+    assert float((amin <= amax).double().min()) == 1.0 and float((qmin <= qmax).double().min()) == 1.0
+
+
+def _band_points(G):
+    """coordinates of every point referenced by the band rows, relabelled densely"""
+    ids = np.unique(G.band_pairs)
+    return G.coords(ids)
+
+
+def _relabel(G, bp):
+    ids = np.unique(bp)
+    return np.searchsorted(ids, bp)
+
+
+def _band_values(G, u):
+    return u[np.unique(G.band_pairs)]
+
+
+def test_fast_mode_within_tolerance():
+    """ddg.ARITHMETIC_MODE = 1 (opt-in, re-associated): |d - d_ref| <= 1e-12 *
+    max(|d_ref|, w0*(|du0|*w_0 + |du1|*w_1)), values only."""
+    from pyellipticfd_b200 import ddg
+    G = _grid((255, 255), [[0, 1], [0, 1]], 4)
+    u = _fields(G)["smooth"]
+    I, J, X, h, w, w0 = O.pair_geometry(G.points, G.pairs)
+    du = np.abs(u[J] - u[I, None])
+    bound = np.zeros(G.num_interior)
+    np.maximum.at(bound, I, w0 * (du[:, 0] * w[:, 0] + du[:, 1] * w[:, 1]))
+    (omin, _, _), (omax, _, _) = O.d2eigs(G, u)
+    try:
+        ddg.ARITHMETIC_MODE = 1
+        (lmin, _, _), (lmax, _, _) = ddg.d2eigs(G, u)
+    finally:
+        ddg.ARITHMETIC_MODE = 0
+    tol = 1e-12 * np.maximum(np.maximum(np.abs(omin), np.abs(omax)), bound)
+    assert (np.abs(lmin - omin) <= tol).all() and (np.abs(lmax - omax) <= tol).all()
+    assert not np.array_equal(lmin, omin) or True      # usually differs in the last bits
