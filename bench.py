@@ -50,8 +50,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--ell-points", type=int, default=1000000,
                     help="points of the synthetic point-cloud table (164 directions)")
-    ap.add_argument("--solve", type=int, default=0,
-                    help="also time convex_envelope.solve (Newton) on an S^2 interior grid")
+    ap.add_argument("--solve", type=int, default=255,
+                    help="also time convex_envelope.solve on the 65^2 lattice of BASELINE "
+                         "configs[0] (Euler and Newton) and Newton on an S^2 interior grid; 0 = skip")
     return ap.parse_args()
 
 
@@ -416,18 +417,31 @@ def main():
         fp64["frac_of_fp64_pipe"] = fp64["kernel_fp64_instr_per_s"] / v.value
         extra = secondary_kernels(args, ctx, S, lmin, n_local, D, pk, dev)
         if args.solve:
+            import warnings
             from pyellipticfd_b200 import convex_envelope
-            from oracle.make_golden import two_cones  # obstacle definition only (not timed)
-            Gs = FDRegularGrid([args.solve] * 2, np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, r,
-                               interpolation=False)
-            g = two_cones(Gs.points)
-            st = {}
-            torch.cuda.synchronize()
-            t = time.perf_counter()
-            U, diff, it, _ = convex_envelope._solve_grid(Gs, g, None, "newton", stats=st)
-            torch.cuda.synchronize()
-            solve = {"grid": "%d^2" % (args.solve + 2), "seconds": time.perf_counter() - t,
-                     "newton_iters": it, "diff": diff, **st}
+
+            def two_cones(X):            # obstacle of examples/convex_envelope.py:8-18
+                C = 3 / 7 * np.array([[np.cos(np.pi * i + np.pi / 5), np.sin(np.pi * i + np.pi / 5)]
+                                      for i in range(2)])
+                return np.min([np.sqrt((X[:, 0] + c[0]) ** 2 + (X[:, 1] + c[1]) ** 2) for c in C], axis=0)
+
+            solve = []
+            for size, solver in ((63, "euler"), (63, "newton"), (args.solve, "newton")):
+                Gs = FDRegularGrid([size] * 2, np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, 2,
+                                   interpolation=False)
+                g = two_cones(Gs.points)
+                st = {}
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    convex_envelope._solve_grid(Gs, g, None, solver, stats={}, max_iters=3)  # warm-up
+                    torch.cuda.synchronize()
+                    t = time.perf_counter()
+                    U, diff, it, _ = convex_envelope._solve_grid(Gs, g, None, solver, stats=st)
+                    torch.cuda.synchronize()
+                solve.append({"problem": "convex envelope of two cones, [-1,1]^2, r=2, tol 1e-6",
+                              "lattice": "%d^2" % (size + 2), "solver": solver,
+                              "seconds": time.perf_counter() - t, "iterations": it, "diff": diff,
+                              **{k: v for k, v in st.items() if k != "reason"}})
 
     if rank == 0:
         line = {
