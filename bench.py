@@ -10,8 +10,9 @@ BASELINE.json configs[1] (4097^2 lattice = 4095^2 interior points, stencil radiu
 * ``value``  Gpoint.dir/s = interior points x 24 / device time, state resident in HBM
              (CUDA events on the launch stream around K steps, max over ranks).
 * ``e2e``    the same metric through the public API ``pyellipticfd_b200.ddg.d2min(G, u)``
-             with the field in pinned HOST memory and the result returned to the host:
-             H2D copy, pack, kernels, unpack, D2H inside the timed region.
+             with the field in pinned HOST memory and the result returned to pinned host
+             memory: H2D copy, kernels and D2H copy (pipelined over row chunks by the API)
+             all inside the timed region.
 * ``roofline`` the deep-interior stencil kernel against the measured HBM copy bandwidth
              (MEASURED_PEAKS.json): algorithmic bytes = 16 B per interior point (read u,
              write lambda_min).  The kernel is bound by the fp64 pipe, not HBM (24 pairs x
@@ -19,8 +20,9 @@ BASELINE.json configs[1] (4097^2 lattice = 4095^2 interior points, stencil radiu
 * ``cpu_baseline`` the NumPy port of the reference operator (oracle/) on the host cores.
 
 N > 1 (torchrun): weak scaling -- the global lattice has N x 4095 rows, each rank owns a
-4095-row slab and exchanges ``r`` halo rows with its neighbours (NCCL send/recv) before
-every operator application.
+4095-row slab and refreshes ``r`` halo rows from its neighbours (one small NCCL all-gather
+over NVLink, overlapped with the interior rows) at every operator application.  ``bicgstab``
+times one policy-iteration linear-solve iteration (slab-parallel at N > 1).
 """
 import argparse
 import json
@@ -76,7 +78,7 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()

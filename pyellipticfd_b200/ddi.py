@@ -28,6 +28,8 @@ def d2(G, v, u=None, jacobian=False):
 def d2eigs(G, u, jacobian=False, control=False, cache_fdmatrices=True):
     """Min / max directional second derivative over ``_num_directions(G)`` directions
     (ddi.py:304-414): ``((lmin, M_min, v_min), (lmax, M_max, v_max))``."""
+    if G.dim == 3:
+        raise NotImplementedError("Eigenvalues not yet implemented in 3d.")      # ddi.py:330-331
     return _ell.d2eigs(G, u, __name__, int(_num_directions(G)), False, jacobian, control,
                        cache_fdmatrices)
 

@@ -1,0 +1,74 @@
+"""CPU: host-side logic and error behaviour of the reference-facing modules (no GPU work)."""
+import numpy as np
+import pytest
+
+from oracle import ddg_oracle
+from pyellipticfd_b200 import _ddutils, ddg, ddi, ddf, pucci, solvers, stencils
+from pyellipticfd_b200.pointclasses import FDPointCloud, FDRegularGrid
+
+
+class _G(object):
+    def __init__(self, n, nb=3, dim=2):
+        self.num_interior, self.num_bdry, self.dim = n, nb, dim
+
+
+@pytest.mark.parametrize("v", [0.3, [1.0, 2.0], np.linspace(0, 1, 7),
+                               np.random.default_rng(0).standard_normal((7, 2))])
+def test_process_v_matches_reference_restatement(v):
+    G = _G(7)
+    a = _ddutils.process_v(G, v)
+    b = ddg_oracle.process_v(G, v)
+    assert a.shape == (7, 2) and np.array_equal(np.asarray(a), np.asarray(b))
+    assert np.allclose(np.linalg.norm(a, axis=1), 1)
+
+
+def test_process_v_boundary_domain():
+    G = _G(7, nb=4)
+    assert _ddutils.process_v(G, [0.0, 1.0], domain="boundary").shape == (4, 2)
+
+
+def test_errors_follow_the_reference():
+    cloud = FDPointCloud(np.zeros((4, 2)), num_interior=2)       # no pairs, no simplices
+    with pytest.raises(TypeError):                                # ddg.py:200-201
+        ddg.d2(cloud, [1, 0], np.zeros(4))
+    with pytest.raises(TypeError):                                # pointclasses.py:158-159
+        FDPointCloud(np.zeros((4, 2)))
+    with pytest.raises(TypeError):                                # pointclasses.py:161-166
+        FDPointCloud(np.zeros((4, 2)), num_interior=2, angular_resolution=4.0)
+    c3 = FDPointCloud(np.zeros((4, 3)), num_interior=2)
+    with pytest.raises(NotImplementedError):                      # ddi.py:330-331
+        ddi.d2eigs(c3, np.zeros(4))
+    with pytest.raises(NotImplementedError):                      # ddf.py:168-169
+        ddf.d2eigs(c3, np.zeros(4))
+    with pytest.raises(NotImplementedError):                      # pucci.py:33-34
+        pucci.operator(c3, np.zeros(4), (2, 1))
+    with pytest.raises(ValueError):                               # solvers.py:150-151
+        solvers.NewtonEulerLS(np.zeros(3), lambda U, jacobian=True: None, euler_ratio=0)
+    with pytest.raises(ValueError):                               # stencils.py:69-70
+        stencils.create(2, 1)
+    with pytest.raises(ValueError):                               # stencils.py:31-32
+        stencils.create(0, 2)
+
+
+def test_generic_euler_on_numpy_closure():
+    """solvers.euler with a plain NumPy operator: stopping rule and iteration count of
+    solvers.py:63-91 (U <- U - dt*F, stop when both tolerances hold, i counted from 1)."""
+    target = np.array([1.0, -2.0, 0.5])
+    U, diff, i, t = solvers.euler(np.zeros(3), lambda U: (U - target, 0.5), max_iters=200)
+    assert np.abs(U - target).max() < 1e-5 and diff < 1e-6 and 1 < i < 200
+    with pytest.warns(UserWarning):          # default max_iters = U.size (solvers.py:56-57)
+        U2, _, i2, _ = solvers.euler(np.zeros(3), lambda U: (U - target, 0.5))
+    assert i2 == 3
+
+
+def test_grid_metadata_and_lazy_pairs():
+    G = FDRegularGrid([12, 9], np.array([[0, 13 / 16.0], [0, 10 / 16.0]]).T, 2, interpolation=False)
+    assert G.uniform_weights() and G.dim == 2
+    assert G.num_points == G.num_interior + G.num_bdry
+    assert G.pairs.shape[1] == 3 and (np.diff(G.pairs[:, 0]) >= 0).all()
+    assert G.num_pairs == G.pairs.shape[0]
+    assert np.array_equal(G.interior, np.arange(G.num_interior))
+    assert np.array_equal(G.bdry_points, G.points[G.num_interior:])
+    assert G.min_radius == G.scaling.min() and G.min_interior_nb_dist == G.scaling.min()
+    with pytest.raises(NotImplementedError):
+        FDRegularGrid([5, 5], np.array([[0, 1], [0, 1.0]]).T, 2, interpolation=True)

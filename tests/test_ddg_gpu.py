@@ -218,3 +218,29 @@ def test_fast_mode_within_tolerance():
     tol = 1e-12 * np.maximum(np.maximum(np.abs(omin), np.abs(omax)), bound)
     assert (np.abs(lmin - omin) <= tol).all() and (np.abs(lmax - omax) <= tol).all()
     assert not np.array_equal(lmin, omin) or True      # usually differs in the last bits
+
+
+def test_config3_8193_r6_bitexact():
+    """BASELINE configs[2] operator at full size (8191^2 interior points, stencil radius 6 ->
+    36 pairs, halo 5): bit-exact against the plain-C oracle on the deep interior."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import c_oracle
+    from pyellipticfd_b200._context import GridContext
+    n, r = 8191, 6
+    G = _grid((n, n), [[0, 1], [0, 1]], r)
+    assert G.uniform_weights() and G.stencil_pairs.shape[0] == 36 and G.halo == 5
+    N = G.num_interior
+    u = np.random.default_rng(1).standard_normal(G.num_points)
+    ctx = GridContext.get(G)
+    S = ctx.pack(torch.from_numpy(u))
+    lmin, lmax, _, _ = ctx.d2eigs(S)
+    lmin, lmax = ctx.unpad(lmin).cpu().numpy(), ctx.unpad(lmax).cpu().numpy()
+    # a sample of row blocks (top, middle, bottom of the deep region) keeps the CPU time bounded
+    out = (np.full(N, np.nan), np.full(N, np.nan), np.full(N, -1, np.int32), np.full(N, -1, np.int32))
+    chunks = [(lo, lo + 128) for lo in (0, 128, 2048, 4000, 6111, n - 256, n - 128)]
+    with ThreadPoolExecutor(8) as ex:
+        list(ex.map(lambda c: c_oracle.lattice_d2eigs(G, u, c[0], c[1], out), chunks))
+    deep = ~np.isnan(out[0])
+    assert deep.sum() > 5_000_000
+    assert np.array_equal(lmin[deep], out[0][deep]) and np.array_equal(lmax[deep], out[1][deep])
