@@ -55,6 +55,10 @@ def parse():
     ap.add_argument("--solve", type=int, default=255,
                     help="also time convex_envelope.solve on the 65^2 lattice of BASELINE "
                          "configs[0] (Euler and Newton) and Newton on an S^2 interior grid; 0 = skip")
+    ap.add_argument("--solve-full", type=int, default=4095,
+                    help="time convex_envelope.solve (Newton = policy iteration, reference defaults) "
+                         "on the S^2 interior grid of BASELINE configs[1] (4095 -> 4097^2 lattice, "
+                         "r = 4) with the per-iteration CPU cost measured beside it; 0 = skip")
     return ap.parse_args()
 
 
@@ -221,6 +225,70 @@ def secondary_kernels(args, ctx, S, lmin, n_local, D, pk, dev):
         L.pde_ell_destroy(h)
     except Exception as e:             # reported, not fatal
         out["ddi.d2eigs_ell"] = {"error": str(e)[:200]}
+    return out
+
+
+def two_cones(X):            # obstacle of examples/convex_envelope.py:8-18
+    import numpy as np
+    C = 3 / 7 * np.array([[np.cos(np.pi * i + np.pi / 5), np.sin(np.pi * i + np.pi / 5)]
+                          for i in range(2)])
+    return np.min([np.sqrt((X[:, 0] + c[0]) ** 2 + (X[:, 1] + c[1]) ** 2) for c in C], axis=0)
+
+
+def solve_full_size(args, obstacle):
+    """BASELINE.json's second metric: seconds for convex_envelope.solve(Grid, g, fdmethod='grid',
+    solver='newton') with the reference's defaults (solution_tol = operator_tol = 1e-6,
+    max_iters = 100: solvers.py:98-100) on the 4097^2 lattice, r = 4.  From U0 = g the number of
+    policy iterations grows about linearly with the lattice size, so at this
+    size the reference's own iteration cap ends the solve ("Maximum iterations reached",
+    solvers.py:226-228); the time reported is for exactly that work, and the CPU figure is the
+    same iteration counts priced with the host's measured per-iteration costs
+    (oracle/cpu_solve_baseline.py; the reference cannot run at this size at all)."""
+    import warnings
+    import numpy as np
+    import torch
+    from pyellipticfd_b200 import convex_envelope
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    from pyellipticfd_b200._context import GridContext
+    n, r = args.solve_full, args.radius
+    out = {"problem": "convex envelope of two cones, [-1,1]^2, r=%d, tol 1e-6, max_iters 100 "
+                      "(reference defaults)" % r, "lattice": "%d^2" % (n + 2), "solver": "newton"}
+    try:
+        t = time.time()
+        Gs = FDRegularGrid([n, n], np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, r, interpolation=False)
+        out["grid_build_s"] = time.time() - t
+        g = torch.from_numpy(obstacle(Gs.points)).cuda()
+        st = {}
+        with warnings.catch_warnings(record=True) as wl:
+            warnings.simplefilter("always")
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            U, diff, it, _ = convex_envelope._solve_grid(Gs, g, None, "newton", stats=st)
+            torch.cuda.synchronize()
+            out["seconds"] = time.perf_counter() - t
+        out.update(iterations=it, diff=diff, warnings=sorted({str(w.message) for w in wl}),
+                   **{k: v for k, v in st.items() if k != "reason"})
+        GridContext.drop(Gs)
+        del U, g, Gs
+        torch.cuda.empty_cache()
+    except Exception as e:                # reported, not fatal
+        out["error"] = str(e)[:300]
+        return out
+    if not args.no_cpu_baseline:
+        try:
+            res = subprocess.run([sys.executable, "-m", "oracle.cpu_solve_baseline", str(n), str(r),
+                                  "48", "4"], cwd=ROOT, capture_output=True, text=True, timeout=900)
+            c = json.loads(res.stdout.strip().splitlines()[-1])
+            cpu_s = (out["newton_iters"] * (c["t_op"] + c["t_jac"]) + out["krylov_iters"] * c["t_kit"])
+            out["cpu_baseline"] = {
+                "seconds_extrapolated": cpu_s, "cores": c["cores"], "kind": "port",
+                "t_operator_s": c["t_op"], "t_jacobian_assembly_s": c["t_jac"],
+                "t_bicgstab_iteration_s": c["t_kit"], "sample": c["sample"],
+                "note": "newton_iters x (t_operator + t_jacobian_assembly) + krylov_iters x "
+                        "t_bicgstab_iteration, iteration counts of the GPU run"}
+            out["speedup_vs_cpu_extrapolated"] = cpu_s / out["seconds"]
+        except Exception as e:
+            out["cpu_baseline"] = {"error": str(e)[:300]}
     return out
 
 
@@ -428,11 +496,6 @@ def main():
             import warnings
             from pyellipticfd_b200 import convex_envelope
 
-            def two_cones(X):            # obstacle of examples/convex_envelope.py:8-18
-                C = 3 / 7 * np.array([[np.cos(np.pi * i + np.pi / 5), np.sin(np.pi * i + np.pi / 5)]
-                                      for i in range(2)])
-                return np.min([np.sqrt((X[:, 0] + c[0]) ** 2 + (X[:, 1] + c[1]) ** 2) for c in C], axis=0)
-
             solve = []
             for size, solver in ((63, "euler"), (63, "newton"), (args.solve, "newton")):
                 Gs = FDRegularGrid([size] * 2, np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, 2,
@@ -450,6 +513,10 @@ def main():
                               "lattice": "%d^2" % (size + 2), "solver": solver,
                               "seconds": time.perf_counter() - t, "iterations": it, "diff": diff,
                               **{k: v for k, v in st.items() if k != "reason"}})
+
+    solve_full = None
+    if world == 1 and args.solve_full:
+        solve_full = solve_full_size(args, two_cones)
 
     if rank == 0:
         line = {
@@ -479,6 +546,8 @@ def main():
             line["cpu_baseline"] = {"value": None, "error": cpu["error"]}
         if solve:
             line["solve"] = solve
+        if solve_full:
+            line["solve_4097"] = solve_full
         if world == 1 and extra:
             line["other_kernels"] = extra
         print(json.dumps(line))

@@ -230,6 +230,13 @@ class GridContext(object):
             cache[key] = GridContext(G, device)
         return cache[key]
 
+    @staticmethod
+    def drop(G):
+        """Release the device contexts cached on ``G`` (their HBM goes back to the pool)."""
+        cache = getattr(G, "_b200ctx", None)
+        if cache:
+            cache.clear()
+
     # ---- buffers ---------------------------------------------------------------------------------
     def zeros(self):
         return torch.zeros(self.n_state, dtype=torch.float64, device=self.device)
