@@ -50,8 +50,9 @@ def parse():
     ap.add_argument("--radius", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--ell-points", type=int, default=1000000,
-                    help="points of the synthetic point-cloud table (164 directions)")
+    ap.add_argument("--cloud-h0", type=float, default=0.003,
+                    help="spacing of the unit-disc point cloud of the ddi line (0.003 -> 0.4 M "
+                         "points; 0.00135 -> the 2 M points of BASELINE configs[3])")
     ap.add_argument("--solve", type=int, default=255,
                     help="also time convex_envelope.solve on the 65^2 lattice of BASELINE "
                          "configs[0] (Euler and Newton) and Newton on an S^2 interior grid; 0 = skip")
@@ -159,6 +160,77 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def disc_cloud(h0, theta, seed=0, jitter=0.1):
+    """Unit-disc point cloud of tests/setup_discs.py:17-39 (interior points at spacing h0
+    inside radius 1-c, boundary ring at spacing hB) with the absent distmesh generator
+    replaced by a jittered hexagonal lattice.  Returns (points, num_interior)."""
+    import numpy as np
+    hB = h0 / 2 * np.tan(theta / 2)
+    c = max(hB * (-1 + 2 / np.sin(theta / 2)), 2 * hB / np.tan(theta / 2))
+    R = 1.0 - c
+    rng = np.random.default_rng(seed)
+    nx = int(np.ceil(2 / h0)) + 2
+    j = np.arange(-nx, nx + 1)
+    X = j[None, :] * h0 + np.where(np.arange(j.size) % 2, h0 / 2, 0.0)[:, None]
+    Y = np.broadcast_to((j * h0 * np.sqrt(3) / 2)[:, None], X.shape)
+    p = np.stack([X.ravel(), Y.ravel()], 1)
+    p = p[(p ** 2).sum(1) <= (R + h0) ** 2]
+    p = p + rng.uniform(-jitter * h0, jitter * h0, p.shape)
+    p = p[np.sqrt((p ** 2).sum(1)) <= R]
+    th = np.arange(0, 2 * np.pi, hB)
+    ring = np.stack([np.cos(th), np.sin(th)], 1)
+    return np.concatenate([p, ring]), p.shape[0]
+
+
+def cloud_section(args, dev, pk, timed):
+    import numpy as np
+    import torch
+    from scipy.spatial import Delaunay
+    from pyellipticfd_b200 import ddi
+    from pyellipticfd_b200.pointclasses import FDTriMesh
+    h0 = args.cloud_h0
+    theta = np.pi * h0 ** (1 / 3)                        # tests/setup_discs.py:45
+    p, nint = disc_cloud(h0, theta)
+    t = time.time()
+    tri = Delaunay(p).simplices
+    t_tri = time.time() - t
+    torch.cuda.synchronize()
+    t = time.time()
+    G = FDTriMesh(p, tri, num_interior=nint, angular_resolution=theta)
+    torch.cuda.synchronize()
+    t_mesh = time.time() - t
+    x, y = torch.from_numpy(p).to(dev).T
+    u = x * x - y * y
+    t = time.time()
+    lo = ddi.d2min(G, u)[0]                               # first call builds the ELL table
+    torch.cuda.synchronize()
+    t_table = time.time() - t
+    nds = int(ddi._num_directions(G))
+    ms = timed(lambda: ddi.d2eigs(G, u), reps=5)
+    bytes_ = (48.0 * nds + 24.0) * nint
+    ach = bytes_ / (ms * 1e-3) / 1e9
+    res = {"ms": ms, "algorithmic_bytes": bytes_, "achieved_GBps": ach, "hbm_frac": ach / pk["hbm_gbs"],
+           "points": int(len(p)), "interior_points": int(nint), "directions": nds,
+           "simplices_per_interior_point": float(G._count[:nint].float().mean()),
+           "gpoint_dir_per_s": nint * nds / ms / 1e6,
+           "delaunay_s": t_tri, "fdtrimesh_build_s": t_mesh, "ell_table_build_s": t_table,
+           "max_abs_lmin_plus_2": float((lo + 2).abs().max()),
+           "note": "unit disc h0=%g, theta=pi*h0^(1/3); u = x^2 - y^2 (lambda_min = -2); "
+                   "both extremes per call; HBM-bound (48 B per point and direction)" % h0}
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import cpu_baseline as cb
+            tab = G._d2cache[2]
+            ks = [0, nds // 3, (2 * nds) // 3]
+            c = cb.time_ddi_cached(tab.idx[ks].cpu().numpy(), tab.w[ks].cpu().numpy(),
+                                   u.cpu().numpy(), nds)
+            res["cpu_baseline"] = {"value": nint * nds / c["seconds"] / 1e9, "unit": "Gpoint.dir/s",
+                                   "cores": 1, "kind": "port", "sample": c["sample"]}
+        except Exception as e:
+            res["cpu_baseline"] = {"error": str(e)[:200]}
+    return res
+
+
 def secondary_kernels(args, ctx, S, lmin, n_local, D, pk, dev):
     """Roofline lines of the other kernels of the path (N = 1 only; not the headline):
     d2eigs (both extremes), the fast re-associated mode, the fused Euler step, one
@@ -201,30 +273,12 @@ def secondary_kernels(args, ctx, S, lmin, n_local, D, pk, dev):
     out["policy_jacobian_matvec"] = line(timed(lambda: ctx.jac_matvec(J, S, out=Y)),
                                          18.0 * n_local, "read x + 2 B policy, write y; HBM-bound")
     del lmax, g, Un, F, P, Y
-    # point-cloud operator: synthetic direction-major ELL table, 164 directions
-    from pyellipticfd_b200 import _lib
-    import ctypes as C
-    npts, nds = args.ell_points, 164
+    # point-cloud operator (BASELINE configs[3]): ddi.d2eigs on a unit-disc cloud built by the
+    # fast FDTriMesh constructor (GPU stencil search), tests/setup_discs.py recipe
     try:
-        idx = torch.randint(0, 64, (nds, npts, 4), device=dev, dtype=torch.int32)
-        idx += (torch.arange(npts, device=dev, dtype=torch.int32) // 64 * 64)[None, :, None]
-        idx.clamp_(max=npts - 1)
-        w = torch.rand((nds, npts, 4), device=dev, dtype=torch.float64)
-        u = torch.randn(npts, device=dev, dtype=torch.float64)
-        lo, hi = torch.empty_like(u), torch.empty_like(u)
-        h = C.c_void_p()
-        L = _lib.lib()
-        _lib.check(L.pde_ell_create(C.byref(h), dev.index, npts, npts, nds, C.c_void_p(idx.data_ptr()),
-                                    C.c_void_p(w.data_ptr())))
-        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-        ms = timed(lambda: _lib.check(L.pde_ell_d2eigs(h, C.c_void_p(u.data_ptr()), C.c_void_p(lo.data_ptr()),
-                                                       C.c_void_p(hi.data_ptr()), None, None, st)), reps=5)
-        out["ddi.d2eigs_ell"] = line(ms, (48.0 * nds + 24.0) * npts,
-                                     "%d points x %d directions, synthetic table; HBM-bound; "
-                                     "%.1f Gpoint.dir/s" % (npts, nds, npts * nds / ms / 1e6))
-        L.pde_ell_destroy(h)
+        out["ddi.d2eigs_disc"] = cloud_section(args, dev, pk, timed)
     except Exception as e:             # reported, not fatal
-        out["ddi.d2eigs_ell"] = {"error": str(e)[:200]}
+        out["ddi.d2eigs_disc"] = {"error": str(e)[:300]}
     return out
 
 

@@ -291,6 +291,27 @@ int pde_band_build(int64_t nx, int64_t ny, int stencil_radius, double sx, double
                    int64_t **out_ptr, int64_t **out_pairs, double *out_min_nb_dist);
 void pde_free(void *p);
 
+/* Stencils of a triangulated point cloud: replaces, per centre point, the O(N^2)
+ * pre-processing of FDTriMesh.__init__ -- neighbours within `depth` edges of the
+ * triangulation graph (pointclasses.py:373-382, sum of adjacency-matrix powers), the radius
+ * mask 0 < D <= max_radius and (D >= min_radius or boundary neighbour) (:385-392), colinear
+ * pruning with prefer="max" (:37-103) and the 2-D simplices (ConvexHull of the unit stencil
+ * vectors = consecutive neighbours in angular order, :105-121).
+ * device >= 0: every pointer is a DEVICE pointer and the work runs on that GPU (one thread per
+ * point); device = -1: HOST pointers, the same routine under OpenMP (constructor usable
+ * without a GPU; also the executable specification the device build is tested against).
+ * adj_ptr/adj: CSR of the triangulation graph (both directions of every edge).
+ * Outputs, rows of `kmax` entries per point: out_count[i] = number of kept neighbours K_i
+ * (negative: 1 BFS, 2 candidate, 3 row capacity exceeded -- retry with larger capacities),
+ * out_nb[i, :K_i] the neighbours by ascending id, out_ring[i, :K_i] the same neighbours in
+ * angular order (simplices of i: (i, ring[k], ring[(k+1) % K_i])).
+ * out_status[1..3] count the points that overflowed. */
+int pde_cloud_build(int device, int64_t n_points, int64_t n_interior, const double *points,
+                    const int64_t *adj_ptr, const int32_t *adj, int depth, double min_radius,
+                    double max_radius, double colinear_tol, int kmax, int bfs_capacity,
+                    int32_t *out_count, int32_t *out_nb, int32_t *out_ring, int32_t *out_status,
+                    void *stream);
+
 /* fp64 FMA-chain microbenchmark: returns achieved DFMA/s of the device in
  * *h_dfma_per_s (synchronous).  Used by bench.py to evidence which roof
  * (HBM or the fp64 pipe) binds the stencil kernel. */

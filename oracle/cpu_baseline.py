@@ -70,6 +70,39 @@ def time_d2eigs(ny, r, table, scaling, b0, rows_per_worker=24, workers=None, rep
                        % (workers, rows_per_worker, ny - 2 * r, prs))
 
 
+def time_ddi_cached(idx, w, u, nds):
+    """The reference's cached ddi.d2eigs path (ddi.py:358-367): Nds SciPy CSR mat-vecs
+    (5 nnz per row) followed by an argsort of the (N, Nds) array.  ``idx``/``w`` hold the
+    rows of K sample directions ((K, N, 4) each); the mat-vec time is measured on those K
+    matrices and scaled to Nds, the argsort is run at full size.  Single-threaded like the
+    reference."""
+    import scipy.sparse as sp
+    K, N, _ = idx.shape
+    n = u.shape[0]
+    I = np.arange(N)
+    mats = []
+    for k in range(K):
+        rows = np.concatenate([np.repeat(I, 4), I])
+        cols = np.concatenate([idx[k].ravel().astype(np.int64), I])
+        vals = np.concatenate([w[k].ravel(), -w[k].sum(1)])
+        mats.append(sp.coo_matrix((vals, (rows, cols)), shape=(N, n)).tocsr())
+    for M in mats:
+        M.dot(u)
+    t = time.perf_counter()
+    cols_ = [M.dot(u) for M in mats]
+    t_mv = (time.perf_counter() - t) / K
+    d2u = np.empty((N, nds))
+    for k in range(nds):
+        d2u[:, k] = cols_[k % K] + 1e-9 * k
+    t = time.perf_counter()
+    arg = np.argsort(d2u)
+    lmin, lmax = d2u[I, arg[:, 0]], d2u[I, arg[:, -1]]
+    t_sort = time.perf_counter() - t
+    return dict(seconds=nds * t_mv + t_sort, t_matvec=t_mv, t_argsort=t_sort,
+                sample="%d of %d direction matrices (CSR, %d rows, 5 nnz/row) timed and scaled, "
+                       "argsort of the full (%d, %d) array" % (K, nds, N, N, nds))
+
+
 def main(argv=None):
     """``python -m oracle.cpu_baseline NY R ROWS_PER_WORKER WORKERS REPS`` on a unit-square
     dyadic lattice; prints one JSON line.  bench.py runs this in a fresh (CUDA-free)

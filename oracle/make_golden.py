@@ -192,9 +192,44 @@ def cloud_case(R, name, h0):
           (name, len(p), nint, len(G.simplices), time.time() - t), flush=True)
 
 
+def trimesh_case(R, name, h0):
+    """Stencils of the reference FDTriMesh constructor (pointclasses.py:289-398) on a disc:
+    the inputs (points, triangulation) and every derived attribute the fast constructor
+    must reproduce -- neighbour and simplex SETS (row order inside a point is arbitrary in
+    the reference: sparse products / joggled Qhull)."""
+    from scipy.spatial import Delaunay
+    from . import disc
+    t = time.time()
+    theta = np.pi * h0 ** (1 / 3)
+    p, nint = disc.disc_points(h0, theta)
+    tri = Delaunay(p).simplices
+    G = R.pointclasses.FDTriMesh(p, tri, num_interior=nint, angular_resolution=theta,
+                                 bdry_normals=p[nint:])
+    nb = np.asarray(G.neighbours)
+    nb = nb[np.lexsort((nb[:, 1], nb[:, 0]))]
+    S = np.asarray(G.simplices)
+    S = np.stack([S[:, 0], S[:, 1:].min(1), S[:, 1:].max(1)], 1)
+    S = S[np.lexsort((S[:, 2], S[:, 1], S[:, 0]))]
+    X, Y = p.T
+    d2x, _ = R.ddi.d2(G, [1, 0], X ** 2 + Y ** 2)          # tests/test_trimesh.py:19-25
+    np.savez_compressed(
+        os.path.join(OUT, "trimesh_%s.npz" % name), points=p, tri=tri.astype(np.int32),
+        num_interior=nint, angular_resolution=theta, neighbours=nb.astype(np.int32),
+        simplices=S.astype(np.int32), spatial_resolution=G.spatial_resolution,
+        dist_to_bdry=G.dist_to_bdry, bdry_resolution=G.bdry_resolution,
+        min_interior_nb_dist=G.min_interior_nb_dist, max_radius=G.max_radius,
+        min_radius=G.min_radius, d2x_of_r2=d2x)
+    print("trimesh_%s: %d points, %d neighbours, %d simplices, %.1fs"
+          % (name, len(p), len(nb), len(S), time.time() - t), flush=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = refshim.modules()
+    if "--trimesh-only" in sys.argv:
+        trimesh_case(R, "disc_h0.1", 0.1)
+        trimesh_case(R, "disc_h0.05", 0.05)
+        return
     if "--clouds-only" in sys.argv:
         cloud_case(R, "disc_h0.1", 0.1)
         cloud_case(R, "disc_h0.06", 0.06)
@@ -209,6 +244,8 @@ def main():
     solve_case(R, "n15_r4", (15, 15), [[-1, 1], [-1, 1]], 4, pucci=True)
     cloud_case(R, "disc_h0.1", 0.1)
     cloud_case(R, "disc_h0.06", 0.06)
+    trimesh_case(R, "disc_h0.1", 0.1)
+    trimesh_case(R, "disc_h0.05", 0.05)
 
 
 if __name__ == "__main__":

@@ -45,9 +45,12 @@ class EllTable(object):
         self.V = np.ascontiguousarray(V, dtype=np.float64)
         self.nds = 1 if per_point else self.V.shape[0]
         dev = self.device
-        S, ptr = _grouped_simplices(G)
         P = torch.from_numpy(np.ascontiguousarray(G.points, dtype=np.float64)).to(dev)
-        dS, dptr = torch.from_numpy(S).to(dev), torch.from_numpy(ptr).to(dev)
+        if hasattr(G, "device_simplices") and getattr(G, "_simplices", None) is None:
+            dS, dptr = G.device_simplices(dev)        # FDTriMesh: stencils already on the device
+        else:
+            S, ptr = _grouped_simplices(G)
+            dS, dptr = torch.from_numpy(S).to(dev), torch.from_numpy(ptr).to(dev)
         dV = torch.from_numpy(self.V).to(dev)
         self.idx = torch.empty((self.nds, self.N, 4), dtype=torch.int32, device=dev)
         self.w = torch.empty((self.nds, self.N, 4), dtype=torch.float64, device=dev)

@@ -79,6 +79,8 @@ SIGNATURES = {
     "pde_band_build": (c_int, [c_i64, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, vp,
                                c_i64, vp, c_dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(c_dbl)]),
     "pde_free": (None, [vp]),
+    "pde_cloud_build": (c_int, [c_int, c_i64, c_i64, vp, vp, vp, c_int, c_dbl, c_dbl, c_dbl, c_int,
+                                c_int, vp, vp, vp, vp, vp]),
 }
 
 

@@ -140,6 +140,218 @@ class FDPointCloud(object):
         self._min_nb = value
 
 
+class FDTriMesh(FDPointCloud):
+    """Fast drop-in for pointclasses.FDTriMesh (pointclasses.py:289-398): finite
+    differences on a triangulated point cloud.
+
+    Same constructor signature ``(p, t, angular_resolution=pi/4, **kwargs)`` and
+    attributes (``triangulation``, ``edges``, ``neighbours``, ``simplices``,
+    ``spatial_resolution``, ``dist_to_bdry``, ``bdry_resolution`` ...).  The mesh
+    statistics are vectorised NumPy with the reference's arithmetic (batched LAPACK
+    ``gesv`` for the circumcentres, like the per-triangle ``np.linalg.solve`` of
+    :322-328); the stencil search -- graph neighbours within ``depth`` edges, radius
+    mask, colinear pruning, hull simplices, O(N^2) in the reference -- is one native
+    pass per point (``pde_cloud_build``: on the GPU when one is present, otherwise the
+    same routine on the host cores).  ``neighbours`` / ``simplices`` are materialised
+    as NumPy arrays on first access; the operators read the device copies.
+
+    Within one centre point the ORDER of neighbours (ascending id) and simplices
+    (counter-clockwise) is this module's own; the reference's comes from SciPy's sparse
+    products and Qhull's joggled hull and only matters for exact ties.
+    """
+
+    def __repr__(self):
+        return ("FDTriMesh in {0.dim}D with {0.num_points} points, "
+                "spatial resolution {0.spatial_resolution:.3g}, "
+                "and angular resolution {0.angular_resolution:.3g}").format(self)
+
+    def __init__(self, p, t, angular_resolution=np.pi / 4, device=None, **kwargs):
+        p = np.ascontiguousarray(p, dtype=np.float64)
+        t = np.asarray(t)
+        super().__init__(p, angular_resolution=angular_resolution, **kwargs)
+        self.neighbours = None                      # pointclasses.py:167 ignores the kwarg
+        self.triangulation = t
+        if self.dim != 2:
+            raise NotImplementedError("only 2-D triangulations are implemented")
+        N = self.num_interior
+
+        def circumradius(ix):                       # :322-328, batched
+            X = p[ix]
+            V = X[:, 1:] - X[:, :1]
+            if ix.shape[1] > 2:
+                rhs = .5 * np.einsum("tij,tij->ti", V, V)
+                c = np.linalg.solve(V, rhs[..., None])[..., 0]
+                return np.sqrt((c * c).sum(1))
+            return np.sqrt((V[:, 0] ** 2).sum(1)) / 2
+
+        if not self.spatial_resolution:
+            self.spatial_resolution = circumradius(t).max()                  # :332-333
+        isb = t >= N
+        if not self.dist_to_bdry:                                             # :339-346
+            tb, bb = t[isb.any(axis=1)], isb[isb.any(axis=1)]
+            if (bb.all(axis=1)).any():
+                raise ValueError("a triangle has only boundary vertices")     # cdist of nothing
+            d = np.inf
+            for a in range(3):
+                for b in range(3):
+                    m = ~bb[:, a] & bb[:, b]
+                    if m.any():
+                        V = p[tb[m, a]] - p[tb[m, b]]
+                        d = min(d, np.sqrt((V * V).sum(1)).min())
+            self.dist_to_bdry = d
+        if not self.bdry_resolution:                                          # :349-356
+            m = isb.sum(axis=1) == 2
+            tb = t[m]
+            fb = tb[isb[m]].reshape(-1, 2)
+            self.bdry_resolution = circumradius(fb).max()
+        if self.dist_to_bdry < self.min_dist_to_bdry:                         # :358-365
+            raise TypeError(
+                ("The interior grid points' minimum distance to the boundary"
+                 " ({0.dist_to_bdry:.3g}) "
+                 "\nmust be greater than "
+                 "({0.min_dist_to_bdry:.3g})."
+                 "\nTry increasing the angular resolution,"
+                 "\nor deleting points close to the boundary.").format(self))
+
+        # edges of the triangulation, both directions (:368-370)
+        cols = [np.stack([t[:, a], t[:, b]], 1) for a, b in itertools.permutations(range(3), 2)]
+        self.edges = np.concatenate(cols)
+        E = self.edges
+        V = p[E[:, 1]] - p[E[:, 0]]
+        L = np.sqrt((V * V).sum(1))
+        self._edge_min_nb = L[E[:, 0] < N].min()
+        depth = int(np.ceil(self.max_radius / self._edge_min_nb))            # :373
+        self.graph_depth = max(depth, 1)
+        self.colinear_tol = 1 - np.cos(angular_resolution / 8)               # :395
+        self._build_stencils(device)
+
+    @property
+    def min_dist_to_bdry(self):
+        d1 = self.Cd * self.bdry_resolution / np.tan(self.angular_resolution / 2)
+        return np.min([self.min_radius, d1])
+
+    @property
+    def maximum_bdry_res(self):
+        return self.dist_to_bdry * np.tan(self.angular_resolution / 2) / self.Cd
+
+    @property
+    def adjacency(self):
+        """Adjacency matrix of each point and its (current) neighbours (:239-244)."""
+        from scipy.sparse import coo_matrix
+        nb = self.neighbours
+        n = self.num_points
+        return coo_matrix((np.ones(nb.shape[0], dtype=np.intp), (nb[:, 0], nb[:, 1])),
+                          shape=(n, n), dtype=np.intp).tocsr()
+
+    # -- the native stencil search -------------------------------------------------------------
+    def _build_stencils(self, device=None):
+        import ctypes as C
+        import torch
+        from . import _lib
+        L = _lib.lib()
+        n, N = self.num_points, self.num_interior
+        key = np.unique(self.edges[:, 0].astype(np.int64) * n + self.edges[:, 1])
+        e0, e1 = key // n, key % n
+        e0, e1 = e0[e0 != e1], e1[e0 != e1]
+        adj_ptr = np.concatenate([[0], np.cumsum(np.bincount(e0, minlength=n))]).astype(np.int64)
+        adj = np.ascontiguousarray(e1, dtype=np.int32)
+        use_gpu = torch.cuda.is_available() if device is None else (str(device) != "cpu")
+        if use_gpu:
+            dev = torch.device("cuda", torch.cuda.current_device()) if device is None \
+                else torch.device(device)
+            if dev.index is None:
+                dev = torch.device("cuda", torch.cuda.current_device())
+        else:
+            dev = torch.device("cpu")
+        dpts = torch.from_numpy(np.ascontiguousarray(self.points)).to(dev)
+        dptr, dadj = torch.from_numpy(adj_ptr).to(dev), torch.from_numpy(adj).to(dev)
+        d = self.graph_depth
+        cap = 256
+        while cap < 3 * (1 + 3 * d * (d + 1)) // 2:
+            cap *= 2
+        kmax = min(cap, 256)
+        while True:
+            count = torch.empty(n, dtype=torch.int32, device=dev)
+            nb = torch.empty((n, kmax), dtype=torch.int32, device=dev)
+            ring = torch.empty((n, kmax), dtype=torch.int32, device=dev)
+            status = torch.zeros(4, dtype=torch.int32, device=dev)
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream if use_gpu else 0)
+            _lib.check(L.pde_cloud_build(
+                dev.index if use_gpu else -1, n, N, C.c_void_p(dpts.data_ptr()),
+                C.c_void_p(dptr.data_ptr()), C.c_void_p(dadj.data_ptr()), d,
+                float(self.min_radius), float(self.max_radius), float(self.colinear_tol),
+                kmax, cap, C.c_void_p(count.data_ptr()), C.c_void_p(nb.data_ptr()),
+                C.c_void_p(ring.data_ptr()), C.c_void_p(status.data_ptr()), stream))
+            st = status.cpu().numpy()
+            if st[1] or st[2]:
+                cap *= 2
+            if st[3]:
+                kmax *= 2
+            cap = max(cap, kmax)
+            if not st[1:].any():
+                break
+            if cap > (1 << 16):
+                raise MemoryError("stencil search capacity exceeded")
+        self._count, self._nb, self._ring, self._kmax = count, nb, ring, kmax
+        self._neighbours = None
+        self._simplices = None
+        # minimum interior neighbour distance of the final stencils (:283-285)
+        mask = torch.arange(kmax, device=dev)[None, :] < count[:N, None]
+        J = nb[:N][mask].long()
+        I = torch.repeat_interleave(torch.arange(N, device=dev), count[:N].long())
+        Vv = dpts[J] - dpts[I]
+        self._min_nb = float(torch.sqrt((Vv * Vv).sum(1)).min()) if J.numel() else np.inf
+        self.stencil_device = dev
+
+    def _flat(self, which, interior_only=False, device=None):
+        """(I, J[, J_next]) flat tensors of the neighbour rows / hull edges."""
+        import torch
+        n = self.num_interior if interior_only else self.num_points
+        count, tab = self._count[:n], (self._nb if which == "nb" else self._ring)[:n]
+        dev = count.device
+        k = torch.arange(self._kmax, device=dev)[None, :]
+        mask = k < count[:, None]
+        I = torch.repeat_interleave(torch.arange(n, device=dev), count.long())
+        J = tab[mask].long()
+        if which == "nb":
+            return I, J
+        nxt = (k + 1) % count.clamp(min=1)[:, None]
+        Jn = torch.gather(tab, 1, nxt.long())[mask].long()
+        return I, J, Jn
+
+    def device_simplices(self, device):
+        """Interior simplices (S, 3) int64 grouped by centre point and their CSR pointer,
+        as tensors on ``device`` (what ``pde_ell_build`` consumes)."""
+        import torch
+        I, J, Jn = self._flat("ring", interior_only=True)
+        S = torch.stack([I, J, Jn], 1).to(device)
+        ptr = torch.zeros(self.num_interior + 1, dtype=torch.int64, device=self._count.device)
+        ptr[1:] = torch.cumsum(self._count[:self.num_interior].long(), 0)
+        return S.contiguous(), ptr.to(device)
+
+    @property
+    def neighbours(self):
+        if getattr(self, "_neighbours", None) is None and getattr(self, "_count", None) is not None:
+            I, J = self._flat("nb")
+            self._neighbours = np.stack([I.cpu().numpy(), J.cpu().numpy()], 1)
+        return getattr(self, "_neighbours", None)
+
+    @neighbours.setter
+    def neighbours(self, value):
+        self._neighbours = value
+
+    @property
+    def simplices(self):
+        if getattr(self, "_simplices", None) is None and getattr(self, "_count", None) is not None:
+            I, J, Jn = self._flat("ring")
+            self._simplices = np.stack([I.cpu().numpy(), J.cpu().numpy(), Jn.cpu().numpy()], 1)
+        return getattr(self, "_simplices", None)
+
+    @simplices.setter
+    def simplices(self, value):
+        self._simplices = value
+
+
 # ---------------------------------------------------------------------------
 # stencil rules, restated for a batch of centre points
 # ---------------------------------------------------------------------------

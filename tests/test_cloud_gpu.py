@@ -122,3 +122,67 @@ def test_pucci_on_cloud():
     f = -val                                   # manufactured: Uex solves the discrete problem
     U, diff, it, _ = pucci.solve(G, f, Uex[N:], A=(2, 1), fdmethod="interpolate", solver="newton")
     assert np.abs(U - Uex).max() < 1e-5
+
+
+# ---- fast FDTriMesh constructor on the GPU --------------------------------
+MESH = sorted(glob.glob(os.path.join(GOLD, "trimesh_*.npz")))
+
+
+def _trimesh(z, device=None):
+    from pyellipticfd_b200.pointclasses import FDTriMesh
+    n = int(z["num_interior"])
+    return FDTriMesh(z["points"], z["tri"].astype(np.int64), num_interior=n,
+                     angular_resolution=float(z["angular_resolution"]),
+                     bdry_normals=z["points"][n:], device=device)
+
+
+@pytest.mark.parametrize("path", MESH, ids=[os.path.basename(p) for p in MESH])
+def test_trimesh_device_build_matches_reference(path):
+    """Device stencil search == host build of the same routine, bit for bit, and the
+    neighbour / simplex sets of the reference constructor (pointclasses.py:289-398)."""
+    z = np.load(path)
+    Gd, Gh = _trimesh(z), _trimesh(z, device="cpu")
+    assert Gd.stencil_device.type == "cuda"
+    assert np.array_equal(Gd._count.cpu().numpy(), Gh._count.numpy())
+    assert np.array_equal(Gd.neighbours, Gh.neighbours)
+    assert np.array_equal(Gd.simplices, Gh.simplices)
+    nb = np.asarray(Gd.neighbours)
+    assert np.array_equal(nb[np.lexsort((nb[:, 1], nb[:, 0]))], z["neighbours"])
+    S = np.asarray(Gd.simplices)
+    S = np.stack([S[:, 0], S[:, 1:].min(1), S[:, 1:].max(1)], 1)
+    assert np.array_equal(S[np.lexsort((S[:, 2], S[:, 1], S[:, 0]))], z["simplices"])
+    assert Gd.min_interior_nb_dist == pytest.approx(float(z["min_interior_nb_dist"]), rel=1e-14)
+    # ddi.d2 on the fast mesh against the reference's values on ITS mesh (tests/test_trimesh.py:19-25)
+    import pyellipticfd_b200.ddi as ddi
+    X, Y = Gd.points.T
+    d2x, M = ddi.d2(Gd, [1, 0], X ** 2 + Y ** 2, jacobian=True)
+    assert np.abs(d2x - z["d2x_of_r2"]).max() < 1e-9 * np.abs(z["d2x_of_r2"]).max()
+    assert d2x.max() - 2 < 0.17
+
+
+def test_trimesh_large_disc_device_equals_host():
+    """A 40 k-point disc: device and host builds agree exactly; the reference's own
+    known-answer test (tests/test_trimesh.py:19-25, |d2 - 2| < 0.17) holds on it."""
+    from scipy.spatial import Delaunay
+    from oracle import disc
+    from pyellipticfd_b200.pointclasses import FDTriMesh
+    import pyellipticfd_b200.ddi as ddi
+    h0 = 0.01
+    theta = np.pi * h0 ** (1 / 3)
+    p, nint = disc.disc_points(h0, theta)
+    tri = Delaunay(p).simplices
+    Gd = FDTriMesh(p, tri, num_interior=nint, angular_resolution=theta)
+    Gh = FDTriMesh(p, tri, num_interior=nint, angular_resolution=theta, device="cpu")
+    assert np.array_equal(Gd._count.cpu().numpy(), Gh._count.numpy())
+    k = Gd._kmax
+    m = np.arange(k)[None, :] < Gh._count.numpy()[:, None]
+    assert np.array_equal(Gd._nb.cpu().numpy()[m], Gh._nb.numpy()[m])
+    ring_d, ring_h = Gd._ring.cpu().numpy()[m], Gh._ring.numpy()[m]
+    assert (ring_d != ring_h).mean() < 1e-6        # atan2 may differ in the last ulp
+    X, Y = p.T
+    U2 = X ** 2 + Y ** 2
+    for v in ([1, 0], [0, 1]):
+        d2, _ = ddi.d2(Gd, v, U2)
+        assert d2.max() - 2 < 0.17 and 2 - d2.min() < 0.17
+    (lmin, _, _), (lmax, _, _) = ddi.d2eigs(Gd, X ** 2 - Y ** 2)
+    assert np.abs(lmin + 2).max() < 0.2 and np.abs(lmax - 2).max() < 0.2
