@@ -568,6 +568,37 @@ def main():
                               "seconds": time.perf_counter() - t, "iterations": it, "diff": diff,
                               **{k: v for k, v in st.items() if k != "reason"}})
 
+    if world > 1:
+        # e2e at N GPUs: every rank moves its slab of the field from pinned host memory to its
+        # GPU, applies the slab-parallel operator (halo exchange inside) and reads lambda_min of
+        # its rows back into pinned host memory; max over ranks of the wall time per step
+        host = torch.empty(flat.numel(), dtype=torch.float64, pin_memory=True)
+        host.copy_(flat)
+        res_host = torch.empty(n_local, dtype=torch.float64, pin_memory=True)
+        stage = torch.empty_like(flat)
+
+        def e2e_step():
+            stage.copy_(host, non_blocking=True)
+            ctx.pack(stage, out=S)
+            sharded.d2eigs(S, out)
+            res_host.copy_(ctx.unpad(lmin), non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+        for _ in range(3):
+            e2e_step()
+        dist.barrier()
+        t = time.perf_counter()
+        for _ in range(args.e2e_steps):
+            e2e_step()
+        dt = (time.perf_counter() - t) / args.e2e_steps
+        tt = torch.tensor([dt], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": total_points * D / dt / 1e9, "unit": UNIT, "ms_per_step": dt * 1e3,
+               "h2d_bytes_per_step": int(host.numel() * 8) * world,
+               "d2h_bytes_per_step": int(res_host.numel() * 8) * world,
+               "note": "per-rank slabs through ShardedGrid.d2eigs, max over ranks"}
+
     solve_full = None
     if world == 1 and args.solve_full:
         solve_full = solve_full_size(args, two_cones)

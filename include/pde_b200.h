@@ -233,18 +233,42 @@ int pde_ell_d2eigs(pde_ell *e, const double *d_u, double *d_lmin, double *d_lmax
  * replaces the per-row CSR slicing loop ddi.py:369-404). */
 int pde_ell_apply_policy(pde_ell *e, const int32_t *d_k, const double *d_x,
                          double *d_y, void *stream);
-/* Build the table on the device (ddi.py:253-299): for every interior point and
+/* Build the table on the device (ddi.py:253-299): for every row (centre point) and
  * direction V[k], the first simplex (row order) whose cone contains +v and the
  * first containing -v (2x2 solves with partial pivoting), barycentric weights,
- * 2/(hf+hb) scaling.  simplices: (S,3) int64 rows (i, s1, s2) grouped by
- * ascending i with simp_ptr (n_interior+1).  eps_over_h = 1e-15/spatial_resolution
- * (ddi.py:10,267).  v_per_point != 0: nds must be 1 and d_V is (n,2), one direction
- * per point (ddi.d2 / ddf.d2).  froese != 0 builds Froese's weights instead
- * (ddf.py:46-116).  *d_fail counts (point, direction) units with no enclosing cone. */
-int pde_ell_build(int device, int64_t n_interior, const double *d_points /* (npts,2) */,
+ * 2/(hf+hb) scaling.  simplices: (S,3) int64 rows (i, s1, s2) grouped by ascending centre
+ * with simp_ptr (n_rows+1).  eps_over_h = 1e-15/spatial_resolution
+ * (ddi.py:10,267).  v_per_point != 0: nds must be 1 and d_V is (n_rows,2), one direction
+ * per row (ddi.d2 / ddf.d2 / ddi.d1).
+ * scheme 0: ddi second derivative; 1: Froese's weights (ddf.py:46-116);
+ *        2: ddi FIRST derivative (ddi.py:61-80: forward simplex only, weights = cone
+ *           coordinates, row padded with two zero-weight entries);
+ *        3: the same on the boundary domain (ddi.py:66-68: only simplices whose vertices
+ *           are interior points, id < n_interior_pts).
+ * row_offset: centre point of row i is point i + row_offset (0 for the interior domain,
+ * num_interior for the boundary domain).
+ * *d_fail counts (row, direction) units with no enclosing cone. */
+int pde_ell_build(int device, int64_t n_rows, const double *d_points /* (npts,2) */,
                   const int64_t *d_simplices, const int64_t *d_simp_ptr,
                   int nds, const double *d_V, int v_per_point, double eps_over_h,
-                  int froese, int32_t *d_idx, double *d_w, int32_t *d_fail, void *stream);
+                  int scheme, int64_t row_offset, int64_t n_interior_pts,
+                  int32_t *d_idx, double *d_w, int32_t *d_fail, void *stream);
+
+/* First derivatives on a neighbour list (ddg.d1 ddg.py:8-81, ddg.d1grad ddg.py:110-175).
+ * Row r has centre point r + centre_offset and the neighbours d_J[d_ptr[r] .. d_ptr[r+1]).
+ * d_v != NULL ((n_rows,2) unit directions): the neighbour with the largest cosine against
+ * the direction is selected (ddg.py:59-66).  d_v == NULL: the neighbour with the largest
+ * difference quotient (u[J]-u[I])/h (ddg.py:146-153; d_u required).  First maximal
+ * neighbour in row order wins.  Outputs per row: d_d1 (value, may be NULL when d_u is NULL),
+ * d_sel (selected neighbour id), d_w (1/h), d_vout ((n_rows,2) = w*X, ddg.py:160; may be NULL). */
+int pde_nb_d1(int device, int64_t n_rows, int64_t centre_offset, const int64_t *d_ptr,
+              const int32_t *d_J, const double *d_points, const double *d_u, const double *d_v,
+              double *d_d1, int32_t *d_sel, double *d_w, double *d_vout, void *stream);
+/* y[r] = sum_j w[r,j] * (x[idx[r,j]] - x[r + centre_offset]) for row-major 4-wide rows
+ * ((n_rows,4) int32 / double, 16-byte aligned): the finite-difference matrices of
+ * ddg.py:73-79,164-171 and ddi.py:84-90 applied matrix-free. */
+int pde_rows_apply(int device, int64_t n_rows, int64_t centre_offset, const int32_t *d_idx,
+                   const double *d_w, const double *d_x, double *d_y, void *stream);
 
 /* Problems and the Newton linear solve on point clouds (fdmethod 'interpolate' /
  * 'froese').  All vectors are the reference's flat vectors (n_points doubles,
@@ -288,7 +312,10 @@ int pde_ell_newton_update(pde_ell *e, const double *d_U, const double *d_d, cons
 int pde_band_build(int64_t nx, int64_t ny, int stencil_radius, double sx, double sy,
                    double bx, double by, int64_t nb, const double *h_wall,
                    int64_t n_band, const int64_t *h_band_ids, double colinear_tol,
-                   int64_t **out_ptr, int64_t **out_pairs, double *out_min_nb_dist);
+                   int64_t **out_ptr, int64_t **out_pairs, double *out_min_nb_dist,
+                   /* optional (may be NULL): the pruned neighbour lists themselves, CSR over the
+                    * band points (what ddg.d1 / d1grad walk, ddg.py:44-47) */
+                   int64_t **out_nb_ptr, int64_t **out_nb);
 void pde_free(void *p);
 
 /* Stencils of a triangulated point cloud: replaces, per centre point, the O(N^2)

@@ -223,9 +223,75 @@ def trimesh_case(R, name, h0):
           % (name, len(p), len(nb), len(S), time.time() - t), flush=True)
 
 
+def d1_case(R):
+    """First-derivative operators of the reference (ddg.py:8-175, ddi.py:12-221): outputs on
+    the reference tests' own grids (tests/test_ddg.py:17-56, tests/test_ddi.py:10-43), with
+    the NumPy restatement oracle/d1_oracle.py pinned against them."""
+    from scipy.spatial import Delaunay
+    from . import disc, d1_oracle
+    from pyellipticfd_b200._ddutils import process_v
+    t = time.time()
+    out = {}
+    G = R.pointclasses.FDRegularGrid([9, 9], np.array([[0, 1], [0, 1]]).T, 2, interpolation=False)
+    nb = np.asarray(G.neighbours)
+    nb = nb[nb[:, 0] < G.num_interior]
+    out["grid_neighbours"] = nb[np.lexsort((nb[:, 1], nb[:, 0]))].astype(np.int32)
+    X, Y = G.points.T
+    flds = {"lin": X - Y, "random": np.random.default_rng(0).standard_normal(len(X))}
+    for fname, u in flds.items():
+        for k, v in enumerate(([1, 0], [0, 1], 0.3)):
+            d, M = R.ddg.d1(G, v, u, jacobian=True)
+            od, oJ, ow = d1_oracle.ddg_d1(G, process_v(G, v), u)
+            assert np.array_equal(d, od) and np.abs(M.dot(u) - d).max() < 1e-12
+            out["ddg_d1_%s_%d" % (fname, k)] = d
+        d, M, vv = R.ddg.d1grad(G, u, jacobian=True, control=True)
+        od, oJ, ow, ov = d1_oracle.ddg_d1grad(G, u)
+        assert np.array_equal(d, od) and np.array_equal(vv, ov)
+        out["ddg_d1grad_%s" % fname], out["ddg_d1grad_v_%s" % fname] = d, vv
+    # disc (the trimesh fixture's points): ddg.d1n, ddi.d1 / d1n / d1grad
+    for name, h0 in (("h0.1", 0.1), ("h0.05", 0.05)):
+        theta = np.pi * h0 ** (1 / 3)
+        p, nint = disc.disc_points(h0, theta)
+        tri = Delaunay(p).simplices
+        G = R.pointclasses.FDTriMesh(p, tri, num_interior=nint, angular_resolution=theta,
+                                     bdry_normals=p[nint:])
+        X, Y = p.T
+        Un = np.linalg.norm(p, axis=1)
+        rnd = np.random.default_rng(1).standard_normal(len(p))
+        lin = X - Y
+        d, M = R.ddg.d1n(G, u=Un, jacobian=True)
+        od, _, _ = d1_oracle.ddg_d1(G, process_v(G, -G.bdry_normals, "boundary"), Un, "boundary")
+        assert np.array_equal(d, od)
+        out["%s_ddg_d1n" % name] = d
+        out["%s_ddg_d1grad_random" % name] = R.ddg.d1grad(G, rnd)[0]
+        for k, v in enumerate(([1, 0], 0.3)):
+            for fname, u in (("lin", lin), ("random", rnd)):
+                d, M = R.ddi.d1(G, v, u, jacobian=True)
+                od, _, _ = d1_oracle.ddi_d1(G, process_v(G, v), u)
+                assert np.abs(d - od).max() <= 1e-12 * np.abs(d).max(), np.abs(d - od).max()
+                assert np.abs(M.dot(u) - d).max() < 1e-9 * np.abs(d).max()
+                out["%s_ddi_d1_%s_%d" % (name, fname, k)] = d
+        d, M = R.ddi.d1n(G, u=Un, jacobian=True)
+        od, _, _ = d1_oracle.ddi_d1(G, process_v(G, -G.bdry_normals, "boundary"), Un, "boundary")
+        assert np.abs(d - od).max() <= 1e-12
+        out["%s_ddi_d1n" % name] = d
+        for fname, u in (("lin", lin), ("random", rnd)):
+            G._d1cache = None
+            d, M, vv = R.ddi.d1grad(G, u, jacobian=True, control=True)
+            od, oix, ov = d1_oracle.ddi_d1grad(G, u, int(R.ddi._num_directions(G)))
+            assert np.abs(d - od).max() <= 1e-12 * np.abs(d).max() and np.array_equal(vv, ov)
+            assert np.abs(M.dot(u) - d).max() < 1e-9 * np.abs(d).max()
+            out["%s_ddi_d1grad_%s" % (name, fname)], out["%s_ddi_d1grad_v_%s" % (name, fname)] = d, vv
+    np.savez_compressed(os.path.join(OUT, "d1_ops.npz"), **out)
+    print("d1_ops: %d arrays, %.1fs" % (len(out), time.time() - t), flush=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = refshim.modules()
+    if "--d1-only" in sys.argv:
+        d1_case(R)
+        return
     if "--trimesh-only" in sys.argv:
         trimesh_case(R, "disc_h0.1", 0.1)
         trimesh_case(R, "disc_h0.05", 0.05)
@@ -246,6 +312,7 @@ def main():
     cloud_case(R, "disc_h0.06", 0.06)
     trimesh_case(R, "disc_h0.1", 0.1)
     trimesh_case(R, "disc_h0.05", 0.05)
+    d1_case(R)
 
 
 if __name__ == "__main__":

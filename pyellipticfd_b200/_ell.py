@@ -20,54 +20,63 @@ from ._context import require_cuda, to_device, like_input, _ptr, _stream
 EPS = 1e-15          # ddi.py:10
 
 
-def _grouped_simplices(G):
-    """Interior simplices grouped by centre point, original row order kept inside a
-    group (the reference takes the FIRST matching row per point, ddi.py:270-271)."""
+def _grouped_simplices(G, lo=0, hi=None):
+    """Simplices whose centre lies in [lo, hi), grouped by centre point, original row order
+    kept inside a group (the reference takes the FIRST matching row per point, ddi.py:270-271)."""
     S = np.asarray(G.simplices, dtype=np.int64)
-    N = int(G.num_interior)
-    S = S[S[:, 0] < N]
+    hi = int(G.num_interior) if hi is None else hi
+    S = S[(S[:, 0] >= lo) & (S[:, 0] < hi)]
     order = np.argsort(S[:, 0], kind="stable")
     S = np.ascontiguousarray(S[order])
-    counts = np.bincount(S[:, 0], minlength=N)
+    counts = np.bincount(S[:, 0] - lo, minlength=hi - lo)
     ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
     return S, ptr
 
 
 class EllTable(object):
-    """Device ELL table of one (grid, scheme)."""
+    """Device ELL table of one (grid, scheme).  ``scheme``: 0 ddi second derivative,
+    1 Froese, 2 ddi first derivative (interior rows), 3 ddi first derivative on the
+    boundary rows (``pde_ell_build``)."""
 
-    def __init__(self, G, V, froese, device=None, per_point=False):
+    def __init__(self, G, V, froese, device=None, per_point=False, scheme=None):
         self.lib = _lib.lib()
         self.device = require_cuda(device)
         self.G = G
-        self.N = int(G.num_interior)
+        self.scheme = int(froese) if scheme is None else int(scheme)
         self.n_points = int(np.asarray(G.points).shape[0])
+        n_int = int(G.num_interior)
+        self.row_offset = n_int if self.scheme == 3 else 0
+        self.N = self.n_points - n_int if self.scheme == 3 else n_int
         self.V = np.ascontiguousarray(V, dtype=np.float64)
         self.nds = 1 if per_point else self.V.shape[0]
         dev = self.device
         P = torch.from_numpy(np.ascontiguousarray(G.points, dtype=np.float64)).to(dev)
+        lo, hi = self.row_offset, self.row_offset + self.N
         if hasattr(G, "device_simplices") and getattr(G, "_simplices", None) is None:
-            dS, dptr = G.device_simplices(dev)        # FDTriMesh: stencils already on the device
+            dS, dptr = G.device_simplices(dev, lo, hi)   # FDTriMesh: stencils already on the device
         else:
-            S, ptr = _grouped_simplices(G)
+            S, ptr = _grouped_simplices(G, lo, hi)
             dS, dptr = torch.from_numpy(S).to(dev), torch.from_numpy(ptr).to(dev)
         dV = torch.from_numpy(self.V).to(dev)
         self.idx = torch.empty((self.nds, self.N, 4), dtype=torch.int32, device=dev)
         self.w = torch.empty((self.nds, self.N, 4), dtype=torch.float64, device=dev)
         fail = torch.zeros(1, dtype=torch.int32, device=dev)
-        eps_h = 0.0 if froese else EPS / G.spatial_resolution
+        eps_h = 0.0 if self.scheme == 1 else EPS / G.spatial_resolution
         check(self.lib.pde_ell_build(dev.index, self.N, _ptr(P), _ptr(dS), _ptr(dptr), self.nds,
-                                     _ptr(dV), int(per_point), float(eps_h), int(froese),
+                                     _ptr(dV), int(per_point), float(eps_h), self.scheme,
+                                     self.row_offset, n_int,
                                      _ptr(self.idx), _ptr(self.w), _ptr(fail), _stream()))
         nfail = int(fail.item())
         if nfail:
             raise ValueError("%d (point, direction) pairs are not enclosed by any simplex cone; "
                              "the stencil does not resolve the requested angular resolution"
                              % nfail)
-        h = vp()
-        check(self.lib.pde_ell_create(C.byref(h), dev.index, self.N, self.n_points, self.nds,
-                                      _ptr(self.idx), _ptr(self.w)))
-        self.h = h
+        self.h = None
+        if self.row_offset == 0:
+            h = vp()
+            check(self.lib.pde_ell_create(C.byref(h), dev.index, self.N, self.n_points, self.nds,
+                                          _ptr(self.idx), _ptr(self.w)))
+            self.h = h
 
     def __del__(self):
         try:
@@ -179,6 +188,47 @@ def d2(G, v, u, jacobian, froese):
     if u is not None:
         d2u = like_input(u, table.apply(k, to_device(u, table.device)))
     return d2u, (M if jacobian else None)
+
+
+def d1(G, v, u, jacobian, domain="interior"):
+    """ddi.d1 (ddi.py:12-92): first derivative along ``v`` by linear interpolation inside
+    the first simplex (row order) whose cone contains ``v``; on the boundary domain only
+    simplices made of interior points qualify (ddi.py:66-68).  Returns ``(d1u, M)``."""
+    from ._nbops import RowsMatrix
+    if u is None:
+        jacobian = True
+    if G.dim != 2:
+        raise NotImplementedError("only 2-D point clouds are implemented")
+    V = np.ascontiguousarray(_ddutils.process_v(G, v, domain=domain), dtype=np.float64)
+    table = EllTable(G, V, False, per_point=True, scheme=2 if domain == "interior" else 3)
+    M = RowsMatrix(table.idx[0], table.w[0], table.row_offset, table.n_points, table.device)
+    d1u = M.dot(u) if u is not None else None
+    return d1u, (M if jacobian else None)
+
+
+def d1grad(G, u, module_name, nds, jacobian=False, control=False, cache_fdmatrices=True):
+    """ddi.d1grad (ddi.py:124-221): maximum over ``nds`` fixed directions of the
+    interpolated first derivative; ``np.argmax`` keeps the FIRST maximal direction, which
+    the table reproduces by storing the directions in reverse order (the min/max kernel
+    keeps the highest index on ties).  Returns ``(d1_max, M, v)``."""
+    if G.dim == 3:
+        raise NotImplementedError("Gradient not yet implemented in 3d.")        # ddi.py:157-158
+    V = directions(nds)
+    cache = getattr(G, "_d1cache", None)
+    if cache is not None and cache[0] == module_name and isinstance(cache[2], EllTable):
+        table = cache[2]
+    else:
+        table = EllTable(G, V[::-1], False, scheme=2)
+        if cache_fdmatrices:
+            G._d1cache = (module_name, V, table)
+    U = to_device(u, table.device)
+    _, d1max, _, krev = table.d2eigs(U, want_k=jacobian or control)
+    M = EllMatrix(table, krev) if jacobian else None
+    vout = None
+    if control:
+        Vd = torch.from_numpy(V).to(table.device)
+        vout = like_input(u, Vd[(nds - 1 - krev).long()])
+    return like_input(u, d1max), M, vout
 
 
 # ---------------------------------------------------------------------------------------------

@@ -67,8 +67,10 @@ SIGNATURES = {
     "pde_ell_destroy": (c_int, [vp]),
     "pde_ell_d2eigs": (c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "pde_ell_apply_policy": (c_int, [vp, vp, vp, vp, vp]),
-    "pde_ell_build": (c_int, [c_int, c_i64, vp, vp, vp, c_int, vp, c_int, c_dbl, c_int,
-                              vp, vp, vp, vp]),
+    "pde_ell_build": (c_int, [c_int, c_i64, vp, vp, vp, c_int, vp, c_int, c_dbl, c_int, c_i64,
+                              c_i64, vp, vp, vp, vp]),
+    "pde_nb_d1": (c_int, [c_int, c_i64, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "pde_rows_apply": (c_int, [c_int, c_i64, c_i64, vp, vp, vp, vp, vp]),
     "pde_ell_residual": (c_int, [vp, vp, vp, c_int, c_dbl, c_dbl, vp, vp, vp, vp, vp]),
     "pde_ell_jac_matvec": (c_int, [vp, C.POINTER(pde_ell_jac), vp, vp, vp]),
     "pde_ell_jac_diagonal": (c_int, [vp, C.POINTER(pde_ell_jac), vp, vp]),
@@ -77,7 +79,8 @@ SIGNATURES = {
     "pde_ell_newton_update": (c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "pde_fp64_peak": (c_int, [c_int, C.POINTER(c_dbl)]),
     "pde_band_build": (c_int, [c_i64, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, vp,
-                               c_i64, vp, c_dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(c_dbl)]),
+                               c_i64, vp, c_dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(c_dbl),
+                               C.POINTER(vp), C.POINTER(vp)]),
     "pde_free": (None, [vp]),
     "pde_cloud_build": (c_int, [c_int, c_i64, c_i64, vp, vp, vp, c_int, c_dbl, c_dbl, c_dbl, c_int,
                                 c_int, vp, vp, vp, vp, vp]),

@@ -37,7 +37,7 @@ void pde_free(void *p) { free(p); }
 int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double bx, double by,
                    int64_t nb, const double *wall /* nb x 2 unscaled */, int64_t n_band,
                    const int64_t *band_ids, double tol, int64_t **out_ptr, int64_t **out_pairs,
-                   double *out_min_nb_dist) {
+                   double *out_min_nb_dist, int64_t **out_nb_ptr, int64_t **out_nb) {
     PDE_REQUIRE(out_ptr && out_pairs && out_min_nb_dist && (n_band == 0 || band_ids), "null argument");
     const int64_t N = nx * ny;
     // four wall lists, as in the Python reference implementation
@@ -65,6 +65,8 @@ int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double b
     }
 
     std::vector<std::vector<int64_t>> rows(n_band);   // per point: flattened (J0, J1)
+    const bool want_nb = out_nb_ptr && out_nb;
+    std::vector<std::vector<int64_t>> nbs(want_nb ? n_band : 0);   // per point: kept neighbours
     std::vector<double> min_nb(n_band, INFINITY);
     int64_t bad_point = -1;
 
@@ -133,6 +135,9 @@ int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double b
                 if (keep[k]) mnb = std::min(mnb, D[k]);
             }
             min_nb[p] = mnb;
+            if (want_nb)
+                for (int k = 0; k < K; ++k)
+                    if (keep[k]) nbs[p].push_back(ID[k]);
             std::vector<int64_t> &out = rows[p];
             for (int k = 0; k < K; ++k) {
                 if (!keep[k]) continue;
@@ -175,6 +180,16 @@ int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double b
             pairs[3 * (o + k) + 1] = rows[p][2 * k];
             pairs[3 * (o + k) + 2] = rows[p][2 * k + 1];
         }
+    }
+    if (want_nb) {
+        int64_t *nptr = (int64_t *)malloc(sizeof(int64_t) * (n_band + 1));
+        nptr[0] = 0;
+        for (int64_t p = 0; p < n_band; ++p) nptr[p + 1] = nptr[p] + (int64_t)nbs[p].size();
+        int64_t *nb_out = (int64_t *)malloc(sizeof(int64_t) * (nptr[n_band] > 0 ? nptr[n_band] : 1));
+        for (int64_t p = 0; p < n_band; ++p)
+            std::copy(nbs[p].begin(), nbs[p].end(), nb_out + nptr[p]);
+        *out_nb_ptr = nptr;
+        *out_nb = nb_out;
     }
     double m = INFINITY;
     for (int64_t p = 0; p < n_band; ++p) m = std::min(m, min_nb[p]);

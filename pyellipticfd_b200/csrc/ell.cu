@@ -104,20 +104,26 @@ __device__ __forceinline__ void solve2(double a, double b, double c, double d, d
 __global__ void __launch_bounds__(128)
 k_ell_build(int64_t n, int nds, const double *__restrict__ P, const int64_t *__restrict__ simp,
             const int64_t *__restrict__ sptr, const double *__restrict__ V, int v_per_point,
-            double eps_h, int froese, int32_t *__restrict__ idx, double *__restrict__ w,
-            int32_t *__restrict__ fail) {
+            double eps_h, int scheme, int64_t row_offset, int64_t n_interior_pts,
+            int32_t *__restrict__ idx, double *__restrict__ w, int32_t *__restrict__ fail) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int k = blockIdx.y;
     if (i >= n) return;
+    const bool froese = scheme == 1;
+    const bool first = scheme >= 2;          // first derivative: forward simplex only
     const double vx = v_per_point ? V[2 * i] : V[2 * k];
     const double vy = v_per_point ? V[2 * i + 1] : V[2 * k + 1];
-    const double px = P[2 * i], py = P[2 * i + 1];
+    const int64_t ctr = i + row_offset;      // centre point of this row
+    const double px = P[2 * ctr], py = P[2 * ctr + 1];
     bool have_f = false, have_b = false;
     int64_t f1 = 0, f2 = 0, b1 = 0, b2 = 0;
     double xf1 = 0, xf2 = 0, xb1 = 0, xb2 = 0;
     const double lo = froese ? 0.0 : -eps_h, hi = froese ? 0.0 : eps_h;
+    if (first) have_b = true;
     for (int64_t s = sptr[i]; s < sptr[i + 1] && !(have_f && have_b); ++s) {
         int64_t s1 = simp[3 * s + 1], s2 = simp[3 * s + 2];
+        // boundary domain of ddi.d1 (ddi.py:66-68): only simplices made of interior points
+        if (scheme == 3 && (s1 >= n_interior_pts || s2 >= n_interior_pts)) continue;
         double a = P[2 * s1] - px, c = P[2 * s1 + 1] - py;       // first simplex vector
         double b = P[2 * s2] - px, d = P[2 * s2 + 1] - py;       // second
         double x0, x1;
@@ -132,8 +138,15 @@ k_ell_build(int64_t n, int nds, const double *__restrict__ P, const int64_t *__r
     int64_t o = ((int64_t)k * n + i) * 4;
     if (!(have_f && have_b)) {
         atomicAdd(fail, 1);
-        idx[o] = idx[o + 1] = idx[o + 2] = idx[o + 3] = (int32_t)i;
+        idx[o] = idx[o + 1] = idx[o + 2] = idx[o + 3] = (int32_t)ctr;
         w[o] = w[o + 1] = w[o + 2] = w[o + 3] = 0.0;
+        return;
+    }
+    if (first) {
+        // ddi.py:72-80: d1u = xi_1 (u[S1]-u_i) + xi_2 (u[S2]-u_i); the row is padded to the
+        // 4-wide table format with two zero-weight references to the centre point
+        idx[o] = (int32_t)f1; idx[o + 1] = (int32_t)f2; idx[o + 2] = idx[o + 3] = (int32_t)ctr;
+        w[o] = xf1; w[o + 1] = xf2; w[o + 2] = w[o + 3] = 0.0;
         return;
     }
     if (!froese) {
@@ -245,17 +258,19 @@ int pde_ell_apply_policy(pde_ell *e, const int32_t *d_k, const double *d_x, doub
 
 int pde_ell_build(int device, int64_t n_interior, const double *d_points,
                   const int64_t *d_simplices, const int64_t *d_simp_ptr, int nds,
-                  const double *d_V, int v_per_point, double eps_over_h, int froese,
+                  const double *d_V, int v_per_point, double eps_over_h, int scheme,
+                  int64_t row_offset, int64_t n_interior_pts,
                   int32_t *d_idx, double *d_w, int32_t *d_fail, void *stream) {
     PDE_REQUIRE(d_points && d_simplices && d_simp_ptr && d_V && d_idx && d_w && d_fail,
                 "null argument");
     PDE_REQUIRE(nds > 0 && nds < 65536, "bad direction count");
     PDE_REQUIRE(!v_per_point || nds == 1, "per-point directions need nds == 1");
+    PDE_REQUIRE(scheme >= 0 && scheme <= 3, "unknown scheme");
     DeviceGuard guard(device);
     dim3 grid((unsigned)((n_interior + 127) / 128), (unsigned)nds);
     k_ell_build<<<grid, 128, 0, (cudaStream_t)stream>>>(n_interior, nds, d_points, d_simplices,
-                                                        d_simp_ptr, d_V, v_per_point, eps_over_h, froese,
-                                                        d_idx, d_w, d_fail);
+                                                        d_simp_ptr, d_V, v_per_point, eps_over_h, scheme,
+                                                        row_offset, n_interior_pts, d_idx, d_w, d_fail);
     PDE_LAUNCH_CHECK();
     return 0;
 }

@@ -7,8 +7,8 @@ device); results come back in the container type of ``u``.  The Jacobians are
 :class:`~pyellipticfd_b200.linop.PolicyMatrix` objects (``.dot``,
 ``.transpose()``, ``.tocsr()``) instead of SciPy CSR matrices.
 
-The first-derivative functions ``d1`` / ``d1n`` / ``d1grad`` (ddg.py:8-175) are
-not on the hot path and are not provided.
+The first-derivative functions ``d1`` / ``d1n`` / ``d1grad`` (ddg.py:8-175) work on the
+grid's neighbour list (``_nbops``).
 """
 import numpy as np
 import torch
@@ -16,6 +16,7 @@ import torch
 from . import _ddutils
 from ._context import GridContext, like_input, to_device
 from .linop import PolicyMatrix
+from ._nbops import d1, d1n, d1grad          # noqa: F401  (ddg.py:8-175)
 
 # 0 = reference operation order (bit-exact values and selection); 1 = re-associated fast mode
 ARITHMETIC_MODE = 0

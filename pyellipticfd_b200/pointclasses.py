@@ -303,15 +303,16 @@ class FDTriMesh(FDPointCloud):
         self._min_nb = float(torch.sqrt((Vv * Vv).sum(1)).min()) if J.numel() else np.inf
         self.stencil_device = dev
 
-    def _flat(self, which, interior_only=False, device=None):
-        """(I, J[, J_next]) flat tensors of the neighbour rows / hull edges."""
+    def _flat(self, which, lo=0, hi=None):
+        """(I, J[, J_next]) flat tensors of the neighbour rows / hull edges of the centre
+        points [lo, hi)."""
         import torch
-        n = self.num_interior if interior_only else self.num_points
-        count, tab = self._count[:n], (self._nb if which == "nb" else self._ring)[:n]
+        hi = self.num_points if hi is None else hi
+        count, tab = self._count[lo:hi], (self._nb if which == "nb" else self._ring)[lo:hi]
         dev = count.device
         k = torch.arange(self._kmax, device=dev)[None, :]
         mask = k < count[:, None]
-        I = torch.repeat_interleave(torch.arange(n, device=dev), count.long())
+        I = torch.repeat_interleave(torch.arange(lo, hi, device=dev), count.long())
         J = tab[mask].long()
         if which == "nb":
             return I, J
@@ -319,14 +320,16 @@ class FDTriMesh(FDPointCloud):
         Jn = torch.gather(tab, 1, nxt.long())[mask].long()
         return I, J, Jn
 
-    def device_simplices(self, device):
-        """Interior simplices (S, 3) int64 grouped by centre point and their CSR pointer,
-        as tensors on ``device`` (what ``pde_ell_build`` consumes)."""
+    def device_simplices(self, device, lo=0, hi=None):
+        """Simplices (S, 3) int64 of the centre points [lo, hi) (default: the interior
+        points) grouped by centre and their CSR pointer, as tensors on ``device`` (what
+        ``pde_ell_build`` consumes)."""
         import torch
-        I, J, Jn = self._flat("ring", interior_only=True)
+        hi = self.num_interior if hi is None else hi
+        I, J, Jn = self._flat("ring", lo, hi)
         S = torch.stack([I, J, Jn], 1).to(device)
-        ptr = torch.zeros(self.num_interior + 1, dtype=torch.int64, device=self._count.device)
-        ptr[1:] = torch.cumsum(self._count[:self.num_interior].long(), 0)
+        ptr = torch.zeros(hi - lo + 1, dtype=torch.int64, device=self._count.device)
+        ptr[1:] = torch.cumsum(self._count[lo:hi].long(), 0)
         return S.contiguous(), ptr.to(device)
 
     @property
@@ -498,10 +501,11 @@ class FDRegularGrid(FDPointCloud):
         W = np.ascontiguousarray(self._wall_unscaled, dtype=np.float64)
         ids = np.ascontiguousarray(self.band_index, dtype=np.int64)
         ptr, pairs, mn = C.c_void_p(), C.c_void_p(), C.c_double()
+        nptr, nbl = C.c_void_p(), C.c_void_p()
         rc = fn(nx, ny, self.stencil_radius, float(self.scaling[0]), float(self.scaling[1]),
                 float(self.bounds[0][0]), float(self.bounds[0][1]), W.shape[0],
                 C.c_void_p(W.ctypes.data), ids.size, C.c_void_p(ids.ctypes.data), COLINEAR_TOL,
-                C.byref(ptr), C.byref(pairs), C.byref(mn))
+                C.byref(ptr), C.byref(pairs), C.byref(mn), C.byref(nptr), C.byref(nbl))
         if rc == 2:
             raise TypeError(L.pde_last_error().decode())          # "Point i has no pairs"
         _lib.check(rc)
@@ -512,9 +516,16 @@ class FDRegularGrid(FDPointCloud):
             P = int(self.band_ptr[-1])
             self.band_pairs = np.ctypeslib.as_array(
                 C.cast(pairs, C.POINTER(C.c_int64)), shape=(max(P, 1) * 3,)).copy()[:3 * P].reshape(P, 3)
+            self.band_nb_ptr = np.ctypeslib.as_array(
+                C.cast(nptr, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+            T = int(self.band_nb_ptr[-1])
+            self.band_nb = np.ctypeslib.as_array(
+                C.cast(nbl, C.POINTER(C.c_int64)), shape=(max(T, 1),)).copy()[:T]
         finally:
             L.pde_free(ptr)
             L.pde_free(pairs)
+            L.pde_free(nptr)
+            L.pde_free(nbl)
         min_nb = mn.value
         if self.num_interior - n > 0:
             offs_k = self.stencil_offsets * self.scaling
@@ -612,6 +623,7 @@ class FDRegularGrid(FDPointCloud):
             lists.append((axis, val, ids[o], t[o]))
 
         rows_I, rows_J0, rows_J1 = [], [], []
+        nb_I, nb_J = [], []
         min_nb = np.inf
         sx, sy = self.scaling
         b0 = self.bounds[0]
@@ -668,6 +680,9 @@ class FDRegularGrid(FDPointCloud):
             keep, pair = _prune_and_pair(V, OK, isb)
             Dk = np.sqrt(VX * VX + VY * VY)
             min_nb = min(min_nb, np.where(keep, Dk, np.inf).min())
+            kb, kk = np.nonzero(keep)
+            nb_I.append(self.band_index[s + kb])
+            nb_J.append(ID[kb, kk])
             b, k, l = np.nonzero(pair)
             rows_I.append(self.band_index[s + b])
             rows_J0.append(ID[b, k])
@@ -685,6 +700,10 @@ class FDRegularGrid(FDPointCloud):
         counts = np.bincount(np.searchsorted(self.band_index, self.band_pairs[:, 0]),
                              minlength=nb)
         self.band_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        nbI = np.concatenate(nb_I) if nb else np.zeros(0, np.int64)
+        self.band_nb = (np.concatenate(nb_J) if nb else np.zeros(0, np.int64)).astype(np.int64)
+        ncnt = np.bincount(np.searchsorted(self.band_index, nbI), minlength=nb)
+        self.band_nb_ptr = np.concatenate([[0], np.cumsum(ncnt)]).astype(np.int64)
         n_deep = N - nb
         if n_deep > 0:
             offs_k = self.stencil_offsets * self.scaling
@@ -715,6 +734,34 @@ class FDRegularGrid(FDPointCloud):
     @property
     def bdry_points(self):
         return self._wall_unscaled * self.scaling + self.bounds[0]
+
+    @property
+    def neighbours(self):
+        """(T, 2) rows ``(I, J)`` of the pruned stencil neighbours of the INTERIOR points,
+        grouped by ascending I (pointclasses.py:576-578; the reference also lists the
+        neighbours of the wall points, which only ``d1n`` reads -- not built here).
+        Materialised on demand."""
+        if getattr(self, "_neighbours", None) is None and hasattr(self, "band_nb"):
+            nx, ny = self.interior_shape
+            K = self.stencil_offsets.shape[0]
+            if self.num_deep * K + self.band_nb.size > 2 ** 28:
+                raise MemoryError("refusing to materialise %d neighbour rows"
+                                  % (self.num_deep * K + self.band_nb.size))
+            isband = np.zeros(self.num_interior, bool)
+            isband[self.band_index] = True
+            deep = np.flatnonzero(~isband)
+            di, dj = deep // ny, deep % ny
+            so = self.stencil_offsets
+            J = (di[:, None] + so[None, :, 0]) * ny + dj[:, None] + so[None, :, 1]
+            rows = np.concatenate([
+                np.stack([np.repeat(deep, K), J.ravel()], 1),
+                np.stack([np.repeat(self.band_index, np.diff(self.band_nb_ptr)), self.band_nb], 1)])
+            self._neighbours = rows[np.argsort(rows[:, 0], kind="stable")]
+        return getattr(self, "_neighbours", None)
+
+    @neighbours.setter
+    def neighbours(self, value):
+        self._neighbours = value
 
     @property
     def num_deep(self):
