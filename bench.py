@@ -542,9 +542,24 @@ def main():
                 "kernel_fp64_instr_per_s": n_local * instr_per_point / (ms_kernel * 1e-3),
                 "note": "mode-0 d2min issues 7 fp64-pipe instructions per pair (2 DADD, 2 DMUL, "
                         "DADD, DMUL, DSETP), one less per couple of equal-length pairs; "
-                        "frac_of_fp64_pipe = kernel rate / measured DFMA-chain rate",
+                        "frac_of_fp64_pipe = kernel rate / measured DFMA-chain rate (counts a "
+                        "DSETP like a DADD although it costs 3-4x the pipe time: see probe)",
                 }
         fp64["frac_of_fp64_pipe"] = fp64["kernel_fp64_instr_per_s"] / v.value
+        try:
+            probe = {}
+            for kind, name in ((1, "dadd_per_s"), (2, "dmul_per_s"), (3, "cmpsel_per_s"),
+                               (4, "exact_pairs_per_s")):
+                _lib.check(_lib.lib().pde_fp64_probe(local, kind, ctypes.byref(v)))
+                probe[name] = v.value
+            fp64["probe"] = probe
+            fp64["kernel_pairs_per_s"] = n_local * D / (ms_kernel * 1e-3)
+            fp64["frac_of_exact_formula_peak"] = fp64["kernel_pairs_per_s"] / probe["exact_pairs_per_s"]
+            fp64["probe_note"] = ("register-only probes with K1's blocking; exact_pairs_per_s = the "
+                                  "reference's 7-instruction pair formula + min update without any "
+                                  "memory traffic = arithmetic speed of light of mode 0")
+        except Exception as e:
+            fp64["probe"] = {"error": str(e)[:200]}
         extra = secondary_kernels(args, ctx, S, lmin, n_local, D, pk, dev)
         if args.solve:
             import warnings

@@ -93,7 +93,9 @@ int pde_grid_unpack(pde_grid *g, const double *d_state, double *d_u_flat, void *
  * flat vector, pinned for asynchronous copies) and the state layout, for owned rows
  * [row_lo, row_hi) only; with_wall also copies the nb wall values.  Together with
  * pde_grid_set_row_window this pipelines H2D / stencil / D2H over row chunks (the
- * state buffer's padding columns must already be zero). */
+ * state buffer's padding columns must already be zero).  The "host" pointer may also be a
+ * DEVICE pointer (unified addressing): the copy is then a device-side 2-D copy, which lets
+ * the PCIe transfer itself be a plain linear copy into a flat staging buffer. */
 int pde_grid_h2d_rows(pde_grid *g, const double *h_flat, double *d_state,
                       int64_t row_lo, int64_t row_hi, int with_wall, void *stream);
 int pde_grid_d2h_rows(pde_grid *g, const double *d_state, double *h_flat_interior,
@@ -224,6 +226,11 @@ int pde_vec_newton_update(pde_grid *g, const double *d_U, const double *d_d,
 int pde_ell_create(pde_ell **out, int device, int64_t n_interior, int64_t n_points,
                    int nds, const int32_t *d_idx, const double *d_w);
 int pde_ell_destroy(pde_ell *e);
+/* Point-range shard (multi-GPU): the table holds the rows of the interior points
+ * [row_offset, row_offset + n_interior) only; pde_ell_d2eigs / pde_ell_apply_policy then read
+ * the centre value u[i + row_offset] and write outputs at the local row i.  The problem /
+ * Krylov entry points below need the full table (row_offset 0). */
+int pde_ell_set_row_offset(pde_ell *e, int64_t row_offset);
 /* d2u[i,k] = sum_j w[k,i,j]*(u[idx[k,i,j]] - u[i]); min/max over k (ddi.py:358-367).
  * Ties: lowest k for the minimum, highest k for the maximum (np.argsort's tie
  * order is unspecified in the reference, ddi.py:363). Outputs may be NULL. */
@@ -343,6 +350,12 @@ int pde_cloud_build(int device, int64_t n_points, int64_t n_interior, const doub
  * *h_dfma_per_s (synchronous).  Used by bench.py to evidence which roof
  * (HBM or the fp64 pipe) binds the stencil kernel. */
 int pde_fp64_peak(int device, double *h_dfma_per_s);
+/* Arithmetic-only probes with K1's register blocking (8 independent rows per thread, 2 CTAs of
+ * 256 threads per SM): kind 1 DADD, 2 DMUL, 3 compare-select (DSETP + 2 FSEL) -- units/s = thread
+ * instructions per second; kind 4 = the exact pair formula of ddg.py:281 plus the min update on
+ * register operands (units/s = pairs per second): the speed of light of the reference's
+ * operation order, which K1 is compared against in bench.py. */
+int pde_fp64_probe(int device, int kind, double *h_units_per_s);
 
 #ifdef __cplusplus
 }

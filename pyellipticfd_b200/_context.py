@@ -18,6 +18,7 @@ from . import _lib
 from ._lib import pde_jac, check, vp
 
 POLICY_IDENTITY = 0xFFFF
+HOST_COPY_LINEAR = False      # see GridContext.d2eigs_host
 
 
 def _ptr(t):
@@ -290,16 +291,24 @@ class GridContext(object):
                                       _ptr(pmax), int(mode), _stream()))
         return lmin, lmax, pmin, pmax
 
-    def d2eigs_host(self, u_host, want_min=True, want_max=True, mode=0, chunk_rows=256):
+    def d2eigs_host(self, u_host, want_min=True, want_max=True, mode=0, chunk_rows=256,
+                    linear=None):
         """ddg.d2eigs values for a field in PINNED host memory, results in pinned host
         memory: the H2D copy, the stencil kernels and the D2H copy are pipelined over
-        chunks of rows on three streams (PCIe is full duplex), and the layout conversion
-        is done by the 2-D DMA copies themselves (no pack / unpack kernels)."""
+        chunks of rows on three streams (PCIe is full duplex).  ``linear=False``: the layout
+        conversion is done by the 2-D DMA copies themselves; ``linear=True``: the PCIe copies
+        are plain linear copies to / from flat device staging buffers and the conversion is
+        a device-side 2-D copy (default: ``HOST_COPY_LINEAR``)."""
+        linear = HOST_COPY_LINEAR if linear is None else linear
         nloc, ny, H = self.nx_local, self.ny, max(self.radius, 1)
         if not hasattr(self, "_stage"):
             self._stage = (self.zeros(), self.zeros(), self.zeros(),
                            torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
         S, Lmin, Lmax, s_in, s_out = self._stage
+        if linear and not hasattr(self, "_stage_flat"):
+            self._stage_flat = (torch.empty(self.n_flat(), dtype=torch.float64, device=self.device),
+                                torch.empty(nloc * ny, dtype=torch.float64, device=self.device),
+                                torch.empty(nloc * ny, dtype=torch.float64, device=self.device))
         main = torch.cuda.current_stream()
         out_min = torch.empty(nloc * ny, dtype=torch.float64, pin_memory=True) if want_min else None
         out_max = torch.empty(nloc * ny, dtype=torch.float64, pin_memory=True) if want_max else None
@@ -310,24 +319,37 @@ class GridContext(object):
         s_out.wait_stream(main)
         with torch.cuda.stream(s_in):
             for k in range(nchunk):
-                check(self.lib.pde_grid_h2d_rows(self.h, vp(u_host.data_ptr()), _ptr(S), edges[k],
-                                                 edges[k + 1], int(k == 0), _stream()))
+                lo, hi = edges[k], edges[k + 1]
+                src = u_host
+                if linear:
+                    fin = self._stage_flat[0]
+                    fin[lo * ny:hi * ny].copy_(u_host[lo * ny:hi * ny], non_blocking=True)
+                    if k == 0 and self.nb:
+                        fin[nloc * ny:].copy_(u_host[nloc * ny:], non_blocking=True)
+                    src = fin
+                check(self.lib.pde_grid_h2d_rows(self.h, vp(src.data_ptr()), _ptr(S), lo, hi,
+                                                 int(k == 0), _stream()))
                 ev_in[k].record()
         outs = (Lmin if want_min else None, Lmax if want_max else None, None, None)
         try:
             for k in range(nchunk):
+                lo, hi = edges[k], edges[k + 1]
                 # rows of chunk k read up to H rows of chunk k+1
                 main.wait_event(ev_in[min(k + 1, nchunk - 1)])
-                self.set_row_window(edges[k], edges[k + 1])
+                self.set_row_window(lo, hi)
                 self.d2eigs(S, want_min=want_min, want_max=want_max, mode=mode, out=outs)
                 ev = torch.cuda.Event()
                 ev.record(main)
                 s_out.wait_event(ev)
                 with torch.cuda.stream(s_out):
-                    for L, o in ((Lmin, out_min), (Lmax, out_max)):
-                        if o is not None:
-                            check(self.lib.pde_grid_d2h_rows(self.h, _ptr(L), vp(o.data_ptr()),
-                                                             edges[k], edges[k + 1], _stream()))
+                    for q, (L, o) in enumerate(((Lmin, out_min), (Lmax, out_max))):
+                        if o is None:
+                            continue
+                        dst = self._stage_flat[1 + q] if linear else o
+                        check(self.lib.pde_grid_d2h_rows(self.h, _ptr(L), vp(dst.data_ptr()),
+                                                         lo, hi, _stream()))
+                        if linear:
+                            o[lo * ny:hi * ny].copy_(dst[lo * ny:hi * ny], non_blocking=True)
         finally:
             self.set_row_window()
         main.wait_stream(s_out)

@@ -38,7 +38,7 @@ class EllTable(object):
     1 Froese, 2 ddi first derivative (interior rows), 3 ddi first derivative on the
     boundary rows (``pde_ell_build``)."""
 
-    def __init__(self, G, V, froese, device=None, per_point=False, scheme=None):
+    def __init__(self, G, V, froese, device=None, per_point=False, scheme=None, rows=None):
         self.lib = _lib.lib()
         self.device = require_cuda(device)
         self.G = G
@@ -47,6 +47,8 @@ class EllTable(object):
         n_int = int(G.num_interior)
         self.row_offset = n_int if self.scheme == 3 else 0
         self.N = self.n_points - n_int if self.scheme == 3 else n_int
+        if rows is not None:                       # point-range shard [lo, hi) of the interior
+            self.row_offset, self.N = int(rows[0]), int(rows[1] - rows[0])
         self.V = np.ascontiguousarray(V, dtype=np.float64)
         self.nds = 1 if per_point else self.V.shape[0]
         dev = self.device
@@ -72,10 +74,12 @@ class EllTable(object):
                              "the stencil does not resolve the requested angular resolution"
                              % nfail)
         self.h = None
-        if self.row_offset == 0:
+        if self.scheme != 3:
             h = vp()
             check(self.lib.pde_ell_create(C.byref(h), dev.index, self.N, self.n_points, self.nds,
                                           _ptr(self.idx), _ptr(self.w)))
+            if self.row_offset:
+                check(self.lib.pde_ell_set_row_offset(h, self.row_offset))
             self.h = h
 
     def __del__(self):

@@ -65,6 +65,7 @@ SIGNATURES = {
     "pde_vec_newton_update": (c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "pde_ell_create": (c_int, [C.POINTER(vp), c_int, c_i64, c_i64, c_int, vp, vp]),
     "pde_ell_destroy": (c_int, [vp]),
+    "pde_ell_set_row_offset": (c_int, [vp, c_i64]),
     "pde_ell_d2eigs": (c_int, [vp, vp, vp, vp, vp, vp, vp]),
     "pde_ell_apply_policy": (c_int, [vp, vp, vp, vp, vp]),
     "pde_ell_build": (c_int, [c_int, c_i64, vp, vp, vp, c_int, vp, c_int, c_dbl, c_int, c_i64,
@@ -78,6 +79,7 @@ SIGNATURES = {
                                  vp, vp, vp]),
     "pde_ell_newton_update": (c_int, [vp, vp, vp, vp, vp, vp, vp, vp]),
     "pde_fp64_peak": (c_int, [c_int, C.POINTER(c_dbl)]),
+    "pde_fp64_probe": (c_int, [c_int, c_int, C.POINTER(c_dbl)]),
     "pde_band_build": (c_int, [c_i64, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, vp,
                                c_i64, vp, c_dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(c_dbl),
                                C.POINTER(vp), C.POINTER(vp)]),

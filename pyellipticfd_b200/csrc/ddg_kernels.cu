@@ -140,7 +140,7 @@ static int make_tmap(const pde_grid *g, const double *S, int boxy, int boxx, CUt
     return 0;
 }
 
-template <class Eval, int H, int P, int MODE, class Epi, int MINB = 2>
+template <class Eval, int H, int P, int MODE, class Epi, int MINB = 2, int ICMP = 0>
 static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *red,
                           const unsigned long long *done, cudaStream_t st) {
     DeepRegion dr = deep_region(g);
@@ -158,7 +158,7 @@ static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *
     int rc = make_tmap(g, S, K1_TY + 2 * H + 2, TX + 2 * H, &tmap);
     if (rc) return rc;
     constexpr int smem = k_deep_smem_bytes<H, P>();
-    auto kern = k_deep<Eval, H, P, MODE, Epi, MINB>;
+    auto kern = k_deep<Eval, H, P, MODE, Epi, MINB, ICMP>;
     static bool attr_set = false;   // per template instantiation
     if (!attr_set) {
         PDE_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -188,6 +188,14 @@ static int launch_deep(pde_grid *g, const double *S, const Epi &epi, double *red
             return launch_deep_hp<EvalCt<3>, 4, 16, MODE, Epi, 1>(g, S, epi, red, done, st);
         if (g->ct_id == 3 && variant == 5)
             return launch_deep_hp<EvalCt<3>, 4, 6, MODE, Epi, 3>(g, S, epi, red, done, st);
+        if (g->ct_id == 3 && variant == 6)       // integer compare-select: all pairs
+            return launch_deep_hp<EvalCt<3>, 4, 8, MODE, Epi, 2, 4>(g, S, epi, red, done, st);
+        if (g->ct_id == 3 && variant == 7)       // 3 of 4 pairs
+            return launch_deep_hp<EvalCt<3>, 4, 8, MODE, Epi, 2, 3>(g, S, epi, red, done, st);
+        if (g->ct_id == 3 && variant == 8)       // 2 of 4 pairs
+            return launch_deep_hp<EvalCt<3>, 4, 8, MODE, Epi, 2, 2>(g, S, epi, red, done, st);
+        if (g->ct_id == 3 && variant == 9)       // all pairs, 3 CTAs / SM of P = 4
+            return launch_deep_hp<EvalCt<3>, 4, 4, MODE, Epi, 3, 4>(g, S, epi, red, done, st);
     }
     // compile-time table (square cells): fully unrolled evaluator with register windows
     switch (g->ct_id) {

@@ -15,6 +15,7 @@ struct pde_ell {
     int nds;
     const int32_t *idx;   // (nds, n_interior, 4), caller-owned device memory
     const double *w;      // (nds, n_interior, 4)
+    int64_t row_offset;   // centre point of table row i is point i + row_offset (point-range shards)
     int num_sms;
 };
 
@@ -26,12 +27,12 @@ namespace pde {
 // ascending sort would give for arg[:,0] / arg[:,-1]; np.argsort's order is unspecified).
 template <int UNROLL>
 __global__ void __launch_bounds__(256)
-k_ell_d2eigs(int64_t n, int nds, const int4 *__restrict__ idx, const double2 *__restrict__ w,
-             const double *__restrict__ u, double *__restrict__ lmin, double *__restrict__ lmax,
-             int32_t *__restrict__ kmin, int32_t *__restrict__ kmax) {
+k_ell_d2eigs(int64_t n, int64_t off, int nds, const int4 *__restrict__ idx,
+             const double2 *__restrict__ w, const double *__restrict__ u, double *__restrict__ lmin,
+             double *__restrict__ lmax, int32_t *__restrict__ kmin, int32_t *__restrict__ kmax) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const double ui = u[i];
+    const double ui = u[i + off];
     double mn = __longlong_as_double(0x7ff0000000000000LL);
     double mx = __longlong_as_double(0xfff0000000000000LL);
     int an = 0, ax = 0;
@@ -69,16 +70,16 @@ k_ell_d2eigs(int64_t n, int nds, const int4 *__restrict__ idx, const double2 *__
     if (kmax) kmax[i] = ax;
 }
 
-__global__ void k_ell_apply(int64_t n, const int4 *__restrict__ idx, const double2 *__restrict__ w,
-                            const int32_t *__restrict__ ksel, const double *__restrict__ x,
-                            double *__restrict__ y) {
+__global__ void k_ell_apply(int64_t n, int64_t off, const int4 *__restrict__ idx,
+                            const double2 *__restrict__ w, const int32_t *__restrict__ ksel,
+                            const double *__restrict__ x, double *__restrict__ y) {
     int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (i >= n) return;
     int k = ksel[i];
     const int64_t e = (int64_t)k * n + i;
     int4 id = idx[e];
     double2 wa = w[2 * e], wb = w[2 * e + 1];
-    double xi = x[i];
+    double xi = x[i + off];
     y[i] = wa.x * (x[id.x] - xi) + wa.y * (x[id.y] - xi) + wb.x * (x[id.z] - xi) +
            wb.y * (x[id.w] - xi);
 }
@@ -221,8 +222,15 @@ int pde_ell_create(pde_ell **out, int device, int64_t n_interior, int64_t n_poin
     e->nds = nds;
     e->idx = d_idx;
     e->w = d_w;
+    e->row_offset = 0;
     e->num_sms = prop.multiProcessorCount;
     *out = e;
+    return 0;
+}
+
+int pde_ell_set_row_offset(pde_ell *e, int64_t row_offset) {
+    PDE_REQUIRE(e && row_offset >= 0 && row_offset + e->n_interior <= e->n_points, "bad row offset");
+    e->row_offset = row_offset;
     return 0;
 }
 
@@ -238,7 +246,7 @@ int pde_ell_d2eigs(pde_ell *e, const double *d_u, double *d_lmin, double *d_lmax
     int64_t n = e->n_interior;
     unsigned grid = (unsigned)((n + 255) / 256);
     k_ell_d2eigs<4><<<grid, 256, 0, (cudaStream_t)stream>>>(
-        n, e->nds, reinterpret_cast<const int4 *>(e->idx), reinterpret_cast<const double2 *>(e->w),
+        n, e->row_offset, e->nds, reinterpret_cast<const int4 *>(e->idx), reinterpret_cast<const double2 *>(e->w),
         d_u, d_lmin, d_lmax, d_kmin, d_kmax);
     PDE_LAUNCH_CHECK();
     return 0;
@@ -250,7 +258,7 @@ int pde_ell_apply_policy(pde_ell *e, const int32_t *d_k, const double *d_x, doub
     DeviceGuard guard(e->device);
     int64_t n = e->n_interior;
     k_ell_apply<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        n, reinterpret_cast<const int4 *>(e->idx), reinterpret_cast<const double2 *>(e->w), d_k,
+        n, e->row_offset, reinterpret_cast<const int4 *>(e->idx), reinterpret_cast<const double2 *>(e->w), d_k,
         d_x, d_y);
     PDE_LAUNCH_CHECK();
     return 0;
@@ -395,6 +403,7 @@ int pde_ell_residual(pde_ell *e, const double *d_W, const double *d_g, int mode,
                      double A1, double *d_F, int32_t *d_kmin, int32_t *d_kmax, double *d_red,
                      void *stream) {
     PDE_REQUIRE(e && d_W && d_g && d_F, "null argument");
+    PDE_REQUIRE(e->row_offset == 0, "the point-cloud problems need the full table (row_offset 0)");
     DeviceGuard guard(e->device);
     unsigned grid = (unsigned)((e->n_points + 255) / 256);
     k_ell_residual<<<grid, 256, 0, (cudaStream_t)stream>>>(
@@ -419,6 +428,7 @@ template <int MODE, int NRED>
 static int ell_rows(pde_ell *e, const pde::EllJacDev &J, const double *x, const double *aux,
                     double *y, int invert, double *partials, const pde::BicgScal *scal,
                     cudaStream_t st, int *nb) {
+    PDE_REQUIRE(e->row_offset == 0, "the point-cloud Jacobian needs the full table (row_offset 0)");
     int nblk = pde::elem_grid(e->n_points, e->num_sms);
     pde::k_ell_rows<MODE, NRED><<<nblk, pde::PASS_THREADS, 0, st>>>(
         e->n_interior, e->n_points, reinterpret_cast<const int4 *>(e->idx),

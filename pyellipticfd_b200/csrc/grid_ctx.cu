@@ -284,10 +284,10 @@ int pde_grid_h2d_rows(pde_grid *g, const double *h_flat, double *d_state, int64_
     if (row_hi > row_lo)
         PDE_CHECK(cudaMemcpy2DAsync(d_state + (g->halo_rows + row_lo) * g->pitch, g->pitch * 8,
                                     h_flat + row_lo * g->ny, g->ny * 8, g->ny * 8,
-                                    (size_t)(row_hi - row_lo), cudaMemcpyHostToDevice, st));
+                                    (size_t)(row_hi - row_lo), cudaMemcpyDefault, st));
     if (with_wall && g->nb > 0)
         PDE_CHECK(cudaMemcpyAsync(d_state + g->rows * g->pitch, h_flat + g->nx_local * g->ny,
-                                  g->nb * 8, cudaMemcpyHostToDevice, st));
+                                  g->nb * 8, cudaMemcpyDefault, st));
     return 0;
 }
 
@@ -299,7 +299,7 @@ int pde_grid_d2h_rows(pde_grid *g, const double *d_state, double *h_flat, int64_
     if (row_hi > row_lo)
         PDE_CHECK(cudaMemcpy2DAsync(h_flat + row_lo * g->ny, g->ny * 8,
                                     d_state + (g->halo_rows + row_lo) * g->pitch, g->pitch * 8,
-                                    g->ny * 8, (size_t)(row_hi - row_lo), cudaMemcpyDeviceToHost,
+                                    g->ny * 8, (size_t)(row_hi - row_lo), cudaMemcpyDefault,
                                     (cudaStream_t)stream));
     return 0;
 }

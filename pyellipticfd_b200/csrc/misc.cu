@@ -55,6 +55,44 @@ __global__ void k_dfma_chain(double *out, int iters) {
     out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
 }
 
+// Arithmetic-only probes of the fp64 pipe, 8 independent rows per thread like K1:
+//   kind 1: DADD chain        2: DMUL chain        3: compare-select (DSETP + 2 FSEL)
+//   kind 4: the exact pair formula of ddg.py:281 + the min update (7 fp64-pipe
+//           instructions per pair) on register operands perturbed by one integer op each,
+//           i.e. K1's inner loop without shared-memory traffic: the arithmetic speed of
+//           light of the reference's operation order.
+template <int KIND>
+__global__ void k_fp64_probe(double *out, int iters) {
+    double a[8], m[8];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) {
+        a[p] = 1.0 + threadIdx.x * 1e-6 + p * 1e-3;
+        m[p] = 1e300;
+    }
+    const double w = 0.70710678118654752, w0 = 1.4142135623730951, c = 1.0000001;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int p = 0; p < 8; ++p) {
+            if (KIND == 1) a[p] = __dadd_rn(a[p], c);
+            if (KIND == 2) a[p] = __dmul_rn(a[p], c);
+            if (KIND == 3) {
+                double d = __hiloint2double(__double2hiint(a[p]), __double2loint(a[p]) ^ i);
+                m[p] = d <= m[p] ? d : m[p];
+            }
+            if (KIND == 4) {
+                int hi = __double2hiint(a[p]), lo = __double2loint(a[p]);
+                double u0 = __hiloint2double(hi, lo ^ i), u1 = __hiloint2double(hi, lo + i);
+                double d = pair_value_exact(a[p], u0, u1, w, w, w0);
+                m[p] = d <= m[p] ? d : m[p];
+            }
+        }
+    }
+    double s = 0;
+#pragma unroll
+    for (int p = 0; p < 8; ++p) s += a[p] + m[p];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 }  // namespace pde
 
 extern "C" {
@@ -105,6 +143,40 @@ int pde_fp64_peak(int device, double *h_dfma_per_s) {
     cudaEventDestroy(e1);
     cudaFree(out);
     *h_dfma_per_s = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
+    return 0;
+}
+
+int pde_fp64_probe(int device, int kind, double *h_units_per_s) {
+    PDE_REQUIRE(h_units_per_s && kind >= 1 && kind <= 4, "bad argument");
+    DeviceGuard guard(device);
+    cudaDeviceProp prop;
+    PDE_CHECK(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 2, threads = 256, iters = 1 << 13;
+    double *out = nullptr;
+    PDE_CHECK(cudaMalloc((void **)&out, sizeof(double) * blocks * threads));
+    cudaEvent_t e0, e1;
+    PDE_CHECK(cudaEventCreate(&e0));
+    PDE_CHECK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        PDE_CHECK(cudaEventRecord(e0));
+        switch (kind) {
+            case 1: k_fp64_probe<1><<<blocks, threads>>>(out, iters); break;
+            case 2: k_fp64_probe<2><<<blocks, threads>>>(out, iters); break;
+            case 3: k_fp64_probe<3><<<blocks, threads>>>(out, iters); break;
+            default: k_fp64_probe<4><<<blocks, threads>>>(out, iters); break;
+        }
+        pde::count_launch();
+        PDE_CHECK(cudaEventRecord(e1));
+        PDE_CHECK(cudaEventSynchronize(e1));
+        float ms = 0;
+        PDE_CHECK(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    *h_units_per_s = (double)blocks * threads * 8.0 * iters / (best * 1e-3);
     return 0;
 }
 

@@ -152,7 +152,7 @@ struct EpiPucciResidual {   // pucci.py:48, :127-141
 // Run-time table (any grid whose weights are position independent, e.g. hx != hy): the
 // offsets come from the kernel-parameter constant bank.
 struct EvalRuntime {
-    template <int P, int TYH, int MODE, bool WMIN, bool WMAX, bool WPOL>
+    template <int P, int TYH, int MODE, bool WMIN, bool WMAX, bool WPOL, int ICMP>
     static __device__ __forceinline__ void run(const double *__restrict__ ctr, const DeepTable &tab,
                                                const double (&uc)[P], double (&mn)[P],
                                                double (&mx)[P], int (&kmn)[P], int (&kmx)[P]) {
@@ -186,7 +186,7 @@ struct EvalRuntime {
 };
 
 // ---- the kernel ------------------------------------------------------------------
-template <class Eval, int H, int P, int MODE, class Epi, int MINB = 2>
+template <class Eval, int H, int P, int MODE, class Epi, int MINB = 2, int ICMP = 0>
 __global__ void __launch_bounds__(K1_THREADS, MINB)
 k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTable tab,
        const DeepGeom geo, const Epi epi, double *red_out,
@@ -262,7 +262,7 @@ k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTab
             kmn[p] = 0;
             kmx[p] = 0;
         }
-        Eval::template run<P, TYH, MODE, Epi::kMin, Epi::kMax, Epi::kPol>(ctr, tab, uc, mn, mx, kmn, kmx);
+        Eval::template run<P, TYH, MODE, Epi::kMin, Epi::kMax, Epi::kPol, ICMP>(ctr, tab, uc, mn, mx, kmn, kmx);
         if (ly < geo.ncols) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {

@@ -288,3 +288,57 @@ class ShardedGrid(object):
             it += n
             diff, fmax = float(h[-1, 1]), float(h[-1, 0])
         return U, diff, it, fmax
+
+
+# ---------------------------------------------------------------------------------------------
+# point clouds: independent (point, direction) units, sharded by point range
+# ---------------------------------------------------------------------------------------------
+
+def gather_rows(local, sizes, group=None):
+    """All-gather of per-rank row blocks of (possibly) different lengths ``sizes`` into one
+    tensor, in rank order.  Blocks are padded to the longest one so that a single
+    ``all_gather_into_tensor`` (one NCCL kernel over NVLink; gloo on CPU tensors) does it."""
+    world = len(sizes)
+    if world == 1:
+        return local
+    m = max(sizes)
+    pad = local
+    if local.shape[0] < m:
+        pad = torch.zeros((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        pad[:local.shape[0]] = local
+    got = torch.empty((world * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(got, pad.contiguous(), group=group)
+    if all(s == m for s in sizes):
+        return got
+    return torch.cat([got[r * m:r * m + sizes[r]] for r in range(world)])
+
+
+class ShardedCloud(object):
+    """One rank's share of the ``ddi`` / ``ddf`` operator on a point cloud: the ELL table of
+    the interior points ``[lo, hi)`` only (``Nds * 48`` bytes per point stay local), the
+    function values ``u`` replicated (16 MB at 2 M points) and re-assembled after an update
+    by one all-gather of the ranks' slices."""
+
+    def __init__(self, G, rank, world, device, scheme="ddi"):
+        from . import ddi, ddf, _ell
+        mod = {"ddi": ddi, "ddf": ddf}[scheme]
+        self.G, self.rank, self.world = G, rank, world
+        self.parts = slab_partition(int(G.num_interior), world)
+        self.lo, self.hi = self.parts[rank]
+        self.sizes = [b - a for a, b in self.parts]
+        self.nds = int(mod._num_directions(G))
+        self.V = _ell.directions(self.nds)
+        self.table = _ell.EllTable(G, self.V, scheme == "ddf", device=device,
+                                   rows=(self.lo, self.hi))
+
+    def d2eigs(self, u, want_k=False):
+        """(lmin, lmax, kmin, kmax) of this rank's points; ``u``: values on ALL points."""
+        return self.table.d2eigs(u, want_k=want_k)
+
+    def gather(self, local):
+        """Values over all interior points from every rank's slice."""
+        return gather_rows(local, self.sizes)
+
+    def d2eigs_all(self, u):
+        lmin, lmax, _, _ = self.d2eigs(u)
+        return self.gather(lmin), self.gather(lmax)

@@ -72,3 +72,39 @@ def test_halo_exchange_gloo(world):
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(world))
     assert all(res.values()) and len(res) == world
+
+
+def _gather_worker(rank, world, port, n, q):
+    from pyellipticfd_b200.multigpu import gather_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        parts = slab_partition(n, world)
+        lo, hi = parts[rank]
+        local = torch.arange(lo, hi, dtype=torch.float64) * 2.0
+        full = gather_rows(local, [b - a for a, b in parts])
+        ok = bool(torch.equal(full, torch.arange(n, dtype=torch.float64) * 2.0))
+        loc2 = torch.stack([local, -local], 1)
+        full2 = gather_rows(loc2, [b - a for a, b in parts])
+        ok &= full2.shape == (n, 2) and bool(torch.equal(full2[:, 1], -full))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 10), (3, 10), (2, 7)])
+@pytest.mark.timeout(120)
+def test_point_range_gather_gloo(world, n):
+    """Point-cloud sharding: ragged point ranges re-assembled by one padded all-gather."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(100)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert all(res.values()) and len(res) == world

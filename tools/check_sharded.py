@@ -73,5 +73,25 @@ ref_local = np.concatenate([Uref[lo * ny:hi * ny], Uref[N:]])
 err = float(np.abs(mine - ref_local).max())
 report("Newton 127^2 r=2: %d its / %d Krylov (1 GPU %d its), |dU| %.1e" %
        (it, st["krylov_iters"], itref, err), err < 2e-6 and abs(it - itref) <= 6)
+# point cloud sharded by point range: ddi / ddf operators on every rank's slice, re-assembled
+# by one all-gather, against the single-GPU table
+from scipy.spatial import Delaunay
+from oracle import disc
+from pyellipticfd_b200.pointclasses import FDTriMesh
+from pyellipticfd_b200.multigpu import ShardedCloud
+from pyellipticfd_b200 import ddi, ddf
+h0 = 0.02
+theta = np.pi * h0 ** (1 / 3)
+p, nint = disc.disc_points(h0, theta)
+Gc = FDTriMesh(p, Delaunay(p).simplices, num_interior=nint, angular_resolution=theta)
+uc = torch.from_numpy(np.random.default_rng(3).standard_normal(len(p))).to(dev)
+for name, mod in (("ddi", ddi), ("ddf", ddf)):
+    sc = ShardedCloud(Gc, rank, world, dev, scheme=name)
+    lo_all, hi_all = sc.d2eigs_all(uc)
+    Gc._d2cache = None
+    (rmin, _, _), (rmax, _, _) = mod.d2eigs(Gc, uc)
+    report("%s.d2eigs on %d points, %d point ranges (bit-exact vs 1 GPU)" % (name, len(p), world),
+           bool(torch.equal(lo_all, rmin)) and bool(torch.equal(hi_all, rmax))
+           and lo_all.shape[0] == nint)
 dist.destroy_process_group()
 sys.exit(0 if ok_all else 1)

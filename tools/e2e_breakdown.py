@@ -30,8 +30,13 @@ print("unpad %.3f ms" % t(lambda: ctx.unpad(lm)))
 print("d2h   %.2f ms (%.1f GB/s)" % ((b := t(lambda: out_host.copy_(flat, non_blocking=True))), flat.numel()*8/b/1e6))
 print("pin alloc+d2h %.2f ms" % t(lambda: torch.empty(flat.shape, dtype=flat.dtype, pin_memory=True).copy_(flat, non_blocking=True)))
 print("api   %.2f ms" % t(lambda: ddg.d2min(G, host)))
-for cr in (64, 128, 256, 512, 1024, 2048):
-    print("chunk_rows %4d: %.2f ms" % (cr, t(lambda: ctx.d2eigs_host(host, want_min=True, want_max=False, chunk_rows=cr))))
+for lin in (False, True):
+    for cr in (128, 256, 512):
+        print("linear %s chunk_rows %4d: %.2f ms" % (lin, cr, t(lambda: ctx.d2eigs_host(
+            host, want_min=True, want_max=False, chunk_rows=cr, linear=lin), reps=10)))
+ref = ctx.d2eigs_host(host, want_min=True, want_max=False, linear=False)[0]
+alt = ctx.d2eigs_host(host, want_min=True, want_max=False, linear=True)[0]
+print("linear == 2-D result:", bool(torch.equal(ref, alt)))
 # duplex check: H2D and D2H of the same size on two streams at once
 s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
 def duplex():
