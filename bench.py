@@ -60,6 +60,9 @@ def parse():
                     help="time convex_envelope.solve (Newton = policy iteration, reference defaults) "
                          "on the S^2 interior grid of BASELINE configs[1] (4095 -> 4097^2 lattice, "
                          "r = 4) with the per-iteration CPU cost measured beside it; 0 = skip")
+    ap.add_argument("--pucci-full", type=int, default=8191,
+                    help="BASELINE configs[2]: time the Pucci residual + policy kernel and the "
+                         "matrix-free BiCGStab iteration on the S^2 interior grid, r = 6; 0 = skip")
     return ap.parse_args()
 
 
@@ -346,6 +349,73 @@ def solve_full_size(args, obstacle):
     return out
 
 
+def pucci_full_size(args):
+    """BASELINE configs[2] (Pucci Dirichlet problem, 8193^2 lattice, radius-6 stencil = 36 pairs,
+    Newton with matrix-free BiCGStab): device time of the two kernels a Newton iteration is made
+    of -- the fused residual + policy pass (pucci.py:45-58,127-141) and one Jacobi-BiCGStab
+    iteration on the two-policy Jacobian A0*M_max + A1*M_min (pucci.py:50-54, solvers.py:179-181).
+    A converged solve is not timed at this size: with wide stencils the reference's Newton loop
+    cycles between policies (the CPU oracle needs 101 iterations without converging at 63^2, r=4;
+    tools/pucci_scaling.py), so its 100-iteration cap would be what is measured."""
+    import numpy as np
+    import torch
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    from pyellipticfd_b200._context import GridContext
+    from pyellipticfd_b200.linop import PolicyJacobian
+    n, r = args.pucci_full, 6
+    out = {"lattice": "%d^2" % (n + 2), "radius": r}
+    try:
+        t = time.time()
+        G = FDRegularGrid([n, n], np.array([[0.0, 1.0], [0.0, 1.0]]).T, r, interpolation=False)
+        out["grid_build_s"] = time.time() - t
+        ctx = GridContext.get(G)
+        dev = ctx.device
+        N, nb = ctx.n_interior_local, ctx.nb
+        out["pairs_per_point"] = int(G.stencil_pairs.shape[0])
+        xs = torch.arange(1, n + 1, device=dev, dtype=torch.float64) / (n + 1)
+        wp = torch.from_numpy(G.bdry_points).to(dev)
+        U = torch.empty(N + nb, dtype=torch.float64, device=dev)
+        U[:N] = (torch.sin(3 * xs)[:, None] * torch.cos(2 * xs)[None, :]
+                 + (xs ** 2)[:, None] + 2 * (xs ** 2)[None, :]).reshape(-1)
+        U[N:] = torch.sin(3 * wp[:, 0]) * torch.cos(2 * wp[:, 1]) + wp[:, 0] ** 2 + 2 * wp[:, 1] ** 2
+        Fv = torch.full((N + nb,), 10.0, dtype=torch.float64, device=dev)
+        Fv[N:] = U[N:]
+        Us, Fs = ctx.pack(U), ctx.pack(Fv)
+        del U, Fv
+
+        def timed(fn, reps):
+            for _ in range(2):
+                fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / reps
+
+        ms = timed(lambda: ctx.pucci_residual(Us, Fs, 2.0, 1.0, policy=True), 5)
+        out["residual_policy_ms"] = ms
+        out["residual_gpoint_dir_per_s"] = N * out["pairs_per_point"] / ms / 1e6
+        R, pmin, pmax, _ = ctx.pucci_residual(Us, Fs, 2.0, 1.0, policy=True)
+        Jac = PolicyJacobian(ctx, pmin, pmax, cmin=1.0, cmax=2.0)
+        Jac.bicgstab_state(-R, rtol=1e-300, maxiter=4, check_every=4)
+        torch.cuda.synchronize()
+        kit = 32
+        t = time.perf_counter()
+        _, _, done = Jac.bicgstab_state(-R, rtol=1e-300, maxiter=kit, check_every=kit)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t
+        out["bicgstab_ms_per_iteration"] = dt / max(int(done), 1) * 1e3
+        out["unknowns"] = int(N + nb)
+        out["bicgstab_GBps_at_200B_per_unknown"] = 200.0 * (N + nb) / (dt / max(int(done), 1)) / 1e9
+        GridContext.drop(G)
+    except Exception as e:                # reported, not fatal
+        out["error"] = str(e)[:300]
+    return out
+
+
 def main():
     args = parse()
     if args.impl == "reference":
@@ -618,6 +688,12 @@ def main():
     if world == 1 and args.solve_full:
         solve_full = solve_full_size(args, two_cones)
 
+    pucci_full = None
+    if world == 1 and args.pucci_full:
+        del S, lmin, out
+        torch.cuda.empty_cache()
+        pucci_full = pucci_full_size(args)
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -648,6 +724,8 @@ def main():
             line["solve"] = solve
         if solve_full:
             line["solve_4097"] = solve_full
+        if pucci_full:
+            line["pucci_8193"] = pucci_full
         if world == 1 and extra:
             line["other_kernels"] = extra
         print(json.dumps(line))
