@@ -23,21 +23,6 @@ __global__ void __launch_bounds__(PASS_THREADS)
 k_rows(const GridDev G, const __grid_constant__ DeepTable tab, Op op, double *partials,
        const BicgScal *scal, const int nrb /* row blocks; the rest are tail blocks */) {
     double acc[Op::NRED > 0 ? Op::NRED : 1] = {0.0};
-    // The policy index differs from thread to thread, and a per-thread index into the
-    // kernel-parameter constant bank serialises (one LDC per distinct value in the warp, 7
-    // table fields per row).  The used part of the table is therefore copied to shared
-    // memory once per block and the rows index that copy.
-    __shared__ DeepTable stab;
-    if ((int)blockIdx.x < nrb) {
-        const int k = threadIdx.x;
-        if (k < tab.D) {
-            stab.a0[k] = tab.a0[k]; stab.b0[k] = tab.b0[k];
-            stab.a1[k] = tab.a1[k]; stab.b1[k] = tab.b1[k];
-            stab.w_0[k] = tab.w_0[k]; stab.w_1[k] = tab.w_1[k]; stab.w0[k] = tab.w0[k];
-        }
-        if (k == 0) { stab.D = tab.D; stab.H = tab.H; }
-        __syncthreads();
-    }
     bool skip = scal && (scal->done || (Op::kSkipOnHalf && scal->half));
     if (!skip) {
         op.prepare(scal);
@@ -53,7 +38,7 @@ k_rows(const GridDev G, const __grid_constant__ DeepTable tab, Op op, double *pa
                     const int64_t base = br * G.pitch;
                     const int c1 = (int)G.ny - G.radius;
                     for (int c = G.radius + threadIdx.x; c < c1; c += PASS_THREADS)
-                        op.deep(stab, G, base + c, acc);
+                        op.deep(tab, G, base + c, acc);
                 }
             }
         } else {

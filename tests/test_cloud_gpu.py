@@ -186,3 +186,39 @@ def test_trimesh_large_disc_device_equals_host():
         assert d2.max() - 2 < 0.17 and 2 - d2.min() < 0.17
     (lmin, _, _), (lmax, _, _) = ddi.d2eigs(Gd, X ** 2 - Y ** 2)
     assert np.abs(lmin + 2).max() < 0.2 and np.abs(lmax - 2).max() < 0.2
+
+
+def test_trimesh_quarter_million_points_properties():
+    """Size-independent properties of ddi.d2eigs on a 237 k-point disc built on the GPU
+    (towards BASELINE configs[3]): zero on affine functions, -2 / +2 on x^2 - y^2 within the
+    scheme's consistency error, M.dot(u) == lambda (the reference tests' identity,
+    tests/test_ddi.py:56-81), linear in u for a fixed direction, cached == first call."""
+    import torch
+    from scipy.spatial import Delaunay
+    from oracle import disc
+    from pyellipticfd_b200.pointclasses import FDTriMesh
+    import pyellipticfd_b200.ddi as ddi
+    h0 = 0.004
+    theta = np.pi * h0 ** (1 / 3)
+    p, nint = disc.disc_points(h0, theta)
+    G = FDTriMesh(p, Delaunay(p).simplices, num_interior=nint, angular_resolution=theta)
+    assert int(G._count.min()) >= 3
+    P = torch.from_numpy(p).cuda()
+    x, y = P[:, 0], P[:, 1]
+    (amin, _, _), (amax, _, _) = ddi.d2eigs(G, 3 * x - 2 * y + 0.5)
+    scale = 1e-13 / h0 ** 2
+    assert float(amin.abs().max()) < scale and float(amax.abs().max()) < scale
+    u = x * x - y * y
+    (lmin, Mmin, _), (lmax, Mmax, _) = ddi.d2eigs(G, u, jacobian=True)
+    assert float((lmin + 2).abs().max()) < 0.05 and float((lmax - 2).abs().max()) < 0.05
+    assert float((Mmin.dot(u) - lmin).abs().max()) < 1e-12 * 2 / h0 ** 2 * 1e-3 + 1e-9
+    assert float((Mmax.dot(u) - lmax).abs().max()) < 1e-12 * 2 / h0 ** 2 * 1e-3 + 1e-9
+    (lmin2, _, _), _ = ddi.d2eigs(G, u)                    # cached table, same kernel
+    assert torch.equal(lmin, lmin2)
+    r = torch.randn(len(p), dtype=torch.float64, device="cuda",
+                    generator=torch.Generator("cuda").manual_seed(1))
+    d_u, _ = ddi.d2(G, [1, 0], u)
+    d_r, _ = ddi.d2(G, [1, 0], r)
+    d_s, _ = ddi.d2(G, [1, 0], u + 0.5 * r)
+    tol = 1e-12 * float(d_r.abs().max())
+    assert float((d_s - (d_u + 0.5 * d_r)).abs().max()) < 50 * tol
