@@ -250,7 +250,8 @@ class FDTriMesh(FDPointCloud):
         from . import _lib
         L = _lib.lib()
         n, N = self.num_points, self.num_interior
-        key = np.unique(self.edges[:, 0].astype(np.int64) * n + self.edges[:, 1])
+        key = np.sort(self.edges[:, 0].astype(np.int64) * n + self.edges[:, 1])
+        key = key[np.concatenate([[True], key[1:] != key[:-1]])]
         e0, e1 = key // n, key % n
         e0, e1 = e0[e0 != e1], e1[e0 != e1]
         adj_ptr = np.concatenate([[0], np.cumsum(np.bincount(e0, minlength=n))]).astype(np.int64)
