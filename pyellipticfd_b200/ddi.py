@@ -36,6 +36,8 @@ def d1n(G, u=None, **kwargs):
 def d1grad(G, u, jacobian=False, control=False, cache_fdmatrices=True):
     """First derivative in the direction of the gradient: maximum over
     ``_num_directions(G)`` directions (ddi.py:124-221).  Returns ``(d1_max, M, v)``."""
+    if G.dim == 3:
+        raise NotImplementedError("Gradient not yet implemented in 3d.")        # ddi.py:157-158
     return _ell.d1grad(G, u, __name__, int(_num_directions(G)), jacobian, control,
                        cache_fdmatrices)
 

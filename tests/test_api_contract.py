@@ -72,3 +72,57 @@ def test_grid_metadata_and_lazy_pairs():
     assert G.min_radius == G.scaling.min() and G.min_interior_nb_dist == G.scaling.min()
     with pytest.raises(NotImplementedError):
         FDRegularGrid([5, 5], np.array([[0, 1], [0, 1.0]]).T, 2, interpolation=True)
+
+
+def test_public_signatures_match_the_reference():
+    """Names, parameter names and defaults of the reference's public functions
+    (ddg.py, ddi.py, ddf.py, convex_envelope.py, pucci.py, solvers.py, pointclasses.py)."""
+    import inspect
+    from pyellipticfd_b200 import convex_envelope
+    from pyellipticfd_b200.pointclasses import FDTriMesh
+
+    def params(f):
+        return [(p.name, p.default if p.default is not inspect._empty else None)
+                for p in inspect.signature(f).parameters.values()
+                if p.kind in (p.POSITIONAL_OR_KEYWORD, p.KEYWORD_ONLY)]
+
+    for mod in (ddg, ddi):
+        assert params(mod.d1) == [("G", None), ("v", None), ("u", None), ("jacobian", False),
+                                  ("domain", "interior")]                 # ddg.py:8, ddi.py:12
+        assert [n for n, _ in params(mod.d1n)][:2] == ["G", "u"]             # ddg.py:86, ddi.py:94
+    assert params(ddg.d1grad) == [("G", None), ("u", None), ("jacobian", False), ("control", False)]
+    assert params(ddi.d1grad) == [("G", None), ("u", None), ("jacobian", False), ("control", False),
+                                  ("cache_fdmatrices", True)]                # ddi.py:124
+    for mod in (ddg, ddi, ddf):
+        assert params(mod.d2) == [("G", None), ("v", None), ("u", None), ("jacobian", False)]
+    assert params(ddg.d2eigs) == [("G", None), ("u", None), ("jacobian", False), ("control", False)]
+    for mod in (ddi, ddf):
+        assert params(mod.d2eigs) == [("G", None), ("u", None), ("jacobian", False),
+                                      ("control", False), ("cache_fdmatrices", True)]
+    assert params(convex_envelope.operator) == [("Grid", None), ("W", None), ("g", None),
+                                                ("jacobian", True), ("fdmethod", "interpolate")]
+    assert params(convex_envelope.solve)[:5] == [("Grid", None), ("g", None), ("U0", None),
+                                                 ("fdmethod", "interpolate"), ("solver", "newton")]
+    assert params(pucci.solve)[:7] == [("Grid", None), ("f", None), ("dirichlet", None),
+                                       ("A", (2, 1)), ("U0", None), ("fdmethod", "interpolate"),
+                                       ("solver", "newton")]
+    assert [n for n, _ in params(solvers.euler)] == [
+        "U", "operator", "solution_tol", "operator_tol", "max_iters", "timeout", "zeromean",
+        "zeromax", "plotter"]                                                # solvers.py:13-15
+    assert [n for n, _ in params(solvers.NewtonEulerLS)] == [
+        "U", "operator", "solution_tol", "operator_tol", "max_iters", "euler_ratio", "plotter",
+        "max_euler_iters", "verbose", "force_euler"]                         # solvers.py:98-101
+    assert [n for n, _ in params(FDTriMesh.__init__)][1:4] == ["p", "t", "angular_resolution"]
+    assert [n for n, _ in params(FDRegularGrid.__init__)][1:5] == [
+        "interior_shape", "bounds", "stencil_radius", "interpolation"]     # pointclasses.py:480
+
+
+def test_first_derivative_errors():
+    cloud = FDPointCloud(np.zeros((4, 2)), num_interior=2)
+    with pytest.raises(TypeError):                       # no boundary normals
+        ddg.d1n(cloud, np.zeros(4))
+    with pytest.raises(TypeError):
+        ddi.d1n(cloud, np.zeros(4))
+    c3 = FDPointCloud(np.zeros((4, 3)), num_interior=2)
+    with pytest.raises(NotImplementedError):             # ddi.py:157-158
+        ddi.d1grad(c3, np.zeros(4))
