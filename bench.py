@@ -46,7 +46,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--n", type=int, default=4095, help="interior points per side")
+    ap.add_argument("--n", "--rows", dest="n", type=int, default=4095,
+                    help="interior points per side / rows per GPU (use --rows under torchrun: its "
+                         "parser rejects the abbreviation-like --n)")
+    ap.add_argument("--cols", type=int, default=0,
+                    help="interior points per row (default: --n); --n 4096 --cols 32766 --gpus 8 is "
+                         "the 32768^2 lattice of BASELINE configs[4], one 4096-row slab per GPU")
     ap.add_argument("--radius", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -446,18 +451,18 @@ def main():
         except Exception as e:        # reported, not fatal
             cpu = {"error": str(e)}
 
-    bounds = np.array([[0.0, 1.0], [0.0, 1.0]]).T
+    # lattice spacing h = 2^-k in both directions (exact weights); the extent follows the shape:
+    # N x n rows (weak scaling) and `cols` columns
+    cols = args.cols or n
+    h = 2.0 ** -int(np.ceil(np.log2(max(n, cols) + 1)))
+    bounds = np.array([[0.0, (world * n + 1) * h], [0.0, (cols + 1) * h]]).T
     t0 = time.time()
     if world == 1:
-        G = FDRegularGrid([n, n], bounds, r, interpolation=False)
+        G = FDRegularGrid([n, cols], bounds, r, interpolation=False)
         ctx = GridContext.get(G, dev)
         sharded = None
     else:
-        # weak scaling: world x n rows, n columns; spacing stays dyadic in y only if n+1 is;
-        # keep h = 1/(n+1) in both directions by stretching the x extent
-        bounds = np.array([[0.0, float(world)], [0.0, 1.0]]).T
-        bounds[1, 0] = (world * n + 1) / (n + 1.0)
-        sharded = multigpu.ShardedGrid([world * n, n], bounds, r, rank, world, dev)
+        sharded = multigpu.ShardedGrid([world * n, cols], bounds, r, rank, world, dev)
         ctx = sharded.ctx
         G = sharded.G
     t_grid = time.time() - t0
@@ -699,11 +704,11 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "ddg.d2min on a %d^2 lattice (%d^2 interior points%s), "
+            "config": {"workload": "ddg.d2min on a %d x %d lattice (%d x %d interior points%s), "
                                    "stencil radius %d (%d pairs/point), arithmetic mode 0 "
                                    "(reference operation order)"
-                                   % (n + 2, n, " per GPU, slab-sharded rows" if world > 1 else "",
-                                      r, D),
+                                   % (n + 2, cols + 2, n, cols,
+                                      " per GPU, slab-sharded rows" if world > 1 else "", r, D),
                        "l2": "input field %.0f MB + output %.0f MB per step exceed the 126 MB L2"
                              % (n_local * 8 / 1e6, n_local * 8 / 1e6),
                        "parallelism": "slab%d" % world, "grid_build_s": t_grid},

@@ -81,6 +81,10 @@ int pde_grid_destroy(pde_grid *g);
  * slab.  Used to overlap the halo exchange (edge rows last) and host<->device copies
  * (row chunks) with the arithmetic. */
 int pde_grid_set_row_window(pde_grid *g, int64_t row_lo, int64_t row_hi);
+/* Two disjoint row ranges [lo, hi) and [lo2, hi2) (lo <= hi <= lo2 <= hi2) served by ONE set of
+ * launches: the two edge strips of a slab after its halo exchange (multigpu.py), which would
+ * otherwise cost a second, almost empty launch group per operator application. */
+int pde_grid_set_row_windows2(pde_grid *g, int64_t lo, int64_t hi, int64_t lo2, int64_t hi2);
 int64_t pde_grid_pitch(const pde_grid *g);      /* doubles per lattice row        */
 int64_t pde_grid_rows(const pde_grid *g);       /* nx_local + 2*halo_rows         */
 int64_t pde_grid_state_len(const pde_grid *g);  /* rows*pitch + nb                */
@@ -324,6 +328,10 @@ int pde_band_build(int64_t nx, int64_t ny, int stencil_radius, double sx, double
                     * band points (what ddg.d1 / d1grad walk, ddg.py:44-47) */
                    int64_t **out_nb_ptr, int64_t **out_nb);
 void pde_free(void *p);
+/* Number of host threads of the pre-processing routines (pde_band_build, host pde_cloud_build);
+ * n <= 0 only queries.  torchrun exports OMP_NUM_THREADS=1, which would build an N-GPU job's
+ * grid on one core per rank. */
+int pde_set_host_threads(int n);
 
 /* Stencils of a triangulated point cloud: replaces, per centre point, the O(N^2)
  * pre-processing of FDTriMesh.__init__ -- neighbours within `depth` edges of the

@@ -277,6 +277,10 @@ class GridContext(object):
         """Restrict the stencil launches to owned rows [lo, hi) (None = all rows)."""
         check(self.lib.pde_grid_set_row_window(self.h, int(lo), int(self.nx_local if hi is None else hi)))
 
+    def set_row_windows2(self, lo, hi, lo2, hi2):
+        """Two disjoint row ranges served by one set of launches (the edge strips of a slab)."""
+        check(self.lib.pde_grid_set_row_windows2(self.h, int(lo), int(hi), int(lo2), int(hi2)))
+
     # ---- operators --------------------------------------------------------------------------------
     def d2eigs(self, S, want_min=True, want_max=True, policy=False, mode=0, out=None):
         """Raw ddg.d2eigs on a state tensor -> (lmin, lmax, pmin, pmax) state-layout."""

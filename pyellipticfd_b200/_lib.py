@@ -37,6 +37,7 @@ SIGNATURES = {
                                 c_i64, vp, vp, vp, vp, vp]),
     "pde_grid_destroy": (c_int, [vp]),
     "pde_grid_set_row_window": (c_int, [vp, c_i64, c_i64]),
+    "pde_grid_set_row_windows2": (c_int, [vp, c_i64, c_i64, c_i64, c_i64]),
     "pde_grid_pitch": (c_i64, [vp]),
     "pde_grid_rows": (c_i64, [vp]),
     "pde_grid_state_len": (c_i64, [vp]),
@@ -84,6 +85,7 @@ SIGNATURES = {
                                c_i64, vp, c_dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(c_dbl),
                                C.POINTER(vp), C.POINTER(vp)]),
     "pde_free": (None, [vp]),
+    "pde_set_host_threads": (c_int, [c_int]),
     "pde_cloud_build": (c_int, [c_int, c_i64, c_i64, vp, vp, vp, c_int, c_dbl, c_dbl, c_dbl, c_int,
                                 c_int, vp, vp, vp, vp, vp]),
 }

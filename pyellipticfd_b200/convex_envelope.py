@@ -21,7 +21,7 @@ from .linop import PolicyJacobian
 
 
 def _is_pairs_grid(Grid):
-    return getattr(Grid, "pairs", None) is not None or hasattr(Grid, "stencil_pairs")
+    return hasattr(Grid, "stencil_pairs") or getattr(Grid, "pairs", None) is not None
 
 
 def operator(Grid, W, g, jacobian=True, fdmethod='interpolate'):

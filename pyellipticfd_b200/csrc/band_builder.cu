@@ -16,6 +16,9 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 
 #include "common.cuh"
 
@@ -33,6 +36,16 @@ struct WallList {
 extern "C" {
 
 void pde_free(void *p) { free(p); }
+
+int pde_set_host_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+    return omp_get_max_threads();
+#else
+    (void)n;
+    return 1;
+#endif
+}
 
 int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double bx, double by,
                    int64_t nb, const double *wall /* nb x 2 unscaled */, int64_t n_band,

@@ -110,10 +110,10 @@ struct DeepRegion {
     int row0, col0, nrows, ncols;   // buffer coordinates
 };
 
-static DeepRegion deep_region(const pde_grid *g) {
+static DeepRegion deep_region(const pde_grid *g, int64_t win_lo, int64_t win_hi) {
     int64_t r = g->radius;
-    int64_t gx0 = std::max<int64_t>(r, g->x_offset + g->win_lo);
-    int64_t gx1 = std::min<int64_t>(g->nx_global - r, g->x_offset + g->win_hi);
+    int64_t gx0 = std::max<int64_t>(r, g->x_offset + win_lo);
+    int64_t gx1 = std::min<int64_t>(g->nx_global - r, g->x_offset + win_hi);
     DeepRegion d;
     d.row0 = (int)(gx0 - g->x_offset + g->halo_rows);
     d.nrows = (int)std::max<int64_t>(0, gx1 - gx0);
@@ -143,7 +143,12 @@ static int make_tmap(const pde_grid *g, const double *S, int boxy, int boxx, CUt
 template <class Eval, int H, int P, int MODE, class Epi, int MINB = 2, int ICMP = 0>
 static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *red,
                           const unsigned long long *done, cudaStream_t st) {
-    DeepRegion dr = deep_region(g);
+    DeepRegion dr = deep_region(g, g->win_lo, g->win_hi);
+    DeepRegion dr2 = deep_region(g, g->win2_lo, g->win2_hi);
+    if (dr.nrows <= 0) {            // only the second range has deep rows
+        dr = dr2;
+        dr2.nrows = 0;
+    }
     if (dr.nrows <= 0 || dr.ncols <= 0) return 0;
     constexpr int TX = 2 * P;
     DeepGeom geo;
@@ -154,6 +159,10 @@ static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *
     geo.ncols = dr.ncols;
     geo.tiles_x = (dr.nrows + TX - 1) / TX;
     geo.tiles_y = (dr.ncols + K1_TY - 1) / K1_TY;
+    geo.split = geo.tiles_x;
+    geo.row0b = dr2.row0;
+    geo.nrowsb = dr2.nrows > 0 ? dr2.nrows : 0;
+    if (geo.nrowsb > 0) geo.tiles_x += (dr2.nrows + TX - 1) / TX;
     CUtensorMap tmap;
     int rc = make_tmap(g, S, K1_TY + 2 * H + 2, TX + 2 * H, &tmap);
     if (rc) return rc;
@@ -221,16 +230,19 @@ template <int MODE, class Epi>
 static int launch_band(pde_grid *g, const double *S, const Epi &epi, double *red,
                        const unsigned long long *done, cudaStream_t st) {
     if (g->n_band == 0) return 0;
-    // band points of the active row window (band points are sorted by row)
+    // band points of the active row windows (band points are sorted by row)
     const int64_t *rb = g->h_band_row, *re = g->h_band_row + g->n_band;
-    int64_t b_lo = std::lower_bound(rb, re, g->win_lo) - rb;
-    int64_t b_hi = std::lower_bound(rb, re, g->win_hi) - rb;
-    int64_t nbp = b_hi - b_lo;
-    if (nbp <= 0) return 0;
-    int grid = (int)((nbp + 3) / 4);                 // one warp per band point
-    k_band<MODE, Epi><<<grid, 128, 0, st>>>(nbp, g->d_band_center + b_lo, g->d_band_ptr + b_lo,
-                                             g->d_band_j, g->d_band_w, S, epi, red, done);
-    PDE_LAUNCH_CHECK();
+    const int64_t wins[2][2] = {{g->win_lo, g->win_hi}, {g->win2_lo, g->win2_hi}};
+    for (int wdx = 0; wdx < 2; ++wdx) {
+        int64_t b_lo = std::lower_bound(rb, re, wins[wdx][0]) - rb;
+        int64_t b_hi = std::lower_bound(rb, re, wins[wdx][1]) - rb;
+        int64_t nbp = b_hi - b_lo;
+        if (nbp <= 0) continue;
+        int grid = (int)((nbp + 3) / 4);                 // one warp per band point
+        k_band<MODE, Epi><<<grid, 128, 0, st>>>(nbp, g->d_band_center + b_lo, g->d_band_ptr + b_lo,
+                                                 g->d_band_j, g->d_band_w, S, epi, red, done);
+        PDE_LAUNCH_CHECK();
+    }
     return 0;
 }
 

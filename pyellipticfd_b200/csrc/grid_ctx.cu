@@ -154,6 +154,7 @@ int pde_grid_create(pde_grid **out, int device, int64_t nx_global, int64_t ny, i
     g->n_band = n_band;
     g->win_lo = 0;
     g->win_hi = nx_local;
+    g->win2_lo = g->win2_hi = 0;
     g->h_band_row = new int64_t[n_band > 0 ? n_band : 1];
     for (int64_t i = 0; i < n_band; ++i) g->h_band_row[i] = h_band_center[i] / g->pitch - halo_rows;
     g->n_band_pairs = n_band ? h_band_ptr[n_band] : 0;
@@ -219,6 +220,18 @@ int pde_grid_set_row_window(pde_grid *g, int64_t row_lo, int64_t row_hi) {
     if (row_hi < row_lo) row_hi = row_lo;
     g->win_lo = row_lo;
     g->win_hi = row_hi;
+    g->win2_lo = g->win2_hi = 0;
+    return 0;
+}
+
+int pde_grid_set_row_windows2(pde_grid *g, int64_t lo, int64_t hi, int64_t lo2, int64_t hi2) {
+    PDE_REQUIRE(g, "null argument");
+    PDE_REQUIRE(lo >= 0 && lo <= hi && hi <= lo2 && lo2 <= hi2 && hi2 <= g->nx_local,
+                "bad row ranges (need lo <= hi <= lo2 <= hi2)");
+    g->win_lo = lo;
+    g->win_hi = hi;
+    g->win2_lo = lo2;
+    g->win2_hi = hi2;
     return 0;
 }
 

@@ -63,6 +63,8 @@ struct DeepGeom {
     int col0;             // first column of the deep region
     int nrows, ncols;     // extent of the deep region
     int tiles_x, tiles_y;
+    // optional second row range (same columns): tile rows [split, tiles_x) belong to it
+    int split, row0b, nrowsb;
 };
 
 struct BlockMax2 {   // two running maxima per thread, reduced once per CTA at the end
@@ -221,7 +223,7 @@ k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTab
 
     auto issue = [&](int tile, int slot) {
         int tx = tile / geo.tiles_y, ty = tile - tx * geo.tiles_y;
-        int x0 = geo.row0 + tx * TX - H;
+        int x0 = (tx < geo.split ? geo.row0 + tx * TX : geo.row0b + (tx - geo.split) * TX) - H;
         int y0 = geo.col0 + ty * K1_TY - H - ysh;
         uint64_t *bar = &bars[slot];
         mbar_expect_tx(bar, TILE_BYTES);
@@ -238,14 +240,17 @@ k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTab
         if (next < ntiles && tid == 0) issue(next, slot ^ 1);
         const double *sm = slot ? buf1 : buf0;
         const int tx = tile / geo.tiles_y, ty = tile - tx * geo.tiles_y;
-        const int lx0 = tx * TX + grp * P;                // row inside the deep region
+        const bool second = tx >= geo.split;
+        const int rbase = second ? geo.row0b : geo.row0;  // first buffer row of this range
+        const int rcount = second ? geo.nrowsb : geo.nrows;
+        const int lx0 = (second ? tx - geo.split : tx) * TX + grp * P;   // row inside the range
         const int ly = ty * K1_TY + c;
         double pre[Epi::kPre ? P : 1];
         if (Epi::kPre) {      // epilogue operands (obstacle / forcing): loads issued before the wait
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                bool in = ly < geo.ncols && lx0 + p < geo.nrows;
-                pre[p] = in ? epi.pre((int64_t)(geo.row0 + lx0 + p) * geo.pitch + (geo.col0 + ly)) : 0.0;
+                bool in = ly < geo.ncols && lx0 + p < rcount;
+                pre[p] = in ? epi.pre((int64_t)(rbase + lx0 + p) * geo.pitch + (geo.col0 + ly)) : 0.0;
             }
         }
         mbar_wait(&bars[slot], (it >> 1) & 1);
@@ -266,8 +271,8 @@ k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTab
         if (ly < geo.ncols) {
 #pragma unroll
             for (int p = 0; p < P; ++p) {
-                if (lx0 + p < geo.nrows) {
-                    int64_t o = (int64_t)(geo.row0 + lx0 + p) * geo.pitch + (geo.col0 + ly);
+                if (lx0 + p < rcount) {
+                    int64_t o = (int64_t)(rbase + lx0 + p) * geo.pitch + (geo.col0 + ly);
                     epi(o, uc[p], mn[p], mx[p], kmn[p], kmx[p], pre[Epi::kPre ? p : 0], red);
                 }
             }

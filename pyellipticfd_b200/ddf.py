@@ -13,7 +13,7 @@ from . import _ell, ddg
 
 
 def _has_pairs(G):
-    return getattr(G, "pairs", None) is not None or hasattr(G, "stencil_pairs")
+    return hasattr(G, "stencil_pairs") or getattr(G, "pairs", None) is not None
 
 
 def _num_directions(G):

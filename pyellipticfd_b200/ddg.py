@@ -28,7 +28,8 @@ def _pinned_host(u):
 
 
 def _require_pairs(G):
-    if getattr(G, "pairs", None) is None and not hasattr(G, "stencil_pairs"):
+    # structured grids answer without touching `pairs` (a lazily materialised property there)
+    if not hasattr(G, "stencil_pairs") and getattr(G, "pairs", None) is None:
         raise TypeError('The grid was has no finite difference pairs. '
                         'Construct the grid with "interpolation=False"')
 

@@ -62,6 +62,11 @@ class ShardedGrid(object):
 
     def __init__(self, interior_shape, bounds, stencil_radius, rank, world, device, grid=None):
         self.rank, self.world = rank, world
+        if grid is None and world > 1:
+            import os
+            from . import _lib
+            # one process per GPU: share the host cores among the ranks' grid builders
+            _lib.lib().pde_set_host_threads(max(1, (os.cpu_count() or 1) // world))
         self.G = grid if grid is not None else FDRegularGrid(list(interior_shape), bounds,
                                                              stencil_radius, interpolation=False)
         nx, ny = self.G.interior_shape
@@ -84,7 +89,7 @@ class ShardedGrid(object):
         """Run ``launch()`` (stencil launches that read the state ``S``) with the halo
         exchange of ``S`` hidden behind the rows that do not need it: the exchange goes to a
         communication stream, the interior rows [r, nx_local - r) are computed meanwhile on
-        the current stream, the 2*r edge rows afterwards."""
+        the current stream, the 2*r edge rows afterwards (both strips in one launch group)."""
         c, H = self.ctx, self.slab.halo
         if self.world == 1 or H == 0:
             return launch()
@@ -101,9 +106,7 @@ class ShardedGrid(object):
             c.set_row_window(H, c.nx_local - H)
             res = launch()
             main.wait_stream(self._comm)
-            c.set_row_window(0, H)
-            launch()
-            c.set_row_window(c.nx_local - H, c.nx_local)
+            c.set_row_windows2(0, H, c.nx_local - H, c.nx_local)     # both edge strips, one launch
             launch()
         finally:
             c.set_row_window()
