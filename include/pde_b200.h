@@ -85,6 +85,11 @@ int pde_grid_set_row_window(pde_grid *g, int64_t row_lo, int64_t row_hi);
  * launches: the two edge strips of a slab after its halo exchange (multigpu.py), which would
  * otherwise cost a second, almost empty launch group per operator application. */
 int pde_grid_set_row_windows2(pde_grid *g, int64_t lo, int64_t hi, int64_t lo2, int64_t hi2);
+/* on != 0: the persistent CTAs of the stencil kernel draw their tiles from a device counter
+ * instead of a static round robin.  Used by the slab-sharded path, where the NCCL kernel of the
+ * overlapped halo exchange delays some CTAs (it cannot share an SM with two 125-register CTAs);
+ * launches on one context must then not overlap each other (they never do: one stream). */
+int pde_grid_set_dynamic_schedule(pde_grid *g, int on);
 int64_t pde_grid_pitch(const pde_grid *g);      /* doubles per lattice row        */
 int64_t pde_grid_rows(const pde_grid *g);       /* nx_local + 2*halo_rows         */
 int64_t pde_grid_state_len(const pde_grid *g);  /* rows*pitch + nb                */

@@ -38,6 +38,7 @@ SIGNATURES = {
     "pde_grid_destroy": (c_int, [vp]),
     "pde_grid_set_row_window": (c_int, [vp, c_i64, c_i64]),
     "pde_grid_set_row_windows2": (c_int, [vp, c_i64, c_i64, c_i64, c_i64]),
+    "pde_grid_set_dynamic_schedule": (c_int, [vp, c_int]),
     "pde_grid_pitch": (c_i64, [vp]),
     "pde_grid_rows": (c_i64, [vp]),
     "pde_grid_state_len": (c_i64, [vp]),

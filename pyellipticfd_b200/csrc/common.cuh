@@ -72,6 +72,7 @@ struct pde_grid {
     int64_t n_band, n_band_pairs;
     int64_t win_lo, win_hi;      // owned rows [win_lo, win_hi) the stencil launches act on
     int64_t win2_lo, win2_hi;    // optional second range handled by the same launches (empty: 0, 0)
+    int dyn_sched;               // stencil CTAs draw tiles from a device counter (d_ctrl[8..9])
     int64_t *h_band_row;         // host: owned-row number of every band point (ascending)
     int64_t *d_band_center;      // n_band: state offset of the centre
     int64_t *d_band_pcenter;     // n_band: padded-layout offset (policy / per-point outputs)

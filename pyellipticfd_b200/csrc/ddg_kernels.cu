@@ -175,7 +175,8 @@ static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *
     }
     int ntiles = geo.tiles_x * geo.tiles_y;
     int grid = std::min(ntiles, g->num_sms * MINB);
-    kern<<<grid, K1_THREADS, smem, st>>>(tmap, g->tab, geo, epi, red, done);
+    kern<<<grid, K1_THREADS, smem, st>>>(tmap, g->tab, geo, epi, red, done,
+                                         g->dyn_sched ? g->d_ctrl + 8 : nullptr);
     PDE_LAUNCH_CHECK();
     return 0;
 }

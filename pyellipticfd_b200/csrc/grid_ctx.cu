@@ -155,6 +155,7 @@ int pde_grid_create(pde_grid **out, int device, int64_t nx_global, int64_t ny, i
     g->win_lo = 0;
     g->win_hi = nx_local;
     g->win2_lo = g->win2_hi = 0;
+    g->dyn_sched = 0;
     g->h_band_row = new int64_t[n_band > 0 ? n_band : 1];
     for (int64_t i = 0; i < n_band; ++i) g->h_band_row[i] = h_band_center[i] / g->pitch - halo_rows;
     g->n_band_pairs = n_band ? h_band_ptr[n_band] : 0;
@@ -221,6 +222,12 @@ int pde_grid_set_row_window(pde_grid *g, int64_t row_lo, int64_t row_hi) {
     g->win_lo = row_lo;
     g->win_hi = row_hi;
     g->win2_lo = g->win2_hi = 0;
+    return 0;
+}
+
+int pde_grid_set_dynamic_schedule(pde_grid *g, int on) {
+    PDE_REQUIRE(g, "null argument");
+    g->dyn_sched = on ? 1 : 0;
     return 0;
 }
 

@@ -192,7 +192,7 @@ template <class Eval, int H, int P, int MODE, class Epi, int MINB = 2, int ICMP 
 __global__ void __launch_bounds__(K1_THREADS, MINB)
 k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTable tab,
        const DeepGeom geo, const Epi epi, double *red_out,
-       const unsigned long long *done_flag) {
+       const unsigned long long *done_flag, unsigned long long *sched) {
     constexpr int TX = 2 * P;                 // 256 threads = 128 columns x 2 row groups
     // +2 columns: the TMA box must start on a 16-byte boundary of the row, so when the
     // halo origin is odd the box starts one column early and `ysh` re-centres the reads
@@ -230,14 +230,29 @@ k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTab
         tma_load_2d(slot ? buf1 : buf0, &tmap, y0, x0, bar);
     };
 
+    // Tile schedule.  sched == nullptr: static round robin (tile += gridDim.x).  Otherwise the
+    // CTAs draw their next tile from a device counter (sched[0]; sched[1] counts finished CTAs
+    // and the last one resets both): CTAs that start late -- e.g. behind the NCCL kernel of an
+    // overlapped halo exchange, which cannot share an SM with two 125-register CTAs -- then simply
+    // take fewer tiles instead of finishing a full static share late.
+    __shared__ int s_next[2];
     BlockMax2 red{0.0, 0.0};
     int tile = blockIdx.x;
     if (tile < ntiles && tid == 0) issue(tile, 0);
 
-    for (int it = 0; tile < ntiles; ++it, tile += gridDim.x) {
+    for (int it = 0; tile < ntiles; ++it) {
         const int slot = it & 1;
-        const int next = tile + gridDim.x;
-        if (next < ntiles && tid == 0) issue(next, slot ^ 1);
+        int next;
+        if (sched) {
+            if (tid == 0) {
+                next = (int)gridDim.x + (int)atomicAdd(sched, 1ULL);
+                s_next[slot] = next;
+                if (next < ntiles) issue(next, slot ^ 1);
+            }
+        } else {
+            next = tile + gridDim.x;
+            if (next < ntiles && tid == 0) issue(next, slot ^ 1);
+        }
         const double *sm = slot ? buf1 : buf0;
         const int tx = tile / geo.tiles_y, ty = tile - tx * geo.tiles_y;
         const bool second = tx >= geo.split;
@@ -278,6 +293,15 @@ k_deep(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTab
             }
         }
         __syncthreads();     // everyone is done with this slot before it is refilled
+        tile = sched ? s_next[slot] : next;
+    }
+    if (sched && tid == 0) {
+        __threadfence();
+        if (atomicAdd(sched + 1, 1ULL) == (unsigned long long)gridDim.x - 1) {
+            sched[0] = 0ULL;     // last CTA out: re-arm the counters for the next launch
+            sched[1] = 0ULL;
+            __threadfence();
+        }
     }
 
     if (Epi::kRed) {

@@ -9,6 +9,8 @@ refreshed from the neighbouring ranks (NCCL send/recv over NVLink, one message o
 ``r * pitch`` doubles per neighbour).  Wall points are replicated on every rank.
 Infinity-norm / dot-product reductions of the solvers are small all-reduces.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -63,7 +65,6 @@ class ShardedGrid(object):
     def __init__(self, interior_shape, bounds, stencil_radius, rank, world, device, grid=None):
         self.rank, self.world = rank, world
         if grid is None and world > 1:
-            import os
             from . import _lib
             # one process per GPU: share the host cores among the ranks' grid builders
             _lib.lib().pde_set_host_threads(max(1, (os.cpu_count() or 1) // world))
@@ -76,6 +77,9 @@ class ShardedGrid(object):
         halo = stencil_radius if world > 1 else 0
         self.slab = Slab(lo, hi - lo, halo)
         self.ctx = GridContext(self.G, device, slab=self.slab)
+        if world > 1 and os.environ.get("PDE_DYNAMIC_SCHEDULE", "0") == "1":
+            from ._lib import check
+            check(self.ctx.lib.pde_grid_set_dynamic_schedule(self.ctx.h, 1))
 
     def lattice_view(self, S):
         c = self.ctx
