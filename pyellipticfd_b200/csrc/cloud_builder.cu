@@ -232,6 +232,7 @@ int pde_cloud_build(int device, int64_t n_points, int64_t n_interior, const doub
                 "null argument");
     PDE_REQUIRE(n_points < (int64_t)1 << 31, "point ids must fit in 32 bits");
     PDE_REQUIRE(depth >= 1 && kmax >= 3 && bfs_capacity >= 16, "bad depth / capacity");
+    PDE_REQUIRE(kmax <= bfs_capacity, "kmax must not exceed the BFS capacity");
     CloudParams P;
     P.n = n_points;
     P.nint = n_interior;
@@ -288,6 +289,8 @@ int pde_cloud_build(int device, int64_t n_points, int64_t n_interior, const doub
     const int threads = 64;
     int64_t blocks = (int64_t)prop.multiProcessorCount * 8;
     blocks = std::min<int64_t>(blocks, (n_points + threads - 1) / threads);
+    // bound the scratch (one slice per resident thread) to 8 GiB
+    blocks = std::min<int64_t>(blocks, (int64_t)(((size_t)8 << 30) / (stride * threads)));
     blocks = std::max<int64_t>(blocks, 1);
     unsigned char *scratch = nullptr;
     const size_t bytes = stride * (size_t)(blocks * threads);
