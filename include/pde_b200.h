@@ -207,7 +207,7 @@ int pde_bicgstab(pde_grid *g, const pde_jac *J, const double *d_b, double *d_x,
  * place the NCCL traffic in between (pyellipticfd_b200/multigpu.py):
  *   step 0 setup + init pass | 1 finalize | 2 p-update | 3 v = J phat (exchange the
  *   halo of phat = d_work + 4n first) | 4 finalize | 5 s-update | 6 finalize |
- *   7 t = J shat (halo of shat = d_work + 5n first) | 8 finalize | 9 x,r-update | 10 finalize.
+ *   7 t = J shat (halo of shat = d_work + 6n first) | 8 finalize | 9 x,r-update | 10 finalize.
  * Every "pass" step leaves this rank's partial dot products in d_sums (3 doubles); the
  * caller all-reduces them (SUM) before the following "finalize" step, which updates the
  * device-resident scalars d_scal (pde_bicgstab_scal_bytes() bytes).  d_partials:

@@ -10,8 +10,12 @@
 // (per-block partials, then one fixed-order pass), hence deterministic.
 #include <algorithm>
 
+#include <cstdlib>
+
 #include "jacobian.cuh"
 #include "krylov.cuh"
+#include "jac_tiled.cuh"
+#include "tiles.cuh"
 
 using namespace pde;
 
@@ -56,9 +60,14 @@ k_rows(const GridDev G, const __grid_constant__ DeepTable tab, Op op, double *pa
 struct OpMatvec {
     static constexpr int NRED = 0;
     static constexpr bool kSkipOnHalf = false;
+    static constexpr bool kTiled = true;
     JacDev J;
     const double *x;
     double *y;
+    const double *source() const { return x; }
+    __device__ const JacDev &jac() const { return J; }
+    __device__ double aux(int64_t) const { return 0.0; }
+    __device__ void tile(int64_t o, double v, double, double *) { y[o] = v; }
     __device__ void prepare(const BicgScal *) {}
     __device__ void deep(const DeepTable &tab, const GridDev &G, int64_t o, double *) {
         y[o] = jac_row_deep(tab, J, x, o, G.pitch);
@@ -73,6 +82,7 @@ struct OpMatvec {
 struct OpMatvecT {
     static constexpr int NRED = 0;
     static constexpr bool kSkipOnHalf = false;
+    static constexpr bool kTiled = false;
     JacDev J;
     const double *x;
     double *y;
@@ -124,6 +134,7 @@ struct OpMatvecT {
 struct OpDiag {
     static constexpr int NRED = 0;
     static constexpr bool kSkipOnHalf = false;
+    static constexpr bool kTiled = false;
     JacDev J;
     double *d;
     int invert;
@@ -144,9 +155,17 @@ struct OpDiag {
 struct OpAv {
     static constexpr int NRED = 1;
     static constexpr bool kSkipOnHalf = false;
+    static constexpr bool kTiled = true;
     JacDev J;
     const double *src, *rtilde;
     double *dst;
+    const double *source() const { return src; }
+    __device__ const JacDev &jac() const { return J; }
+    __device__ double aux(int64_t o) const { return rtilde[o]; }
+    __device__ void tile(int64_t o, double v, double rt, double *acc) {
+        dst[o] = v;
+        acc[0] += rt * v;
+    }
     __device__ void prepare(const BicgScal *) {}
     __device__ void deep(const DeepTable &tab, const GridDev &G, int64_t o, double *acc) {
         double v = jac_row_deep(tab, J, src, o, G.pitch);
@@ -170,9 +189,18 @@ struct OpAv {
 struct OpAt {
     static constexpr int NRED = 2;
     static constexpr bool kSkipOnHalf = true;
+    static constexpr bool kTiled = true;
     JacDev J;
     const double *src, *s;
     double *dst;
+    const double *source() const { return src; }
+    __device__ const JacDev &jac() const { return J; }
+    __device__ double aux(int64_t o) const { return s[o]; }
+    __device__ void tile(int64_t o, double t, double so, double *acc) {
+        dst[o] = t;
+        acc[0] += t * so;
+        acc[1] += t * t;
+    }
     __device__ void prepare(const BicgScal *) {}
     __device__ void one(int64_t o, double t, double *acc) {
         dst[o] = t;
@@ -188,10 +216,84 @@ struct OpAt {
     __device__ void wall(int64_t o, double *acc) { one(o, src[o], acc); }
 };
 
+// deep-interior rows through the TMA-tiled kernel (jac_tiled.cuh); *nblocks = CTAs launched
+template <class Op, int H>
+static int launch_tiled_h(pde_grid *g, const Op &op, double *partials, const BicgScal *scal,
+                          cudaStream_t st, int *nblocks) {
+    constexpr int P = 8, TX = 2 * P;
+    DeepRegion dr = deep_region(g, 0, g->nx_local);
+    *nblocks = 0;
+    if (dr.nrows <= 0 || dr.ncols <= 0) return 0;
+    DeepGeom geo;
+    geo.pitch = g->pitch;
+    geo.row0 = dr.row0;
+    geo.col0 = dr.col0;
+    geo.nrows = dr.nrows;
+    geo.ncols = dr.ncols;
+    geo.tiles_x = (dr.nrows + TX - 1) / TX;
+    geo.tiles_y = (dr.ncols + K1_TY - 1) / K1_TY;
+    geo.split = geo.tiles_x;
+    geo.row0b = 0;
+    geo.nrowsb = 0;
+    CUtensorMap tmap;
+    int rc = make_tmap(g, op.source(), K1_TY + 2 * H + 2, TX + 2 * H, &tmap);
+    if (rc) return rc;
+    constexpr int smem = k_jac_tiled_smem_bytes<H, P>();
+    auto kern = k_jac_tiled<Op, H, P>;
+    static bool attr_set = false;   // per template instantiation
+    if (!attr_set) {
+        PDE_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set = true;
+    }
+    int ntiles = geo.tiles_x * geo.tiles_y;
+    int grid = std::min(ntiles, g->num_sms * 3);
+    kern<<<grid, K1_THREADS, smem, st>>>(tmap, g->tab, geo, op, partials, scal);
+    PDE_LAUNCH_CHECK();
+    *nblocks = grid;
+    return 0;
+}
+
+template <class Op>
+static int launch_tiled(pde_grid *g, const Op &op, double *partials, const BicgScal *scal,
+                        cudaStream_t st, int *nblocks) {
+    switch (g->tab.H) {
+        case 1: return launch_tiled_h<Op, 1>(g, op, partials, scal, st, nblocks);
+        case 2: return launch_tiled_h<Op, 2>(g, op, partials, scal, st, nblocks);
+        case 3: return launch_tiled_h<Op, 3>(g, op, partials, scal, st, nblocks);
+        case 4: return launch_tiled_h<Op, 4>(g, op, partials, scal, st, nblocks);
+        case 5: return launch_tiled_h<Op, 5>(g, op, partials, scal, st, nblocks);
+        case 6: return launch_tiled_h<Op, 6>(g, op, partials, scal, st, nblocks);
+    }
+    return pde::fail("unsupported stencil halo", __FILE__, __LINE__);
+}
+
+static bool jac_tiled_enabled() {
+    static const bool on = !(getenv("PDE_JAC_TILED") && atoi(getenv("PDE_JAC_TILED")) == 0);
+    return on;
+}
+
 template <class Op>
 static int launch_rows(pde_grid *g, const Op &op, double *partials, const BicgScal *scal,
                        cudaStream_t st, int *nblocks_out = nullptr) {
     GridDev G = grid_dev(g);
+    if constexpr (Op::kTiled) {
+        if (g->tab.D > 0 && g->tab.H >= 1 && g->tab.H <= 6 && jac_tiled_enabled() &&
+            (reinterpret_cast<uintptr_t>(op.source()) & 15) == 0) {      // TMA: 16-byte aligned base
+            // deep-interior points: TMA-tiled kernel; band points and wall entries: the tail
+            // blocks of the plain kernel, their partial sums appended after the tiled CTAs'
+            int nd = 0;
+            int rc = launch_tiled(g, op, partials, scal, st, &nd);
+            if (rc) return rc;
+            int64_t tb = tail_blocks(g->n_band, g->nb);
+            if (tb > 0) {
+                k_rows<Op><<<(unsigned)tb, PASS_THREADS, 0, st>>>(
+                    G, g->tab, op, partials ? partials + (int64_t)nd * Op::NRED : nullptr, scal, 0);
+                PDE_LAUNCH_CHECK();
+            }
+            if (nblocks_out) *nblocks_out = nd + (int)tb;
+            return 0;
+        }
+    }
     int nrb = (int)g->rows;
     int64_t nblk = nrb + tail_blocks(g->n_band, g->nb);
     k_rows<Op><<<(unsigned)nblk, PASS_THREADS, 0, st>>>(G, g->tab, op, partials, scal, nrb);
@@ -301,7 +403,8 @@ int pde_bicgstab_dist_step(pde_grid *g, const pde_jac *J, int step, const double
     BicgScal *scal = static_cast<BicgScal *>(d_scal);
     JacDev Jd = jac_dev(J);
     double *r = d_work, *rtilde = r + n, *p = rtilde + n, *v = p + n, *phat = v + n,
-           *shat = phat + n, *t = shat + n, *dinv = t + n;
+           *t = phat + n, *shat = t + n, *dinv = shat + n;   // phat, shat at even multiples of n:
+    // 16-byte aligned sources for the TMA-tiled operator passes whatever the parity of n
     int rc = 0, nb = 0;
     auto reduce = [&](int stage, int nred) {
         if (nred == 1) k_stage<1><<<1, PASS_THREADS, 0, st>>>(stage, d_partials, nb, scal, rtol, atol, d_sums, 1);

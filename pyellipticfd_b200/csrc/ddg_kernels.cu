@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <type_traits>
 #include "stencil_deep.cuh"
+#include "tiles.cuh"
 
 using namespace pde;
 
@@ -105,41 +106,7 @@ __global__ void k_wall(int64_t nb, int64_t off, const double *__restrict__ W,
     }
 }
 
-// ---- host-side launch helpers ----------------------------------------------------------
-struct DeepRegion {
-    int row0, col0, nrows, ncols;   // buffer coordinates
-};
-
-static DeepRegion deep_region(const pde_grid *g, int64_t win_lo, int64_t win_hi) {
-    int64_t r = g->radius;
-    int64_t gx0 = std::max<int64_t>(r, g->x_offset + win_lo);
-    int64_t gx1 = std::min<int64_t>(g->nx_global - r, g->x_offset + win_hi);
-    DeepRegion d;
-    d.row0 = (int)(gx0 - g->x_offset + g->halo_rows);
-    d.nrows = (int)std::max<int64_t>(0, gx1 - gx0);
-    d.col0 = (int)r;
-    d.ncols = (int)std::max<int64_t>(0, g->ny - 2 * r);
-    return d;
-}
-
-static int make_tmap(const pde_grid *g, const double *S, int boxy, int boxx, CUtensorMap *out) {
-    PDE_REQUIRE((reinterpret_cast<uintptr_t>(S) & 15) == 0, "state buffer must be 16-byte aligned");
-    cuuint64_t gdim[2] = {(cuuint64_t)g->ny, (cuuint64_t)g->rows};
-    cuuint64_t gstr[1] = {(cuuint64_t)g->pitch * 8};
-    cuuint32_t box[2] = {(cuuint32_t)boxy, (cuuint32_t)boxx};
-    cuuint32_t estr[2] = {1, 1};
-    CUresult r = g->encode(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double *>(S), gdim,
-                           gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        char buf[128];
-        snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
-        return pde::fail(buf, __FILE__, __LINE__);
-    }
-    return 0;
-}
-
+// ---- host-side launch helpers (deep_region, make_tmap: tiles.cuh) -------------------------
 template <class Eval, int H, int P, int MODE, class Epi, int MINB = 2, int ICMP = 0>
 static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *red,
                           const unsigned long long *done, cudaStream_t st) {

@@ -296,7 +296,8 @@ static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol,
     if (maxiter <= 0) maxiter = 10 * B.unknowns();     // iterative.py: maxiter = n*10
     if (check_every < 1) check_every = 32;
     double *r = d_work, *rtilde = r + n, *p = rtilde + n, *v = p + n, *phat = v + n,
-           *shat = phat + n, *t = shat + n, *dinv = t + n;
+           *t = phat + n, *shat = t + n, *dinv = shat + n;   // phat, shat at even multiples of n:
+    // 16-byte aligned sources for the TMA-tiled operator passes whatever the parity of n
     int64_t max_blocks = B.max_row_blocks() + (int64_t)sms * 8;
     double *partials = nullptr;
     BicgScal *scal = nullptr;

@@ -169,7 +169,7 @@ class ShardedGrid(object):
         partials = torch.zeros(3 * nblk, dtype=torch.float64, device=dev)
         sums = torch.zeros(3, dtype=torch.float64, device=dev)
         J = Jac._J
-        phat, shat = work[4 * n:5 * n], work[5 * n:6 * n]
+        phat, shat = work[4 * n:5 * n], work[6 * n:7 * n]
 
         def step(k):
             check(c.lib.pde_bicgstab_dist_step(
