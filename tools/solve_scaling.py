@@ -10,6 +10,8 @@ r = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 KW = {}
 if os.environ.get("KRYLOV_RTOL"):
     KW["krylov_rtol"] = float(os.environ["KRYLOV_RTOL"])
+if os.environ.get("MAX_ITERS"):          # the reference's cap is 100 (solvers.py:100)
+    KW["max_iters"] = int(os.environ["MAX_ITERS"])
 sizes = [int(s) for s in sys.argv[2:]] or [63, 127, 255, 511]
 for n in sizes:
     t = time.time()
