@@ -286,9 +286,31 @@ def d1_case(R):
     print("d1_ops: %d arrays, %.1fs" % (len(out), time.time() - t), flush=True)
 
 
+def ddg3d_case(R):
+    """ddg.d2eigs is dimension agnostic: a 3-D pairs grid built by the
+    reference constructor (5^3 interior points, r = 1, 13 pairs per deep point)."""
+    b = np.array([[0, 1], [0, 1], [0, 1]], dtype=float).T
+    G = R.pointclasses.FDRegularGrid([5, 5, 5], b, 1, interpolation=False)
+    out = dict(points=G.points, pairs=G.pairs.astype(np.int32), num_interior=G.num_interior)
+    rng = np.random.default_rng(0)
+    X, Y, Z = G.points.T
+    for fname, u in (("random", rng.standard_normal(G.num_points)), ("quad", X ** 2 - Y ** 2 + 2 * Z ** 2)):
+        (lmin, Mmin, vmin), (lmax, Mmax, vmax) = R.ddg.d2eigs(G, u, jacobian=True, control=True)
+        (omin, _, ovmin), (omax, _, ovmax) = ddg_oracle.d2eigs(G, u, True, True)
+        assert bitwise(lmin, omin) and bitwise(lmax, omax) and bitwise(vmin, ovmin) and bitwise(vmax, ovmax)
+        assert np.abs(Mmin.dot(u) - lmin).max() < 1e-10
+        out["lmin_" + fname], out["lmax_" + fname] = lmin, lmax
+        out["vmin_" + fname], out["vmax_" + fname] = vmin, vmax
+    np.savez_compressed(os.path.join(OUT, "ddg3d_n5_r1.npz"), **out)
+    print("ddg3d_n5_r1: %d pairs" % len(G.pairs), flush=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = refshim.modules()
+    if "--3d-only" in sys.argv:
+        ddg3d_case(R)
+        return
     if "--d1-only" in sys.argv:
         d1_case(R)
         return
@@ -313,6 +335,7 @@ def main():
     trimesh_case(R, "disc_h0.1", 0.1)
     trimesh_case(R, "disc_h0.05", 0.05)
     d1_case(R)
+    ddg3d_case(R)
 
 
 if __name__ == "__main__":

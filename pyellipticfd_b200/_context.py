@@ -69,11 +69,17 @@ def like_input(u, t):
 
 
 def pair_weights(PI, PJ0, PJ1):
-    """(w_0, w_1, w0) and X0 with the reference's arithmetic (ddg.py:276-280)."""
+    """(w_0, w_1, w0) and X0 with the reference's arithmetic (ddg.py:276-280).  Any
+    dimension: the norm is NumPy's ``sqrt(add.reduce(x*x))`` (what ``np.linalg.norm(X, axis=1)``
+    evaluates), written out for the 2-D case."""
     X0 = PJ0 - PI
     X1 = PJ1 - PI
-    h0 = np.sqrt(X0[:, 0] * X0[:, 0] + X0[:, 1] * X0[:, 1])
-    h1 = np.sqrt(X1[:, 0] * X1[:, 0] + X1[:, 1] * X1[:, 1])
+    if X0.shape[1] == 2:
+        h0 = np.sqrt(X0[:, 0] * X0[:, 0] + X0[:, 1] * X0[:, 1])
+        h1 = np.sqrt(X1[:, 0] * X1[:, 0] + X1[:, 1] * X1[:, 1])
+    else:
+        h0 = np.linalg.norm(X0, axis=1)
+        h1 = np.linalg.norm(X1, axis=1)
     w = np.stack([1 / h0, 1 / h1, 2 / (h0 + h1)], axis=1)
     return np.ascontiguousarray(w), np.ascontiguousarray(X0)
 
@@ -198,6 +204,9 @@ class GridContext(object):
             return np.where(ids < N, ids, pitch + (ids - N))
 
         bw, bX = pair_weights(points[pairs[:, 0]], points[pairs[:, 1]], points[pairs[:, 2]])
+        self.band_X_full = bX                       # (P, dim): control vectors in any dimension
+        if bX.shape[1] != 2:                         # the device copy serves 2-D control only
+            bX = np.zeros((bX.shape[0], 2))
         self.slab = Slab(0, 1, 0)
         self._create(1, N, nb, N + 1, 0, 1, 0, np.zeros((0, 4)), np.zeros((0, 3)), np.zeros((0, 2)),
                      offs(np.arange(N)), ptr, np.stack([offs(pairs[:, 1]), offs(pairs[:, 2])], 1),

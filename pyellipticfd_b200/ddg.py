@@ -56,9 +56,26 @@ def d2eigs(G, u, jacobian=False, control=False):
     if jacobian:
         M_min, M_max = PolicyMatrix(ctx, pmin), PolicyMatrix(ctx, pmax)
     if control:
-        vmn, vmx = ctx.control(pmin, pmax)
+        if getattr(G, "dim", 2) == 2:
+            vmn, vmx = ctx.control(pmin, pmax)
+        else:
+            vmn, vmx = _control_nd(ctx, pmin, pmax)
         v_min, v_max = like_input(u, vmn), like_input(u, vmx)
     return (lam_min, M_min, v_min), (lam_max, M_max, v_max)
+
+
+def _control_nd(ctx, pmin, pmax):
+    """Control directions in dimension != 2 (3-D pairs grids run through the explicit-row
+    kernel): v_min = X[min pair] * w[min pair], v_max = X[max pair] * w[MIN pair]
+    (ddg.py:297-300, quirk Q1 replicated), gathered on the host from the selected rows."""
+    kmin = ctx.unpad_policy(pmin).cpu().numpy().astype(np.int64)
+    kmax = ctx.unpad_policy(pmax).cpu().numpy().astype(np.int64)
+    rows_min, rows_max = ctx.band_ptr[:-1] + kmin, ctx.band_ptr[:-1] + kmax
+    X = ctx.band_X_full
+    h = np.linalg.norm(X[rows_min], axis=1)
+    w = (1 / h)[:, None]
+    dev = ctx.device
+    return torch.from_numpy(X[rows_min] * w).to(dev), torch.from_numpy(X[rows_max] * w).to(dev)
 
 
 def _one_extreme(G, u, which, jacobian=False, control=False):
@@ -99,10 +116,10 @@ def _aligned_policy(G, ctx, v):
     pol = np.zeros(N, dtype=np.int64)
 
     def score(X0, X1, vv):
-        def c2(X):
-            h = np.sqrt(X[..., 0] * X[..., 0] + X[..., 1] * X[..., 1])
+        def c2(X):          # any dimension; identical arithmetic to the 2-D expressions
+            h = np.sqrt(np.add.reduce(X * X, axis=-1))
             Xs = X / h[..., None]
-            return (Xs[..., 0] * vv[..., 0] + Xs[..., 1] * vv[..., 1]) ** 2
+            return np.add.reduce(Xs * vv, axis=-1) ** 2
         return c2(X0) + c2(X1)
 
     if ctx.structured:

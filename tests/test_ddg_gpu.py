@@ -244,3 +244,29 @@ def test_config3_8193_r6_bitexact():
     deep = ~np.isnan(out[0])
     assert deep.sum() > 5_000_000
     assert np.array_equal(lmin[deep], out[0][deep]) and np.array_equal(lmax[deep], out[1][deep])
+
+
+def test_3d_pairs_grid_bitexact():
+    """ddg.d2eigs is dimension agnostic in the reference: a 3-D pairs grid
+    built by the reference constructor (5^3 points, r = 1) runs through the explicit-row
+    kernel; values and control vectors bit-exact against the reference's outputs."""
+    from pyellipticfd_b200 import ddg
+    from pyellipticfd_b200.pointclasses import FDPointCloud
+    import os
+    gold = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+    z = np.load(os.path.join(gold, "ddg3d_n5_r1.npz"))
+    G = FDPointCloud(z["points"], num_interior=int(z["num_interior"]))
+    G.pairs = z["pairs"].astype(np.int64)
+    assert G.dim == 3
+    X, Y, Z = G.points.T
+    rng = np.random.default_rng(0)
+    for fname, u in (("random", rng.standard_normal(len(X))), ("quad", X ** 2 - Y ** 2 + 2 * Z ** 2)):
+        (lmin, Mmin, vmin), (lmax, Mmax, vmax) = ddg.d2eigs(G, u, jacobian=True, control=True)
+        assert np.array_equal(lmin, z["lmin_" + fname]) and np.array_equal(lmax, z["lmax_" + fname])
+        assert np.abs(Mmin.dot(u) - lmin).max() < 1e-12 * max(1.0, np.abs(lmin).max())
+        assert Mmin.tocsr().shape == (G.num_interior, G.num_points)
+        if fname == "random":                        # no ties: the selected pairs are the reference's
+            assert np.array_equal(vmin, z["vmin_" + fname]) and np.array_equal(vmax, z["vmax_" + fname])
+            assert vmin.shape == (G.num_interior, 3)
+    lam, _, _ = ddg.d2min(G, X ** 2 - Y ** 2 + 2 * Z ** 2)
+    assert np.abs(lam[np.abs(z["lmin_quad"] + 2) < 1e-9] + 2).max() < 1e-9
