@@ -144,7 +144,7 @@ def run_reference(args):
     sample = None
     steps = max(1, min(args.steps, 3))
     for k in range(min(args.warmup, 1) + steps):
-        res = cpu_baseline(args.n, args.radius, workers)
+        res = cpu_baseline(args.cols or args.n, args.radius, workers)
         sample = res
         vals.append(res["points_per_s"] * res["D"] / 1e9)
     vals = vals[-steps:]
@@ -152,13 +152,14 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": min(args.warmup, 1),
-        "ms_per_step": 1e3 * (args.n - 2 * args.radius) ** 2 * sample["D"] / (v * 1e9),
+        "ms_per_step": 1e3 * args.n * (args.cols or args.n) * sample["D"] / (v * 1e9),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic", "gpu_launches": 0,
-        "config": {"workload": "ddg.d2min on a %d^2 lattice (%d^2 interior points), stencil radius "
-                               "%d (%d pairs/point), NumPy port of the reference (ddg.py:251-292) "
-                               "on %d host processes" % (args.n + 2, args.n, args.radius,
-                                                         sample["D"], sample["cores"]),
+        "config": {"workload": "ddg.d2min on a %d x %d lattice (%d x %d interior points), stencil "
+                               "radius %d (%d pairs/point), NumPy port of the reference "
+                               "(ddg.py:251-292) on %d host processes"
+                               % (args.n + 2, (args.cols or args.n) + 2, args.n, args.cols or args.n,
+                                  args.radius, sample["D"], sample["cores"]),
                    "note": "each step evaluates a bounded sample of rows of that lattice; "
                            "ms_per_step is extrapolated to the full lattice"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": sample["cores"], "kind": "port",
