@@ -210,6 +210,9 @@ def trimesh_case(R, name, h0):
     S = np.asarray(G.simplices)
     S = np.stack([S[:, 0], S[:, 1:].min(1), S[:, 1:].max(1)], 1)
     S = S[np.lexsort((S[:, 2], S[:, 1], S[:, 0]))]
+    from . import trimesh_oracle
+    onb, oS = trimesh_oracle.stencils(p, tri, nint, theta, G.spatial_resolution)
+    assert np.array_equal(onb, nb) and np.array_equal(oS, S), "trimesh oracle differs from the reference"
     X, Y = p.T
     d2x, _ = R.ddi.d2(G, [1, 0], X ** 2 + Y ** 2)          # tests/test_trimesh.py:19-25
     np.savez_compressed(

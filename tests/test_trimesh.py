@@ -68,3 +68,34 @@ def test_given_resolutions_are_kept():
               dist_to_bdry=float(z["dist_to_bdry"]), bdry_resolution=float(z["bdry_resolution"]))
     assert G.spatial_resolution == float(z["spatial_resolution"])
     assert len(G.neighbours) == len(z["neighbours"])
+
+
+@pytest.mark.parametrize("path", MESH, ids=[os.path.basename(p) for p in MESH])
+def test_oracle_restatement_matches_reference(path):
+    """oracle/trimesh_oracle.py (brute-force NumPy/SciPy restatement of pointclasses.py:367-398,
+    :37-121) reproduces the reference constructor's neighbour and simplex sets."""
+    from oracle import trimesh_oracle
+    z = np.load(path)
+    nb, S = trimesh_oracle.stencils(z["points"], z["tri"].astype(np.int64), int(z["num_interior"]),
+                                    float(z["angular_resolution"]), float(z["spatial_resolution"]))
+    assert np.array_equal(nb, z["neighbours"]) and np.array_equal(S, z["simplices"])
+
+
+def test_native_build_equals_oracle_on_random_clouds():
+    """Randomly jittered disc clouds (different seeds, spacings, jitter): the native stencil
+    search equals the brute-force oracle -- graph-depth rule, radius mask, colinear pruning with
+    the boundary re-admission, hull ring."""
+    from scipy.spatial import Delaunay
+    from oracle import disc, trimesh_oracle
+    for seed, h0, jitter in ((1, 0.12, 0.1), (2, 0.09, 0.25), (3, 0.08, 0.05), (4, 0.15, 0.3)):
+        theta = np.pi * h0 ** (1 / 3)
+        p, nint = disc.disc_points(h0, theta, seed=seed, jitter=jitter)
+        tri = Delaunay(p).simplices
+        try:
+            G = FDTriMesh(p, tri, num_interior=nint, angular_resolution=theta, device="cpu")
+        except TypeError:          # interior points too close to the boundary for this jitter
+            continue
+        nb, S = trimesh_oracle.stencils(p, tri.astype(np.int64), nint, theta, G.spatial_resolution)
+        mine = np.asarray(G.neighbours)
+        assert np.array_equal(mine[np.lexsort((mine[:, 1], mine[:, 0]))], nb), (seed, h0)
+        assert np.array_equal(canon_simplices(G.simplices), S), (seed, h0)
