@@ -332,6 +332,15 @@ int pde_band_build(int64_t nx, int64_t ny, int stencil_radius, double sx, double
                    /* optional (may be NULL): the pruned neighbour lists themselves, CSR over the
                     * band points (what ddg.d1 / d1grad walk, ddg.py:44-47) */
                    int64_t **out_nb_ptr, int64_t **out_nb);
+/* The same pre-processing for lattices of any dimension (dim = 2, 3 or 4; used for the 3-D grids
+ * of stencils.py:46-61 `create_nd`): shape, scaling, bounds0 have `dim` entries, h_wall is
+ * (nb, dim), band ids are C-order lattice numbers (last axis fastest, pointclasses.py:513-515).
+ * Same outputs and error behaviour as pde_band_build. */
+int pde_band_build_nd(int dim, const int64_t *shape, int stencil_radius, const double *scaling,
+                      const double *bounds0, int64_t nb, const double *h_wall,
+                      int64_t n_band, const int64_t *h_band_ids, double colinear_tol,
+                      int64_t **out_ptr, int64_t **out_pairs, double *out_min_nb_dist,
+                      int64_t **out_nb_ptr, int64_t **out_nb);
 void pde_free(void *p);
 /* Number of host threads of the pre-processing routines (pde_band_build, host pde_cloud_build);
  * n <= 0 only queries.  torchrun exports OMP_NUM_THREADS=1, which would build an N-GPU job's

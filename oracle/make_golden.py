@@ -18,7 +18,7 @@ import warnings
 
 import numpy as np
 
-from . import refshim, ddg_oracle, solvers_oracle
+from . import refshim, ddg_oracle, solvers_oracle, grid_oracle
 
 OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
 
@@ -62,6 +62,9 @@ def ddg_case(R, name, shape, bounds, r):
                meta=np.array([G.spatial_resolution, G.angular_resolution, G.dist_to_bdry,
                               G.bdry_resolution, G.max_radius, G.min_radius,
                               G.min_interior_nb_dist]))
+    if G.num_interior <= 200:                  # brute-force constructor restatement (2-D too)
+        og = grid_oracle.build(shape, b, r)
+        assert bitwise(og["points"], G.points) and bitwise(canon_pairs(og["pairs"]), out["pairs"]), name
     for fname, u in fields(G).items():
         (lmin, Mmin, vmin), (lmax, Mmax, vmax) = R.ddg.d2eigs(G, u, jacobian=True, control=True)
         (omin, oMmin, ovmin), (omax, oMmax, ovmax) = ddg_oracle.d2eigs(G, u, True, True)
@@ -308,11 +311,68 @@ def ddg3d_case(R):
     print("ddg3d_n5_r1: %d pairs" % len(G.pairs), flush=True)
 
 
+def cones3d(X):
+    """3-D analogue of the example's obstacle: distance to the nearer of two centres."""
+    C = 3 / 7 * np.array([[np.cos(np.pi / 5), np.sin(np.pi / 5), 0.3],
+                          [-np.cos(np.pi / 5), -np.sin(np.pi / 5), -0.3]])
+    return np.min([np.sqrt(((X + c) ** 2).sum(1)) for c in C], axis=0)
+
+
+def grid3d_case(R, name, shape, bounds, r, solve=True):
+    """3-D pairs grid of the REFERENCE constructor: points, metadata, pair and
+    neighbour sets (what the fast constructor is compared with), ddg.d2eigs outputs and the
+    convex-envelope Euler / Newton solves of a two-centre distance obstacle."""
+    t = time.time()
+    b = np.array(bounds, dtype=float).T
+    G = R.pointclasses.FDRegularGrid(list(shape), b, r, interpolation=False)
+    N = G.num_interior
+    nbI = G.neighbours[G.neighbours[:, 0] < N]
+    out = dict(shape=np.array(shape), bounds=b, radius=r, num_bdry=G.num_bdry,
+               bdry_points=G.points[N:], pairs=canon_pairs(G.pairs), normals=G.normals,
+               neighbours=nbI[np.lexsort((nbI[:, 1], nbI[:, 0]))].astype(np.int32),
+               meta=np.array([G.spatial_resolution, G.angular_resolution, G.dist_to_bdry,
+                              G.bdry_resolution, G.max_radius, G.min_radius,
+                              G.min_interior_nb_dist]))
+    # the brute-force restatement of the constructor against the reference
+    og = grid_oracle.build(shape, b, r)
+    assert bitwise(og["points"], G.points) and og["num_interior"] == N
+    assert bitwise(canon_pairs(og["pairs"]), out["pairs"]), name
+    assert bitwise(og["neighbours"][np.lexsort((og["neighbours"][:, 1], og["neighbours"][:, 0]))],
+                   out["neighbours"].astype(np.int64)), name
+    rng = np.random.default_rng(0)
+    X, Y, Z = G.points.T
+    for fname, u in (("random", rng.standard_normal(G.num_points)),
+                     ("quad", X ** 2 - Y ** 2 + 2 * Z ** 2)):
+        (lmin, Mmin, vmin), (lmax, Mmax, vmax) = R.ddg.d2eigs(G, u, jacobian=True, control=True)
+        (omin, _, ovmin), (omax, _, ovmax) = ddg_oracle.d2eigs(G, u, True, True)
+        assert bitwise(lmin, omin) and bitwise(lmax, omax) and bitwise(vmin, ovmin) and bitwise(vmax, ovmax)
+        out["lmin_" + fname], out["lmax_" + fname] = lmin, lmax
+        out["vmin_" + fname], out["vmax_" + fname] = vmin, vmax
+    if solve:
+        g = cones3d(G.points)
+        out["g"] = g
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            U, diff, it, _ = R.convex_envelope.solve(G, g, fdmethod="grid", solver="euler")
+        oU, odiff, oit, _ = solvers_oracle.ce_solve(G, g, solver="euler")
+        assert bitwise(U, oU) and it == oit and diff == odiff, (name, it, oit)
+        out.update(euler_U=U, euler_diff=diff, euler_iters=it)
+        U, diff, it, _ = R.convex_envelope.solve(G, g, fdmethod="grid", solver="newton")
+        oU, odiff, oit, _ = solvers_oracle.ce_solve(G, g, solver="newton")
+        assert it == oit and np.abs(U - oU).max() < 1e-9, (name, it, oit, np.abs(U - oU).max())
+        out.update(newton_U=U, newton_diff=diff, newton_iters=it)
+        print("  3-D solves: euler %d its, newton %d its" % (out["euler_iters"], it), flush=True)
+    np.savez_compressed(os.path.join(OUT, "grid3d_%s.npz" % name), **out)
+    print("grid3d_%s: %d pairs, %.1fs" % (name, len(G.pairs), time.time() - t), flush=True)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     R = refshim.modules()
     if "--3d-only" in sys.argv:
         ddg3d_case(R)
+        grid3d_case(R, "n4x5x6_r2", (4, 5, 6), [[0, 1], [0, 1], [0, 1]], 2, solve=False)
+        grid3d_case(R, "n6_r2", (6, 6, 6), [[-1, 1], [-1, 1], [-1, 1]], 2)
         return
     if "--d1-only" in sys.argv:
         d1_case(R)
@@ -339,6 +399,8 @@ def main():
     trimesh_case(R, "disc_h0.05", 0.05)
     d1_case(R)
     ddg3d_case(R)
+    grid3d_case(R, "n4x5x6_r2", (4, 5, 6), [[0, 1], [0, 1], [0, 1]], 2, solve=False)
+    grid3d_case(R, "n6_r2", (6, 6, 6), [[-1, 1], [-1, 1], [-1, 1]], 2)
 
 
 if __name__ == "__main__":

@@ -85,6 +85,9 @@ SIGNATURES = {
     "pde_band_build": (c_int, [c_i64, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, vp,
                                c_i64, vp, c_dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(c_dbl),
                                C.POINTER(vp), C.POINTER(vp)]),
+    "pde_band_build_nd": (c_int, [c_int, vp, c_int, vp, vp, c_i64, vp, c_i64, vp, c_dbl,
+                                  C.POINTER(vp), C.POINTER(vp), C.POINTER(c_dbl),
+                                  C.POINTER(vp), C.POINTER(vp)]),
     "pde_free": (None, [vp]),
     "pde_set_host_threads": (c_int, [c_int]),
     "pde_cloud_build": (c_int, [c_int, c_i64, c_i64, vp, vp, vp, c_int, c_dbl, c_dbl, c_dbl, c_int,

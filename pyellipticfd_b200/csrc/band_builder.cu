@@ -212,4 +212,227 @@ int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double b
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// n-D (dim >= 2; used for 3-D) version of pde_band_build: the same three rules on lattices of any
+// dimension.  Wall points are bucketed by integer cell (floor of the unscaled coordinates) in a
+// sorted key array; a band point visits the cells of its l-inf box that touch a wall.  Lattice
+// candidates are enumerated in C order of the offset (last axis fastest), then the wall candidates
+// in ascending wall-point number: the row order of a point's group is this library's own (the
+// reference's is an artefact of its joggled Delaunay triangulation and only matters at exact ties).
+int pde_band_build_nd(int dim, const int64_t *shape, int r, const double *scaling,
+                      const double *bounds0, int64_t nb, const double *wall /* nb x dim */,
+                      int64_t n_band, const int64_t *band_ids, double tol, int64_t **out_ptr,
+                      int64_t **out_pairs, double *out_min_nb_dist, int64_t **out_nb_ptr,
+                      int64_t **out_nb) {
+    PDE_REQUIRE(dim >= 2 && dim <= 4, "pde_band_build_nd: dim must be 2, 3 or 4");
+    PDE_REQUIRE(shape && scaling && bounds0 && out_ptr && out_pairs && out_min_nb_dist &&
+                    (n_band == 0 || band_ids) && (nb == 0 || wall),
+                "null argument");
+    int64_t N = 1, cstride[4], lstride[4];
+    for (int d = 0; d < dim; ++d) N *= shape[d];
+    lstride[dim - 1] = 1;
+    cstride[dim - 1] = 1;
+    for (int d = dim - 2; d >= 0; --d) {
+        lstride[d] = lstride[d + 1] * shape[d + 1];
+        cstride[d] = cstride[d + 1] * (shape[d + 1] + 2);
+    }
+    // wall points sorted by cell key
+    std::vector<std::pair<int64_t, int64_t>> cells(nb);
+    for (int64_t i = 0; i < nb; ++i) {
+        int64_t key = 0;
+        for (int d = 0; d < dim; ++d) {
+            int64_t c = (int64_t)std::floor(wall[dim * i + d]);
+            c = c < 0 ? 0 : (c > shape[d] + 1 ? shape[d] + 1 : c);
+            key += c * cstride[d];
+        }
+        cells[i] = {key, i};
+    }
+    std::sort(cells.begin(), cells.end());
+
+    std::vector<std::vector<int64_t>> rows(n_band);
+    const bool want_nb = out_nb_ptr && out_nb;
+    std::vector<std::vector<int64_t>> nbs(want_nb ? n_band : 0);
+    std::vector<double> min_nb(n_band, INFINITY);
+    int64_t bad_point = -1;
+
+#pragma omp parallel
+    {
+        std::vector<double> V, D, S;      // K x dim, K, K x dim
+        std::vector<int64_t> ID, wids;
+        std::vector<char> isb, disc, discm, keep;
+#pragma omp for schedule(dynamic, 8)
+        for (int64_t p = 0; p < n_band; ++p) {
+            const int64_t id = band_ids[p];
+            double c[4], pc[4];
+            int64_t ci[4];
+            {
+                int64_t rem = id;
+                for (int d = 0; d < dim; ++d) {
+                    ci[d] = rem / lstride[d] + 1;
+                    rem %= lstride[d];
+                    c[d] = (double)ci[d];
+                    pc[d] = c[d] * scaling[d] + bounds0[d];
+                }
+            }
+            V.clear(); ID.clear(); isb.clear();
+            // lattice candidates: odometer over the offset box
+            int o[4];
+            for (int d = 0; d < dim; ++d) o[d] = -r;
+            for (;;) {
+                bool zero = true, inside = true;
+                int64_t lid = 0;
+                for (int d = 0; d < dim; ++d) {
+                    zero &= o[d] == 0;
+                    int64_t x = ci[d] + o[d];
+                    inside &= x >= 1 && x <= shape[d];
+                    lid += (x - 1) * lstride[d];
+                }
+                if (!zero && inside) {
+                    for (int d = 0; d < dim; ++d)
+                        V.push_back(((c[d] + o[d]) * scaling[d] + bounds0[d]) - pc[d]);
+                    ID.push_back(lid);
+                    isb.push_back(0);
+                }
+                int d = dim - 1;
+                while (d >= 0 && ++o[d] > r) o[d--] = -r;
+                if (d < 0) break;
+            }
+            // wall candidates: cells [c-r-1, c+r] per axis that lie on a wall
+            wids.clear();
+            int64_t lo[4], hi[4], cc[4];
+            bool near_wall = false;
+            for (int d = 0; d < dim; ++d) {
+                lo[d] = std::max<int64_t>(0, ci[d] - r - 1);
+                hi[d] = std::min<int64_t>(shape[d] + 1, ci[d] + r);
+                near_wall |= lo[d] == 0 || hi[d] >= shape[d];
+                cc[d] = lo[d];
+            }
+            if (near_wall && nb > 0)
+                for (;;) {
+                    bool on_wall = false;
+                    int64_t key = 0;
+                    for (int d = 0; d < dim; ++d) {
+                        on_wall |= cc[d] == 0 || cc[d] >= shape[d];   // cell n too: (n+1)-eps after rounding
+                        key += cc[d] * cstride[d];
+                    }
+                    if (on_wall) {
+                        auto it = std::lower_bound(cells.begin(), cells.end(),
+                                                   std::make_pair(key, (int64_t)-1));
+                        for (; it != cells.end() && it->first == key; ++it) {
+                            const double *w = wall + dim * it->second;
+                            double dinf = 0;
+                            for (int d = 0; d < dim; ++d) dinf = std::max(dinf, std::fabs(w[d] - c[d]));
+                            if (dinf <= r && dinf > 0) wids.push_back(it->second);
+                        }
+                    }
+                    int d = dim - 1;
+                    while (d >= 0 && ++cc[d] > hi[d]) { cc[d] = lo[d]; --d; }
+                    if (d < 0) break;
+                }
+            std::sort(wids.begin(), wids.end());
+            for (int64_t wid : wids) {
+                const double *w = wall + dim * wid;
+                for (int d = 0; d < dim; ++d) V.push_back((w[d] * scaling[d] + bounds0[d]) - pc[d]);
+                ID.push_back(N + wid);
+                isb.push_back(1);
+            }
+            const int K = (int)ID.size();
+            D.resize(K); S.resize((size_t)K * dim);
+            disc.assign(K, 0); discm.assign(K, 0); keep.assign(K, 0);
+            for (int k = 0; k < K; ++k) {
+                double s = 0;
+                for (int d = 0; d < dim; ++d) s += V[(size_t)k * dim + d] * V[(size_t)k * dim + d];
+                D[k] = std::sqrt(s);
+            }
+            for (int k = 0; k < K; ++k)
+                for (int l = k + 1; l < K; ++l) {
+                    double dot = 0;
+                    for (int d = 0; d < dim; ++d) dot += V[(size_t)k * dim + d] * V[(size_t)l * dim + d];
+                    double cosv = dot / (D[k] * D[l]);
+                    cosv = cosv < -1.0 ? -1.0 : (cosv > 1.0 ? 1.0 : cosv);
+                    if ((1.0 - cosv) < tol) {
+                        int loser = D[k] >= D[l] ? k : l;
+                        disc[loser] = 1;
+                        if (isb[k] != isb[l]) discm[loser] = 1;
+                    }
+                }
+            double mnb = INFINITY;
+            for (int k = 0; k < K; ++k) {
+                keep[k] = !disc[k] || (isb[k] && !discm[k]);
+                for (int d = 0; d < dim; ++d) S[(size_t)k * dim + d] = V[(size_t)k * dim + d] / D[k];
+                if (keep[k]) mnb = std::min(mnb, D[k]);
+            }
+            min_nb[p] = mnb;
+            if (want_nb)
+                for (int k = 0; k < K; ++k)
+                    if (keep[k]) nbs[p].push_back(ID[k]);
+            std::vector<int64_t> &out = rows[p];
+            for (int k = 0; k < K; ++k) {
+                if (!keep[k]) continue;
+                for (int l = k + 1; l < K; ++l) {
+                    if (!keep[l]) continue;
+                    double cs = 0;
+                    for (int d = 0; d < dim; ++d) cs += S[(size_t)k * dim + d] * S[(size_t)l * dim + d];
+                    if (cs < -1 + tol) {
+                        out.push_back(ID[k]);
+                        out.push_back(ID[l]);
+                    }
+                }
+            }
+            if (out.empty()) {
+#pragma omp critical
+                if (bad_point < 0 || id < bad_point) bad_point = id;
+            }
+        }
+    }
+    if (bad_point >= 0) {
+        char buf[96];
+        snprintf(buf, sizeof buf, "Point %lld has no pairs", (long long)bad_point);
+        pde::set_error(buf);
+        return 2;
+    }
+    int64_t *ptr = (int64_t *)malloc(sizeof(int64_t) * (n_band + 1));
+    PDE_REQUIRE(ptr, "out of memory");
+    ptr[0] = 0;
+    for (int64_t p = 0; p < n_band; ++p) ptr[p + 1] = ptr[p] + (int64_t)rows[p].size() / 2;
+    const int64_t P = ptr[n_band];
+    int64_t *pairs = (int64_t *)malloc(sizeof(int64_t) * 3 * (P > 0 ? P : 1));
+    if (!pairs) {
+        free(ptr);
+        return pde::fail("out of memory", __FILE__, __LINE__);
+    }
+#pragma omp parallel for schedule(static)
+    for (int64_t p = 0; p < n_band; ++p) {
+        int64_t o = ptr[p];
+        for (size_t k = 0; k < rows[p].size() / 2; ++k) {
+            pairs[3 * (o + k)] = band_ids[p];
+            pairs[3 * (o + k) + 1] = rows[p][2 * k];
+            pairs[3 * (o + k) + 2] = rows[p][2 * k + 1];
+        }
+    }
+    if (want_nb) {
+        int64_t *nptr = (int64_t *)malloc(sizeof(int64_t) * (n_band + 1));
+        int64_t *nb_out = nullptr;
+        if (nptr) {
+            nptr[0] = 0;
+            for (int64_t p = 0; p < n_band; ++p) nptr[p + 1] = nptr[p] + (int64_t)nbs[p].size();
+            nb_out = (int64_t *)malloc(sizeof(int64_t) * (nptr[n_band] > 0 ? nptr[n_band] : 1));
+        }
+        if (!nptr || !nb_out) {
+            free(ptr); free(pairs); free(nptr); free(nb_out);
+            return pde::fail("out of memory", __FILE__, __LINE__);
+        }
+        for (int64_t p = 0; p < n_band; ++p)
+            std::copy(nbs[p].begin(), nbs[p].end(), nb_out + nptr[p]);
+        *out_nb_ptr = nptr;
+        *out_nb = nb_out;
+    }
+    double m = INFINITY;
+    for (int64_t p = 0; p < n_band; ++p) m = std::min(m, min_nb[p]);
+    *out_ptr = ptr;
+    *out_pairs = pairs;
+    *out_min_nb_dist = m;
+    return 0;
+}
+
 }  // extern "C"

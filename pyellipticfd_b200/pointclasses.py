@@ -363,15 +363,25 @@ class FDTriMesh(FDPointCloud):
 def _prune_and_pair(V, valid, is_bdry, tol=COLINEAR_TOL):
     """Apply the reference's colinear pruning and antipodal pairing to a batch.
 
-    V       (B, K, 2) scaled stencil vectors (garbage where ``valid`` is False)
+    V       (B, K, dim) scaled stencil vectors (garbage where ``valid`` is False)
     valid   (B, K) candidate mask
     is_bdry (B, K) candidate is a wall point
     Returns (keep (B, K) bool, pair_mask (B, K, K) bool upper-triangular over kept).
     """
-    B, K, _ = V.shape
-    D = np.sqrt(V[..., 0] * V[..., 0] + V[..., 1] * V[..., 1])
+    B, K, dim = V.shape
+
+    def gram(A):                      # sum over the axes in order: the 2-D expression a0*b0 + a1*b1
+        g = A[:, :, None, 0] * A[:, None, :, 0]
+        for d in range(1, dim):
+            g = g + A[:, :, None, d] * A[:, None, :, d]
+        return g
+
+    sq = V[..., 0] * V[..., 0]
+    for d in range(1, dim):
+        sq = sq + V[..., d] * V[..., d]
+    D = np.sqrt(sq)
     D = np.where(valid, D, 1.0)
-    dot = V[:, :, None, 0] * V[:, None, :, 0] + V[:, :, None, 1] * V[:, None, :, 1]
+    dot = gram(V)
     cosv = dot / (D[:, :, None] * D[:, None, :])
     np.clip(cosv, -1.0, 1.0, out=cosv)
     both = valid[:, :, None] & valid[:, None, :]
@@ -388,7 +398,7 @@ def _prune_and_pair(V, valid, is_bdry, tol=COLINEAR_TOL):
     keep = valid & (~discarded | (is_bdry & ~disc_mixed))
     # antipodal pairing on normalised vectors (pointclasses.py:18-33)
     Vs = V / D[..., None]
-    cs = Vs[:, :, None, 0] * Vs[:, None, :, 0] + Vs[:, :, None, 1] * Vs[:, None, :, 1]
+    cs = gram(Vs)
     pair = (cs < -1 + tol) & keep[:, :, None] & keep[:, None, :] & upper
     return keep, pair
 
@@ -409,18 +419,17 @@ class FDRegularGrid(FDPointCloud):
                 "pyellipticfd_b200.FDRegularGrid builds antipodal pairs only "
                 "(interpolation=False); simplices on regular grids are not on the hot path")
         dim = len(interior_shape)
-        if dim != 2:
-            raise NotImplementedError("only 2-D regular grids are implemented")
+        if dim < 2 or dim > 4:
+            raise NotImplementedError("regular grids are implemented in 2, 3 and 4 dimensions")
         self._interp = interpolation
         self.stencil_radius = r = int(stencil_radius)
         shape = np.array(interior_shape)
         bounds = np.array(bounds)
         self.interior_shape = tuple(int(s) for s in shape)
         self.bounds = bounds
-        nx, ny = self.interior_shape
         self.scaling = (bounds[1] - bounds[0]) / (shape + 1)             # :508
         self.spatial_resolution = np.linalg.norm(bounds / (shape + 1)) / 2   # :510-511 (quirk Q11)
-        self.num_interior = nx * ny
+        self.num_interior = int(np.prod(shape))
         self._points = None
         self._pairs = None
         self.simplices = None
@@ -431,30 +440,37 @@ class FDRegularGrid(FDPointCloud):
         stcl = stencils.create(r, dim)
         self._make_wall_points(stcl)
         self._make_metadata(stcl)
-        self._make_deep_table()
-        self._make_band()
+        if dim == 2:
+            self._make_deep_table()
+            self._make_band()
+        else:
+            self._make_nd()
 
     # -- geometry -------------------------------------------------------------
     def _make_wall_points(self, stcl):
         """Wall points with the reference's literal arithmetic (:520-540)."""
-        nx, ny = self.interior_shape
         shape = np.array(self.interior_shape)
+        dim = len(shape)
         bounds = self.bounds
         stcl_l1 = stcl / np.max(np.abs(stcl), axis=1)[:, None]
         # interior points adjacent to a wall, as lattice coordinates
         edge = []
-        ix = np.arange(1, nx + 1)
-        iy = np.arange(1, ny + 1)
-        edge.append(np.stack([np.full(ny, 1), iy], 1))
-        edge.append(np.stack([np.full(ny, nx), iy], 1))
-        edge.append(np.stack([ix, np.full(nx, 1)], 1))
-        edge.append(np.stack([ix, np.full(nx, ny)], 1))
+        for d in range(dim):
+            others = [np.arange(1, n + 1) for k, n in enumerate(shape) if k != d]
+            mesh = np.meshgrid(*others, indexing="ij")
+            for val in (1, shape[d]):
+                cols = [m.ravel() for m in mesh]
+                cols.insert(d, np.full(cols[0].size, val))
+                edge.append(np.stack(cols, 1))
         edge = np.unique(np.concatenate(edge), axis=0)
-        X = edge[:, :, None] + stcl_l1.T[None, :, :]
-        X = np.moveaxis(X, 2, 0).reshape(-1, 2)
-        on_wall = ((X[:, 0] == 0) | (X[:, 0] == nx + 1) |
-                   (X[:, 1] == 0) | (X[:, 1] == ny + 1))
-        X = X[on_wall]
+        found = []
+        step = max(1, 2_000_000 // (stcl_l1.shape[0] * dim))
+        for s0 in range(0, edge.shape[0], step):            # chunked: 3-D stencils are large
+            X = edge[s0:s0 + step, :, None] + stcl_l1.T[None, :, :]
+            X = np.moveaxis(X, 2, 0).reshape(-1, dim)
+            on_wall = ((X == 0) | (X == shape + 1)).any(axis=1)
+            found.append(np.unique(X[on_wall], axis=0))
+        X = np.concatenate(found)
         h = (bounds[1] - bounds[0]) / (shape + 1)
         self._wall_unscaled = (np.unique(h * X + bounds[0], axis=0) - bounds[0]) / h
         self.num_bdry = self._wall_unscaled.shape[0]
@@ -462,7 +478,7 @@ class FDRegularGrid(FDPointCloud):
         Xb = self._wall_unscaled
         nrm = np.zeros(Xb.shape)
         M = Xb.max(0)
-        for i in range(2):
+        for i in range(dim):
             nrm[Xb[:, i] == 0, i] = -1.0
             nrm[Xb[:, i] == M[i], i] = 1.0
         self.normals = nrm / np.linalg.norm(nrm, axis=1)[:, None]
@@ -474,17 +490,19 @@ class FDRegularGrid(FDPointCloud):
         s = s[np.logical_not(s == 0).all(axis=1)]
         vs = s / np.linalg.norm(s, axis=1)[:, None]
 
+        dim = len(self.interior_shape)
+
         def dtheta(i):
-            e = np.zeros(2)
+            e = np.zeros(dim)
             e[i] = 1
             th = np.arccos(vs.dot(e))
             return th[th > 0].min()
 
-        self.angular_resolution = max(dtheta(i) for i in range(2))
+        self.angular_resolution = max(dtheta(i) for i in range(dim))
         self.dist_to_bdry = self.scaling.min()
-        b_rect = np.full(2, 1 / r) * self.scaling
+        b_rect = np.full(dim, 1 / r) * self.scaling
         self.bdry_resolution = max(np.linalg.norm(v) / 2
-                                   for v in itertools.combinations(b_rect, 1))
+                                   for v in itertools.combinations(b_rect, dim - 1))
 
     def _scaled(self, P):
         """Lattice coordinates -> physical coordinates, as :551."""
@@ -533,6 +551,87 @@ class FDRegularGrid(FDPointCloud):
             min_nb = min(min_nb, np.sqrt((offs_k ** 2).sum(1)).min())
         self._min_interior_nb_dist = float(min_nb)
         return True
+
+    def _make_nd(self):
+        """3-D (and 4-D) pairs grids, SURVEY 8f rank 4: the same three rules as in 2-D (l-inf
+        box on the unscaled coordinates, colinear pruning, antipodal pairing; checked against the
+        reference constructor in tests/test_grid.py).  Band points go through the native host
+        builder ``pde_band_build_nd``; deep points share one offset table.  The result is stored
+        explicitly (``points``, ``pairs``, ``neighbours`` of the interior points) and evaluated by
+        the explicit-row kernel (``_context.GridContext._init_generic``)."""
+        import ctypes as C
+        from . import _lib
+        L = _lib.lib()
+        shape = np.array(self.interior_shape, dtype=np.int64)
+        dim = len(shape)
+        r = self.stencil_radius
+        N = self.num_interior
+        band = np.zeros(tuple(shape), bool)
+        for d, n in enumerate(shape):
+            sl = [None] * dim
+            sl[d] = slice(None)
+            band |= self._band_mask_1d(n)[tuple(sl)]
+        band_index = np.flatnonzero(band.ravel()).astype(np.int64)
+        deep = np.flatnonzero(~band.ravel()).astype(np.int64)
+        self.band_index = band_index
+        # band points: native builder
+        W = np.ascontiguousarray(self._wall_unscaled, dtype=np.float64)
+        sc = np.ascontiguousarray(self.scaling, dtype=np.float64)
+        b0 = np.ascontiguousarray(self.bounds[0], dtype=np.float64)
+        ptr, pairs, mn = C.c_void_p(), C.c_void_p(), C.c_double()
+        nptr, nbl = C.c_void_p(), C.c_void_p()
+        rc = L.pde_band_build_nd(dim, C.c_void_p(shape.ctypes.data), r, C.c_void_p(sc.ctypes.data),
+                                 C.c_void_p(b0.ctypes.data), W.shape[0], C.c_void_p(W.ctypes.data),
+                                 band_index.size, C.c_void_p(band_index.ctypes.data), COLINEAR_TOL,
+                                 C.byref(ptr), C.byref(pairs), C.byref(mn), C.byref(nptr),
+                                 C.byref(nbl))
+        if rc == 2:
+            raise TypeError(L.pde_last_error().decode())          # "Point i has no pairs"
+        _lib.check(rc)
+        n = band_index.size
+        try:
+            bptr = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+            P = int(bptr[-1])
+            band_pairs = np.ctypeslib.as_array(
+                C.cast(pairs, C.POINTER(C.c_int64)), shape=(max(P, 1) * 3,)).copy()[:3 * P].reshape(P, 3)
+            bnptr = np.ctypeslib.as_array(C.cast(nptr, C.POINTER(C.c_int64)), shape=(n + 1,)).copy()
+            T = int(bnptr[-1])
+            band_nb = np.ctypeslib.as_array(
+                C.cast(nbl, C.POINTER(C.c_int64)), shape=(max(T, 1),)).copy()[:T]
+        finally:
+            for q in (ptr, pairs, nptr, nbl):
+                L.pde_free(q)
+        min_nb = mn.value if n else np.inf
+        # deep points: one translation-invariant table
+        offs = np.stack(np.meshgrid(*[np.arange(-r, r + 1)] * dim, indexing="ij"), -1).reshape(-1, dim)
+        offs = offs[(offs != 0).any(axis=1)]
+        c = np.full(dim, r + 1.0)
+        V = self._scaled(c + offs) - self._scaled(c)
+        keep, pair = _prune_and_pair(V[None], np.ones((1, len(offs)), bool),
+                                     np.zeros((1, len(offs)), bool))
+        k, l = np.nonzero(pair[0])
+        self.stencil_offsets = offs[keep[0]]
+        self.stencil_pairs_nd = np.concatenate([offs[k], offs[l]], axis=1).astype(np.int32)
+        rows, nbrows = [band_pairs], [np.stack([np.repeat(band_index, np.diff(bnptr)), band_nb], 1)]
+        if deep.size:
+            stride = np.array([int(np.prod(shape[d + 1:])) for d in range(dim)], dtype=np.int64)
+            sp = self.stencil_pairs_nd.astype(np.int64)
+            J0 = deep[:, None] + (sp[:, :dim] * stride).sum(1)[None, :]
+            J1 = deep[:, None] + (sp[:, dim:] * stride).sum(1)[None, :]
+            I = np.broadcast_to(deep[:, None], J0.shape)
+            rows.append(np.stack([I.ravel(), J0.ravel(), J1.ravel()], axis=1))
+            Jn = deep[:, None] + (self.stencil_offsets.astype(np.int64) * stride).sum(1)[None, :]
+            nbrows.append(np.stack([np.broadcast_to(deep[:, None], Jn.shape).ravel(), Jn.ravel()], 1))
+            offs_k = self.stencil_offsets * self.scaling
+            min_nb = min(min_nb, np.sqrt((offs_k ** 2).sum(1)).min())
+        allrows = np.concatenate(rows)
+        self._pairs = allrows[np.argsort(allrows[:, 0], kind="stable")]
+        nbrows = np.concatenate(nbrows)
+        self._neighbours = nbrows[np.argsort(nbrows[:, 0], kind="stable")]
+        self._min_interior_nb_dist = float(min_nb)
+        grids = np.meshgrid(*[np.arange(1, m + 1) for m in shape], indexing="ij")
+        Xint = np.stack([g.ravel() for g in grids], axis=1)
+        self._points = np.concatenate([Xint, self._wall_unscaled]) * self.scaling + self.bounds[0]
 
     def coords(self, ids):
         """Physical coordinates of the given point ids, with the arithmetic of
@@ -730,7 +829,7 @@ class FDRegularGrid(FDPointCloud):
 
     @property
     def dim(self):
-        return 2
+        return len(self.interior_shape)
 
     @property
     def bdry_points(self):
