@@ -70,6 +70,8 @@ class ShardedGrid(object):
             _lib.lib().pde_set_host_threads(max(1, (os.cpu_count() or 1) // world))
         self.G = grid if grid is not None else FDRegularGrid(list(interior_shape), bounds,
                                                              stencil_radius, interpolation=False)
+        if len(self.G.interior_shape) != 2:
+            raise NotImplementedError("slab sharding is implemented for 2-D regular grids")
         nx, ny = self.G.interior_shape
         lo, hi = slab_partition(nx, world)[rank]
         if world > 1 and hi - lo < stencil_radius:

@@ -510,11 +510,13 @@ class FDRegularGrid(FDPointCloud):
 
     def _make_band_native(self):
         import ctypes as C
+        from . import _lib
         try:
-            from . import _lib
             L = _lib.lib()
             fn = L.pde_band_build
-        except Exception:
+        except (_lib.PdeError, OSError, AttributeError):
+            # library not built: the NumPy specification below builds the same rows (host
+            # pre-processing either way; the operators themselves have no such path)
             return False
         nx, ny = self.interior_shape
         W = np.ascontiguousarray(self._wall_unscaled, dtype=np.float64)
@@ -637,12 +639,10 @@ class FDRegularGrid(FDPointCloud):
         """Physical coordinates of the given point ids, with the arithmetic of
         ``points`` (:551) but without materialising the whole array."""
         ids = np.asarray(ids, dtype=np.int64)
-        nx, ny = self.interior_shape
         N = self.num_interior
-        P = np.empty((ids.size, 2))
+        P = np.empty((ids.size, self.dim))
         lat = ids < N
-        P[lat, 0] = ids[lat] // ny + 1
-        P[lat, 1] = ids[lat] % ny + 1
+        P[lat] = np.stack(np.unravel_index(ids[lat], self.interior_shape), axis=1) + 1
         P[~lat] = self._wall_unscaled[ids[~lat] - N]
         return P * self.scaling + self.bounds[0]
 
@@ -869,6 +869,8 @@ class FDRegularGrid(FDPointCloud):
 
     @property
     def num_pairs(self):
+        if self.dim != 2:
+            return int(self._pairs.shape[0])
         return self.num_deep * self.stencil_pairs.shape[0] + self.band_pairs.shape[0]
 
     @property

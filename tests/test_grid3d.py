@@ -131,3 +131,14 @@ def test_grid_invariants_3d():
     assert np.array_equal(G.stencil_pairs_nd[:, :3], -G.stencil_pairs_nd[:, 3:])
     with pytest.raises(NotImplementedError):
         FDRegularGrid([5, 5, 5], np.array([[0.0, 1.0]] * 3).T, 1, interpolation=True)
+
+
+def test_nd_helpers():
+    G = FDRegularGrid([5, 6, 7], np.array([[0.0, 1.0]] * 3).T, 2, interpolation=False)
+    ids = np.array([0, 17, G.num_interior - 1, G.num_interior, G.num_points - 1])
+    assert np.array_equal(G.coords(ids), G.points[ids])
+    assert G.num_pairs == len(G.pairs) and G.num_deep == 1 * 2 * 3
+    assert "3D" in repr(G)
+    from pyellipticfd_b200.multigpu import ShardedGrid
+    with pytest.raises(NotImplementedError):
+        ShardedGrid(None, None, 2, 0, 1, None, grid=G)
