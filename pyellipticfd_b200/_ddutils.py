@@ -1,37 +1,42 @@
 """Argument normalisation for the directional-derivative routines
-(mirror of /root/reference/_ddutils.py:6-47)."""
+(same contract as /root/reference/_ddutils.py:6-47)."""
 import numpy as np
+
+_COUNT = {"interior": "num_interior", "boundary": "num_bdry"}
+
+
+def _components(angles, dim):
+    """Cartesian components of the direction given by polar angle(s), in the reference's
+    convention: (cos a, sin a) in 2-D; (sin t cos p, sin t sin p, cos p) in 3-D."""
+    if dim == 2:
+        a, = angles
+        return [np.cos(a), np.sin(a)]
+    t, p = angles
+    return [np.sin(t) * np.cos(p), np.sin(t) * np.sin(p), np.cos(p)]
 
 
 def process_v(G, v, domain="interior"):
-    """Turn the user's direction argument into an (N, dim) array of unit vectors.
+    """Turn the user's direction argument into an (n, dim) array of unit vectors, one per
+    point of ``domain``.
 
-    Accepted forms, as in the reference: a scalar angle (2-D), a pair of angles
-    (3-D), one constant vector, one angle per point (2-D), two angles per point
-    (3-D), or one vector per point."""
-    if domain == "interior":
-        N = G.num_interior
-    elif domain == "boundary":
-        N = G.num_bdry
-    else:
+    Accepted forms, tried in this order: constant angle(s) (one in 2-D, two in 3-D), one
+    constant vector, angle(s) per point, one vector per point.  Anything else is returned
+    unchanged, as the reference does."""
+    if domain not in _COUNT:
         raise ValueError("domain must be 'interior' or 'boundary'")
-    dim = G.dim
+    n, dim = getattr(G, _COUNT[domain]), G.dim
     if hasattr(v, "detach"):          # torch tensor
         v = v.detach().cpu().numpy()
     v = np.array(v, dtype=np.float64)
-    if v.size == 1 and dim == 2:
-        return np.broadcast_to([np.cos(v).item(), np.sin(v).item()], (N, dim))
-    if v.size == 2 and dim == 3:
-        return np.broadcast_to([np.sin(v[0]) * np.cos(v[1]), np.sin(v[0]) * np.sin(v[1]),
-                                np.cos(v[1])], (N, dim))
+    angular = dim in (2, 3)
+    if angular and v.size == dim - 1:
+        const = [float(c) for c in _components(v.reshape(dim - 1), dim)]
+        return np.broadcast_to(const, (n, dim))
     if v.size == dim:
-        return np.broadcast_to(v / np.linalg.norm(v), (N, dim))
-    if v.size == N and dim == 2:
-        v = v.reshape(N)
-        return np.array([np.cos(v), np.sin(v)]).T
-    if v.shape == (N, 2) and dim == 3:
-        return np.array([np.sin(v[:, 0]) * np.cos(v[:, 1]), np.sin(v[:, 0]) * np.sin(v[:, 1]),
-                         np.cos(v[:, 1])]).T
-    if v.shape == (N, dim):
-        return v / np.linalg.norm(v, axis=1)[:, None]
+        return np.broadcast_to(v / np.linalg.norm(v), (n, dim))
+    if angular and (v.size == n if dim == 2 else v.shape == (n, 2)):
+        return np.array(_components(v.reshape(n, dim - 1).T, dim)).T
+    if v.shape == (n, dim):
+        lengths = np.linalg.norm(v, axis=1)
+        return v / lengths[:, None]
     return v
