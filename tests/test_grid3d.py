@@ -142,3 +142,14 @@ def test_nd_helpers():
     from pyellipticfd_b200.multigpu import ShardedGrid
     with pytest.raises(NotImplementedError):
         ShardedGrid(None, None, 2, 0, 1, None, grid=G)
+
+
+def test_4d_box_equals_brute_force_oracle():
+    """dim = 4 (3x4x3x3, r = 1; the reference constructor builds the same points and pair sets,
+    checked once in this container): native builder == brute-force restatement."""
+    shape, b = [3, 4, 3, 3], np.array([[0.0, 1.0]] * 4).T
+    G = FDRegularGrid(shape, b, 1, interpolation=False)
+    og = grid_oracle.build(shape, b, 1)
+    assert G.dim == 4 and np.array_equal(G.points, og["points"])
+    assert np.array_equal(canon_pairs(G.pairs), canon_pairs(og["pairs"]))
+    assert G.stencil_pairs_nd.shape == (40, 8)
