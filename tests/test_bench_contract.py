@@ -52,3 +52,38 @@ def test_obstacle_is_the_reference_example():
     from oracle.make_golden import two_cones
     X = np.random.default_rng(0).uniform(-1, 1, (50, 2))
     assert np.array_equal(b.two_cones(X), two_cones(X))
+
+
+def _line(name):
+    import json
+    path = os.path.join(ROOT, "profiles", name)
+    return [json.loads(l) for l in open(path) if l.startswith("{")][-1]
+
+
+def test_committed_bench_lines_carry_the_contract_keys():
+    """profiles/r01_bench*.json are bench.py's own output on the B200 box: every key of the
+    driver contract is present and consistent."""
+    d = _line("r01_bench.json")
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step",
+              "higher_is_better", "scaling", "vs_baseline", "dtype", "data", "config",
+              "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks"):
+        assert k in d, k
+    assert d["unit"] == "Gpoint.dir/s" and d["dtype"] == "f64" and d["vs_baseline"] is None
+    assert "workload" in d["config"] and "model" not in d["config"]
+    r = d["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    assert r["traffic"] is None or r["traffic"] > 0
+    c = d["cpu_baseline"]
+    assert c["kind"] in ("port", "reference") and c["cores"] >= 1 and c["sample"]
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0
+    assert e["value"] < d["value"]                      # host copies inside the timed region
+    assert d["gpu_launches"] >= d["steps"]
+    assert d["warmup"] >= 3 and not set(d["clocks"]["reasons"]) & {
+        "hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    # value = interior points x pairs / time
+    assert abs(d["value"] - 4095 * 4095 * 24 / d["ms_per_step"] / 1e6) < 1e-6 * d["value"]
+    ref = _line("r01_bench_reference.json")
+    assert ref["impl"] == "reference" and ref["unit"] == d["unit"]
+    assert ref["e2e"]["h2d_bytes_per_step"] == 0 and ref["cpu_baseline"]["value"] == ref["value"]
