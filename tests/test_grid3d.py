@@ -153,3 +153,19 @@ def test_4d_box_equals_brute_force_oracle():
     assert G.dim == 4 and np.array_equal(G.points, og["points"])
     assert np.array_equal(canon_pairs(G.pairs), canon_pairs(og["pairs"]))
     assert G.stencil_pairs_nd.shape == (40, 8)
+
+
+def test_3d_error_behaviour_follows_the_reference():
+    """pucci refuses 3-D grids (pucci.py:33-34) before anything touches the device; ddf on a
+    pairs grid delegates to ddg (ddf.py:36-37,165-166), so it needs the device like ddg."""
+    from pyellipticfd_b200 import pucci, ddi
+    G = FDRegularGrid([5, 5, 5], np.array([[0.0, 1.0]] * 3).T, 1, interpolation=False)
+    u = np.zeros(G.num_points)
+    with pytest.raises(NotImplementedError):
+        pucci.operator(G, u, (2, 1), fdmethod="grid")
+    with pytest.raises(NotImplementedError):
+        pucci.solve(G, np.zeros(G.num_interior), np.zeros(G.num_bdry), fdmethod="grid")
+    with pytest.raises(NotImplementedError):
+        ddi.d2eigs(G, u)                                   # ddi.py:330-331
+    with pytest.raises(NotImplementedError):
+        ddi.d1grad(G, u)                                   # ddi.py:157-158
