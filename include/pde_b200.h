@@ -316,6 +316,31 @@ int pde_ell_newton_update(pde_ell *e, const double *d_U, const double *d_d, cons
                           const double *d_Jd, double *d_Unew, double *h_out, void *stream);
 
 /* ------------------------------------------------------------------------
+ * EXTENSION (no counterpart in the reference): the convex envelope of convex_envelope.py:44-46
+ * on a structured 2-D pairs grid by directional convex-hull sweeps.  The discrete solution is
+ * the largest u <= g with a non-negative second difference for every pair (ddg.py:281) of every
+ * interior point; one sweep hulls every lattice line of every stencil direction (runs of points
+ * that carry the lattice pair, neighbours as fixed ends) and lowers the band points to the
+ * chords of their other pairs.  Same fixed point as the reference's Euler / Newton solvers.
+ *   U          state layout (lattice rows x pitch, wall points from `wall_base`); in: g, out: u
+ *   h_dirs     (ndir, 2) first offset (a, b) of every deep pair (HOST pointer)
+ *   ring       wall-point number of the integer ring points, [i=0 | i=nx+1] (ny+2 each, by j)
+ *              then [j=0 | j=ny+1] (nx+2 each, by i)
+ *   flags      per lattice offset, bit k set = the point carries the lattice pair of direction k
+ *              (only read at points within stencil_radius cells of a wall)
+ *   rest_rows  (n_rest, 3) state offsets (I, J0, J1) of the remaining band pairs, rest_theta =
+ *              w_0 / (w_0 + w_1)
+ *   scratch    (nx+2)*(ny+2) int32
+ *   h_out      [last sweep's largest decrease, sweeps done]; stops when the decrease < tol
+ * device >= 0: every pointer but h_dirs / h_out is a DEVICE pointer; device = -1: host pointers,
+ * the same line routine under OpenMP (used by the CPU tests only). */
+int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall_base,
+                 int stencil_radius, int ndir, const int32_t *h_dirs, const int64_t *ring,
+                 const uint64_t *flags, int64_t n_rest, const int64_t *rest_rows,
+                 const double *rest_theta, double *U, int32_t *scratch, double tol,
+                 int64_t max_sweeps, int relax_reps, double *h_out, void *stream);
+
+/* ------------------------------------------------------------------------
  * Host-side pre-processing (no GPU needed): pair rows of the band points of a
  * regular grid.  Replaces, for the points within `stencil_radius` cells of a wall,
  * pointclasses.py:421-471 (neighbour search), :37-103 (colinear pruning, tol 1e-3)

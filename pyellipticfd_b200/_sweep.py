@@ -1,0 +1,62 @@
+"""Host-side tables of the convex-hull sweep solver (``pde_ce_sweep``, an extension beyond the
+reference: see ``csrc/ce_sweep.cu``) for a structured 2-D pairs grid, in state-layout offsets."""
+import numpy as np
+
+
+def tables(G, pitch, rows):
+    """-> dict(dirs (D,2) int32, ring int64, flags uint64 (rows*pitch), rest (R,3) int64,
+    theta (R,) f64).  ``rows`` x ``pitch`` is the lattice part of the state layout; wall points
+    follow at offset rows*pitch."""
+    nx, ny = G.interior_shape
+    N, r = G.num_interior, G.stencil_radius
+    dirs = np.ascontiguousarray(G.stencil_pairs[:, :2], dtype=np.int32)
+    D = dirs.shape[0]
+    if D > 64:
+        raise ValueError("the sweep solver handles at most 64 stencil directions")
+    W = G._wall_unscaled
+    # the integer ring of wall points (every lattice line ends on it)
+    # (unscaled wall coordinates carry the rounding of pointclasses.py:538: 17.999999999999996)
+    integer = (np.abs(W - np.round(W)) < 1e-9).all(axis=1)
+    wi, wid = np.round(W[integer]).astype(np.int64), np.flatnonzero(integer)
+    ring = np.full(2 * (ny + 2) + 2 * (nx + 2), -1, dtype=np.int64)
+    for mask, base, along in ((wi[:, 0] == 0, 0, 1), (wi[:, 0] == nx + 1, ny + 2, 1),
+                              (wi[:, 1] == 0, 2 * (ny + 2), 0),
+                              (wi[:, 1] == ny + 1, 2 * (ny + 2) + nx + 2, 0)):
+        ring[base + wi[mask, along]] = wid[mask]
+    if (ring < 0).any():
+        raise ValueError("the grid's wall does not contain the full integer ring")
+
+    def ucoord(ids):
+        P = np.empty((ids.size, 2))
+        lat = ids < N
+        P[lat, 0] = ids[lat] // ny + 1
+        P[lat, 1] = ids[lat] % ny + 1
+        P[~lat] = W[ids[~lat] - N]
+        return P
+
+    def offs(ids):
+        return np.where(ids < N, (ids // ny) * pitch + ids % ny, rows * pitch + (ids - N))
+
+    bp = np.asarray(G.band_pairs, dtype=np.int64)
+    PI, P0, P1 = ucoord(bp[:, 0]), ucoord(bp[:, 1]), ucoord(bp[:, 2])
+    V0, V1 = P0 - PI, P1 - PI
+    exact = ((np.abs(V0 - np.round(V0)) < 1e-9).all(axis=1) & (np.abs(V1 + V0) < 1e-9).all(axis=1)
+             & (np.abs(V0) <= r + 1e-9).all(axis=1))
+    lut = np.full((2 * r + 1, 2 * r + 1), -1, dtype=np.int64)
+    k = np.arange(D)
+    lut[dirs[:, 0] + r, dirs[:, 1] + r] = k
+    lut[-dirs[:, 0] + r, -dirs[:, 1] + r] = k
+    Vi = np.where(exact[:, None], np.round(V0), 0).astype(np.int64)
+    kk = np.where(exact, lut[Vi[:, 0] + r, Vi[:, 1] + r], -1)
+    line = kk >= 0
+    flags = np.zeros(rows * pitch, dtype=np.uint64)
+    np.bitwise_or.at(flags, offs(bp[line, 0]), np.uint64(1) << kk[line].astype(np.uint64))
+    rest = bp[~line]
+    XI = G.coords(rest[:, 0])
+    h0 = np.linalg.norm(G.coords(rest[:, 1]) - XI, axis=1)
+    h1 = np.linalg.norm(G.coords(rest[:, 2]) - XI, axis=1)
+    theta = (1 / h0) / (1 / h0 + 1 / h1)
+    rest_off = np.ascontiguousarray(np.stack([offs(rest[:, 0]), offs(rest[:, 1]), offs(rest[:, 2])],
+                                             axis=1), dtype=np.int64)
+    return dict(dirs=dirs, ring=ring, flags=flags, rest=rest_off,
+                theta=np.ascontiguousarray(theta, dtype=np.float64))

@@ -113,4 +113,24 @@ def _solve_grid(Grid, g, U0, solver, stats=None, **kwargs):
         Us, diff, iters = solvers.newton_state(ctx, Us, residual, euler_fallback, stats=stats,
                                                **kwargs)
         return like_input(proto, ctx.unpack(Us)), diff, iters, time.time() - t0
-    raise ValueError("solver must be 'euler' or 'newton'")
+    elif solver == "sweep":
+        # extension (csrc/ce_sweep.cu): directional convex-hull sweeps; stops on the criterion
+        # of solvers.euler (solvers.py:84) -- largest change < solution_tol and max|F| < operator_tol
+        sol = kwargs.get("solution_tol", 1e-6)
+        opt = kwargs.get("operator_tol", 1e-6)
+        mi = int(kwargs.get("max_iters") or 1000)
+        chunk = int(kwargs.get("check_every", 4))
+        iters, diff, fmax = 0, float("inf"), float("inf")
+        Us = gs.clone()            # sweeps only lower values: start from the obstacle, not from U0
+        while iters < mi:
+            Us, diff, n = ctx.ce_sweep(gs, 0.0, min(chunk, mi - iters), U=Us)
+            iters += n
+            fmax = float(ctx.ce_residual(Us, gs, policy=False)[2][0])
+            if (diff < sol and fmax < opt) or diff == 0.0:
+                break
+        if not (diff < sol and fmax < opt):
+            warnings.warn("Maximum iterations reached")
+        if stats is not None:
+            stats.update(residual=fmax)
+        return like_input(proto, ctx.unpack(Us)), diff, iters, time.time() - t0
+    raise ValueError("solver must be 'euler', 'newton' or 'sweep'")

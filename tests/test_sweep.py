@@ -1,0 +1,67 @@
+"""CPU: the convex-hull sweep solver (csrc/ce_sweep.cu, an extension beyond the reference)
+through its HOST build (pde_ce_sweep with device = -1: the same line routine the GPU runs, one
+OpenMP thread per lattice line) against the reference's converged solutions
+(tests/golden/solve_*.npz) and the NumPy restatement of the residual."""
+import ctypes as C
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import solvers_oracle as SO
+from oracle.make_golden import two_cones
+from pyellipticfd_b200 import _lib, _sweep
+from pyellipticfd_b200.pointclasses import FDRegularGrid
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+SOLVE = sorted(glob.glob(os.path.join(GOLD, "solve_*.npz")))
+
+
+def host_sweep(G, g, tol=1e-11, max_sweeps=400, relax_reps=2):
+    """Flat vector in, flat vector out; state layout with pitch = ny (no padding needed on the host)."""
+    nx, ny = G.interior_shape
+    N = G.num_interior
+    t = _sweep.tables(G, ny, nx)
+    U = np.ascontiguousarray(g, dtype=np.float64).copy()       # [lattice | wall] == state layout
+    scratch = np.zeros((nx + 2) * (ny + 2), dtype=np.int32)
+    out = (C.c_double * 2)()
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    _lib.check(_lib.lib().pde_ce_sweep(-1, nx, ny, ny, N, G.stencil_radius, t["dirs"].shape[0],
+                                       p(t["dirs"]), p(t["ring"]), p(t["flags"]), t["rest"].shape[0],
+                                       p(t["rest"]), p(t["theta"]), p(U), p(scratch), tol,
+                                       max_sweeps, relax_reps, out, None))
+    return U, out[0], int(out[1])
+
+
+@pytest.mark.parametrize("path", SOLVE, ids=[os.path.basename(p) for p in SOLVE])
+def test_sweeps_reach_the_reference_solution(path):
+    z = np.load(path)
+    G = FDRegularGrid([int(s) for s in z["shape"]], z["bounds"], int(z["radius"]), interpolation=False)
+    U, change, sweeps = host_sweep(G, z["g"])
+    assert change < 1e-11 and sweeps < 120
+    # the reference's Newton solution solves the discrete equation to 1e-13
+    assert np.abs(U - z["newton_U"]).max() < 1e-8
+    F, _ = SO.ce_operator(G, U.copy(), z["g"], False)
+    assert np.abs(F).max() < 1e-6                                  # the reference's operator_tol
+    assert (U <= z["g"]).all()
+
+
+def test_sweep_counts_do_not_grow_with_the_lattice():
+    counts = []
+    for n in (31, 63, 127):
+        G = FDRegularGrid([n, n], np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, 3, interpolation=False)
+        g = two_cones(G.points)
+        U, change, sweeps = host_sweep(G, g, tol=1e-9)
+        F, _ = SO.ce_operator(G, U.copy(), g, False)
+        assert np.abs(F).max() < 1e-5
+        counts.append(sweeps)
+    assert max(counts) <= 2 * min(counts) + 8, counts
+
+
+def test_convex_obstacle_is_a_fixed_point():
+    G = FDRegularGrid([21, 17], np.array([[0.0, 1.0], [0.0, 2.0]]).T, 2, interpolation=False)
+    X, Y = G.points.T
+    g = (X - 0.3) ** 2 + 2 * (Y - 1.1) ** 2 + X * Y
+    U, change, sweeps = host_sweep(G, g, tol=1e-13)
+    assert sweeps <= 2 and np.abs(U - g).max() < 1e-13
