@@ -19,6 +19,11 @@ BASELINE.json configs[1] (4097^2 lattice = 4095^2 interior points, stencil radiu
              7 fp64 instructions per point): see ``fp64`` and DESIGN.md.
 * ``cpu_baseline`` the NumPy port of the reference operator (oracle/) on the host cores.
 
+``solve_4097`` times BASELINE's second metric (convex_envelope.solve, Newton = policy iteration
+with the reference's defaults, on the 4097^2 lattice) and, under ``solve_4097.sweep``, the same
+discrete problem by the convex-hull sweep solver (``solver='sweep'``, an extension; DESIGN K9)
+stopped on the reference's criteria.
+
 N > 1 (torchrun): weak scaling -- the global lattice has N x 4095 rows, each rank owns a
 4095-row slab and refreshes ``r`` halo rows from its neighbours (one small NCCL all-gather
 over NVLink, overlapped with the interior rows) at every operator application.  ``bicgstab``
@@ -321,6 +326,29 @@ def solve_full_size(args, obstacle):
         Gs = FDRegularGrid([n, n], np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, r, interpolation=False)
         out["grid_build_s"] = time.time() - t
         g = torch.from_numpy(obstacle(Gs.points)).cuda()
+        # extension (DESIGN K9): the same discrete problem by directional convex-hull sweeps,
+        # stopped on the reference's criteria (change < 1e-6 and max|F| < 1e-6)
+        try:
+            ctx_s = GridContext.get(Gs)
+            t = time.perf_counter()
+            ctx_s.ce_sweep(ctx_s.pack(g), 0.0, 0)                 # builds / uploads the sweep tables
+            torch.cuda.synchronize()
+            t_tab = time.perf_counter() - t
+            sst = {}
+            with warnings.catch_warnings(record=True) as wl2:
+                warnings.simplefilter("always")
+                t = time.perf_counter()
+                _, sdiff, sit, _ = convex_envelope._solve_grid(Gs, g, None, "sweep", stats=sst,
+                                                               max_iters=160)
+                torch.cuda.synchronize()
+                t_sw = time.perf_counter() - t
+            out["sweep"] = {"solver": "sweep (extension: convex-hull sweeps, same discrete solution)",
+                            "seconds": t_sw, "tables_s": t_tab, "sweeps": int(sit), "diff": float(sdiff),
+                            "residual": sst.get("residual"),
+                            "converged": bool(sdiff < 1e-6 and (sst.get("residual") or 1.0) < 1e-6),
+                            "warnings": sorted({str(w.message) for w in wl2})}
+        except Exception as e:            # reported, not fatal
+            out["sweep"] = {"error": str(e)[:300]}
         st = {}
         with warnings.catch_warnings(record=True) as wl:
             warnings.simplefilter("always")
@@ -697,7 +725,10 @@ def main():
     pucci_full = None
     if world == 1 and args.pucci_full:
         del S, lmin, out
-        torch.cuda.empty_cache()
+        try:
+            torch.cuda.empty_cache()
+        except Exception:                 # a failed optional section must not cost the bench line
+            pass
         pucci_full = pucci_full_size(args)
 
     if rank == 0:
