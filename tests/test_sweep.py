@@ -65,3 +65,30 @@ def test_convex_obstacle_is_a_fixed_point():
     g = (X - 0.3) ** 2 + 2 * (Y - 1.1) ** 2 + X * Y
     U, change, sweeps = host_sweep(G, g, tol=1e-13)
     assert sweeps <= 2 and np.abs(U - g).max() < 1e-13
+
+
+from hypothesis import given, settings, strategies as st
+
+
+@settings(max_examples=10, deadline=None)
+@given(nx=st.integers(7, 22), ny=st.integers(7, 22), r=st.integers(1, 3), seed=st.integers(0, 10 ** 6),
+       sx=st.sampled_from([1.0, 0.5, 0.37]), rough=st.sampled_from([0.0, 0.05, 0.5]))
+def test_random_obstacles_against_the_reference_algorithm(nx, ny, r, seed, sx, rough):
+    """Random boxes (anisotropic, non-dyadic spacing) and obstacles: the sweeps end on a function
+    that solves the discrete equation (NumPy restatement of convex_envelope.operator) and that
+    the restated Newton iteration of the reference, started from it, leaves where it is."""
+    if min(nx, ny) < 2 * r + 1:
+        return
+    bounds = np.array([[-0.3, -0.3 + sx * (nx + 1) / 8.0], [0.0, (ny + 1) / 8.0]]).T
+    G = FDRegularGrid([nx, ny], bounds, r, interpolation=False)
+    X, Y = G.points.T
+    rng = np.random.default_rng(seed)
+    g = np.sin(5 * X + rng.uniform(0, 3)) * np.cos(4 * Y) + rough * rng.standard_normal(X.size)
+    U, change, sweeps = host_sweep(G, g, tol=1e-13)
+    assert change < 1e-13 and sweeps < 300
+    F, _ = SO.ce_operator(G, U.copy(), g, False)
+    scale = 1.0 / G.scaling.min() ** 2
+    assert np.abs(F).max() < 1e-11 * scale and (U <= g).all()
+    with np.errstate(all="ignore"):
+        Un, diff, it, _ = SO.ce_solve(G, g, U0=U.copy(), solver="newton")
+    assert it <= 2 and np.abs(Un - U).max() < 1e-9
