@@ -120,6 +120,7 @@ def _solve_grid(Grid, g, U0, solver, stats=None, **kwargs):
         opt = kwargs.get("operator_tol", 1e-6)
         mi = int(kwargs.get("max_iters") or 1000)
         chunk = int(kwargs.get("check_every", 4))
+        timeout = kwargs.get("timeout")            # seconds, like solvers.euler's (solvers.py:58-61)
         iters, diff, fmax = 0, float("inf"), float("inf")
         Us = gs.clone()            # sweeps only lower values: start from the obstacle, not from U0
         while iters < mi:
@@ -127,6 +128,8 @@ def _solve_grid(Grid, g, U0, solver, stats=None, **kwargs):
             iters += n
             fmax = float(ctx.ce_residual(Us, gs, policy=False)[2][0])
             if (diff < sol and fmax < opt) or diff == 0.0:
+                break
+            if timeout is not None and time.time() - t0 > timeout:
                 break
         if not (diff < sol and fmax < opt):
             warnings.warn("Maximum iterations reached")

@@ -92,3 +92,56 @@ def test_random_obstacles_against_the_reference_algorithm(nx, ny, r, seed, sx, r
     with np.errstate(all="ignore"):
         Un, diff, it, _ = SO.ce_solve(G, g, U0=U.copy(), solver="newton")
     assert it <= 2 and np.abs(Un - U).max() < 1e-9
+
+
+class _HostCtx(object):
+    """Stand-in for GridContext in the host logic of convex_envelope._solve_grid(solver='sweep'):
+    flat torch CPU vectors, the host build of the line routine, the NumPy residual."""
+
+    def __init__(self, G):
+        import torch
+        self.G, self.torch = G, torch
+        self.calls = []
+
+    def pack(self, u):
+        return self.torch.as_tensor(np.asarray(u, dtype=np.float64)).clone()
+
+    def unpack(self, S):
+        return S
+
+    def ce_sweep(self, g, tol, max_sweeps, relax_reps=2, U=None):
+        self.calls.append(int(max_sweeps))
+        start = g if U is None else U
+        out, change, n = host_sweep(self.G, start.numpy(), tol=tol, max_sweeps=max_sweeps,
+                                    relax_reps=relax_reps)
+        return self.torch.from_numpy(out), change, n
+
+    def ce_residual(self, W, g, policy=True):
+        F, _ = SO.ce_operator(self.G, W.numpy().copy(), g.numpy(), False)
+        return self.torch.from_numpy(F), None, self.torch.tensor([np.abs(F).max(), 0.0])
+
+
+def test_solver_option_host_logic(monkeypatch):
+    """Stopping rule, iteration cap, warning and timeout of solver='sweep' (Python side)."""
+    import warnings
+    from pyellipticfd_b200 import convex_envelope as CE
+    z = np.load(os.path.join(GOLD, "solve_n31_r2.npz"))
+    G = FDRegularGrid([int(s) for s in z["shape"]], z["bounds"], int(z["radius"]), interpolation=False)
+    ctx = _HostCtx(G)
+    monkeypatch.setattr(CE.GridContext, "get", staticmethod(lambda Grid, device=None: ctx))
+    st = {}
+    U, diff, sweeps, secs = CE.solve(G, z["g"], fdmethod="grid", solver="sweep", stats=st)
+    assert diff < 1e-6 and st["residual"] < 1e-6 and sweeps % 4 == 0
+    assert np.abs(U - z["newton_U"]).max() < 2e-6 and isinstance(U, np.ndarray)
+    assert all(c == 4 for c in ctx.calls)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        U, diff, sweeps, _ = CE.solve(G, z["g"], fdmethod="grid", solver="sweep", max_iters=3)
+    assert sweeps == 3 and any("Maximum iterations" in str(x.message) for x in w)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        U, diff, sweeps, _ = CE.solve(G, z["g"], fdmethod="grid", solver="sweep", check_every=1,
+                                      solution_tol=1e-300, timeout=0.0)
+    assert sweeps == 1 and len(w) == 1
+    with pytest.raises(ValueError):
+        CE.solve(G, z["g"], fdmethod="grid", solver="nope")
