@@ -340,7 +340,7 @@ def solve_full_size(args, obstacle):
                 t = time.perf_counter()
                 _, sdiff, sit, _ = convex_envelope._solve_grid(Gs, g, None, "sweep", stats=sst,
                                                                max_iters=160, check_every=2,
-                                                               timeout=90.0)
+                                                               timeout=45.0)
                 torch.cuda.synchronize()
                 t_sw = time.perf_counter() - t
             out["sweep"] = {"solver": "sweep (extension: convex-hull sweeps, same discrete solution)",
