@@ -328,17 +328,22 @@ int pde_ell_newton_update(pde_ell *e, const double *d_U, const double *d_d, cons
  *              then [j=0 | j=ny+1] (nx+2 each, by i)
  *   flags      per lattice offset, bit k set = the point carries the lattice pair of direction k
  *              (only read at points within stencil_radius cells of a wall)
- *   rest_rows  (n_rest, 3) state offsets (I, J0, J1) of the remaining band pairs, rest_theta =
- *              w_0 / (w_0 + w_1)
- *   scratch    (nx+2)*(ny+2) int32
+ *   band_ptr   (n_band + 1) CSR over the band points that own pairs which are NOT lattice pairs,
+ *   band_center (n_band) their state offsets, rest_j (n_rest, 2) state offsets (J0, J1) of those
+ *              pairs, rest_theta (n_rest) = w_0 / (w_0 + w_1): u_I <- min(u_I, theta u_J0 +
+ *              (1 - theta) u_J1), a Jacobi step repeated relax_reps times after every
+ *              relax_every direction passes (0: once per sweep)
+ *   work       device scratch, n_band + 80 doubles (device path only)
  *   h_out      [last sweep's largest decrease, sweeps done]; stops when the decrease < tol
- * device >= 0: every pointer but h_dirs / h_out is a DEVICE pointer; device = -1: host pointers,
- * the same line routine under OpenMP (used by the CPU tests only). */
+ * device >= 0: every pointer but h_dirs / h_out is a DEVICE pointer; up to 64 sweeps are enqueued
+ * per host synchronisation.  device = -1: host pointers, the serial monotone chain per line under
+ * OpenMP (used by the CPU tests and as the CPU baseline of bench.py). */
 int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall_base,
                  int stencil_radius, int ndir, const int32_t *h_dirs, const int64_t *ring,
-                 const uint64_t *flags, int64_t n_rest, const int64_t *rest_rows,
-                 const double *rest_theta, double *U, int32_t *scratch, double tol,
-                 int64_t max_sweeps, int relax_reps, double *h_out, void *stream);
+                 const uint64_t *flags, int64_t n_band, const int64_t *band_ptr,
+                 const int64_t *band_center, const int64_t *rest_j, const double *rest_theta,
+                 double *U, double *work, double tol, int64_t max_sweeps, int relax_every,
+                 int relax_reps, double *h_out, void *stream);
 
 /* ------------------------------------------------------------------------
  * Host-side pre-processing (no GPU needed): pair rows of the band points of a

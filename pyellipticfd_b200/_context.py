@@ -438,22 +438,27 @@ class GridContext(object):
         U = U1 if int(out[1]) == 1 else U0
         return U, float(out[2]), iters, float(out[3]), int(out[4])
 
-    def ce_sweep(self, g, tol, max_sweeps, relax_reps=2, U=None):
+    def ce_sweep(self, g, tol, max_sweeps, relax_reps=2, U=None, relax_every=0):
         """Convex-hull sweeps (``pde_ce_sweep``, extension): lowers ``U`` (default: a copy of
         ``g``) towards the convex-envelope solution until one sweep changes no value by ``tol``
-        or more.  Returns (U, last change, sweeps)."""
+        or more.  ``relax_every``: direction passes between band relaxations (0: once per
+        sweep).  Returns (U, last change, sweeps)."""
         if not self.structured or self.halo_rows or self.nx_local != self.nx_global:
             raise _lib.PdeError("the sweep solver needs a structured, unsharded 2-D pairs grid")
         if not hasattr(self, "_sweep"):
             from . import _sweep
             t = _sweep.tables(self.G, self.pitch, self.rows)
             dev = self.device
+            nb = int(t["band_center"].shape[0])
             self._sweep = dict(
-                dirs=t["dirs"], D=int(t["dirs"].shape[0]), n_rest=int(t["rest"].shape[0]),
+                dirs=t["dirs"], D=int(t["dirs"].shape[0]), n_band=nb,
                 ring=torch.from_numpy(t["ring"]).to(dev),
                 flags=torch.from_numpy(t["flags"].view(np.int64)).to(dev),
-                rest=torch.from_numpy(t["rest"]).to(dev), theta=torch.from_numpy(t["theta"]).to(dev),
-                scratch=torch.empty((self.nx_local + 2) * (self.ny + 2), dtype=torch.int32, device=dev))
+                band_ptr=torch.from_numpy(t["band_ptr"]).to(dev),
+                band_center=torch.from_numpy(t["band_center"]).to(dev),
+                rest_j=torch.from_numpy(t["rest_j"]).to(dev),
+                theta=torch.from_numpy(t["theta"]).to(dev),
+                work=torch.zeros(nb + 80, dtype=torch.float64, device=dev))
         t = self._sweep
         if U is None:
             U = g.clone()
@@ -461,9 +466,10 @@ class GridContext(object):
         check(self.lib.pde_ce_sweep(self.device.index, self.nx_local, self.ny, self.pitch,
                                     self.n_lattice, self.G.stencil_radius, t["D"],
                                     _np_ptr(t["dirs"]), _ptr(t["ring"]), _ptr(t["flags"]),
-                                    t["n_rest"], _ptr(t["rest"]), _ptr(t["theta"]), _ptr(U),
-                                    _ptr(t["scratch"]), float(tol), int(max_sweeps),
-                                    int(relax_reps), out, _stream()))
+                                    t["n_band"], _ptr(t["band_ptr"]), _ptr(t["band_center"]),
+                                    _ptr(t["rest_j"]), _ptr(t["theta"]), _ptr(U),
+                                    _ptr(t["work"]), float(tol), int(max_sweeps),
+                                    int(relax_every), int(relax_reps), out, _stream()))
         return U, float(out[0]), int(out[1])
 
     def ce_euler_step(self, U, g, dt, out=None):

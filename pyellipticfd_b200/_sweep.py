@@ -4,9 +4,10 @@ import numpy as np
 
 
 def tables(G, pitch, rows):
-    """-> dict(dirs (D,2) int32, ring int64, flags uint64 (rows*pitch), rest (R,3) int64,
-    theta (R,) f64).  ``rows`` x ``pitch`` is the lattice part of the state layout; wall points
-    follow at offset rows*pitch."""
+    """-> dict(dirs (D,2) int32, ring int64, flags uint64 (rows*pitch), band_ptr (B+1,) int64,
+    band_center (B,) int64, rest_j (R,2) int64, theta (R,) f64): the band pairs that are not
+    lattice pairs, CSR over the B band points that own any (state offsets).  ``rows`` x ``pitch``
+    is the lattice part of the state layout; wall points follow at offset rows*pitch."""
     nx, ny = G.interior_shape
     N, r = G.num_interior, G.stencil_radius
     dirs = np.ascontiguousarray(G.stencil_pairs[:, :2], dtype=np.int32)
@@ -52,11 +53,16 @@ def tables(G, pitch, rows):
     flags = np.zeros(rows * pitch, dtype=np.uint64)
     np.bitwise_or.at(flags, offs(bp[line, 0]), np.uint64(1) << kk[line].astype(np.uint64))
     rest = bp[~line]
+    rest = rest[np.argsort(rest[:, 0], kind="stable")]
     XI = G.coords(rest[:, 0])
     h0 = np.linalg.norm(G.coords(rest[:, 1]) - XI, axis=1)
     h1 = np.linalg.norm(G.coords(rest[:, 2]) - XI, axis=1)
     theta = (1 / h0) / (1 / h0 + 1 / h1)
-    rest_off = np.ascontiguousarray(np.stack([offs(rest[:, 0]), offs(rest[:, 1]), offs(rest[:, 2])],
-                                             axis=1), dtype=np.int64)
-    return dict(dirs=dirs, ring=ring, flags=flags, rest=rest_off,
+    centers, counts = np.unique(rest[:, 0], return_counts=True)
+    band_ptr = np.zeros(centers.size + 1, dtype=np.int64)
+    np.cumsum(counts, out=band_ptr[1:])
+    rest_j = np.ascontiguousarray(np.stack([offs(rest[:, 1]), offs(rest[:, 2])], axis=1),
+                                  dtype=np.int64)
+    return dict(dirs=dirs, ring=ring, flags=flags, band_ptr=band_ptr,
+                band_center=np.ascontiguousarray(offs(centers), dtype=np.int64), rest_j=rest_j,
                 theta=np.ascontiguousarray(theta, dtype=np.float64))

@@ -119,20 +119,31 @@ def _solve_grid(Grid, g, U0, solver, stats=None, **kwargs):
         sol = kwargs.get("solution_tol", 1e-6)
         opt = kwargs.get("operator_tol", 1e-6)
         mi = int(kwargs.get("max_iters") or 1000)
-        chunk = int(kwargs.get("check_every", 4))
+        chunk = int(kwargs.get("check_every", 8))
         timeout = kwargs.get("timeout")            # seconds, like solvers.euler's (solvers.py:58-61)
-        iters, diff, fmax = 0, float("inf"), float("inf")
-        Us = gs.clone()            # sweeps only lower values: start from the obstacle, not from U0
+        relax_every = int(kwargs.get("relax_every", 4))
+        if U0 is not None:
+            # sweeps only lower values, so they must start on or above the solution: from g
+            warnings.warn("solver='sweep' starts from the obstacle; U0 is ignored")
+        iters, diff, fmax, why = 0, float("inf"), float("inf"), "Maximum iterations reached"
+        Us = gs.clone()
         while iters < mi:
-            Us, diff, n = ctx.ce_sweep(gs, 0.0, min(chunk, mi - iters), U=Us)
+            # the device ends a batch early after a sweep whose largest change is below what an
+            # Euler step of the reference at max|F| = operator_tol / 2 would make (dt * |F|)
+            Us, diff, n = ctx.ce_sweep(gs, min(sol, 0.5 * opt * dt), min(chunk, mi - iters), U=Us,
+                                       relax_every=relax_every)
             iters += n
             fmax = float(ctx.ce_residual(Us, gs, policy=False)[2][0])
-            if (diff < sol and fmax < opt) or diff == 0.0:
+            if diff < sol and fmax < opt:
+                break
+            if diff == 0.0:
+                why = "The sweeps stalled above operator_tol"
                 break
             if timeout is not None and time.time() - t0 > timeout:
+                why = "Maximum computation time reached"      # solvers.py:89
                 break
         if not (diff < sol and fmax < opt):
-            warnings.warn("Maximum iterations reached")
+            warnings.warn(why)
         if stats is not None:
             stats.update(residual=fmax)
         return like_input(proto, ctx.unpack(Us)), diff, iters, time.time() - t0

@@ -5,21 +5,43 @@
 // the LARGEST u <= g whose second difference is >= 0 for every pair of every interior point.
 // For an antipodal lattice pair (x - v, x + v) "second difference >= 0 at every point of the
 // lattice line x + t v" says that the sequence along the line is convex, and the largest
-// minorant with that property is the lower convex hull of the sequence (monotone chain, O(L)).
-// One sweep = for every stencil direction, hull every lattice line (runs of points that carry
-// this pair, with the neighbouring points as fixed ends), then lower the band points to the
-// chords of their remaining pairs (the pairs with fractional wall points).  Every operation
-// returns the largest minorant under a subset of the constraints, so the iterates decrease
-// monotonically from g to the discrete solution -- the same fixed point the reference's Euler
-// and Newton solvers approach -- and information travels along whole lines per sweep instead of
-// one stencil width per iteration (sweep counts are mesh independent: 13 at 65^2 r=2, 35-37 at
-// 129^2 / 257^2 r=4 for the two-cone obstacle).
+// minorant with that property is the lower convex hull of the sequence.  One sweep = for every
+// stencil direction, hull every lattice line (points that do not carry this pair are fixed
+// vertices), and lower the band points to the chords of their remaining pairs (the pairs with
+// fractional wall points).  Every operation returns the largest minorant under a subset of the
+// constraints, so the iterates decrease monotonically from g to the discrete solution -- the same
+// fixed point the reference's Euler and Newton solvers approach -- and information travels along
+// whole lines per sweep instead of one stencil width per iteration.
 //
-// The line routine is compiled for the device (one thread per lattice line) and for the host
-// (OpenMP over lines, device = -1: used by the CPU tests of this file only; the Python package
-// calls the device path).  --fmad=false / -ffp-contract=off: identical arithmetic.
+// DEVICE (k_hull_pass): one CTA stages a bundle of WL adjacent lattice lines of one direction in
+// shared memory (adjacent lines are adjacent in memory at every step: 32-byte sectors are used
+// whole).  Lines that leave the lattice through a side wall are continued at the opposite side
+// ("wrapped"), so that every line of a direction has the same number of points and every padded
+// lattice point belongs to exactly one line; the pieces of a wrapped line are separated by fixed
+// vertices.  The hull of a line is found by divide and conquer on a BITMAP of hull vertices:
+//   level 0   one thread per 32-point word: monotone chain, the stack is the word's bit mask;
+//   level k   one thread per pair of 32*2^(k-1)-point blocks finds the common lower tangent
+//             (bridge) of the two block hulls -- a junction that is already convex costs two
+//             cross products; otherwise a binary search for the left tangent point whose
+//             predicate is a binary search for the right one, both by POSITION with O(1)
+//             predecessor / successor queries on the two-level bitmap -- and clears the vertices
+//             the bridge spans;
+//   fill      every thread lowers the non-vertices of its word onto the chord of the
+//             neighbouring vertices (never raises), records the largest decrease;
+// and only changed values are written back.  Any chord between two points of the line lies on or
+// above the line's hull, so a tangent misjudged at rounding level costs efficiency, never
+// correctness.  The band relaxation is a two-kernel Jacobi step (deterministic).  A batch of
+// sweeps is enqueued without host synchronisation; a one-thread kernel after every sweep raises a
+// `done` flag when the sweep changed no value by `tol`, which turns the rest of the batch into
+// no-ops.
+//
+// HOST (device = -1): the serial monotone chain per line under OpenMP, the same relaxation --
+// used by the CPU tests of this file and as the CPU baseline of bench.py; the Python package
+// only calls the device path.  --fmad=false / -ffp-contract=off.
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstring>
 #include <vector>
 #ifdef _OPENMP
 #include <omp.h>
@@ -65,10 +87,14 @@ PDE_HD bool sw_constrained(const SweepGeom &g, int k, int64_t i, int64_t j) {
     return (g.flags[(i - 1) * g.pitch + (j - 1)] >> k) & 1ull;
 }
 
+// ---------------------------------------------------------------------------------------------
+// host: serial monotone chain per line
+// ---------------------------------------------------------------------------------------------
+
 // Lower convex hull of the points t = lo..hi of the line (i0 + t a, j0 + t b); the two ends
 // stay, the points in between are lowered onto the hull.  The stack of hull vertices lives in
 // `stk` at the padded positions of the line's own points (lines of one direction are disjoint).
-PDE_HD double sw_hull_run(const SweepGeom &g, double *U, int32_t *stk, int64_t i0, int64_t j0,
+static double sw_hull_run(const SweepGeom &g, double *U, int32_t *stk, int64_t i0, int64_t j0,
                           int a, int b, int64_t lo, int64_t hi) {
     const int64_t W = g.ny + 2;
 #define SW_STK(s) stk[(i0 + (lo + (s)) * a) * W + (j0 + (lo + (s)) * b)]
@@ -102,9 +128,9 @@ PDE_HD double sw_hull_run(const SweepGeom &g, double *U, int32_t *stk, int64_t i
         const int64_t ta = SW_STK(s), tb = SW_STK(s + 1);
         if (tb == ta + 1) continue;
         const double ya = SW_U(ta), yb = SW_U(tb);
-        const double slope_num = yb - ya, len = (double)(tb - ta);
+        const double slope = (yb - ya) / (double)(tb - ta);
         for (int64_t t = ta + 1; t < tb; ++t) {
-            double v = ya + slope_num * ((double)(t - ta) / len);
+            double v = ya + slope * (double)(t - ta);
             const int64_t ad = sw_addr(g, i0 + t * a, j0 + t * b);
             const double old = U[ad];
             if (v < old) {                       // never raise (rounding of the chord)
@@ -119,7 +145,7 @@ PDE_HD double sw_hull_run(const SweepGeom &g, double *U, int32_t *stk, int64_t i
 }
 
 // all runs of the line that starts at the padded point (i0, j0) (its predecessor is outside)
-PDE_HD double sw_line(const SweepGeom &g, double *U, int32_t *stk, int64_t i0, int64_t j0, int a,
+static double sw_line(const SweepGeom &g, double *U, int32_t *stk, int64_t i0, int64_t j0, int a,
                       int b, int k) {
     int64_t L = 0;
     for (int64_t i = i0, j = j0; sw_inside(g, i, j); i += a, j += b) ++L;
@@ -138,34 +164,574 @@ PDE_HD double sw_line(const SweepGeom &g, double *U, int32_t *stk, int64_t i0, i
     return change;
 }
 
-__global__ void __launch_bounds__(64)
-k_sweep_lines(SweepGeom g, double *U, int32_t *stk, int a, int b, int k, double *change) {
-    const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    const int64_t W = g.ny + 2;
-    if (idx >= (g.nx + 2) * W) return;
-    const int64_t i = idx / W, j = idx % W;
-    if (sw_inside(g, i - a, j - b)) return;          // not the first point of its line
-    const double c = sw_line(g, U, stk, i, j, a, b, k);
-    if (c > 0.0) atomic_max_nonneg(change, c);
+// ---------------------------------------------------------------------------------------------
+// band relaxation (pairs that are not lattice pairs): u_I <- min(u_I, theta u_J0 + (1-theta) u_J1)
+// Jacobi: phase A evaluates all band points from the old values, phase B commits.
+// ---------------------------------------------------------------------------------------------
+PDE_HD double sw_relax_value(int64_t b, const int64_t *ptr, const int64_t *center,
+                             const int64_t *rj, const double *theta, const double *U) {
+    double v = U[center[b]];
+    for (int64_t q = ptr[b]; q < ptr[b + 1]; ++q) {
+        const double th = theta[q];
+#ifdef __CUDA_ARCH__
+        const double c = __dadd_rn(__dmul_rn(th, U[rj[2 * q]]),
+                                   __dmul_rn(__dsub_rn(1.0, th), U[rj[2 * q + 1]]));
+#else
+        const double c = th * U[rj[2 * q]] + (1.0 - th) * U[rj[2 * q + 1]];
+#endif
+        if (c < v) v = c;
+    }
+    return v;
 }
 
-// band pairs that are not lattice pairs: u_I <- min(u_I, theta u_J0 + (1 - theta) u_J1)
-__global__ void k_sweep_relax(int64_t n, const int64_t *__restrict__ rows,
-                              const double *__restrict__ theta, double *U, double *change) {
-    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    const double th = theta[q];
-    const double v = __dadd_rn(__dmul_rn(th, U[rows[3 * q + 1]]),
-                               __dmul_rn(__dsub_rn(1.0, th), U[rows[3 * q + 2]]));
-    unsigned long long *p = reinterpret_cast<unsigned long long *>(U + rows[3 * q]);
-    unsigned long long old = *p;
-    const double first = __longlong_as_double((long long)old);
-    while (v < __longlong_as_double((long long)old)) {
-        const unsigned long long assumed = old;
-        old = atomicCAS(p, assumed, (unsigned long long)__double_as_longlong(v));
-        if (old == assumed) break;
+__global__ void k_relax_eval(int64_t n, const int64_t *__restrict__ ptr,
+                             const int64_t *__restrict__ center, const int64_t *__restrict__ rj,
+                             const double *__restrict__ theta, const double *__restrict__ U,
+                             double *__restrict__ tmp, const int *done) {
+    if (*done) return;
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (b < n) tmp[b] = sw_relax_value(b, ptr, center, rj, theta, U);
+}
+
+__global__ void k_relax_commit(int64_t n, const int64_t *__restrict__ center,
+                               const double *__restrict__ tmp, double *U, double *change,
+                               const int *done) {
+    if (*done) return;
+    const int64_t b = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    double c = 0.0;
+    if (b < n) {
+        const double v = tmp[b], old = U[center[b]];
+        if (v < old) {
+            U[center[b]] = v;
+            c = old - v;
+        }
     }
-    if (v < first) atomic_max_nonneg(change, first - v);
+    c = warp_max(c);
+    if ((threadIdx.x & 31) == 0 && c > 0.0) atomic_max_nonneg(change, c);
+}
+
+// after a sweep: the next sweep's accumulator is already zero; raise `done` when converged
+__global__ void k_sweep_end(const double *change, double tol, int *done, int *sweeps_done) {
+    if (*done) return;
+    *sweeps_done += 1;
+    if (*change < tol) *done = 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// bitmap hull of a bundle of lines in shared memory.  The phases are __host__ __device__ so that
+// the CPU tests can replay a CTA thread by thread (device = -2) against the serial chain.
+// ---------------------------------------------------------------------------------------------
+struct HullPass {
+    int a, b, k;          // direction (a >= 1, any b), or rows mode; flag bit k
+    int rows_mode;        // 1: direction (0, 1): lines are the lattice rows i = 1..nx
+    int Ns;               // generic: ny + 2 (wrap modulus); rows: number of lines nx
+    int wl_log2;          // lines per CTA = 1 << wl_log2
+    int LW;               // 32-point words per line
+    int SW;               // summary words per line
+    int groups;           // CTAs per start row i0
+};
+
+PDE_HD int hp_clz(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __clz((int)x);
+#else
+    return x ? __builtin_clz(x) : 32;
+#endif
+}
+PDE_HD int hp_ffs(uint32_t x) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)x);
+#else
+    return __builtin_ffs((int)x);
+#endif
+}
+PDE_HD void hp_and(uint32_t *p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+    atomicAnd(p, v);
+#else
+    *p &= v;
+#endif
+}
+PDE_HD void hp_or(uint32_t *p, uint32_t v) {
+#ifdef __CUDA_ARCH__
+    atomicOr(p, v);
+#else
+    *p |= v;
+#endif
+}
+PDE_HD double hp_mul(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dmul_rn(a, b);
+#else
+    return a * b;
+#endif
+}
+PDE_HD double hp_sub(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(a, b);
+#else
+    return a - b;
+#endif
+}
+PDE_HD double hp_add(double a, double b) {
+#ifdef __CUDA_ARCH__
+    return __dadd_rn(a, b);
+#else
+    return a + b;
+#endif
+}
+
+// largest set bit <= pos (-1 if none)
+PDE_HD int bm_pred(const uint32_t *M, const uint32_t *S, int pos) {
+    int w = pos >> 5;
+    const uint32_t x = M[w] & (0xffffffffu >> (31 - (pos & 31)));
+    if (x) return (w << 5) + 31 - hp_clz(x);
+    int sw = w >> 5;
+    uint32_t s = S[sw] & ((1u << (w & 31)) - 1u);
+    while (!s) {
+        if (--sw < 0) return -1;
+        s = S[sw];
+    }
+    w = (sw << 5) + 31 - hp_clz(s);
+    return (w << 5) + 31 - hp_clz(M[w]);
+}
+
+// smallest set bit >= pos (INT_MAX if none)
+PDE_HD int bm_succ(const uint32_t *M, const uint32_t *S, int pos, int LW, int SW) {
+    int w = pos >> 5;
+    if (w >= LW) return 0x7fffffff;
+    const uint32_t x = M[w] & (0xffffffffu << (pos & 31));
+    if (x) return (w << 5) + hp_ffs(x) - 1;
+    int sw = w >> 5;
+    uint32_t s = ((w & 31) == 31) ? 0u : (S[sw] & (0xffffffffu << ((w & 31) + 1)));
+    while (!s) {
+        if (++sw >= SW) return 0x7fffffff;
+        s = S[sw];
+    }
+    w = (sw << 5) + hp_ffs(s) - 1;
+    return (w << 5) + hp_ffs(M[w]) - 1;
+}
+
+// middle point (t1, y1) on or above the chord (t0, y0) -> (t2, y2): not a hull vertex
+PDE_HD bool hp_drop(int t0, double y0, int t1, double y1, int t2, double y2) {
+    return hp_mul(hp_sub(y1, y0), (double)(t2 - t0)) >= hp_mul(hp_sub(y2, y0), (double)(t1 - t0));
+}
+
+// shared-memory index of point t of a line: one padding double per 32-point word, so that the
+// 32 word owners of a warp (stride 33 doubles) hit distinct banks
+PDE_HD int hp_ix(int t) { return t + (t >> 5); }
+
+struct LineView {
+    double *y;
+    uint32_t *V, *SV, *F, *SF, *C;
+    int LW, SW;
+    PDE_HD double &Y(int t) const { return y[hp_ix(t)]; }
+};
+
+// tangent from the point v (left of the chain) to the convex chain of vertices in [lo, hi]:
+// the vertex of smallest slope seen from v, the rightmost one on ties
+PDE_HD int hp_tangent_right(const LineView &L, int v, int lo, int hi) {
+    const double yv = L.Y(v);
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const int c = bm_pred(L.V, L.SV, mid);
+        const int c2 = bm_succ(L.V, L.SV, c + 1, L.LW, L.SW);
+        // slope(v -> c2) <= slope(v -> c): c is on or above the chord v -> c2
+        if (hp_drop(v, yv, c, L.Y(c), c2, L.Y(c2))) lo = c2;
+        else hi = c;
+    }
+    return lo;
+}
+
+PDE_HD void hp_clear(const LineView &L, int lo, int hi) {   // inclusive
+    if (lo > hi) return;
+    for (int w = lo >> 5; w <= (hi >> 5); ++w) {
+        uint32_t mask = 0xffffffffu;
+        if (w == (lo >> 5)) mask &= 0xffffffffu << (lo & 31);
+        if (w == (hi >> 5)) mask &= 0xffffffffu >> (31 - (hi & 31));
+        const uint32_t old = L.V[w], nw = old & ~mask;
+        if (nw != old) {
+            L.V[w] = nw;
+            if (!nw) hp_and(&L.SV[w >> 5], ~(1u << (w & 31)));
+        }
+    }
+}
+
+// merge the hulls of the blocks [w-h, w) and [w, w+h) (in words) of one line: find the bridge
+// (p, q) -- p the last vertex of the left hull, q the first of the right hull that survive --
+// and clear the vertices in between.  First by walking from the junction (every step removes
+// one vertex: a convex junction costs two cross products, a few removals a few more), and after
+// HP_WALK removals by binary search on the rest: for the left tangent point, with the tangent
+// search on the right hull as its predicate.
+#define HP_WALK 12
+PDE_HD void hp_merge(const LineView &L, int w, int h, int Lp) {
+    const int J = w << 5;
+    if (J >= Lp) return;
+    int aLo = (w - h) << 5;
+    int bHi = ((w + h) << 5 < Lp ? (w + h) << 5 : Lp) - 1;
+    int f = bm_pred(L.F, L.SF, J - 1);
+    if (f > aLo) aLo = f;
+    f = bm_succ(L.F, L.SF, J, L.LW, L.SW);
+    if (f < bHi) bHi = f;
+    int p = J - 1, q = J;
+    if (aLo == p && bHi == q) return;
+    double yp = L.Y(p), yq = L.Y(q);
+    int budget = HP_WALK;
+    bool moved = true;
+    while (moved && budget > 0) {
+        moved = false;
+        while (p > aLo && budget > 0) {
+            const int pp = bm_pred(L.V, L.SV, p - 1);
+            const double ypp = L.Y(pp);
+            if (!hp_drop(pp, ypp, p, yp, q, yq)) break;
+            p = pp; yp = ypp;
+            moved = true;
+            --budget;
+        }
+        while (q < bHi && budget > 0) {
+            const int qq = bm_succ(L.V, L.SV, q + 1, L.LW, L.SW);
+            const double yqq = L.Y(qq);
+            if (!hp_drop(p, yp, q, yq, qq, yqq)) break;
+            q = qq; yq = yqq;
+            moved = true;
+            --budget;
+        }
+    }
+    if (moved) {                                  // budget spent: search the remaining chains
+        int lo = aLo, hi = p;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            const int v = bm_succ(L.V, L.SV, mid, L.LW, L.SW);
+            const int pv = bm_pred(L.V, L.SV, v - 1);
+            const int qv = hp_tangent_right(L, v, q, bHi);
+            if (hp_drop(pv, L.Y(pv), v, L.Y(v), qv, L.Y(qv))) hi = pv;
+            else lo = v;
+        }
+        p = lo;
+        q = hp_tangent_right(L, p, q, bHi);
+    }
+    hp_clear(L, p + 1, J - 1);
+    hp_clear(L, J, q - 1);
+}
+
+PDE_HD int hp_mod(int x, int n) {
+    x %= n;
+    return x < 0 ? x + n : x;
+}
+
+// shared-memory stride of a line in doubles: 33 per word, and = 16 / WL mod 16 so that the WL
+// lines a half-warp stages side by side fall into distinct banks
+PDE_HD int hull_line_stride(int LW, int wl_log2) {
+    const int base = (LW * 33 + 15) / 16 * 16;
+    return base + (wl_log2 >= 4 ? 1 : 16 >> wl_log2);
+}
+
+// one CTA's view of its bundle
+struct HullCta {
+    SweepGeom g;
+    HullPass P;
+    double *U, *ys;
+    uint32_t *Vs, *Fs, *Cs, *SVs, *SFs;
+    int WL, LW, SW, LPS, i0, s_base, nlines, Lp, NJ;
+    unsigned deep_nx, deep_ny;       // extent of the deep interior (0 when there is none)
+};
+
+PDE_HD void hc_init(HullCta &c, const SweepGeom &g, const HullPass &P, double *U,
+                    unsigned char *smem, unsigned block) {
+    c.g = g; c.P = P; c.U = U;
+    c.WL = 1 << P.wl_log2; c.LW = P.LW; c.SW = P.SW;
+    c.LPS = hull_line_stride(P.LW, P.wl_log2);
+    c.ys = reinterpret_cast<double *>(smem);
+    c.Vs = reinterpret_cast<uint32_t *>(c.ys + (size_t)c.WL * c.LPS);
+    c.Fs = c.Vs + c.WL * c.LW;
+    c.Cs = c.Fs + c.WL * c.LW;
+    c.SVs = c.Cs + c.WL * c.LW;
+    c.SFs = c.SVs + c.WL * c.SW;
+    c.i0 = P.rows_mode ? 0 : (int)(block / P.groups);
+    c.s_base = (int)(block % P.groups) << P.wl_log2;
+    c.nlines = c.WL < P.Ns - c.s_base ? c.WL : P.Ns - c.s_base;
+    c.Lp = P.rows_mode ? (int)g.ny + 2 : (int)((g.nx + 1 - c.i0) / P.a) + 1;
+    c.NJ = (int)g.ny + 2;
+    c.deep_nx = g.nx > 2 * g.r ? (unsigned)(g.nx - 2 * g.r) : 0u;
+    c.deep_ny = g.ny > 2 * g.r ? (unsigned)(g.ny - 2 * g.r) : 0u;
+}
+
+PDE_HD LineView hc_line(const HullCta &c, int l) {
+    LineView L;
+    L.y = c.ys + l * c.LPS;
+    L.V = c.Vs + l * c.LW;
+    L.F = c.Fs + l * c.LW;
+    L.C = c.Cs + l * c.LW;
+    L.SV = c.SVs + l * c.SW;
+    L.SF = c.SFs + l * c.SW;
+    L.LW = c.LW;
+    L.SW = c.SW;
+    return L;
+}
+
+// stage the bundle (adjacent lines fastest: contiguous in memory) and clear the summaries
+PDE_HD void hc_load(const HullCta &c, int tid, int nthr) {
+    if (c.P.rows_mode) {
+        for (int idx = tid; idx < c.nlines * c.Lp; idx += nthr) {
+            const int l = idx / c.Lp, t = idx - l * c.Lp;
+            c.ys[l * c.LPS + hp_ix(t)] = c.U[sw_addr(c.g, c.s_base + l + 1, t)];
+        }
+    } else {
+        // nthr is a multiple of WL: a thread keeps its line and advances t by nthr / WL
+        const int l = tid & (c.WL - 1), dt = nthr >> c.P.wl_log2;
+        const int dj = hp_mod(dt * c.P.b, c.NJ);
+        int t = tid >> c.P.wl_log2;
+        int j = hp_mod(c.s_base + l + t * c.P.b, c.NJ);
+        if (l < c.nlines)
+            for (; t < c.Lp; t += dt) {
+                c.ys[l * c.LPS + hp_ix(t)] = c.U[sw_addr(c.g, c.i0 + t * c.P.a, j)];
+                j += dj;
+                if (j >= c.NJ) j -= c.NJ;
+            }
+    }
+    for (int idx = tid; idx < c.WL * c.SW; idx += nthr) {
+        c.SVs[idx] = 0u;
+        c.SFs[idx] = 0u;
+    }
+}
+
+// level 0: fixed-vertex mask + monotone chain within the 32-point word (the stack is the mask)
+PDE_HD void hc_level0(const HullCta &c, int tid) {
+    const int l = tid / c.LW, w = tid - l * c.LW;
+    if (l >= c.WL) return;
+    const LineView L = hc_line(c, l);
+    const SweepGeom &g = c.g;
+    const HullPass &P = c.P;
+    uint32_t m = 0u, fm = 0u;
+    const int base = w << 5;
+    if (l < c.nlines && base < c.Lp) {
+        const int cnt = 32 < c.Lp - base ? 32 : c.Lp - base;
+        const int NJ = c.NJ;
+        int i, j;
+        if (P.rows_mode) {
+            i = c.s_base + l + 1;
+            j = base;
+        } else {
+            i = c.i0 + base * P.a;
+            j = hp_mod(c.s_base + l + base * P.b, NJ);
+        }
+        int t1 = -1, t0 = -1;
+        double y1 = 0.0, y0 = 0.0;
+        for (int q = 0; q < cnt; ++q) {
+            // deep points (more than r cells from every wall) carry every lattice pair
+            const bool deep = (unsigned)(i - g.r - 1) < c.deep_nx &&
+                              (unsigned)(j - g.r - 1) < c.deep_ny;
+            if (!deep) {
+                bool forced;
+                if (P.rows_mode) {
+                    forced = (j == 0 || j == NJ - 1);
+                } else {
+                    const int t = base + q;
+                    forced = (i == 0 || i == (int)g.nx + 1 || j == 0 || j == NJ - 1) || t == 0 ||
+                             t == c.Lp - 1 || j - P.b < 0 || j - P.b >= NJ || j + P.b < 0 ||
+                             j + P.b >= NJ;
+                }
+                if (!forced)
+                    forced = !((g.flags[(int64_t)(i - 1) * g.pitch + (j - 1)] >> P.k) & 1ull);
+                if (forced) fm |= 1u << q;
+            }
+            const double yq = L.Y(base + q);
+            while (t0 >= 0 && !((fm >> t1) & 1u)) {
+                if (!hp_drop(t0, y0, t1, y1, q, yq)) break;
+                m &= ~(1u << t1);
+                t1 = t0;
+                y1 = y0;
+                const uint32_t below = m & ((1u << t1) - 1u);
+                if (below) {
+                    t0 = 31 - hp_clz(below);
+                    y0 = L.Y(base + t0);
+                } else {
+                    t0 = -1;
+                }
+            }
+            m |= 1u << q;
+            t0 = t1; y0 = y1;
+            t1 = q;  y1 = yq;
+            if (P.rows_mode) {
+                ++j;
+            } else {
+                i += P.a;
+                j += P.b;
+                if (j >= NJ) j -= NJ;
+                else if (j < 0) j += NJ;
+            }
+        }
+    }
+    L.V[w] = m;
+    L.F[w] = fm;
+    L.C[w] = 0u;
+    if (m) hp_or(&L.SV[w >> 5], 1u << (w & 31));
+    if (fm) hp_or(&L.SF[w >> 5], 1u << (w & 31));
+}
+
+// junction k of a line at this level sits at word (2k + 1) h; the first threads of the line
+// take them, so that the active lanes of a warp are contiguous
+PDE_HD void hc_merge(const HullCta &c, int tid, int h) {
+    const int l = tid / c.LW, k = tid - l * c.LW;
+    const int w = (2 * k + 1) * h;
+    if (l >= c.nlines || w >= c.LW) return;
+    hp_merge(hc_line(c, l), w, h, c.Lp);
+}
+
+// lower the non-vertices of a word onto the chord of the neighbouring vertices
+PDE_HD double hc_fill(const HullCta &c, int tid) {
+    const int l = tid / c.LW, w = tid - l * c.LW;
+    const int base = w << 5;
+    if (l >= c.nlines || base >= c.Lp) return 0.0;
+    const LineView L = hc_line(c, l);
+    const int cnt = 32 < c.Lp - base ? 32 : c.Lp - base;
+    const uint32_t valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
+    uint32_t nonv = ~L.V[w] & valid, changed = 0u;
+    int ta = -1, tb = -1;
+    double ya = 0.0, slope = 0.0, cmax = 0.0;
+    while (nonv) {
+        const int q = hp_ffs(nonv) - 1;
+        nonv &= nonv - 1u;
+        const int t = base + q;
+        if (t > tb) {
+            ta = bm_pred(L.V, L.SV, t);
+            tb = bm_succ(L.V, L.SV, t, c.LW, c.SW);
+            ya = L.Y(ta);
+            slope = hp_sub(L.Y(tb), ya) / (double)(tb - ta);
+        }
+        const double v = hp_add(ya, hp_mul(slope, (double)(t - ta)));
+        const double old = L.Y(t);
+        if (v < old) {                               // never raise (rounding of the chord)
+            L.Y(t) = v;
+            changed |= 1u << q;
+            if (old - v > cmax) cmax = old - v;
+        }
+    }
+    L.C[w] = changed;
+    return cmax;
+}
+
+PDE_HD void hc_store(const HullCta &c, int tid, int nthr) {
+    if (c.P.rows_mode) {
+        for (int idx = tid; idx < c.nlines * c.Lp; idx += nthr) {
+            const int l = idx / c.Lp, t = idx - l * c.Lp;
+            if ((c.Cs[l * c.LW + (t >> 5)] >> (t & 31)) & 1u)
+                c.U[(int64_t)(c.s_base + l) * c.g.pitch + (t - 1)] = c.ys[l * c.LPS + hp_ix(t)];
+        }
+    } else {
+        const int l = tid & (c.WL - 1), dt = nthr >> c.P.wl_log2;
+        const int dj = hp_mod(dt * c.P.b, c.NJ);
+        int t = tid >> c.P.wl_log2;
+        int j = hp_mod(c.s_base + l + t * c.P.b, c.NJ);
+        if (l < c.nlines)
+            for (; t < c.Lp; t += dt) {
+                if ((c.Cs[l * c.LW + (t >> 5)] >> (t & 31)) & 1u)
+                    c.U[(int64_t)(c.i0 + t * c.P.a - 1) * c.g.pitch + (j - 1)] =
+                        c.ys[l * c.LPS + hp_ix(t)];
+                j += dj;
+                if (j >= c.NJ) j -= c.NJ;
+            }
+    }
+}
+
+__global__ void __launch_bounds__(1024, 1)
+k_hull_pass(SweepGeom g, HullPass P, double *U, double *change, const int *done) {
+    if (*done) return;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    HullCta c;
+    hc_init(c, g, P, U, smem_raw, blockIdx.x);
+    const int tid = threadIdx.x, nthr = blockDim.x;
+    hc_load(c, tid, nthr);
+    __syncthreads();
+    hc_level0(c, tid);
+    for (int h = 1; h < c.LW; h <<= 1) {
+        __syncthreads();
+        hc_merge(c, tid, h);
+    }
+    __syncthreads();
+    double cmax = hc_fill(c, tid);
+    __syncthreads();
+    hc_store(c, tid, nthr);
+    cmax = warp_max(cmax);
+    if ((tid & 31) == 0 && cmax > 0.0) atomic_max_nonneg(change, cmax);
+}
+
+// host replay of the kernel, one CTA after the other, phase by phase (tests: device = -2)
+static double hull_pass_replay(const SweepGeom &g, const HullPass &P, double *U, unsigned grid,
+                               unsigned block, size_t smem) {
+    double change = 0.0;
+#pragma omp parallel reduction(max : change)
+    {
+        std::vector<unsigned char> buf(smem + 16);
+#pragma omp for schedule(dynamic, 1)
+        for (long blk = 0; blk < (long)grid; ++blk) {
+            HullCta c;
+            hc_init(c, g, P, U, buf.data(), (unsigned)blk);
+            const int n = (int)block;
+            for (int t = 0; t < n; ++t) hc_load(c, t, n);
+            for (int t = 0; t < n; ++t) hc_level0(c, t);
+            for (int h = 1; h < c.LW; h <<= 1)
+                for (int t = 0; t < n; ++t) hc_merge(c, t, h);
+            for (int t = 0; t < n; ++t) {
+                const double v = hc_fill(c, t);
+                if (v > change) change = v;
+            }
+            for (int t = 0; t < n; ++t) hc_store(c, t, n);
+        }
+    }
+    return change;
+}
+
+static size_t hull_smem_bytes(int wl_log2, int LW, int SW) {
+    const int WL = 1 << wl_log2;
+    return (size_t)WL * hull_line_stride(LW, wl_log2) * sizeof(double) +
+           (size_t)(3 * WL * LW + 2 * WL * SW) * sizeof(uint32_t);
+}
+
+struct HullPlan {
+    HullPass P;
+    unsigned grid, block;
+    size_t smem;
+};
+
+// launch shape of every direction pass; false if a line does not fit one CTA
+static bool hull_plan(std::vector<HullPlan> &plan, int64_t nx, int64_t ny, int ndir,
+                      const int32_t *h_dirs, size_t budget, size_t max_smem) {
+    plan.resize((size_t)ndir);
+    for (int k = 0; k < ndir; ++k) {
+        int a = h_dirs[2 * k], b = h_dirs[2 * k + 1];
+        HullPass P;
+        P.k = k;
+        int Lp, nstart;
+        if (a == 0) {
+            if (b != 1 && b != -1) return false;
+            P.rows_mode = 1; P.a = 0; P.b = 1;
+            P.Ns = (int)nx;
+            Lp = (int)ny + 2;
+            nstart = 1;
+        } else {
+            if (a < 0) { a = -a; b = -b; }
+            P.rows_mode = 0; P.a = a; P.b = b;
+            P.Ns = (int)ny + 2;
+            Lp = (int)((nx + 1) / a) + 1;
+            nstart = (int)std::min<int64_t>(a, nx + 2);
+        }
+        P.LW = (Lp + 31) / 32;
+        P.SW = (P.LW + 31) / 32;
+        int wl = 0;
+        while (wl < 5 && hull_smem_bytes(wl + 1, P.LW, P.SW) <= budget &&
+               (2 << wl) * P.LW <= 1024 && (2 << wl) <= P.Ns)
+            ++wl;
+        if (hull_smem_bytes(wl, P.LW, P.SW) > max_smem || (1 << wl) * P.LW > 1024)
+            return false;
+        P.wl_log2 = wl;
+        P.groups = (P.Ns + (1 << wl) - 1) >> wl;
+        plan[k].P = P;
+        plan[k].grid = (unsigned)(nstart * P.groups);
+        plan[k].block = (unsigned)((((1 << wl) * P.LW) + 31) / 32 * 32);
+        plan[k].smem = hull_smem_bytes(wl, P.LW, P.SW);
+    }
+    return true;
 }
 
 }  // namespace pde
@@ -176,44 +742,68 @@ extern "C" {
 
 int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall_base,
                  int stencil_radius, int ndir, const int32_t *h_dirs, const int64_t *ring,
-                 const uint64_t *flags, int64_t n_rest, const int64_t *rest_rows,
-                 const double *rest_theta, double *U, int32_t *scratch, double tol,
-                 int64_t max_sweeps, int relax_reps, double *h_out, void *stream) {
+                 const uint64_t *flags, int64_t n_band, const int64_t *band_ptr,
+                 const int64_t *band_center, const int64_t *rest_j, const double *rest_theta,
+                 double *U, double *work, double tol, int64_t max_sweeps, int relax_every,
+                 int relax_reps, double *h_out, void *stream) {
     PDE_REQUIRE(nx >= 1 && ny >= 1 && pitch >= ny && ndir >= 1 && ndir <= 64, "bad sweep geometry");
-    PDE_REQUIRE(h_dirs && ring && flags && U && scratch && h_out, "null argument");
-    PDE_REQUIRE(n_rest == 0 || (rest_rows && rest_theta), "null argument");
+    PDE_REQUIRE(h_dirs && ring && flags && U && h_out, "null argument");
+    PDE_REQUIRE(n_band == 0 || (band_ptr && band_center && rest_j && rest_theta), "null argument");
+    PDE_REQUIRE(max_sweeps >= 0 && ny + 2 < (1 << 24) && nx + 2 < (1 << 24), "bad sweep arguments");
     SweepGeom g;
     g.nx = nx; g.ny = ny; g.pitch = pitch; g.wall_base = wall_base; g.r = stencil_radius;
     g.ring = ring;
     g.flags = reinterpret_cast<const unsigned long long *>(flags);
     const int64_t W = ny + 2, npad = (nx + 2) * W;
+    if (relax_every <= 0 || relax_every > ndir) relax_every = ndir;
+    size_t budget = 110 * 1024;                       // two bundles per SM
+    if (const char *e = getenv("PDE_SWEEP_SMEM_KB")) budget = (size_t)atoi(e) * 1024;
+    std::vector<HullPlan> plan;
     double change = 0.0;
     int64_t sweeps = 0;
-    if (device < 0) {                                   // host build of the same routine (tests)
+    if (device < 0) {                // host builds: -1 serial chain per line, -2 kernel replay
+        if (device == -2)
+            PDE_REQUIRE(hull_plan(plan, nx, ny, ndir, h_dirs, budget, 227 * 1024),
+                        "lattice line too long for the sweep kernel");
+        std::vector<int32_t> stk((size_t)(device == -1 ? npad : 1));
+        std::vector<double> tmp((size_t)std::max<int64_t>(n_band, 1));
+        auto relax = [&]() {
+            double cmax = 0.0;
+            for (int rep = 0; rep < relax_reps && n_band > 0; ++rep) {
+#pragma omp parallel for schedule(static)
+                for (int64_t b = 0; b < n_band; ++b)
+                    tmp[b] = sw_relax_value(b, band_ptr, band_center, rest_j, rest_theta, U);
+#pragma omp parallel for schedule(static) reduction(max : cmax)
+                for (int64_t b = 0; b < n_band; ++b) {
+                    double &u = U[band_center[b]];
+                    if (tmp[b] < u) {
+                        if (u - tmp[b] > cmax) cmax = u - tmp[b];
+                        u = tmp[b];
+                    }
+                }
+            }
+            return cmax;
+        };
         while (sweeps < max_sweeps) {
             change = 0.0;
             for (int k = 0; k < ndir; ++k) {
                 const int a = h_dirs[2 * k], b = h_dirs[2 * k + 1];
                 double cmax = 0.0;
+                if (device == -2) {
+                    cmax = hull_pass_replay(g, plan[k].P, U, plan[k].grid, plan[k].block,
+                                            plan[k].smem);
+                } else {
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : cmax)
-                for (int64_t idx = 0; idx < npad; ++idx) {
-                    const int64_t i = idx / W, j = idx % W;
-                    if (sw_inside(g, i - a, j - b)) continue;
-                    const double c = sw_line(g, U, scratch, i, j, a, b, k);
-                    if (c > cmax) cmax = c;
-                }
-                if (cmax > change) change = cmax;
-            }
-            for (int rep = 0; rep < relax_reps; ++rep)
-                for (int64_t q = 0; q < n_rest; ++q) {
-                    const double th = rest_theta[q];
-                    const double v = th * U[rest_rows[3 * q + 1]] + (1.0 - th) * U[rest_rows[3 * q + 2]];
-                    double &u = U[rest_rows[3 * q]];
-                    if (v < u) {
-                        if (u - v > change) change = u - v;
-                        u = v;
+                    for (int64_t idx = 0; idx < npad; ++idx) {
+                        const int64_t i = idx / W, j = idx % W;
+                        if (sw_inside(g, i - a, j - b)) continue;
+                        const double c = sw_line(g, U, stk.data(), i, j, a, b, k);
+                        if (c > cmax) cmax = c;
                     }
                 }
+                if (cmax > change) change = cmax;
+                if ((k + 1) % relax_every == 0 || k == ndir - 1) change = std::max(change, relax());
+            }
             ++sweeps;
             if (change < tol) break;
         }
@@ -221,37 +811,66 @@ int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall
         h_out[1] = (double)sweeps;
         return 0;
     }
+
+    PDE_REQUIRE(work, "null argument");
     DeviceGuard guard(device);
     cudaStream_t st = (cudaStream_t)stream;
-    double *d_change = nullptr;
-    PDE_CHECK(cudaMalloc(&d_change, sizeof(double)));
+    int max_smem = 0;
+    PDE_CHECK(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    PDE_CHECK(cudaFuncSetAttribute(k_hull_pass, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   max_smem));
+    PDE_REQUIRE(hull_plan(plan, nx, ny, ndir, h_dirs, std::min(budget, (size_t)max_smem),
+                          (size_t)max_smem),
+                "lattice line too long for the sweep kernel");
+
+    // work: [n_band tmp | change per sweep (batch_cap + 1) | done, sweeps_done (two ints)]
+    constexpr int64_t batch_cap = 64;
+    double *d_tmp = work, *d_change = work + n_band;
+    int *d_flags = reinterpret_cast<int *>(d_change + batch_cap + 1);
     int rc = 0;
-    const unsigned nblk = (unsigned)((npad + 63) / 64);
+    const unsigned rblk = (unsigned)((n_band + 127) / 128);
     while (sweeps < max_sweeps && rc == 0) {
-        cudaError_t e = cudaMemsetAsync(d_change, 0, sizeof(double), st);
-        for (int k = 0; k < ndir && e == cudaSuccess; ++k) {
-            k_sweep_lines<<<nblk, 64, 0, st>>>(g, U, scratch, h_dirs[2 * k], h_dirs[2 * k + 1], k,
-                                               d_change);
-            count_launch();
-            e = cudaGetLastError();
+        const int64_t batch = std::min<int64_t>(batch_cap, max_sweeps - sweeps);
+        cudaError_t e = cudaMemsetAsync(d_change, 0, (batch_cap + 2) * sizeof(double), st);
+        for (int64_t s = 0; s < batch && e == cudaSuccess; ++s) {
+            double *ch = d_change + s;
+            for (int k = 0; k < ndir && e == cudaSuccess; ++k) {
+                const HullPlan &pl = plan[k];
+                k_hull_pass<<<pl.grid, pl.block, pl.smem, st>>>(g, pl.P, U, ch, d_flags);
+                count_launch();
+                if (n_band > 0 && ((k + 1) % relax_every == 0 || k == ndir - 1)) {
+                    for (int rep = 0; rep < relax_reps; ++rep) {
+                        k_relax_eval<<<rblk, 128, 0, st>>>(n_band, band_ptr, band_center, rest_j,
+                                                           rest_theta, U, d_tmp, d_flags);
+                        k_relax_commit<<<rblk, 128, 0, st>>>(n_band, band_center, d_tmp, U, ch,
+                                                             d_flags);
+                        count_launch(2);
+                    }
+                }
+                e = cudaGetLastError();
+            }
+            if (e == cudaSuccess) {
+                k_sweep_end<<<1, 1, 0, st>>>(ch, tol, d_flags, d_flags + 1);
+                count_launch();
+                e = cudaGetLastError();
+            }
         }
-        for (int rep = 0; rep < relax_reps && n_rest > 0 && e == cudaSuccess; ++rep) {
-            k_sweep_relax<<<(unsigned)((n_rest + 255) / 256), 256, 0, st>>>(n_rest, rest_rows,
-                                                                            rest_theta, U, d_change);
-            count_launch();
-            e = cudaGetLastError();
-        }
-        if (e == cudaSuccess) e = cudaMemcpyAsync(&change, d_change, sizeof(double),
-                                                  cudaMemcpyDeviceToHost, st);
+        double h_change[batch_cap + 2];
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(h_change, d_change, (batch_cap + 2) * sizeof(double),
+                                cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
         if (e != cudaSuccess) {
             rc = fail_cuda(e, "convex-hull sweep", __FILE__, __LINE__);
             break;
         }
-        ++sweeps;
-        if (change < tol) break;
+        int h_flags[2];
+        memcpy(h_flags, &h_change[batch_cap + 1], sizeof(h_flags));
+        const int done_sweeps = h_flags[1];
+        if (done_sweeps > 0) change = h_change[done_sweeps - 1];
+        sweeps += done_sweeps;
+        if (h_flags[0] || done_sweeps < batch) break;
     }
-    cudaFree(d_change);
     h_out[0] = change;
     h_out[1] = (double)sweeps;
     return rc;
