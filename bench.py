@@ -19,10 +19,10 @@ BASELINE.json configs[1] (4097^2 lattice = 4095^2 interior points, stencil radiu
              7 fp64 instructions per point): see ``fp64`` and DESIGN.md.
 * ``cpu_baseline`` the NumPy port of the reference operator (oracle/) on the host cores.
 
-``solve_4097`` times BASELINE's second metric (convex_envelope.solve, Newton = policy iteration
-with the reference's defaults, on the 4097^2 lattice) and, under ``solve_4097.sweep``, the same
-discrete problem by the convex-hull sweep solver (``solver='sweep'``, an extension; DESIGN K9)
-stopped on the reference's criteria.
+``solve_4097`` times BASELINE's second metric, the 4097^2 convex-envelope solve: the convex-hull
+sweep solver (``solver='sweep'``, an extension; DESIGN K9) followed by the reference's policy
+iteration started from its result (``U0=``) as the certifier, with the host/OpenMP build of the
+sweep timed beside it.
 
 N > 1 (torchrun): weak scaling -- the global lattice has N x 4095 rows, each rank owns a
 4095-row slab and refreshes ``r`` halo rows from its neighbours (one small NCCL all-gather
@@ -70,6 +70,9 @@ def parse():
                     help="time convex_envelope.solve (Newton = policy iteration, reference defaults) "
                          "on the S^2 interior grid of BASELINE configs[1] (4095 -> 4097^2 lattice, "
                          "r = 4) with the per-iteration CPU cost measured beside it; 0 = skip")
+    ap.add_argument("--solve-policy-from-g", action="store_true",
+                    help="also time the reference's policy iteration from U0 = g on that lattice "
+                         "(does not converge within its 100-iteration cap; ~50 s)")
     ap.add_argument("--pucci-full", type=int, default=8191,
                     help="BASELINE configs[2]: time the Pucci residual + policy kernel and the "
                          "matrix-free BiCGStab iteration on the S^2 interior grid, r = 6; 0 = skip")
@@ -304,81 +307,127 @@ def two_cones(X):            # obstacle of examples/convex_envelope.py:8-18
 
 
 def solve_full_size(args, obstacle):
-    """BASELINE.json's second metric: seconds for convex_envelope.solve(Grid, g, fdmethod='grid',
-    solver='newton') with the reference's defaults (solution_tol = operator_tol = 1e-6,
-    max_iters = 100: solvers.py:98-100) on the 4097^2 lattice, r = 4.  From U0 = g the number of
-    policy iterations grows about linearly with the lattice size, so at this
-    size the reference's own iteration cap ends the solve ("Maximum iterations reached",
-    solvers.py:226-228); the time reported is for exactly that work, and the CPU figure is the
-    same iteration counts priced with the host's measured per-iteration costs
-    (oracle/cpu_solve_baseline.py; the reference cannot run at this size at all)."""
+    """BASELINE.json's second metric: seconds to solve the convex envelope on the 4097^2 lattice,
+    r = 4 (reference defaults: solution_tol = operator_tol = 1e-6, solvers.py:98-100), to the
+    reference's own stopping criteria, in two timed legs:
+
+      sweep    ``convex_envelope.solve(G, g, fdmethod='grid', solver='sweep')`` -- the convex-hull
+               sweep solver (extension, DESIGN K9): the same discrete problem, stopped on
+               ``solvers.euler``'s rule (solvers.py:84);
+      certify  ``convex_envelope.solve(G, g, U0=U_sweep, fdmethod='grid', solver='newton')`` -- the
+               REFERENCE's algorithm (policy iteration, convex_envelope.py:107, solvers.py:98-233)
+               through its own ``U0`` argument: it must accept the sweep result (stop on
+               ``diff < solution_tol and max|F| < operator_tol`` without an Euler fallback).
+
+    ``converged`` is true only if both legs end on their criteria; ``seconds`` is their sum.
+    The reference's policy iteration from ``U0 = g`` cannot do this problem (its iteration count
+    grows linearly with the lattice and its cap is 100): ``--solve-policy-from-g`` still
+    times that run, without any speed-up figure.
+    CPU baseline of the same run: the host/OpenMP build of the sweep (``pde_ce_sweep``,
+    device = -1) timed on this box for a bounded number of sweeps and multiplied by the sweep
+    count, plus the certifying Newton iterations priced with the host's measured per-iteration
+    costs of the reference's building blocks (oracle/cpu_solve_baseline.py)."""
     import warnings
     import numpy as np
     import torch
-    from pyellipticfd_b200 import convex_envelope
+    from pyellipticfd_b200 import convex_envelope, _sweep
     from pyellipticfd_b200.pointclasses import FDRegularGrid
     from pyellipticfd_b200._context import GridContext
     n, r = args.solve_full, args.radius
-    out = {"problem": "convex envelope of two cones, [-1,1]^2, r=%d, tol 1e-6, max_iters 100 "
-                      "(reference defaults)" % r, "lattice": "%d^2" % (n + 2), "solver": "newton"}
+    out = {"problem": "convex envelope of two cones, [-1,1]^2, r=%d, solution_tol = operator_tol = "
+                      "1e-6 (reference defaults)" % r, "lattice": "%d^2" % (n + 2),
+           "algorithm": "sweep (extension) -> convex_envelope.solve(U0=U_sweep, solver='newton') "
+                        "(the reference's policy iteration as certifier)"}
     try:
         t = time.time()
         Gs = FDRegularGrid([n, n], np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, r, interpolation=False)
         out["grid_build_s"] = time.time() - t
-        g = torch.from_numpy(obstacle(Gs.points)).cuda()
-        # extension (DESIGN K9): the same discrete problem by directional convex-hull sweeps,
-        # stopped on the reference's criteria (change < 1e-6 and max|F| < 1e-6)
-        try:
-            ctx_s = GridContext.get(Gs)
-            t = time.perf_counter()
-            ctx_s.ce_sweep(ctx_s.pack(g), 0.0, 0)                 # builds / uploads the sweep tables
-            torch.cuda.synchronize()
-            t_tab = time.perf_counter() - t
-            sst = {}
-            with warnings.catch_warnings(record=True) as wl2:
-                warnings.simplefilter("always")
-                t = time.perf_counter()
-                _, sdiff, sit, _ = convex_envelope._solve_grid(Gs, g, None, "sweep", stats=sst,
-                                                               max_iters=160, check_every=2,
-                                                               timeout=45.0)
-                torch.cuda.synchronize()
-                t_sw = time.perf_counter() - t
-            out["sweep"] = {"solver": "sweep (extension: convex-hull sweeps, same discrete solution)",
-                            "seconds": t_sw, "tables_s": t_tab, "sweeps": int(sit), "diff": float(sdiff),
-                            "residual": sst.get("residual"),
-                            "converged": bool(sdiff < 1e-6 and (sst.get("residual") or 1.0) < 1e-6),
-                            "warnings": sorted({str(w.message) for w in wl2})}
-        except Exception as e:            # reported, not fatal
-            out["sweep"] = {"error": str(e)[:300]}
-        st = {}
+        g_host = obstacle(Gs.points)
+        g = torch.from_numpy(g_host).cuda()
+        ctx_s = GridContext.get(Gs)
+        t = time.perf_counter()
+        ctx_s.ce_sweep(ctx_s.pack(g), 0.0, 0)                 # builds / uploads the sweep tables
+        torch.cuda.synchronize()
+        out["sweep_tables_s"] = time.perf_counter() - t
+        sst, nst = {}, {}
         with warnings.catch_warnings(record=True) as wl:
             warnings.simplefilter("always")
             torch.cuda.synchronize()
             t = time.perf_counter()
-            U, diff, it, _ = convex_envelope._solve_grid(Gs, g, None, "newton", stats=st)
+            Us, sdiff, sit, _ = convex_envelope.solve(Gs, g, fdmethod="grid", solver="sweep",
+                                                      stats=sst, max_iters=400, timeout=60.0)
             torch.cuda.synchronize()
-            out["seconds"] = time.perf_counter() - t
-        out.update(iterations=it, diff=diff, warnings=sorted({str(w.message) for w in wl}),
-                   **{k: v for k, v in st.items() if k != "reason"})
+            t_sw = time.perf_counter() - t
+        sw_ok = bool(sdiff < 1e-6 and (sst.get("residual") or 1.0) < 1e-6)
+        out["sweep"] = {"seconds": t_sw, "sweeps": int(sit), "diff": float(sdiff),
+                        "residual": sst.get("residual"), "converged": sw_ok,
+                        "ms_per_sweep": 1e3 * t_sw / max(int(sit), 1),
+                        "warnings": sorted({str(w.message) for w in wl})}
+        with warnings.catch_warnings(record=True) as wl:
+            warnings.simplefilter("always")
+            torch.cuda.synchronize()
+            t = time.perf_counter()
+            Un, ndiff, nit, _ = convex_envelope.solve(Gs, g, U0=Us, fdmethod="grid",
+                                                      solver="newton", stats=nst)
+            torch.cuda.synchronize()
+            t_nw = time.perf_counter() - t
+        nw_ok = bool(ndiff < 1e-6 and nst.get("residual", 1.0) < 1e-6 and nit <= 100
+                     and nst.get("euler_fallbacks", 1) == 0)
+        out["certify"] = {"seconds": t_nw, "newton_iters": int(nit), "diff": float(ndiff),
+                          "krylov_iters": int(nst.get("krylov_iters", -1)),
+                          "euler_fallbacks": int(nst.get("euler_fallbacks", -1)),
+                          "residual": nst.get("residual"), "converged": nw_ok,
+                          "max_abs_U_sweep_minus_U_newton": float((Us - Un).abs().max()),
+                          "warnings": sorted({str(w.message) for w in wl})}
+        out["seconds"] = t_sw + t_nw
+        out["converged"] = bool(sw_ok and nw_ok)
+        if args.solve_policy_from_g:
+            st = {}
+            with warnings.catch_warnings(record=True) as wl:
+                warnings.simplefilter("always")
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                _, diff, it, _ = convex_envelope.solve(Gs, g, fdmethod="grid", solver="newton",
+                                                       stats=st)
+                torch.cuda.synchronize()
+                dt = time.perf_counter() - t
+            out["policy_iteration_from_g"] = dict(
+                seconds=dt, iterations=int(it), diff=float(diff),
+                converged=bool(diff < 1e-6 and st.get("residual", 1.0) < 1e-6 and it <= 100),
+                warnings=sorted({str(w.message) for w in wl}),
+                **{k: v for k, v in st.items() if k != "reason"})
         GridContext.drop(Gs)
-        del U, g, Gs
+        del Us, Un, g
         torch.cuda.empty_cache()
     except Exception as e:                # reported, not fatal
         out["error"] = str(e)[:300]
         return out
     if not args.no_cpu_baseline:
         try:
+            cores = os.cpu_count() or 1
+            k = 2
+            t = time.perf_counter()
+            _, _, done = _sweep.host_sweep(Gs, g_host, tol=0.0, max_sweeps=k, relax_every=4)
+            t_host = (time.perf_counter() - t) / max(done, 1)
+            cb = {"kind": "port (host/OpenMP build of the same sweep, pde_ce_sweep device=-1)",
+                  "cores": cores, "seconds_per_sweep": t_host,
+                  "sample": "%d sweeps of the full %s lattice, x %d sweeps" % (k, out["lattice"], sit),
+                  "sweep_seconds": t_host * sit}
             res = subprocess.run([sys.executable, "-m", "oracle.cpu_solve_baseline", str(n), str(r),
                                   "48", "4"], cwd=ROOT, capture_output=True, text=True, timeout=900)
             c = json.loads(res.stdout.strip().splitlines()[-1])
-            cpu_s = (out["newton_iters"] * (c["t_op"] + c["t_jac"]) + out["krylov_iters"] * c["t_kit"])
-            out["cpu_baseline"] = {
-                "seconds_extrapolated": cpu_s, "cores": c["cores"], "kind": "port",
-                "t_operator_s": c["t_op"], "t_jacobian_assembly_s": c["t_jac"],
-                "t_bicgstab_iteration_s": c["t_kit"], "sample": c["sample"],
-                "note": "newton_iters x (t_operator + t_jacobian_assembly) + krylov_iters x "
-                        "t_bicgstab_iteration, iteration counts of the GPU run"}
-            out["speedup_vs_cpu_extrapolated"] = cpu_s / out["seconds"]
+            cert = (out["certify"]["newton_iters"] * (c["t_op"] + c["t_jac"])
+                    + out["certify"]["krylov_iters"] * c["t_kit"])
+            cb.update(certify_seconds=cert, t_operator_s=c["t_op"], t_jacobian_assembly_s=c["t_jac"],
+                      t_bicgstab_iteration_s=c["t_kit"], certify_cores=c["cores"],
+                      certify_sample=c["sample"], seconds=t_host * sit + cert,
+                      note="sweep leg: measured host seconds per sweep x sweeps of the GPU run; "
+                           "certify leg: newton_iters x (t_operator + t_jacobian_assembly) + "
+                           "krylov_iters x t_bicgstab_iteration with the reference's building "
+                           "blocks (NumPy operator port, SciPy CSR + bicgstab) on this host")
+            out["cpu_baseline"] = cb
+            if out["converged"]:
+                out["speedup_vs_cpu"] = cb["seconds"] / out["seconds"]
         except Exception as e:
             out["cpu_baseline"] = {"error": str(e)[:300]}
     return out

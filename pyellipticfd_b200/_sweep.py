@@ -3,8 +3,25 @@ reference: see ``csrc/ce_sweep.cu``) for a structured 2-D pairs grid, in state-l
 import numpy as np
 
 
+def band_slots(nx, ny, r):
+    """Number of compact flag slots (csrc/ce_sweep.cu::sw_band_slot)."""
+    return nx * ny if nx <= 2 * r else 2 * r * ny + (nx - 2 * r) * 2 * r
+
+
+def band_slot(nx, ny, r, i, j):
+    """Compact index of the band point (i, j), 1-based interior coordinates: the 2r full rows next
+    to the i-walls first, then 2r columns of every other row (csrc/ce_sweep.cu::sw_band_slot)."""
+    i, j = np.asarray(i, dtype=np.int64), np.asarray(j, dtype=np.int64)
+    if nx <= 2 * r:
+        return (i - 1) * ny + (j - 1)
+    top = (i - 1) * ny + (j - 1)
+    bot = (i - (nx - r) - 1 + r) * ny + (j - 1)
+    mid = 2 * r * ny + (i - r - 1) * 2 * r + np.where(j <= r, j - 1, j - (ny - r) - 1 + r)
+    return np.where(i <= r, top, np.where(i > nx - r, bot, mid))
+
+
 def tables(G, pitch, rows):
-    """-> dict(dirs (D,2) int32, ring int64, flags uint64 (rows*pitch), band_ptr (B+1,) int64,
+    """-> dict(dirs (D,2) int32, ring int64, flags uint64 (one per band point, ``band_slot``), band_ptr (B+1,) int64,
     band_center (B,) int64, rest_j (R,2) int64, theta (R,) f64): the band pairs that are not
     lattice pairs, CSR over the B band points that own any (state offsets).  ``rows`` x ``pitch``
     is the lattice part of the state layout; wall points follow at offset rows*pitch."""
@@ -50,8 +67,10 @@ def tables(G, pitch, rows):
     Vi = np.where(exact[:, None], np.round(V0), 0).astype(np.int64)
     kk = np.where(exact, lut[Vi[:, 0] + r, Vi[:, 1] + r], -1)
     line = kk >= 0
-    flags = np.zeros(rows * pitch, dtype=np.uint64)
-    np.bitwise_or.at(flags, offs(bp[line, 0]), np.uint64(1) << kk[line].astype(np.uint64))
+    flags = np.zeros(band_slots(nx, ny, r), dtype=np.uint64)
+    ids = bp[line, 0]
+    np.bitwise_or.at(flags, band_slot(nx, ny, r, ids // ny + 1, ids % ny + 1),
+                     np.uint64(1) << kk[line].astype(np.uint64))
     rest = bp[~line]
     rest = rest[np.argsort(rest[:, 0], kind="stable")]
     XI = G.coords(rest[:, 0])
@@ -66,3 +85,24 @@ def tables(G, pitch, rows):
     return dict(dirs=dirs, ring=ring, flags=flags, band_ptr=band_ptr,
                 band_center=np.ascontiguousarray(offs(centers), dtype=np.int64), rest_j=rest_j,
                 theta=np.ascontiguousarray(theta, dtype=np.float64))
+
+
+def host_sweep(G, g, tol=1e-11, max_sweeps=400, relax_reps=2, relax_every=0, device=-1):
+    """The HOST builds of ``pde_ce_sweep`` on flat vectors (state layout with pitch = ny):
+    ``device=-1`` the serial monotone chain per lattice line under OpenMP (CPU tests, CPU baseline
+    of bench.py), ``device=-2`` the thread-by-thread replay of the CUDA kernel's phases (CPU tests).
+    Not a product path: ``convex_envelope.solve(..., solver='sweep')`` only runs on the GPU.
+    Returns (U, last change, sweeps)."""
+    import ctypes as C
+    from . import _lib
+    nx, ny = G.interior_shape
+    t = tables(G, ny, nx)
+    U = np.ascontiguousarray(g, dtype=np.float64).copy()       # [lattice | wall] == state layout
+    out = (C.c_double * 2)()
+    p = lambda a: C.c_void_p(a.ctypes.data)
+    _lib.check(_lib.lib().pde_ce_sweep(device, nx, ny, ny, G.num_interior, G.stencil_radius,
+                                       t["dirs"].shape[0], p(t["dirs"]), p(t["ring"]), p(t["flags"]),
+                                       t["band_center"].shape[0], p(t["band_ptr"]),
+                                       p(t["band_center"]), p(t["rest_j"]), p(t["theta"]), p(U),
+                                       None, tol, max_sweeps, relax_every, relax_reps, out, None))
+    return U, out[0], int(out[1])

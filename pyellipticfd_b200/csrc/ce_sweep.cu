@@ -57,8 +57,19 @@ struct SweepGeom {
     int64_t nx, ny, pitch, wall_base;
     int r;
     const int64_t *ring;                 // wall ids of the integer ring: i=0 | i=nx+1 | j=0 | j=ny+1
-    const unsigned long long *flags;     // per lattice offset: bit k = pair k is a lattice pair here
+    const unsigned long long *flags;     // per band point (sw_band_slot): bit k = pair k is a lattice pair
 };
+
+// compact index of a band point (an interior point within r cells of a wall): the 2r full rows
+// next to the i-walls first, then 2r columns of every other row
+PDE_HD int64_t sw_band_slot(const SweepGeom &g, int64_t i, int64_t j) {
+    const int64_t r = g.r;
+    if (g.nx <= 2 * r) return (i - 1) * g.ny + (j - 1);            // every row is a band row
+    if (i <= r) return (i - 1) * g.ny + (j - 1);
+    if (i > g.nx - r) return (i - (g.nx - r) - 1 + r) * g.ny + (j - 1);
+    const int64_t base = 2 * r * g.ny + (i - r - 1) * 2 * r;
+    return base + (j <= r ? j - 1 : j - (g.ny - r) - 1 + r);
+}
 
 PDE_HD bool sw_inside(const SweepGeom &g, int64_t i, int64_t j) {
     return i >= 0 && i <= g.nx + 1 && j >= 0 && j <= g.ny + 1;
@@ -84,7 +95,7 @@ PDE_HD bool sw_constrained(const SweepGeom &g, int k, int64_t i, int64_t j) {
     if (!sw_interior(g, i, j)) return false;
     const bool band = i <= g.r || i > g.nx - g.r || j <= g.r || j > g.ny - g.r;
     if (!band) return true;
-    return (g.flags[(i - 1) * g.pitch + (j - 1)] >> k) & 1ull;
+    return (g.flags[sw_band_slot(g, i, j)] >> k) & 1ull;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -281,6 +292,60 @@ PDE_HD double hp_add(double a, double b) {
 #endif
 }
 
+// exact int -> double for 0 <= k < 2^31 without the conversion pipe
+PDE_HD double hp_i2d(int k) {
+#ifdef __CUDA_ARCH__
+    return __dsub_rn(__hiloint2double(0x43300000, k), 4503599627370496.0);
+#else
+    return (double)k;
+#endif
+}
+
+// largest set bit in [lo, pos] (-1 if none); reads no mask word below lo's
+PDE_HD int bm_pred_in(const uint32_t *M, const uint32_t *S, int pos, int lo) {
+    int w = pos >> 5;
+    const int lw = lo >> 5;
+    const uint32_t x = M[w] & (0xffffffffu >> (31 - (pos & 31)));
+    int r;
+    if (x) {
+        r = (w << 5) + 31 - hp_clz(x);
+    } else {
+        int sw = w >> 5;
+        uint32_t s = S[sw] & ((1u << (w & 31)) - 1u);
+        while (!s) {
+            if (--sw < (lw >> 5)) return -1;
+            s = S[sw];
+        }
+        w = (sw << 5) + 31 - hp_clz(s);
+        if (w < lw) return -1;
+        r = (w << 5) + 31 - hp_clz(M[w]);
+    }
+    return r >= lo ? r : -1;
+}
+
+// smallest set bit in [pos, hi] (INT_MAX if none); reads no mask word above hi's
+PDE_HD int bm_succ_in(const uint32_t *M, const uint32_t *S, int pos, int hi) {
+    int w = pos >> 5;
+    const int hw = hi >> 5;
+    if (w > hw) return 0x7fffffff;
+    const uint32_t x = M[w] & (0xffffffffu << (pos & 31));
+    int r;
+    if (x) {
+        r = (w << 5) + hp_ffs(x) - 1;
+    } else {
+        int sw = w >> 5;
+        uint32_t s = ((w & 31) == 31) ? 0u : (S[sw] & (0xffffffffu << ((w & 31) + 1)));
+        while (!s) {
+            if (++sw > (hw >> 5)) return 0x7fffffff;
+            s = S[sw];
+        }
+        w = (sw << 5) + hp_ffs(s) - 1;
+        if (w > hw) return 0x7fffffff;
+        r = (w << 5) + hp_ffs(M[w]) - 1;
+    }
+    return r <= hi ? r : 0x7fffffff;
+}
+
 // largest set bit <= pos (-1 if none)
 PDE_HD int bm_pred(const uint32_t *M, const uint32_t *S, int pos) {
     int w = pos >> 5;
@@ -314,7 +379,7 @@ PDE_HD int bm_succ(const uint32_t *M, const uint32_t *S, int pos, int LW, int SW
 
 // middle point (t1, y1) on or above the chord (t0, y0) -> (t2, y2): not a hull vertex
 PDE_HD bool hp_drop(int t0, double y0, int t1, double y1, int t2, double y2) {
-    return hp_mul(hp_sub(y1, y0), (double)(t2 - t0)) >= hp_mul(hp_sub(y2, y0), (double)(t1 - t0));
+    return hp_mul(hp_sub(y1, y0), hp_i2d(t2 - t0)) >= hp_mul(hp_sub(y2, y0), hp_i2d(t1 - t0));
 }
 
 // shared-memory index of point t of a line: one padding double per 32-point word, so that the
@@ -369,9 +434,9 @@ PDE_HD void hp_merge(const LineView &L, int w, int h, int Lp) {
     if (J >= Lp) return;
     int aLo = (w - h) << 5;
     int bHi = ((w + h) << 5 < Lp ? (w + h) << 5 : Lp) - 1;
-    int f = bm_pred(L.F, L.SF, J - 1);
+    int f = bm_pred_in(L.F, L.SF, J - 1, aLo);
     if (f > aLo) aLo = f;
-    f = bm_succ(L.F, L.SF, J, L.LW, L.SW);
+    f = bm_succ_in(L.F, L.SF, J, bHi);
     if (f < bHi) bHi = f;
     int p = J - 1, q = J;
     if (aLo == p && bHi == q) return;
@@ -469,24 +534,45 @@ PDE_HD LineView hc_line(const HullCta &c, int l) {
     return L;
 }
 
-// stage the bundle (adjacent lines fastest: contiguous in memory) and clear the summaries
+// Thread <-> word: thread tid owns word (tid & (LWp - 1)...) -- precisely line l = tid / LWp,
+// word w = tid % LWp with LWp = 32 SW threads per line, so that the 32 words of a summary word
+// belong to one warp: level 0 and the first five merge levels only need __syncwarp().
+
+// stage the bundle and clear the summaries
 PDE_HD void hc_load(const HullCta &c, int tid, int nthr) {
+    const SweepGeom &g = c.g;
     if (c.P.rows_mode) {
-        for (int idx = tid; idx < c.nlines * c.Lp; idx += nthr) {
-            const int l = idx / c.Lp, t = idx - l * c.Lp;
-            c.ys[l * c.LPS + hp_ix(t)] = c.U[sw_addr(c.g, c.s_base + l + 1, t)];
+        // a warp takes a line at a time: consecutive lanes, consecutive addresses
+        const int lane = tid & 31, nwarp = nthr >> 5;
+        for (int l = tid >> 5; l < c.nlines; l += nwarp) {
+            const int i = c.s_base + l + 1;
+            const double *row = c.U + (int64_t)(i - 1) * g.pitch - 1;
+            double *yl = c.ys + l * c.LPS;
+            for (int t = lane; t < c.Lp; t += 32)
+                yl[hp_ix(t)] = (t == 0 || t == c.Lp - 1) ? c.U[sw_addr(g, i, t)] : row[t];
         }
     } else {
-        // nthr is a multiple of WL: a thread keeps its line and advances t by nthr / WL
+        // nthr is a multiple of WL: a thread keeps its line and advances t by nthr / WL, so
+        // that the WL lines of the bundle are read side by side (contiguous in memory)
         const int l = tid & (c.WL - 1), dt = nthr >> c.P.wl_log2;
         const int dj = hp_mod(dt * c.P.b, c.NJ);
         int t = tid >> c.P.wl_log2;
-        int j = hp_mod(c.s_base + l + t * c.P.b, c.NJ);
+        int i = c.i0 + t * c.P.a, j = hp_mod(c.s_base + l + t * c.P.b, c.NJ);
+        const int di = dt * c.P.a;
+        const int64_t doff = (int64_t)di * g.pitch;
+        int64_t off = (int64_t)(i - 1) * g.pitch + (j - 1);
+        double *yl = c.ys + l * c.LPS;
         if (l < c.nlines)
             for (; t < c.Lp; t += dt) {
-                c.ys[l * c.LPS + hp_ix(t)] = c.U[sw_addr(c.g, c.i0 + t * c.P.a, j)];
+                const bool ring = i == 0 || i == (int)g.nx + 1 || j == 0 || j == c.NJ - 1;
+                yl[hp_ix(t)] = c.U[ring ? sw_addr(g, i, j) : off];
+                i += di;
                 j += dj;
-                if (j >= c.NJ) j -= c.NJ;
+                off += doff + dj;
+                if (j >= c.NJ) {
+                    j -= c.NJ;
+                    off -= c.NJ;
+                }
             }
     }
     for (int idx = tid; idx < c.WL * c.SW; idx += nthr) {
@@ -495,10 +581,33 @@ PDE_HD void hc_load(const HullCta &c, int tid, int nthr) {
     }
 }
 
-// level 0: fixed-vertex mask + monotone chain within the 32-point word (the stack is the mask)
+// monotone chain step: pop the vertices that (t, y) makes redundant, push t; the stack is the
+// bit mask m of the word, its two top entries are cached in (t1, y1), (t0, y0)
+#define HP_CHAIN_STEP(q, yq, may_pop)                                                  \
+    {                                                                                  \
+        while (t0 >= 0 && (may_pop)) {                                                 \
+            if (!hp_drop(t0, y0, t1, y1, (q), (yq))) break;                            \
+            m &= ~(1u << t1);                                                          \
+            t1 = t0;                                                                   \
+            y1 = y0;                                                                   \
+            const uint32_t below = m & ((1u << t1) - 1u);                              \
+            if (below) {                                                               \
+                t0 = 31 - hp_clz(below);                                               \
+                y0 = yw[t0];                                                           \
+            } else {                                                                   \
+                t0 = -1;                                                               \
+            }                                                                          \
+        }                                                                              \
+        m |= 1u << (q);                                                                \
+        t0 = t1; y0 = y1;                                                              \
+        t1 = (q); y1 = (yq);                                                           \
+    }
+
+// level 0: fixed-vertex mask + monotone chain within the 32-point word
 PDE_HD void hc_level0(const HullCta &c, int tid) {
-    const int l = tid / c.LW, w = tid - l * c.LW;
-    if (l >= c.WL) return;
+    const int LWp = c.SW << 5;
+    const int l = tid / LWp, w = tid - l * LWp;
+    if (l >= c.WL || w >= c.LW) return;
     const LineView L = hc_line(c, l);
     const SweepGeom &g = c.g;
     const HullPass &P = c.P;
@@ -507,58 +616,55 @@ PDE_HD void hc_level0(const HullCta &c, int tid) {
     if (l < c.nlines && base < c.Lp) {
         const int cnt = 32 < c.Lp - base ? 32 : c.Lp - base;
         const int NJ = c.NJ;
-        int i, j;
+        const double *yw = L.y + 33 * w;              // hp_ix(32 w + q) = 33 w + q
+        int i, j, ie, je;                             // first and last point of the word
         if (P.rows_mode) {
-            i = c.s_base + l + 1;
+            i = ie = c.s_base + l + 1;
             j = base;
+            je = base + cnt - 1;
         } else {
             i = c.i0 + base * P.a;
+            ie = i + (cnt - 1) * P.a;
             j = hp_mod(c.s_base + l + base * P.b, NJ);
+            je = j + (cnt - 1) * P.b;                 // not wrapped: out of range if the word wraps
         }
         int t1 = -1, t0 = -1;
         double y1 = 0.0, y0 = 0.0;
-        for (int q = 0; q < cnt; ++q) {
-            // deep points (more than r cells from every wall) carry every lattice pair
-            const bool deep = (unsigned)(i - g.r - 1) < c.deep_nx &&
-                              (unsigned)(j - g.r - 1) < c.deep_ny;
-            if (!deep) {
-                bool forced;
+        // deep points (more than r cells from every wall) carry every lattice pair
+        const bool all_deep = (unsigned)(i - g.r - 1) < c.deep_nx && (unsigned)(ie - g.r - 1) < c.deep_nx &&
+                              (unsigned)(j - g.r - 1) < c.deep_ny && (unsigned)(je - g.r - 1) < c.deep_ny;
+        if (all_deep) {
+            for (int q = 0; q < cnt; ++q) {
+                const double yq = yw[q];
+                HP_CHAIN_STEP(q, yq, true)
+            }
+        } else {
+            for (int q = 0; q < cnt; ++q) {
+                const bool deep = (unsigned)(i - g.r - 1) < c.deep_nx &&
+                                  (unsigned)(j - g.r - 1) < c.deep_ny;
+                if (!deep) {
+                    bool forced;
+                    if (P.rows_mode) {
+                        forced = (j == 0 || j == NJ - 1);
+                    } else {
+                        const int t = base + q;
+                        forced = (i == 0 || i == (int)g.nx + 1 || j == 0 || j == NJ - 1) || t == 0 ||
+                                 t == c.Lp - 1 || j - P.b < 0 || j - P.b >= NJ || j + P.b < 0 ||
+                                 j + P.b >= NJ;
+                    }
+                    if (!forced) forced = !((g.flags[sw_band_slot(g, i, j)] >> P.k) & 1ull);
+                    if (forced) fm |= 1u << q;
+                }
+                const double yq = yw[q];
+                HP_CHAIN_STEP(q, yq, !((fm >> t1) & 1u))
                 if (P.rows_mode) {
-                    forced = (j == 0 || j == NJ - 1);
+                    ++j;
                 } else {
-                    const int t = base + q;
-                    forced = (i == 0 || i == (int)g.nx + 1 || j == 0 || j == NJ - 1) || t == 0 ||
-                             t == c.Lp - 1 || j - P.b < 0 || j - P.b >= NJ || j + P.b < 0 ||
-                             j + P.b >= NJ;
+                    i += P.a;
+                    j += P.b;
+                    if (j >= NJ) j -= NJ;
+                    else if (j < 0) j += NJ;
                 }
-                if (!forced)
-                    forced = !((g.flags[(int64_t)(i - 1) * g.pitch + (j - 1)] >> P.k) & 1ull);
-                if (forced) fm |= 1u << q;
-            }
-            const double yq = L.Y(base + q);
-            while (t0 >= 0 && !((fm >> t1) & 1u)) {
-                if (!hp_drop(t0, y0, t1, y1, q, yq)) break;
-                m &= ~(1u << t1);
-                t1 = t0;
-                y1 = y0;
-                const uint32_t below = m & ((1u << t1) - 1u);
-                if (below) {
-                    t0 = 31 - hp_clz(below);
-                    y0 = L.Y(base + t0);
-                } else {
-                    t0 = -1;
-                }
-            }
-            m |= 1u << q;
-            t0 = t1; y0 = y1;
-            t1 = q;  y1 = yq;
-            if (P.rows_mode) {
-                ++j;
-            } else {
-                i += P.a;
-                j += P.b;
-                if (j >= NJ) j -= NJ;
-                else if (j < 0) j += NJ;
             }
         }
     }
@@ -569,20 +675,25 @@ PDE_HD void hc_level0(const HullCta &c, int tid) {
     if (fm) hp_or(&L.SF[w >> 5], 1u << (w & 31));
 }
 
-// junction k of a line at this level sits at word (2k + 1) h; the first threads of the line
-// take them, so that the active lanes of a warp are contiguous
+// Level h merges the blocks [w - h, w), [w, w + h) at the junction words w = (2k + 1) h.  For
+// h <= 16 a junction stays inside one 32-word group = one warp: lane k of the group's warp takes
+// junction k (contiguous active lanes).  For h >= 32 the first threads of the line take them.
 PDE_HD void hc_merge(const HullCta &c, int tid, int h) {
-    const int l = tid / c.LW, k = tid - l * c.LW;
-    const int w = (2 * k + 1) * h;
-    if (l >= c.nlines || w >= c.LW) return;
+    const int LWp = c.SW << 5;
+    const int l = tid / LWp, x = tid - l * LWp;
+    int w;
+    if (h <= 16) w = (x & ~31) + (2 * (x & 31) + 1) * h;
+    else w = (2 * x + 1) * h;
+    if (l >= c.nlines || w >= c.LW || (h <= 16 && (2 * (x & 31) + 1) * h >= 32)) return;
     hp_merge(hc_line(c, l), w, h, c.Lp);
 }
 
 // lower the non-vertices of a word onto the chord of the neighbouring vertices
 PDE_HD double hc_fill(const HullCta &c, int tid) {
-    const int l = tid / c.LW, w = tid - l * c.LW;
+    const int LWp = c.SW << 5;
+    const int l = tid / LWp, w = tid - l * LWp;
     const int base = w << 5;
-    if (l >= c.nlines || base >= c.Lp) return 0.0;
+    if (l >= c.nlines || w >= c.LW || base >= c.Lp) return 0.0;
     const LineView L = hc_line(c, l);
     const int cnt = 32 < c.Lp - base ? 32 : c.Lp - base;
     const uint32_t valid = cnt == 32 ? 0xffffffffu : ((1u << cnt) - 1u);
@@ -597,9 +708,9 @@ PDE_HD double hc_fill(const HullCta &c, int tid) {
             ta = bm_pred(L.V, L.SV, t);
             tb = bm_succ(L.V, L.SV, t, c.LW, c.SW);
             ya = L.Y(ta);
-            slope = hp_sub(L.Y(tb), ya) / (double)(tb - ta);
+            slope = hp_sub(L.Y(tb), ya) / hp_i2d(tb - ta);
         }
-        const double v = hp_add(ya, hp_mul(slope, (double)(t - ta)));
+        const double v = hp_add(ya, hp_mul(slope, hp_i2d(t - ta)));
         const double old = L.Y(t);
         if (v < old) {                               // never raise (rounding of the chord)
             L.Y(t) = v;
@@ -611,25 +722,36 @@ PDE_HD double hc_fill(const HullCta &c, int tid) {
     return cmax;
 }
 
+// write the changed values back (same thread <-> point map as hc_load)
 PDE_HD void hc_store(const HullCta &c, int tid, int nthr) {
+    const SweepGeom &g = c.g;
     if (c.P.rows_mode) {
-        for (int idx = tid; idx < c.nlines * c.Lp; idx += nthr) {
-            const int l = idx / c.Lp, t = idx - l * c.Lp;
-            if ((c.Cs[l * c.LW + (t >> 5)] >> (t & 31)) & 1u)
-                c.U[(int64_t)(c.s_base + l) * c.g.pitch + (t - 1)] = c.ys[l * c.LPS + hp_ix(t)];
+        const int lane = tid & 31, nwarp = nthr >> 5;
+        for (int l = tid >> 5; l < c.nlines; l += nwarp) {
+            double *row = c.U + (int64_t)(c.s_base + l) * g.pitch - 1;
+            const double *yl = c.ys + l * c.LPS;
+            const uint32_t *Cl = c.Cs + l * c.LW;
+            for (int t = lane; t < c.Lp; t += 32)          // lane == t & 31
+                if ((Cl[t >> 5] >> lane) & 1u) row[t] = yl[hp_ix(t)];
         }
     } else {
         const int l = tid & (c.WL - 1), dt = nthr >> c.P.wl_log2;
         const int dj = hp_mod(dt * c.P.b, c.NJ);
         int t = tid >> c.P.wl_log2;
         int j = hp_mod(c.s_base + l + t * c.P.b, c.NJ);
+        const int64_t doff = (int64_t)dt * c.P.a * g.pitch;
+        int64_t off = (int64_t)(c.i0 + t * c.P.a - 1) * g.pitch + (j - 1);
+        const double *yl = c.ys + l * c.LPS;
+        const uint32_t *Cl = c.Cs + l * c.LW;
         if (l < c.nlines)
             for (; t < c.Lp; t += dt) {
-                if ((c.Cs[l * c.LW + (t >> 5)] >> (t & 31)) & 1u)
-                    c.U[(int64_t)(c.i0 + t * c.P.a - 1) * c.g.pitch + (j - 1)] =
-                        c.ys[l * c.LPS + hp_ix(t)];
+                if ((Cl[t >> 5] >> (t & 31)) & 1u) c.U[off] = yl[hp_ix(t)];
                 j += dj;
-                if (j >= c.NJ) j -= c.NJ;
+                off += doff + dj;
+                if (j >= c.NJ) {
+                    j -= c.NJ;
+                    off -= c.NJ;
+                }
             }
     }
 }
@@ -644,7 +766,11 @@ k_hull_pass(SweepGeom g, HullPass P, double *U, double *change, const int *done)
     hc_load(c, tid, nthr);
     __syncthreads();
     hc_level0(c, tid);
-    for (int h = 1; h < c.LW; h <<= 1) {
+    for (int h = 1; h < c.LW && h <= 16; h <<= 1) {      // inside one warp's 32 words
+        __syncwarp();
+        hc_merge(c, tid, h);
+    }
+    for (int h = 32; h < c.LW; h <<= 1) {
         __syncthreads();
         hc_merge(c, tid, h);
     }
@@ -720,15 +846,15 @@ static bool hull_plan(std::vector<HullPlan> &plan, int64_t nx, int64_t ny, int n
         P.SW = (P.LW + 31) / 32;
         int wl = 0;
         while (wl < 5 && hull_smem_bytes(wl + 1, P.LW, P.SW) <= budget &&
-               (2 << wl) * P.LW <= 1024 && (2 << wl) <= P.Ns)
+               (2 << wl) * P.SW * 32 <= 1024 && (2 << wl) <= P.Ns)
             ++wl;
-        if (hull_smem_bytes(wl, P.LW, P.SW) > max_smem || (1 << wl) * P.LW > 1024)
+        if (hull_smem_bytes(wl, P.LW, P.SW) > max_smem || (1 << wl) * P.SW * 32 > 1024)
             return false;
         P.wl_log2 = wl;
         P.groups = (P.Ns + (1 << wl) - 1) >> wl;
         plan[k].P = P;
         plan[k].grid = (unsigned)(nstart * P.groups);
-        plan[k].block = (unsigned)((((1 << wl) * P.LW) + 31) / 32 * 32);
+        plan[k].block = (unsigned)((1 << wl) * P.SW * 32);
         plan[k].smem = hull_smem_bytes(wl, P.LW, P.SW);
     }
     return true;

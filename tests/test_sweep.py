@@ -2,7 +2,6 @@
 through its HOST build (pde_ce_sweep with device = -1: the same line routine the GPU runs, one
 OpenMP thread per lattice line) against the reference's converged solutions
 (tests/golden/solve_*.npz) and the NumPy restatement of the residual."""
-import ctypes as C
 import glob
 import os
 
@@ -18,21 +17,7 @@ GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 SOLVE = sorted(glob.glob(os.path.join(GOLD, "solve_*.npz")))
 
 
-def host_sweep(G, g, tol=1e-11, max_sweeps=400, relax_reps=2, relax_every=0, device=-1):
-    """Flat vector in, flat vector out; state layout with pitch = ny (no padding needed on the host).
-    device = -1: serial monotone chain per line; -2: thread-by-thread replay of the CUDA kernel."""
-    nx, ny = G.interior_shape
-    N = G.num_interior
-    t = _sweep.tables(G, ny, nx)
-    U = np.ascontiguousarray(g, dtype=np.float64).copy()       # [lattice | wall] == state layout
-    out = (C.c_double * 2)()
-    p = lambda a: C.c_void_p(a.ctypes.data)
-    _lib.check(_lib.lib().pde_ce_sweep(device, nx, ny, ny, N, G.stencil_radius, t["dirs"].shape[0],
-                                       p(t["dirs"]), p(t["ring"]), p(t["flags"]),
-                                       t["band_center"].shape[0], p(t["band_ptr"]),
-                                       p(t["band_center"]), p(t["rest_j"]), p(t["theta"]), p(U),
-                                       None, tol, max_sweeps, relax_every, relax_reps, out, None))
-    return U, out[0], int(out[1])
+host_sweep = _sweep.host_sweep     # device=-1: serial chain per line; -2: replay of the CUDA kernel
 
 
 @pytest.mark.parametrize("path", SOLVE, ids=[os.path.basename(p) for p in SOLVE])

@@ -38,10 +38,8 @@ def test_sweep_solver_reaches_the_reference_solution(path):
 def test_device_sweep_equals_the_host_replay(shape, r):
     """One sweep of k_hull_pass on the device against the thread-by-thread host replay of the same
     phases (pde_ce_sweep, device = -2) and the serial chain (device = -1)."""
-    import ctypes as C
-    import torch
     from oracle.make_golden import two_cones
-    from pyellipticfd_b200 import _lib, _sweep
+    from pyellipticfd_b200 import _sweep
     from pyellipticfd_b200._context import GridContext
     from pyellipticfd_b200.pointclasses import FDRegularGrid
     nx, ny = shape            # dyadic spacing on both axes: the structured (K1) context
@@ -51,19 +49,10 @@ def test_device_sweep_equals_the_host_replay(shape, r):
     g = two_cones(G.points) + 0.02 * rng.standard_normal(G.num_points)
     ctx = GridContext.get(G)
     gs = ctx.pack(g)
-    nx, ny = G.interior_shape
-    t = _sweep.tables(G, ny, nx)
-    p = lambda a: C.c_void_p(a.ctypes.data)
     for sweeps in (1, 3):
         Ud, cd, nd = ctx.ce_sweep(gs, 0.0, sweeps, relax_every=4)
         Ud = ctx.unpack(Ud).cpu().numpy()
         for dev in (-2, -1):
-            Uh = np.ascontiguousarray(g, dtype=np.float64).copy()
-            out = (C.c_double * 2)()
-            _lib.check(_lib.lib().pde_ce_sweep(dev, nx, ny, ny, G.num_interior, r, t["dirs"].shape[0],
-                                               p(t["dirs"]), p(t["ring"]), p(t["flags"]),
-                                               t["band_center"].shape[0], p(t["band_ptr"]),
-                                               p(t["band_center"]), p(t["rest_j"]), p(t["theta"]),
-                                               p(Uh), None, 0.0, sweeps, 4, 2, out, None))
+            Uh, ch, _ = _sweep.host_sweep(G, g, tol=0.0, max_sweeps=sweeps, relax_every=4, device=dev)
             assert nd == sweeps and np.abs(Ud - Uh).max() < 1e-13, (dev, np.abs(Ud - Uh).max())
-            assert abs(cd - out[0]) < 1e-13
+            assert abs(cd - ch) < 1e-13
