@@ -333,6 +333,8 @@ int pde_ell_newton_update(pde_ell *e, const double *d_U, const double *d_d, cons
  *              pairs, rest_theta (n_rest) = w_0 / (w_0 + w_1): u_I <- min(u_I, theta u_J0 +
  *              (1 - theta) u_J1), a Jacobi step repeated relax_reps times after every
  *              relax_every direction passes (0: once per sweep)
+ *   flat_tol   a point less than flat_tol below a chord counts as on it (rounding noise on the
+ *              planar pieces of the solution; a few ulps of max|g|; 0: exact comparisons)
  *   work       device scratch, n_band + 80 doubles (device path only)
  *   h_out      [last sweep's largest decrease, sweeps done]; stops when the decrease < tol
  * device >= 0: every pointer but h_dirs / h_out is a DEVICE pointer; up to 64 sweeps are enqueued
@@ -342,8 +344,8 @@ int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall
                  int stencil_radius, int ndir, const int32_t *h_dirs, const int64_t *ring,
                  const uint64_t *flags, int64_t n_band, const int64_t *band_ptr,
                  const int64_t *band_center, const int64_t *rest_j, const double *rest_theta,
-                 double *U, double *work, double tol, int64_t max_sweeps, int relax_every,
-                 int relax_reps, double *h_out, void *stream);
+                 double *U, double *work, double tol, double flat_tol, int64_t max_sweeps,
+                 int relax_every, int relax_reps, double *h_out, void *stream);
 
 /* ------------------------------------------------------------------------
  * Host-side pre-processing (no GPU needed): pair rows of the band points of a

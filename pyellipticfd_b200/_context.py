@@ -438,7 +438,7 @@ class GridContext(object):
         U = U1 if int(out[1]) == 1 else U0
         return U, float(out[2]), iters, float(out[3]), int(out[4])
 
-    def ce_sweep(self, g, tol, max_sweeps, relax_reps=2, U=None, relax_every=0):
+    def ce_sweep(self, g, tol, max_sweeps, relax_reps=2, U=None, relax_every=0, flat_tol=None):
         """Convex-hull sweeps (``pde_ce_sweep``, extension): lowers ``U`` (default: a copy of
         ``g``) towards the convex-envelope solution until one sweep changes no value by ``tol``
         or more.  ``relax_every``: direction passes between band relaxations (0: once per
@@ -462,13 +462,18 @@ class GridContext(object):
         t = self._sweep
         if U is None:
             U = g.clone()
+        if flat_tol is None:
+            if t.get("gmax_of") is not g:
+                from . import _sweep
+                t["gmax_of"], t["flat_tol"] = g, _sweep.flat_tolerance(float(g.abs().max()))
+            flat_tol = t["flat_tol"]
         out = (C.c_double * 2)()
         check(self.lib.pde_ce_sweep(self.device.index, self.nx_local, self.ny, self.pitch,
                                     self.n_lattice, self.G.stencil_radius, t["D"],
                                     _np_ptr(t["dirs"]), _ptr(t["ring"]), _ptr(t["flags"]),
                                     t["n_band"], _ptr(t["band_ptr"]), _ptr(t["band_center"]),
                                     _ptr(t["rest_j"]), _ptr(t["theta"]), _ptr(U),
-                                    _ptr(t["work"]), float(tol), int(max_sweeps),
+                                    _ptr(t["work"]), float(tol), float(flat_tol), int(max_sweeps),
                                     int(relax_every), int(relax_reps), out, _stream()))
         return U, float(out[0]), int(out[1])
 

@@ -87,7 +87,14 @@ def tables(G, pitch, rows):
                 theta=np.ascontiguousarray(theta, dtype=np.float64))
 
 
-def host_sweep(G, g, tol=1e-11, max_sweeps=400, relax_reps=2, relax_every=0, device=-1):
+def flat_tolerance(gmax):
+    """Points less than this below a chord count as on it: 8 ulps of max|g| (rounding noise of
+    the chord values on planar pieces of the solution)."""
+    return 8 * np.finfo(np.float64).eps * float(gmax)
+
+
+def host_sweep(G, g, tol=1e-11, max_sweeps=400, relax_reps=2, relax_every=0, device=-1,
+               flat_tol=None):
     """The HOST builds of ``pde_ce_sweep`` on flat vectors (state layout with pitch = ny):
     ``device=-1`` the serial monotone chain per lattice line under OpenMP (CPU tests, CPU baseline
     of bench.py), ``device=-2`` the thread-by-thread replay of the CUDA kernel's phases (CPU tests).
@@ -104,5 +111,7 @@ def host_sweep(G, g, tol=1e-11, max_sweeps=400, relax_reps=2, relax_every=0, dev
                                        t["dirs"].shape[0], p(t["dirs"]), p(t["ring"]), p(t["flags"]),
                                        t["band_center"].shape[0], p(t["band_ptr"]),
                                        p(t["band_center"]), p(t["rest_j"]), p(t["theta"]), p(U),
-                                       None, tol, max_sweeps, relax_every, relax_reps, out, None))
+                                       None, tol,
+                                       flat_tolerance(np.abs(U).max()) if flat_tol is None else flat_tol,
+                                       max_sweeps, relax_every, relax_reps, out, None))
     return U, out[0], int(out[1])

@@ -56,6 +56,7 @@ namespace pde {
 struct SweepGeom {
     int64_t nx, ny, pitch, wall_base;
     int r;
+    double ytol;                         // a point less than ytol below a chord counts as on it
     const int64_t *ring;                 // wall ids of the integer ring: i=0 | i=nx+1 | j=0 | j=ny+1
     const unsigned long long *flags;     // per band point (sw_band_slot): bit k = pair k is a lattice pair
 };
@@ -117,7 +118,7 @@ static double sw_hull_run(const SweepGeom &g, double *U, int32_t *stk, int64_t i
         const double y = SW_U(t);
         while (top >= 2) {
             // middle vertex t1 on or above the chord t0 -> t: drop it
-            if ((y1 - y0) * (double)(t - t0) >= (y - y0) * (double)(t1 - t0)) {
+            if (((y1 + g.ytol) - y0) * (double)(t - t0) >= (y - y0) * (double)(t1 - t0)) {
                 --top;
                 t1 = t0;
                 y1 = y0;
@@ -377,9 +378,11 @@ PDE_HD int bm_succ(const uint32_t *M, const uint32_t *S, int pos, int LW, int SW
     return (w << 5) + hp_ffs(M[w]) - 1;
 }
 
-// middle point (t1, y1) on or above the chord (t0, y0) -> (t2, y2): not a hull vertex
-PDE_HD bool hp_drop(int t0, double y0, int t1, double y1, int t2, double y2) {
-    return hp_mul(hp_sub(y1, y0), hp_i2d(t2 - t0)) >= hp_mul(hp_sub(y2, y0), hp_i2d(t1 - t0));
+// middle point (t1, y1) on or above the chord (t0, y0) -> (t2, y2) -- or less than tol below
+// it: rounding noise on planar pieces of the solution -- : not a hull vertex
+PDE_HD bool hp_drop(int t0, double y0, int t1, double y1, int t2, double y2, double tol) {
+    return hp_mul(hp_sub(hp_add(y1, tol), y0), hp_i2d(t2 - t0)) >=
+           hp_mul(hp_sub(y2, y0), hp_i2d(t1 - t0));
 }
 
 // shared-memory index of point t of a line: one padding double per 32-point word, so that the
@@ -388,8 +391,9 @@ PDE_HD int hp_ix(int t) { return t + (t >> 5); }
 
 struct LineView {
     double *y;
-    uint32_t *V, *SV, *F, *SF, *C;
+    uint32_t *V, *SV, *F, *SF, *C, *GF;
     int LW, SW;
+    double tol;
     PDE_HD double &Y(int t) const { return y[hp_ix(t)]; }
 };
 
@@ -402,7 +406,7 @@ PDE_HD int hp_tangent_right(const LineView &L, int v, int lo, int hi) {
         const int c = bm_pred(L.V, L.SV, mid);
         const int c2 = bm_succ(L.V, L.SV, c + 1, L.LW, L.SW);
         // slope(v -> c2) <= slope(v -> c): c is on or above the chord v -> c2
-        if (hp_drop(v, yv, c, L.Y(c), c2, L.Y(c2))) lo = c2;
+        if (hp_drop(v, yv, c, L.Y(c), c2, L.Y(c2), L.tol)) lo = c2;
         else hi = c;
     }
     return lo;
@@ -434,10 +438,14 @@ PDE_HD void hp_merge(const LineView &L, int w, int h, int Lp) {
     if (J >= Lp) return;
     int aLo = (w - h) << 5;
     int bHi = ((w + h) << 5 < Lp ? (w + h) << 5 : Lp) - 1;
-    int f = bm_pred_in(L.F, L.SF, J - 1, aLo);
-    if (f > aLo) aLo = f;
-    f = bm_succ_in(L.F, L.SF, J, bHi);
-    if (f < bHi) bHi = f;
+    bool any_fixed = false;                          // summary words the block touches
+    for (int sw = (w - h) >> 5; sw <= (bHi >> 10); ++sw) any_fixed = any_fixed || L.SF[sw] != 0u;
+    if (any_fixed) {
+        int f = bm_pred_in(L.F, L.SF, J - 1, aLo);
+        if (f > aLo) aLo = f;
+        f = bm_succ_in(L.F, L.SF, J, bHi);
+        if (f < bHi) bHi = f;
+    }
     int p = J - 1, q = J;
     if (aLo == p && bHi == q) return;
     double yp = L.Y(p), yq = L.Y(q);
@@ -448,7 +456,7 @@ PDE_HD void hp_merge(const LineView &L, int w, int h, int Lp) {
         while (p > aLo && budget > 0) {
             const int pp = bm_pred(L.V, L.SV, p - 1);
             const double ypp = L.Y(pp);
-            if (!hp_drop(pp, ypp, p, yp, q, yq)) break;
+            if (!hp_drop(pp, ypp, p, yp, q, yq, L.tol)) break;
             p = pp; yp = ypp;
             moved = true;
             --budget;
@@ -456,7 +464,7 @@ PDE_HD void hp_merge(const LineView &L, int w, int h, int Lp) {
         while (q < bHi && budget > 0) {
             const int qq = bm_succ(L.V, L.SV, q + 1, L.LW, L.SW);
             const double yqq = L.Y(qq);
-            if (!hp_drop(p, yp, q, yq, qq, yqq)) break;
+            if (!hp_drop(p, yp, q, yq, qq, yqq, L.tol)) break;
             q = qq; yq = yqq;
             moved = true;
             --budget;
@@ -469,7 +477,7 @@ PDE_HD void hp_merge(const LineView &L, int w, int h, int Lp) {
             const int v = bm_succ(L.V, L.SV, mid, L.LW, L.SW);
             const int pv = bm_pred(L.V, L.SV, v - 1);
             const int qv = hp_tangent_right(L, v, q, bHi);
-            if (hp_drop(pv, L.Y(pv), v, L.Y(v), qv, L.Y(qv))) hi = pv;
+            if (hp_drop(pv, L.Y(pv), v, L.Y(v), qv, L.Y(qv), L.tol)) hi = pv;
             else lo = v;
         }
         p = lo;
@@ -496,7 +504,7 @@ struct HullCta {
     SweepGeom g;
     HullPass P;
     double *U, *ys;
-    uint32_t *Vs, *Fs, *Cs, *SVs, *SFs;
+    uint32_t *Vs, *Fs, *Cs, *SVs, *SFs, *GFs;
     int WL, LW, SW, LPS, i0, s_base, nlines, Lp, NJ;
     unsigned deep_nx, deep_ny;       // extent of the deep interior (0 when there is none)
 };
@@ -512,6 +520,7 @@ PDE_HD void hc_init(HullCta &c, const SweepGeom &g, const HullPass &P, double *U
     c.Cs = c.Fs + c.WL * c.LW;
     c.SVs = c.Cs + c.WL * c.LW;
     c.SFs = c.SVs + c.WL * c.SW;
+    c.GFs = c.SFs + c.WL * c.SW;                    // per 32-word group: closed by hc_groups
     c.i0 = P.rows_mode ? 0 : (int)(block / P.groups);
     c.s_base = (int)(block % P.groups) << P.wl_log2;
     c.nlines = c.WL < P.Ns - c.s_base ? c.WL : P.Ns - c.s_base;
@@ -529,8 +538,10 @@ PDE_HD LineView hc_line(const HullCta &c, int l) {
     L.C = c.Cs + l * c.LW;
     L.SV = c.SVs + l * c.SW;
     L.SF = c.SFs + l * c.SW;
+    L.GF = c.GFs + l * c.SW;
     L.LW = c.LW;
     L.SW = c.SW;
+    L.tol = c.g.ytol;
     return L;
 }
 
@@ -542,30 +553,39 @@ PDE_HD LineView hc_line(const HullCta &c, int l) {
 PDE_HD void hc_load(const HullCta &c, int tid, int nthr) {
     const SweepGeom &g = c.g;
     if (c.P.rows_mode) {
-        // a warp takes a line at a time: consecutive lanes, consecutive addresses
+        // a warp takes 32 consecutive points of a line at a time (consecutive addresses)
         const int lane = tid & 31, nwarp = nthr >> 5;
-        for (int l = tid >> 5; l < c.nlines; l += nwarp) {
+        const int cpl = (c.Lp + 31) >> 5, total = c.nlines * cpl;
+#pragma unroll 4
+        for (int ch = tid >> 5; ch < total; ch += nwarp) {
+            const int l = ch / cpl, t = ((ch - l * cpl) << 5) + lane;
             const int i = c.s_base + l + 1;
-            const double *row = c.U + (int64_t)(i - 1) * g.pitch - 1;
-            double *yl = c.ys + l * c.LPS;
-            for (int t = lane; t < c.Lp; t += 32)
-                yl[hp_ix(t)] = (t == 0 || t == c.Lp - 1) ? c.U[sw_addr(g, i, t)] : row[t];
+            if (t > 0 && t < c.Lp - 1)
+                c.ys[l * c.LPS + hp_ix(t)] = c.U[(int64_t)(i - 1) * g.pitch + (t - 1)];
+        }
+        for (int idx = tid; idx < 2 * c.nlines; idx += nthr) {      // the two wall ends
+            const int l = idx >> 1, t = (idx & 1) ? c.Lp - 1 : 0;
+            c.ys[l * c.LPS + hp_ix(t)] = c.U[sw_addr(g, c.s_base + l + 1, t)];
         }
     } else {
         // nthr is a multiple of WL: a thread keeps its line and advances t by nthr / WL, so
-        // that the WL lines of the bundle are read side by side (contiguous in memory)
+        // that the WL lines of the bundle are read side by side (contiguous in memory).
+        // Interior points first (plain strided loads the compiler can keep in flight together),
+        // then the few points on the wall ring, whose addresses come from the ring table.
         const int l = tid & (c.WL - 1), dt = nthr >> c.P.wl_log2;
         const int dj = hp_mod(dt * c.P.b, c.NJ);
-        int t = tid >> c.P.wl_log2;
-        int i = c.i0 + t * c.P.a, j = hp_mod(c.s_base + l + t * c.P.b, c.NJ);
+        const int t_first = tid >> c.P.wl_log2;
         const int di = dt * c.P.a;
         const int64_t doff = (int64_t)di * g.pitch;
-        int64_t off = (int64_t)(i - 1) * g.pitch + (j - 1);
         double *yl = c.ys + l * c.LPS;
-        if (l < c.nlines)
+        if (l < c.nlines) {
+            int t = t_first;
+            int i = c.i0 + t * c.P.a, j = hp_mod(c.s_base + l + t * c.P.b, c.NJ);
+            int64_t off = (int64_t)(i - 1) * g.pitch + (j - 1);
+#pragma unroll 4
             for (; t < c.Lp; t += dt) {
                 const bool ring = i == 0 || i == (int)g.nx + 1 || j == 0 || j == c.NJ - 1;
-                yl[hp_ix(t)] = c.U[ring ? sw_addr(g, i, j) : off];
+                if (!ring) yl[hp_ix(t)] = c.U[off];
                 i += di;
                 j += dj;
                 off += doff + dj;
@@ -574,10 +594,22 @@ PDE_HD void hc_load(const HullCta &c, int tid, int nthr) {
                     off -= c.NJ;
                 }
             }
+            t = t_first;
+            i = c.i0 + t * c.P.a;
+            j = hp_mod(c.s_base + l + t * c.P.b, c.NJ);
+            for (; t < c.Lp; t += dt) {
+                const bool ring = i == 0 || i == (int)g.nx + 1 || j == 0 || j == c.NJ - 1;
+                if (ring) yl[hp_ix(t)] = c.U[sw_addr(g, i, j)];
+                i += di;
+                j += dj;
+                if (j >= c.NJ) j -= c.NJ;
+            }
+        }
     }
     for (int idx = tid; idx < c.WL * c.SW; idx += nthr) {
         c.SVs[idx] = 0u;
         c.SFs[idx] = 0u;
+        c.GFs[idx] = 0u;
     }
 }
 
@@ -586,7 +618,7 @@ PDE_HD void hc_load(const HullCta &c, int tid, int nthr) {
 #define HP_CHAIN_STEP(q, yq, may_pop)                                                  \
     {                                                                                  \
         while (t0 >= 0 && (may_pop)) {                                                 \
-            if (!hp_drop(t0, y0, t1, y1, (q), (yq))) break;                            \
+            if (!hp_drop(t0, y0, t1, y1, (q), (yq), tol)) break;                            \
             m &= ~(1u << t1);                                                          \
             t1 = t0;                                                                   \
             y1 = y0;                                                                   \
@@ -613,6 +645,7 @@ PDE_HD void hc_level0(const HullCta &c, int tid) {
     const HullPass &P = c.P;
     uint32_t m = 0u, fm = 0u;
     const int base = w << 5;
+    const double tol = g.ytol;
     if (l < c.nlines && base < c.Lp) {
         const int cnt = 32 < c.Lp - base ? 32 : c.Lp - base;
         const int NJ = c.NJ;
@@ -634,9 +667,35 @@ PDE_HD void hc_level0(const HullCta &c, int tid) {
         const bool all_deep = (unsigned)(i - g.r - 1) < c.deep_nx && (unsigned)(ie - g.r - 1) < c.deep_nx &&
                               (unsigned)(j - g.r - 1) < c.deep_ny && (unsigned)(je - g.r - 1) < c.deep_ny;
         if (all_deep) {
-            for (int q = 0; q < cnt; ++q) {
-                const double yq = yw[q];
-                HP_CHAIN_STEP(q, yq, true)
+            // Two usual cases after the first sweeps, tested without the chain's loop: a strictly
+            // convex word keeps every point (the chain would only compare consecutive triples);
+            // a word whose interior points all lie on or above the chord first -> last (planar
+            // pieces of the solution) keeps its two ends.
+            bool convex = cnt == 32, flat = cnt == 32;
+            if (convex) {
+                double ya = yw[0], yb = yw[1];
+                const double yf = ya, dl = hp_sub(yw[31], ya);
+#pragma unroll 6
+                for (int q = 2; q < 32; ++q) {
+                    const double yc = yw[q];
+                    // hp_drop(q-2, ya, q-1, yb, q, yc): (yb + tol - ya) * 2 >= (yc - ya) * 1
+                    const double d = hp_sub(hp_add(yb, tol), ya);
+                    convex = convex && !(hp_add(d, d) >= hp_sub(yc, ya));
+                    // hp_drop(0, yf, q-1, yb, 31, yl)
+                    flat = flat && hp_mul(hp_sub(hp_add(yb, tol), yf), 31.0) >= hp_mul(dl, hp_i2d(q - 1));
+                    ya = yb;
+                    yb = yc;
+                }
+            }
+            if (convex) {
+                m = 0xffffffffu;
+            } else if (flat) {
+                m = 0x80000001u;
+            } else {
+                for (int q = 0; q < cnt; ++q) {
+                    const double yq = yw[q];
+                    HP_CHAIN_STEP(q, yq, true)
+                }
             }
         } else {
             for (int q = 0; q < cnt; ++q) {
@@ -670,9 +729,57 @@ PDE_HD void hc_level0(const HullCta &c, int tid) {
     }
     L.V[w] = m;
     L.F[w] = fm;
-    L.C[w] = 0u;
+    L.C[w] = m == 0x80000001u ? 1u : 0u;              // flat word (hc_groups); then junction note
     if (m) hp_or(&L.SV[w >> 5], 1u << (w & 31));
     if (fm) hp_or(&L.SF[w >> 5], 1u << (w & 31));
+}
+
+// Planar pieces of the solution: a full 32-word group (1024 points) whose words are all flat
+// and whose word ends all lie on or above the chord first -> last of the group keeps those two
+// ends only -- the five warp-local merge levels are skipped.  One lane per group.
+PDE_HD void hc_groups(const HullCta &c, int tid) {
+    const int LWp = c.SW << 5;
+    const int l = tid / LWp, w0 = tid - l * LWp;
+    if (l >= c.nlines || (w0 & 31) != 0 || ((w0 + 32) << 5) > c.Lp) return;
+    const LineView L = hc_line(c, l);
+    if (L.SF[w0 >> 5]) return;
+    const int t0 = w0 << 5, t1 = t0 + 1023;
+    const double y0 = L.Y(t0), y1 = L.Y(t1);
+    for (int k = 0; k < 32; ++k) {
+        if (L.C[w0 + k] != 1u) return;
+        const double *yw = L.y + 33 * (w0 + k);
+        if (k > 0 && !hp_drop(t0, y0, t0 + 32 * k, yw[0], t1, y1, L.tol)) return;
+        if (k < 31 && !hp_drop(t0, y0, t0 + 32 * k + 31, yw[31], t1, y1, L.tol)) return;
+    }
+    for (int k = 1; k < 31; ++k) L.V[w0 + k] = 0u;
+    L.V[w0] = 1u;
+    L.V[w0 + 31] = 0x80000000u;
+    L.SV[w0 >> 5] = 0x80000001u;
+    L.GF[w0 >> 5] = 1u;
+}
+
+// After level 0 every junction between two words of a group without fixed vertices is tested
+// ONCE, by all lanes at the same time: if the last point of word w - 1 and the first point of
+// word w are strictly below the chords to their neighbours in those two words, the junction is
+// convex.  The note (neighbour positions + verdict) goes to C[w]; the merge of this junction,
+// whatever its level, only has to see that the two neighbours are still the same.
+#define HP_NOTE(pp, qq, ok) (0x80000000u | ((uint32_t)(ok) << 16) | ((uint32_t)(pp) << 8) | (uint32_t)(qq))
+PDE_HD void hc_junctions(const HullCta &c, int tid) {
+    const int LWp = c.SW << 5;
+    const int l = tid / LWp, w = tid - l * LWp;
+    if (l >= c.nlines || w >= c.LW) return;
+    const LineView L = hc_line(c, l);
+    L.C[w] = 0u;
+    if ((w & 31) == 0 || ((w + 1) << 5) > c.Lp) return;
+    if (L.SF[w >> 5] || L.GF[w >> 5]) return;
+    const uint32_t va = L.V[w - 1] & 0x7fffffffu, vb = L.V[w] & ~1u;
+    if (!va || !vb) return;
+    const int pp = 31 - hp_clz(va), qq = hp_ffs(vb) - 1;
+    const double *ya = L.y + 33 * (w - 1), *yb = L.y + 33 * w;
+    const double yp = ya[31], yq = yb[0];
+    const bool ok = !hp_drop(pp, ya[pp], 31, yp, 32, yq, L.tol) &&
+                    !hp_drop(31, yp, 32, yq, 32 + qq, yb[qq], L.tol);
+    L.C[w] = HP_NOTE(pp, qq, ok);
 }
 
 // Level h merges the blocks [w - h, w), [w, w + h) at the junction words w = (2k + 1) h.  For
@@ -685,7 +792,17 @@ PDE_HD void hc_merge(const HullCta &c, int tid, int h) {
     if (h <= 16) w = (x & ~31) + (2 * (x & 31) + 1) * h;
     else w = (2 * x + 1) * h;
     if (l >= c.nlines || w >= c.LW || (h <= 16 && (2 * (x & 31) + 1) * h >= 32)) return;
-    hp_merge(hc_line(c, l), w, h, c.Lp);
+    const LineView L = hc_line(c, l);
+    if (h <= 16 && L.GF[w >> 5]) return;             // group closed by hc_groups
+    const uint32_t note = L.C[w];
+    if (note >> 16 == 0x8001u) {                     // noted convex: are the neighbours the same?
+        const uint32_t va = L.V[w - 1], vb = L.V[w];
+        if ((va >> 31) && (vb & 1u) && (va & 0x7fffffffu) && (vb & ~1u) &&
+            31 - hp_clz(va & 0x7fffffffu) == (int)((note >> 8) & 0xff) &&
+            hp_ffs(vb & ~1u) - 1 == (int)(note & 0xff))
+            return;
+    }
+    hp_merge(L, w, h, c.Lp);
 }
 
 // lower the non-vertices of a word onto the chord of the neighbouring vertices
@@ -727,12 +844,12 @@ PDE_HD void hc_store(const HullCta &c, int tid, int nthr) {
     const SweepGeom &g = c.g;
     if (c.P.rows_mode) {
         const int lane = tid & 31, nwarp = nthr >> 5;
-        for (int l = tid >> 5; l < c.nlines; l += nwarp) {
-            double *row = c.U + (int64_t)(c.s_base + l) * g.pitch - 1;
-            const double *yl = c.ys + l * c.LPS;
-            const uint32_t *Cl = c.Cs + l * c.LW;
-            for (int t = lane; t < c.Lp; t += 32)          // lane == t & 31
-                if ((Cl[t >> 5] >> lane) & 1u) row[t] = yl[hp_ix(t)];
+        const int cpl = (c.Lp + 31) >> 5, total = c.nlines * cpl;
+        for (int ch = tid >> 5; ch < total; ch += nwarp) {
+            const int l = ch / cpl, w = ch - l * cpl;
+            if ((c.Cs[l * c.LW + w] >> lane) & 1u)
+                c.U[(int64_t)(c.s_base + l) * g.pitch + ((w << 5) + lane - 1)] =
+                    c.ys[l * c.LPS + hp_ix((w << 5) + lane)];
         }
     } else {
         const int l = tid & (c.WL - 1), dt = nthr >> c.P.wl_log2;
@@ -766,6 +883,10 @@ k_hull_pass(SweepGeom g, HullPass P, double *U, double *change, const int *done)
     hc_load(c, tid, nthr);
     __syncthreads();
     hc_level0(c, tid);
+    __syncwarp();
+    hc_groups(c, tid);
+    __syncwarp();
+    hc_junctions(c, tid);
     for (int h = 1; h < c.LW && h <= 16; h <<= 1) {      // inside one warp's 32 words
         __syncwarp();
         hc_merge(c, tid, h);
@@ -796,6 +917,8 @@ static double hull_pass_replay(const SweepGeom &g, const HullPass &P, double *U,
             const int n = (int)block;
             for (int t = 0; t < n; ++t) hc_load(c, t, n);
             for (int t = 0; t < n; ++t) hc_level0(c, t);
+            for (int t = 0; t < n; ++t) hc_groups(c, t);
+            for (int t = 0; t < n; ++t) hc_junctions(c, t);
             for (int h = 1; h < c.LW; h <<= 1)
                 for (int t = 0; t < n; ++t) hc_merge(c, t, h);
             for (int t = 0; t < n; ++t) {
@@ -811,7 +934,7 @@ static double hull_pass_replay(const SweepGeom &g, const HullPass &P, double *U,
 static size_t hull_smem_bytes(int wl_log2, int LW, int SW) {
     const int WL = 1 << wl_log2;
     return (size_t)WL * hull_line_stride(LW, wl_log2) * sizeof(double) +
-           (size_t)(3 * WL * LW + 2 * WL * SW) * sizeof(uint32_t);
+           (size_t)(3 * WL * LW + 3 * WL * SW) * sizeof(uint32_t);
 }
 
 struct HullPlan {
@@ -870,14 +993,15 @@ int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall
                  int stencil_radius, int ndir, const int32_t *h_dirs, const int64_t *ring,
                  const uint64_t *flags, int64_t n_band, const int64_t *band_ptr,
                  const int64_t *band_center, const int64_t *rest_j, const double *rest_theta,
-                 double *U, double *work, double tol, int64_t max_sweeps, int relax_every,
-                 int relax_reps, double *h_out, void *stream) {
+                 double *U, double *work, double tol, double flat_tol, int64_t max_sweeps,
+                 int relax_every, int relax_reps, double *h_out, void *stream) {
     PDE_REQUIRE(nx >= 1 && ny >= 1 && pitch >= ny && ndir >= 1 && ndir <= 64, "bad sweep geometry");
     PDE_REQUIRE(h_dirs && ring && flags && U && h_out, "null argument");
     PDE_REQUIRE(n_band == 0 || (band_ptr && band_center && rest_j && rest_theta), "null argument");
     PDE_REQUIRE(max_sweeps >= 0 && ny + 2 < (1 << 24) && nx + 2 < (1 << 24), "bad sweep arguments");
     SweepGeom g;
     g.nx = nx; g.ny = ny; g.pitch = pitch; g.wall_base = wall_base; g.r = stencil_radius;
+    g.ytol = flat_tol > 0.0 ? flat_tol : 0.0;
     g.ring = ring;
     g.flags = reinterpret_cast<const unsigned long long *>(flags);
     const int64_t W = ny + 2, npad = (nx + 2) * W;

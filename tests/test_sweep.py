@@ -51,6 +51,27 @@ def test_kernel_replay_equals_the_serial_chain(shape, r):
         assert (Ub <= g).all()
 
 
+@pytest.mark.parametrize("shape,r", [((2300, 20), 2), ((20, 2300), 2), ((1500, 40), 3)])
+def test_kernel_replay_on_long_lines_with_planar_pieces(shape, r):
+    """Lines longer than one 1024-point group, obstacles with planar pieces: exercises the
+    flat-word / flat-group shortcuts and the merge levels across warps of the kernel."""
+    nx, ny = shape
+    Lx, Ly = (nx + 1) / 64.0, (ny + 1) / 64.0
+    G = FDRegularGrid([nx, ny], np.array([[0.0, Lx], [0.0, Ly]]).T, r, interpolation=False)
+    X, Y = G.points.T
+    s, c = (X / Lx, Y / Ly) if nx > ny else (Y / Ly, X / Lx)
+    for g in (np.abs(s - 0.5) * 3 + 0.3 * np.sin(40 * s) * (s > 0.8) + 0.2 * c, 0 * X + 1.0,
+              two_cones(np.stack([2 * X / Lx - 1, 2 * Y / Ly - 1], 1))):
+        U1, _, _ = host_sweep(G, g, max_sweeps=1)
+        U2, _, _ = host_sweep(G, g, max_sweeps=1, device=-2)
+        assert np.abs(U1 - U2).max() < 1e-14
+        Ua, _, sa = host_sweep(G, g, tol=1e-13, relax_every=4)
+        Ub, _, sb = host_sweep(G, g, tol=1e-13, relax_every=4, device=-2)
+        assert np.abs(Ua - Ub).max() < 1e-13 and abs(sa - sb) <= 2 and (Ub <= g).all()
+        F, _ = SO.ce_operator(G, Ub.copy(), g, False)
+        assert np.abs(F).max() < 1e-8
+
+
 def test_sweep_counts_do_not_grow_with_the_lattice():
     counts = []
     for n in (31, 63, 127):

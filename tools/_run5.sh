@@ -1,0 +1,6 @@
+set -x
+python -m pytest tests/test_sweep_gpu.py -x -q 2>&1 | tail -5
+python tools/sweep_kernel_timing.py 4 1023 4095 2>&1 | tail -2
+python tools/certify_breakdown.py 4095 2>&1 | tail -2
+python tools/sweep_profile.py > gpurun_out/plain_sweep.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:k_hull_pass -s 24 -c 6 -o gpurun_out/prof_r2_sweep_d -f python tools/sweep_profile.py > gpurun_out/ncu_sweep2.log 2>&1
+tail -3 gpurun_out/ncu_sweep2.log

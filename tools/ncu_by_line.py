@@ -45,7 +45,8 @@ for (ln, _), r in zip(lines[:n], rows[:n]):
 tot = sum(a[0] for a in agg.values()); tots = sum(a[1] for a in agg.values())
 print("kernel", blk["name"][:60], "sass", len(rows), "disasm", len(lines), "warp-instr", tot, "samples", tots)
 src = {}
-for ln, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:
+key = (lambda kv: -kv[1][0]) if len(sys.argv) > 5 and sys.argv[5] == "instr" else (lambda kv: -kv[1][1])
+for ln, a in sorted(agg.items(), key=key)[:40]:
     if ln and ln[0] not in src:
         try:
             src[ln[0]] = open("pyellipticfd_b200/csrc/" + ln[0]).read().splitlines()

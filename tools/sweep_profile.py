@@ -17,6 +17,7 @@ g = torch.minimum(((P + torch.tensor(C[0]).cuda()) ** 2).sum(1).sqrt(),
                   ((P + torch.tensor(C[1]).cuda()) ** 2).sum(1).sqrt())
 ctx = GridContext.get(G)
 gs = ctx.pack(g)
-U, c, k = ctx.ce_sweep(gs, 0.0, 2, relax_every=4)
+sweeps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+U, c, k = ctx.ce_sweep(gs, 0.0, sweeps, relax_every=4)
 torch.cuda.synchronize()
 print("change", c, "sweeps", k)
