@@ -349,36 +349,41 @@ def solve_full_size(args, obstacle):
         ctx_s.ce_sweep(ctx_s.pack(g), 0.0, 0)                 # builds / uploads the sweep tables
         torch.cuda.synchronize()
         out["sweep_tables_s"] = time.perf_counter() - t
-        sst, nst = {}, {}
-        with warnings.catch_warnings(record=True) as wl:
-            warnings.simplefilter("always")
-            torch.cuda.synchronize()
-            t = time.perf_counter()
-            Us, sdiff, sit, _ = convex_envelope.solve(Gs, g, fdmethod="grid", solver="sweep",
-                                                      stats=sst, max_iters=400, timeout=60.0)
-            torch.cuda.synchronize()
-            t_sw = time.perf_counter() - t
-        sw_ok = bool(sdiff < 1e-6 and (sst.get("residual") or 1.0) < 1e-6)
-        out["sweep"] = {"seconds": t_sw, "sweeps": int(sit), "diff": float(sdiff),
-                        "residual": sst.get("residual"), "converged": sw_ok,
-                        "ms_per_sweep": 1e3 * t_sw / max(int(sit), 1),
-                        "warnings": sorted({str(w.message) for w in wl})}
-        with warnings.catch_warnings(record=True) as wl:
-            warnings.simplefilter("always")
-            torch.cuda.synchronize()
-            t = time.perf_counter()
-            Un, ndiff, nit, _ = convex_envelope.solve(Gs, g, U0=Us, fdmethod="grid",
-                                                      solver="newton", stats=nst)
-            torch.cuda.synchronize()
-            t_nw = time.perf_counter() - t
-        nw_ok = bool(ndiff < 1e-6 and nst.get("residual", 1.0) < 1e-6 and nit <= 100
-                     and nst.get("euler_fallbacks", 1) == 0)
-        out["certify"] = {"seconds": t_nw, "newton_iters": int(nit), "diff": float(ndiff),
-                          "krylov_iters": int(nst.get("krylov_iters", -1)),
-                          "euler_fallbacks": int(nst.get("euler_fallbacks", -1)),
-                          "residual": nst.get("residual"), "converged": nw_ok,
-                          "max_abs_U_sweep_minus_U_newton": float((Us - Un).abs().max()),
-                          "warnings": sorted({str(w.message) for w in wl})}
+        first = None
+        for attempt in range(2):          # the second run is the reported one (allocator, module
+            sst, nst = {}, {}             # loading and the one-off tables are warm); the first is kept
+            with warnings.catch_warnings(record=True) as wl:
+                warnings.simplefilter("always")
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                Us, sdiff, sit, _ = convex_envelope.solve(Gs, g, fdmethod="grid", solver="sweep",
+                                                          stats=sst, max_iters=400, timeout=60.0)
+                torch.cuda.synchronize()
+                t_sw = time.perf_counter() - t
+            sw_ok = bool(sdiff < 1e-6 and (sst.get("residual") or 1.0) < 1e-6)
+            out["sweep"] = {"seconds": t_sw, "sweeps": int(sit), "diff": float(sdiff),
+                            "residual": sst.get("residual"), "converged": sw_ok,
+                            "ms_per_sweep": 1e3 * t_sw / max(int(sit), 1),
+                            "warnings": sorted({str(w.message) for w in wl})}
+            with warnings.catch_warnings(record=True) as wl:
+                warnings.simplefilter("always")
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                Un, ndiff, nit, _ = convex_envelope.solve(Gs, g, U0=Us, fdmethod="grid",
+                                                          solver="newton", stats=nst)
+                torch.cuda.synchronize()
+                t_nw = time.perf_counter() - t
+            nw_ok = bool(ndiff < 1e-6 and nst.get("residual", 1.0) < 1e-6 and nit <= 100
+                         and nst.get("euler_fallbacks", 1) == 0)
+            out["certify"] = {"seconds": t_nw, "newton_iters": int(nit), "diff": float(ndiff),
+                              "krylov_iters": int(nst.get("krylov_iters", -1)),
+                              "euler_fallbacks": int(nst.get("euler_fallbacks", -1)),
+                              "residual": nst.get("residual"), "converged": nw_ok,
+                              "max_abs_U_sweep_minus_U_newton": float((Us - Un).abs().max()),
+                              "warnings": sorted({str(w.message) for w in wl})}
+            if first is None:
+                first = {"sweep_seconds": t_sw, "certify_seconds": t_nw, "seconds": t_sw + t_nw}
+        out["first_call"] = first
         out["seconds"] = t_sw + t_nw
         out["converged"] = bool(sw_ok and nw_ok)
         if args.solve_policy_from_g:

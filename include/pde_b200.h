@@ -335,11 +335,19 @@ int pde_ell_newton_update(pde_ell *e, const double *d_U, const double *d_d, cons
  *              relax_every direction passes (0: once per sweep)
  *   flat_tol   a point less than flat_tol below a chord counts as on it (rounding noise on the
  *              planar pieces of the solution; a few ulps of max|g|; 0: exact comparisons)
- *   work       device scratch, n_band + 80 doubles (device path only)
+ *   work       device scratch of pde_ce_sweep_work_bytes(...) bytes (device path only): relaxation
+ *              and convergence words, then the table of fixed-vertex masks of every 32-point
+ *              word of every lattice line of every direction, which pde_ce_sweep_setup fills
+ *              ONCE per grid (it depends on the grid only) before the first pde_ce_sweep
  *   h_out      [last sweep's largest decrease, sweeps done]; stops when the decrease < tol
  * device >= 0: every pointer but h_dirs / h_out is a DEVICE pointer; up to 64 sweeps are enqueued
  * per host synchronisation.  device = -1: host pointers, the serial monotone chain per line under
  * OpenMP (used by the CPU tests and as the CPU baseline of bench.py). */
+int64_t pde_ce_sweep_work_bytes(int64_t nx, int64_t ny, int ndir, const int32_t *h_dirs,
+                                int64_t n_band);
+int pde_ce_sweep_setup(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall_base,
+                       int stencil_radius, int ndir, const int32_t *h_dirs, const int64_t *ring,
+                       const uint64_t *flags, int64_t n_band, double *work, void *stream);
 int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall_base,
                  int stencil_radius, int ndir, const int32_t *h_dirs, const int64_t *ring,
                  const uint64_t *flags, int64_t n_band, const int64_t *band_ptr,

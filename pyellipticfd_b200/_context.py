@@ -450,6 +450,10 @@ class GridContext(object):
             t = _sweep.tables(self.G, self.pitch, self.rows)
             dev = self.device
             nb = int(t["band_center"].shape[0])
+            wbytes = int(self.lib.pde_ce_sweep_work_bytes(self.nx_local, self.ny, int(t["dirs"].shape[0]),
+                                                          _np_ptr(t["dirs"]), nb))
+            if wbytes < 0:
+                raise _lib.PdeError("lattice line too long for the sweep kernel")
             self._sweep = dict(
                 dirs=t["dirs"], D=int(t["dirs"].shape[0]), n_band=nb,
                 ring=torch.from_numpy(t["ring"]).to(dev),
@@ -458,7 +462,13 @@ class GridContext(object):
                 band_center=torch.from_numpy(t["band_center"]).to(dev),
                 rest_j=torch.from_numpy(t["rest_j"]).to(dev),
                 theta=torch.from_numpy(t["theta"]).to(dev),
-                work=torch.zeros(nb + 80, dtype=torch.float64, device=dev))
+                work=torch.zeros((wbytes + 7) // 8, dtype=torch.float64, device=dev))
+            t = self._sweep
+            # one-off: fixed-vertex masks of every line word of every direction
+            check(self.lib.pde_ce_sweep_setup(self.device.index, self.nx_local, self.ny, self.pitch,
+                                              self.n_lattice, self.G.stencil_radius, t["D"],
+                                              _np_ptr(t["dirs"]), _ptr(t["ring"]), _ptr(t["flags"]),
+                                              t["n_band"], _ptr(t["work"]), _stream()))
         t = self._sweep
         if U is None:
             U = g.clone()

@@ -241,6 +241,8 @@ struct HullPass {
     int LW;               // 32-point words per line
     int SW;               // summary words per line
     int groups;           // CTAs per start row i0
+    int stop_after;       // profiling aid (PDE_SWEEP_STOP_AFTER): leave the kernel after phase n
+    int64_t fm_offset;    // this direction's fixed-vertex masks in the mask table (uint32 words)
 };
 
 PDE_HD int hp_clz(uint32_t x) {
@@ -504,13 +506,14 @@ struct HullCta {
     SweepGeom g;
     HullPass P;
     double *U, *ys;
-    uint32_t *Vs, *Fs, *Cs, *SVs, *SFs, *GFs;
+    const uint32_t *FM;   // fixed-vertex masks of this CTA's first line (LW words per line)
+    uint32_t *Vs, *Fs, *Cs, *SVs, *SFs, *GFs, *Qs, *Qn;
     int WL, LW, SW, LPS, i0, s_base, nlines, Lp, NJ;
     unsigned deep_nx, deep_ny;       // extent of the deep interior (0 when there is none)
 };
 
 PDE_HD void hc_init(HullCta &c, const SweepGeom &g, const HullPass &P, double *U,
-                    unsigned char *smem, unsigned block) {
+                    const uint32_t *fmask, unsigned char *smem, unsigned block) {
     c.g = g; c.P = P; c.U = U;
     c.WL = 1 << P.wl_log2; c.LW = P.LW; c.SW = P.SW;
     c.LPS = hull_line_stride(P.LW, P.wl_log2);
@@ -521,6 +524,8 @@ PDE_HD void hc_init(HullCta &c, const SweepGeom &g, const HullPass &P, double *U
     c.SVs = c.Cs + c.WL * c.LW;
     c.SFs = c.SVs + c.WL * c.SW;
     c.GFs = c.SFs + c.WL * c.SW;                    // per 32-word group: closed by hc_groups
+    c.Qs = c.GFs + c.WL * c.SW;                     // queue of the words that need the chain
+    c.Qn = c.Qs + c.WL * c.LW;
     c.i0 = P.rows_mode ? 0 : (int)(block / P.groups);
     c.s_base = (int)(block % P.groups) << P.wl_log2;
     c.nlines = c.WL < P.Ns - c.s_base ? c.WL : P.Ns - c.s_base;
@@ -528,6 +533,8 @@ PDE_HD void hc_init(HullCta &c, const SweepGeom &g, const HullPass &P, double *U
     c.NJ = (int)g.ny + 2;
     c.deep_nx = g.nx > 2 * g.r ? (unsigned)(g.nx - 2 * g.r) : 0u;
     c.deep_ny = g.ny > 2 * g.r ? (unsigned)(g.ny - 2 * g.r) : 0u;
+    // lines are numbered i0 * Ns + s0 (rows mode: s0), LW mask words each
+    c.FM = fmask + P.fm_offset + ((int64_t)c.i0 * P.Ns + c.s_base) * P.LW;
 }
 
 PDE_HD LineView hc_line(const HullCta &c, int l) {
@@ -550,18 +557,27 @@ PDE_HD LineView hc_line(const HullCta &c, int l) {
 // belong to one warp: level 0 and the first five merge levels only need __syncwarp().
 
 // stage the bundle and clear the summaries
+#define HP_BATCH 8
 PDE_HD void hc_load(const HullCta &c, int tid, int nthr) {
     const SweepGeom &g = c.g;
     if (c.P.rows_mode) {
         // a warp takes 32 consecutive points of a line at a time (consecutive addresses)
         const int lane = tid & 31, nwarp = nthr >> 5;
         const int cpl = (c.Lp + 31) >> 5, total = c.nlines * cpl;
-#pragma unroll 4
-        for (int ch = tid >> 5; ch < total; ch += nwarp) {
-            const int l = ch / cpl, t = ((ch - l * cpl) << 5) + lane;
-            const int i = c.s_base + l + 1;
-            if (t > 0 && t < c.Lp - 1)
-                c.ys[l * c.LPS + hp_ix(t)] = c.U[(int64_t)(i - 1) * g.pitch + (t - 1)];
+        for (int ch = tid >> 5; ch < total; ch += HP_BATCH * nwarp) {
+            double v[HP_BATCH];                        // HP_BATCH loads in flight per thread
+            int at[HP_BATCH];
+#pragma unroll
+            for (int u = 0; u < HP_BATCH; ++u) {
+                const int cu = ch + u * nwarp;
+                const int l = cu / cpl, t = ((cu - l * cpl) << 5) + lane;
+                const bool ok = cu < total && t > 0 && t < c.Lp - 1;
+                at[u] = ok ? l * c.LPS + hp_ix(t) : -1;
+                v[u] = ok ? c.U[(int64_t)(c.s_base + l) * g.pitch + (t - 1)] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < HP_BATCH; ++u)
+                if (at[u] >= 0) c.ys[at[u]] = v[u];
         }
         for (int idx = tid; idx < 2 * c.nlines; idx += nthr) {      // the two wall ends
             const int l = idx >> 1, t = (idx & 1) ? c.Lp - 1 : 0;
@@ -582,17 +598,27 @@ PDE_HD void hc_load(const HullCta &c, int tid, int nthr) {
             int t = t_first;
             int i = c.i0 + t * c.P.a, j = hp_mod(c.s_base + l + t * c.P.b, c.NJ);
             int64_t off = (int64_t)(i - 1) * g.pitch + (j - 1);
-#pragma unroll 4
-            for (; t < c.Lp; t += dt) {
-                const bool ring = i == 0 || i == (int)g.nx + 1 || j == 0 || j == c.NJ - 1;
-                if (!ring) yl[hp_ix(t)] = c.U[off];
-                i += di;
-                j += dj;
-                off += doff + dj;
-                if (j >= c.NJ) {
-                    j -= c.NJ;
-                    off -= c.NJ;
+            while (t < c.Lp) {
+                double v[HP_BATCH];                    // HP_BATCH loads in flight per thread
+                int at[HP_BATCH];
+#pragma unroll
+                for (int u = 0; u < HP_BATCH; ++u) {
+                    const bool ring = i == 0 || i == (int)g.nx + 1 || j == 0 || j == c.NJ - 1;
+                    const bool ok = t < c.Lp && !ring;
+                    at[u] = ok ? hp_ix(t) : -1;
+                    v[u] = ok ? c.U[off] : 0.0;
+                    t += dt;
+                    i += di;
+                    j += dj;
+                    off += doff + dj;
+                    if (j >= c.NJ) {
+                        j -= c.NJ;
+                        off -= c.NJ;
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < HP_BATCH; ++u)
+                    if (at[u] >= 0) yl[at[u]] = v[u];
             }
             t = t_first;
             i = c.i0 + t * c.P.a;
@@ -611,127 +637,147 @@ PDE_HD void hc_load(const HullCta &c, int tid, int nthr) {
         c.SFs[idx] = 0u;
         c.GFs[idx] = 0u;
     }
+    if (tid == 0) *c.Qn = 0u;
 }
 
-// monotone chain step: pop the vertices that (t, y) makes redundant, push t; the stack is the
-// bit mask m of the word, its two top entries are cached in (t1, y1), (t0, y0)
-#define HP_CHAIN_STEP(q, yq, may_pop)                                                  \
-    {                                                                                  \
-        while (t0 >= 0 && (may_pop)) {                                                 \
-            if (!hp_drop(t0, y0, t1, y1, (q), (yq), tol)) break;                            \
-            m &= ~(1u << t1);                                                          \
-            t1 = t0;                                                                   \
-            y1 = y0;                                                                   \
-            const uint32_t below = m & ((1u << t1) - 1u);                              \
-            if (below) {                                                               \
-                t0 = 31 - hp_clz(below);                                               \
-                y0 = yw[t0];                                                           \
-            } else {                                                                   \
-                t0 = -1;                                                               \
-            }                                                                          \
-        }                                                                              \
-        m |= 1u << (q);                                                                \
-        t0 = t1; y0 = y1;                                                              \
-        t1 = (q); y1 = (yq);                                                           \
-    }
-
-// level 0: fixed-vertex mask + monotone chain within the 32-point word
-PDE_HD void hc_level0(const HullCta &c, int tid) {
-    const int LWp = c.SW << 5;
-    const int l = tid / LWp, w = tid - l * LWp;
-    if (l >= c.WL || w >= c.LW) return;
-    const LineView L = hc_line(c, l);
+// Fixed-vertex mask of word w of line l (bit q: point 32 w + q does not carry this direction's
+// lattice pair -- a wall point, a line end, a wrap point, or a band point whose pair is not a
+// lattice pair).  Depends on the grid and the direction only: computed once per grid by
+// k_hull_forced into the mask table.
+PDE_HD uint32_t hc_forced_word(const HullCta &c, int l, int w) {
     const SweepGeom &g = c.g;
     const HullPass &P = c.P;
-    uint32_t m = 0u, fm = 0u;
-    const int base = w << 5;
-    const double tol = g.ytol;
-    if (l < c.nlines && base < c.Lp) {
-        const int cnt = 32 < c.Lp - base ? 32 : c.Lp - base;
-        const int NJ = c.NJ;
-        const double *yw = L.y + 33 * w;              // hp_ix(32 w + q) = 33 w + q
-        int i, j, ie, je;                             // first and last point of the word
-        if (P.rows_mode) {
-            i = ie = c.s_base + l + 1;
-            j = base;
-            je = base + cnt - 1;
-        } else {
-            i = c.i0 + base * P.a;
-            ie = i + (cnt - 1) * P.a;
-            j = hp_mod(c.s_base + l + base * P.b, NJ);
-            je = j + (cnt - 1) * P.b;                 // not wrapped: out of range if the word wraps
-        }
-        int t1 = -1, t0 = -1;
-        double y1 = 0.0, y0 = 0.0;
+    const int base = w << 5, NJ = c.NJ;
+    if (l >= c.nlines || base >= c.Lp) return 0u;
+    const int cnt = 32 < c.Lp - base ? 32 : c.Lp - base;
+    int i, j;
+    if (P.rows_mode) {
+        i = c.s_base + l + 1;
+        j = base;
+    } else {
+        i = c.i0 + base * P.a;
+        j = hp_mod(c.s_base + l + base * P.b, NJ);
+    }
+    uint32_t fm = 0u;
+    for (int q = 0; q < cnt; ++q) {
         // deep points (more than r cells from every wall) carry every lattice pair
-        const bool all_deep = (unsigned)(i - g.r - 1) < c.deep_nx && (unsigned)(ie - g.r - 1) < c.deep_nx &&
-                              (unsigned)(j - g.r - 1) < c.deep_ny && (unsigned)(je - g.r - 1) < c.deep_ny;
-        if (all_deep) {
-            // Two usual cases after the first sweeps, tested without the chain's loop: a strictly
-            // convex word keeps every point (the chain would only compare consecutive triples);
-            // a word whose interior points all lie on or above the chord first -> last (planar
-            // pieces of the solution) keeps its two ends.
-            bool convex = cnt == 32, flat = cnt == 32;
-            if (convex) {
-                double ya = yw[0], yb = yw[1];
-                const double yf = ya, dl = hp_sub(yw[31], ya);
-#pragma unroll 6
-                for (int q = 2; q < 32; ++q) {
-                    const double yc = yw[q];
-                    // hp_drop(q-2, ya, q-1, yb, q, yc): (yb + tol - ya) * 2 >= (yc - ya) * 1
-                    const double d = hp_sub(hp_add(yb, tol), ya);
-                    convex = convex && !(hp_add(d, d) >= hp_sub(yc, ya));
-                    // hp_drop(0, yf, q-1, yb, 31, yl)
-                    flat = flat && hp_mul(hp_sub(hp_add(yb, tol), yf), 31.0) >= hp_mul(dl, hp_i2d(q - 1));
-                    ya = yb;
-                    yb = yc;
-                }
-            }
-            if (convex) {
-                m = 0xffffffffu;
-            } else if (flat) {
-                m = 0x80000001u;
+        const bool deep = (unsigned)(i - g.r - 1) < c.deep_nx && (unsigned)(j - g.r - 1) < c.deep_ny;
+        if (!deep) {
+            bool forced;
+            if (P.rows_mode) {
+                forced = (j == 0 || j == NJ - 1);
             } else {
-                for (int q = 0; q < cnt; ++q) {
-                    const double yq = yw[q];
-                    HP_CHAIN_STEP(q, yq, true)
-                }
+                const int t = base + q;
+                forced = (i == 0 || i == (int)g.nx + 1 || j == 0 || j == NJ - 1) || t == 0 ||
+                         t == c.Lp - 1 || j - P.b < 0 || j - P.b >= NJ || j + P.b < 0 ||
+                         j + P.b >= NJ;
             }
+            if (!forced) forced = !((g.flags[sw_band_slot(g, i, j)] >> P.k) & 1ull);
+            if (forced) fm |= 1u << q;
+        }
+        if (P.rows_mode) {
+            ++j;
         } else {
-            for (int q = 0; q < cnt; ++q) {
-                const bool deep = (unsigned)(i - g.r - 1) < c.deep_nx &&
-                                  (unsigned)(j - g.r - 1) < c.deep_ny;
-                if (!deep) {
-                    bool forced;
-                    if (P.rows_mode) {
-                        forced = (j == 0 || j == NJ - 1);
-                    } else {
-                        const int t = base + q;
-                        forced = (i == 0 || i == (int)g.nx + 1 || j == 0 || j == NJ - 1) || t == 0 ||
-                                 t == c.Lp - 1 || j - P.b < 0 || j - P.b >= NJ || j + P.b < 0 ||
-                                 j + P.b >= NJ;
-                    }
-                    if (!forced) forced = !((g.flags[sw_band_slot(g, i, j)] >> P.k) & 1ull);
-                    if (forced) fm |= 1u << q;
-                }
-                const double yq = yw[q];
-                HP_CHAIN_STEP(q, yq, !((fm >> t1) & 1u))
-                if (P.rows_mode) {
-                    ++j;
-                } else {
-                    i += P.a;
-                    j += P.b;
-                    if (j >= NJ) j -= NJ;
-                    else if (j < 0) j += NJ;
-                }
-            }
+            i += P.a;
+            j += P.b;
+            if (j >= NJ) j -= NJ;
+            else if (j < 0) j += NJ;
         }
     }
+    return fm;
+}
+
+PDE_HD void hc_word_done(const LineView &L, int w, uint32_t m, uint32_t fm) {
     L.V[w] = m;
     L.F[w] = fm;
     L.C[w] = m == 0x80000001u ? 1u : 0u;              // flat word (hc_groups); then junction note
     if (m) hp_or(&L.SV[w >> 5], 1u << (w & 31));
     if (fm) hp_or(&L.SF[w >> 5], 1u << (w & 31));
+}
+
+// Level 0, part 1 -- every thread classifies its 32-point word.  Two usual cases after the first
+// sweeps are settled at once, without the chain's data-dependent loop: a strictly convex word
+// keeps every point (the chain would only compare consecutive triples); a word whose interior
+// points all lie on or above the chord first -> last (planar pieces of the solution) keeps its
+// two ends.  Every other word goes to the CTA's queue (part 2), so that the chain loops run in
+// full warps instead of a few lanes of every warp.
+PDE_HD void hc_level0(const HullCta &c, int tid) {
+    const int LWp = c.SW << 5;
+    const int l = tid / LWp, w = tid - l * LWp;
+    if (l >= c.WL || w >= c.LW) return;
+    const LineView L = hc_line(c, l);
+    if (l >= c.nlines || (w << 5) >= c.Lp) {
+        hc_word_done(L, w, 0u, 0u);
+        return;
+    }
+    const uint32_t fm = c.FM[l * c.LW + w];
+    if (fm == 0u && ((w + 1) << 5) <= c.Lp) {
+        const double tol = c.g.ytol;
+        const double *yw = L.y + 33 * w;              // hp_ix(32 w + q) = 33 w + q
+        bool convex = true, flat = true;
+        double ya = yw[0], yb = yw[1];
+        const double yf = ya, dl = hp_sub(yw[31], ya);
+#pragma unroll 6
+        for (int k = 2; k < 32; ++k) {
+            const double yc = yw[k];
+            // hp_drop(k-2, ya, k-1, yb, k, yc): (yb + tol - ya) * 2 >= (yc - ya) * 1
+            const double d = hp_sub(hp_add(yb, tol), ya);
+            convex = convex && !(hp_add(d, d) >= hp_sub(yc, ya));
+            // hp_drop(0, yf, k-1, yb, 31, yl)
+            flat = flat && hp_mul(hp_sub(hp_add(yb, tol), yf), 31.0) >= hp_mul(dl, hp_i2d(k - 1));
+            ya = yb;
+            yb = yc;
+        }
+        if (convex || flat) {
+            hc_word_done(L, w, convex ? 0xffffffffu : 0x80000001u, 0u);
+            return;
+        }
+    }
+#ifdef __CUDA_ARCH__
+    const uint32_t slot = atomicAdd(c.Qn, 1u);
+#else
+    const uint32_t slot = (*c.Qn)++;
+#endif
+    c.Qs[slot] = (uint32_t)tid;
+}
+
+// Level 0, part 2 -- entry k of the queue: monotone chain within the word.  The stack is the
+// bit mask m of the word, its two top entries are cached in (t1, y1), (t0, y0); a fixed vertex
+// on top of the stack is never popped.
+PDE_HD void hc_chain(const HullCta &c, int k) {
+    if (k >= (int)*c.Qn) return;
+    const int LWp = c.SW << 5;
+    const int owner = (int)c.Qs[k];
+    const int l = owner / LWp, w = owner - l * LWp;
+    const LineView L = hc_line(c, l);
+    const double tol = c.g.ytol;
+    const double *yw = L.y + 33 * w;
+    const int base = w << 5;
+    const int cnt = 32 < c.Lp - base ? 32 : c.Lp - base;
+    const uint32_t fm = c.FM[l * c.LW + w];
+    uint32_t m = 0u;
+    int t1 = -1, t0 = -1;
+    double y1 = 0.0, y0 = 0.0;
+    for (int q = 0; q < cnt; ++q) {
+        const double yq = yw[q];
+        while (t0 >= 0 && !((fm >> t1) & 1u)) {
+            if (!hp_drop(t0, y0, t1, y1, q, yq, tol)) break;
+            m &= ~(1u << t1);
+            t1 = t0;
+            y1 = y0;
+            const uint32_t below = m & ((1u << t1) - 1u);
+            if (below) {
+                t0 = 31 - hp_clz(below);
+                y0 = yw[t0];
+            } else {
+                t0 = -1;
+            }
+        }
+        m |= 1u << q;
+        t0 = t1; y0 = y1;
+        t1 = q;  y1 = yq;
+    }
+    hc_word_done(L, w, m, fm);
 }
 
 // Planar pieces of the solution: a full 32-word group (1024 points) whose words are all flat
@@ -873,39 +919,75 @@ PDE_HD void hc_store(const HullCta &c, int tid, int nthr) {
     }
 }
 
+// one-off per grid: the fixed-vertex masks of every word of every line of one direction
+__global__ void k_hull_forced(SweepGeom g, HullPass P, uint32_t *fmask) {
+    HullCta c;
+    hc_init(c, g, P, nullptr, fmask, nullptr, blockIdx.x);
+    const int LWp = P.SW << 5;
+    const int l = threadIdx.x / LWp, w = threadIdx.x - l * LWp;
+    if (l < c.nlines && w < c.LW) const_cast<uint32_t *>(c.FM)[l * c.LW + w] = hc_forced_word(c, l, w);
+}
+
 __global__ void __launch_bounds__(1024, 1)
-k_hull_pass(SweepGeom g, HullPass P, double *U, double *change, const int *done) {
+k_hull_pass(SweepGeom g, HullPass P, double *U, const uint32_t *fmask, double *change,
+            const int *done) {
     if (*done) return;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     HullCta c;
-    hc_init(c, g, P, U, smem_raw, blockIdx.x);
+    hc_init(c, g, P, U, fmask, smem_raw, blockIdx.x);
     const int tid = threadIdx.x, nthr = blockDim.x;
     hc_load(c, tid, nthr);
+    if (P.stop_after == 1) return;
     __syncthreads();
+    if (P.stop_after == 11) return;
     hc_level0(c, tid);
-    __syncwarp();
+    if (P.stop_after == 12) return;
+    __syncthreads();
+    if (P.stop_after == 13) return;
+    for (int k = tid; k < (int)*c.Qn; k += nthr) hc_chain(c, k);
+    if (P.stop_after == 2) return;
+    __syncthreads();
     hc_groups(c, tid);
     __syncwarp();
     hc_junctions(c, tid);
+    if (P.stop_after == 3) return;
     for (int h = 1; h < c.LW && h <= 16; h <<= 1) {      // inside one warp's 32 words
         __syncwarp();
         hc_merge(c, tid, h);
     }
+    if (P.stop_after == 4) return;
     for (int h = 32; h < c.LW; h <<= 1) {
         __syncthreads();
         hc_merge(c, tid, h);
     }
+    if (P.stop_after == 5) return;
     __syncthreads();
     double cmax = hc_fill(c, tid);
+    if (P.stop_after == 6) return;
     __syncthreads();
     hc_store(c, tid, nthr);
     cmax = warp_max(cmax);
     if ((tid & 31) == 0 && cmax > 0.0) atomic_max_nonneg(change, cmax);
 }
 
+static void hull_forced_replay(const SweepGeom &g, const HullPass &P, uint32_t *fmask, unsigned grid,
+                               unsigned block) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (long blk = 0; blk < (long)grid; ++blk) {
+        HullCta c;
+        hc_init(c, g, P, nullptr, fmask, nullptr, (unsigned)blk);
+        const int LWp = P.SW << 5;
+        for (int t = 0; t < (int)block; ++t) {
+            const int l = t / LWp, w = t - l * LWp;
+            if (l < c.nlines && w < c.LW)
+                const_cast<uint32_t *>(c.FM)[l * c.LW + w] = hc_forced_word(c, l, w);
+        }
+    }
+}
+
 // host replay of the kernel, one CTA after the other, phase by phase (tests: device = -2)
-static double hull_pass_replay(const SweepGeom &g, const HullPass &P, double *U, unsigned grid,
-                               unsigned block, size_t smem) {
+static double hull_pass_replay(const SweepGeom &g, const HullPass &P, double *U,
+                               const uint32_t *fmask, unsigned grid, unsigned block, size_t smem) {
     double change = 0.0;
 #pragma omp parallel reduction(max : change)
     {
@@ -913,10 +995,11 @@ static double hull_pass_replay(const SweepGeom &g, const HullPass &P, double *U,
 #pragma omp for schedule(dynamic, 1)
         for (long blk = 0; blk < (long)grid; ++blk) {
             HullCta c;
-            hc_init(c, g, P, U, buf.data(), (unsigned)blk);
+            hc_init(c, g, P, U, fmask, buf.data(), (unsigned)blk);
             const int n = (int)block;
             for (int t = 0; t < n; ++t) hc_load(c, t, n);
             for (int t = 0; t < n; ++t) hc_level0(c, t);
+            for (int k = 0; k < (int)*c.Qn; ++k) hc_chain(c, k);
             for (int t = 0; t < n; ++t) hc_groups(c, t);
             for (int t = 0; t < n; ++t) hc_junctions(c, t);
             for (int h = 1; h < c.LW; h <<= 1)
@@ -934,7 +1017,7 @@ static double hull_pass_replay(const SweepGeom &g, const HullPass &P, double *U,
 static size_t hull_smem_bytes(int wl_log2, int LW, int SW) {
     const int WL = 1 << wl_log2;
     return (size_t)WL * hull_line_stride(LW, wl_log2) * sizeof(double) +
-           (size_t)(3 * WL * LW + 3 * WL * SW) * sizeof(uint32_t);
+           (size_t)(4 * WL * LW + 3 * WL * SW + 1) * sizeof(uint32_t);
 }
 
 struct HullPlan {
@@ -945,12 +1028,16 @@ struct HullPlan {
 
 // launch shape of every direction pass; false if a line does not fit one CTA
 static bool hull_plan(std::vector<HullPlan> &plan, int64_t nx, int64_t ny, int ndir,
-                      const int32_t *h_dirs, size_t budget, size_t max_smem) {
+                      const int32_t *h_dirs, size_t budget, size_t max_smem,
+                      int64_t *mask_words = nullptr) {
     plan.resize((size_t)ndir);
+    int64_t words = 0;
     for (int k = 0; k < ndir; ++k) {
         int a = h_dirs[2 * k], b = h_dirs[2 * k + 1];
         HullPass P;
         P.k = k;
+        P.stop_after = 0;
+        if (const char *e = getenv("PDE_SWEEP_STOP_AFTER")) P.stop_after = atoi(e);
         int Lp, nstart;
         if (a == 0) {
             if (b != 1 && b != -1) return false;
@@ -975,19 +1062,63 @@ static bool hull_plan(std::vector<HullPlan> &plan, int64_t nx, int64_t ny, int n
             return false;
         P.wl_log2 = wl;
         P.groups = (P.Ns + (1 << wl) - 1) >> wl;
+        P.fm_offset = words;                       // independent of wl: lines are i0 * Ns + s0
+        words += (int64_t)nstart * P.Ns * P.LW;
         plan[k].P = P;
         plan[k].grid = (unsigned)(nstart * P.groups);
         plan[k].block = (unsigned)((1 << wl) * P.SW * 32);
         plan[k].smem = hull_smem_bytes(wl, P.LW, P.SW);
     }
+    if (mask_words) *mask_words = words;
     return true;
 }
+
+// doubles of `work` in front of the mask table: relaxation scratch, per-sweep changes, flags
+static int64_t sweep_work_head(int64_t n_band) { return n_band + 80; }
 
 }  // namespace pde
 
 using namespace pde;
 
 extern "C" {
+
+int64_t pde_ce_sweep_work_bytes(int64_t nx, int64_t ny, int ndir, const int32_t *h_dirs,
+                                int64_t n_band) {
+    std::vector<HullPlan> plan;
+    int64_t words = 0;
+    if (nx < 1 || ny < 1 || ndir < 1 || !h_dirs ||
+        !hull_plan(plan, nx, ny, ndir, h_dirs, 110 * 1024, 227 * 1024, &words))
+        return -1;
+    return sweep_work_head(n_band) * (int64_t)sizeof(double) + words * (int64_t)sizeof(uint32_t);
+}
+
+static void sweep_geom(SweepGeom &g, int64_t nx, int64_t ny, int64_t pitch, int64_t wall_base,
+                       int stencil_radius, const int64_t *ring, const uint64_t *flags,
+                       double flat_tol) {
+    g.nx = nx; g.ny = ny; g.pitch = pitch; g.wall_base = wall_base; g.r = stencil_radius;
+    g.ytol = flat_tol > 0.0 ? flat_tol : 0.0;
+    g.ring = ring;
+    g.flags = reinterpret_cast<const unsigned long long *>(flags);
+}
+
+int pde_ce_sweep_setup(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall_base,
+                       int stencil_radius, int ndir, const int32_t *h_dirs, const int64_t *ring,
+                       const uint64_t *flags, int64_t n_band, double *work, void *stream) {
+    PDE_REQUIRE(nx >= 1 && ny >= 1 && pitch >= ny && ndir >= 1 && ndir <= 64, "bad sweep geometry");
+    PDE_REQUIRE(h_dirs && ring && flags && work && device >= 0, "null argument");
+    SweepGeom g;
+    sweep_geom(g, nx, ny, pitch, wall_base, stencil_radius, ring, flags, 0.0);
+    std::vector<HullPlan> plan;
+    PDE_REQUIRE(hull_plan(plan, nx, ny, ndir, h_dirs, 110 * 1024, 227 * 1024),
+                "lattice line too long for the sweep kernel");
+    DeviceGuard guard(device);
+    uint32_t *fmask = reinterpret_cast<uint32_t *>(work + sweep_work_head(n_band));
+    for (int k = 0; k < ndir; ++k) {
+        k_hull_forced<<<plan[k].grid, plan[k].block, 0, (cudaStream_t)stream>>>(g, plan[k].P, fmask);
+        PDE_LAUNCH_CHECK();
+    }
+    return 0;
+}
 
 int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall_base,
                  int stencil_radius, int ndir, const int32_t *h_dirs, const int64_t *ring,
@@ -1000,10 +1131,7 @@ int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall
     PDE_REQUIRE(n_band == 0 || (band_ptr && band_center && rest_j && rest_theta), "null argument");
     PDE_REQUIRE(max_sweeps >= 0 && ny + 2 < (1 << 24) && nx + 2 < (1 << 24), "bad sweep arguments");
     SweepGeom g;
-    g.nx = nx; g.ny = ny; g.pitch = pitch; g.wall_base = wall_base; g.r = stencil_radius;
-    g.ytol = flat_tol > 0.0 ? flat_tol : 0.0;
-    g.ring = ring;
-    g.flags = reinterpret_cast<const unsigned long long *>(flags);
+    sweep_geom(g, nx, ny, pitch, wall_base, stencil_radius, ring, flags, flat_tol);
     const int64_t W = ny + 2, npad = (nx + 2) * W;
     if (relax_every <= 0 || relax_every > ndir) relax_every = ndir;
     size_t budget = 110 * 1024;                       // two bundles per SM
@@ -1012,9 +1140,15 @@ int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall
     double change = 0.0;
     int64_t sweeps = 0;
     if (device < 0) {                // host builds: -1 serial chain per line, -2 kernel replay
-        if (device == -2)
-            PDE_REQUIRE(hull_plan(plan, nx, ny, ndir, h_dirs, budget, 227 * 1024),
+        std::vector<uint32_t> fmask;
+        if (device == -2) {
+            int64_t words = 0;
+            PDE_REQUIRE(hull_plan(plan, nx, ny, ndir, h_dirs, budget, 227 * 1024, &words),
                         "lattice line too long for the sweep kernel");
+            fmask.resize((size_t)words);
+            for (int k = 0; k < ndir; ++k)
+                hull_forced_replay(g, plan[k].P, fmask.data(), plan[k].grid, plan[k].block);
+        }
         std::vector<int32_t> stk((size_t)(device == -1 ? npad : 1));
         std::vector<double> tmp((size_t)std::max<int64_t>(n_band, 1));
         auto relax = [&]() {
@@ -1040,8 +1174,8 @@ int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall
                 const int a = h_dirs[2 * k], b = h_dirs[2 * k + 1];
                 double cmax = 0.0;
                 if (device == -2) {
-                    cmax = hull_pass_replay(g, plan[k].P, U, plan[k].grid, plan[k].block,
-                                            plan[k].smem);
+                    cmax = hull_pass_replay(g, plan[k].P, U, fmask.data(), plan[k].grid,
+                                            plan[k].block, plan[k].smem);
                 } else {
 #pragma omp parallel for schedule(dynamic, 64) reduction(max : cmax)
                     for (int64_t idx = 0; idx < npad; ++idx) {
@@ -1073,10 +1207,12 @@ int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall
                           (size_t)max_smem),
                 "lattice line too long for the sweep kernel");
 
-    // work: [n_band tmp | change per sweep (batch_cap + 1) | done, sweeps_done (two ints)]
+    // work: [n_band tmp | change per sweep (batch_cap + 1) | done, sweeps_done (two ints) | ..
+    //        sweep_work_head(n_band) doubles in all | fixed-vertex masks (pde_ce_sweep_setup)]
     constexpr int64_t batch_cap = 64;
     double *d_tmp = work, *d_change = work + n_band;
     int *d_flags = reinterpret_cast<int *>(d_change + batch_cap + 1);
+    const uint32_t *fmask = reinterpret_cast<const uint32_t *>(work + sweep_work_head(n_band));
     int rc = 0;
     const unsigned rblk = (unsigned)((n_band + 127) / 128);
     while (sweeps < max_sweeps && rc == 0) {
@@ -1086,7 +1222,7 @@ int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall
             double *ch = d_change + s;
             for (int k = 0; k < ndir && e == cudaSuccess; ++k) {
                 const HullPlan &pl = plan[k];
-                k_hull_pass<<<pl.grid, pl.block, pl.smem, st>>>(g, pl.P, U, ch, d_flags);
+                k_hull_pass<<<pl.grid, pl.block, pl.smem, st>>>(g, pl.P, U, fmask, ch, d_flags);
                 count_launch();
                 if (n_band > 0 && ((k + 1) % relax_every == 0 || k == ndir - 1)) {
                     for (int rep = 0; rep < relax_reps; ++rep) {
