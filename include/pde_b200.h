@@ -316,6 +316,24 @@ int pde_ell_newton_update(pde_ell *e, const double *d_U, const double *d_d, cons
                           const double *d_Jd, double *d_Unew, double *h_out, void *stream);
 
 /* ------------------------------------------------------------------------
+ * Slab halo exchange over NVLink peer memory (no counterpart in the single-process
+ * reference).  Every rank owns a staging buffer of pde_halo_stage_doubles(halo, pitch) doubles
+ * in peer-mapped (symmetric) memory, zero-initialised; `peer_*_stage` are the neighbours' staging
+ * buffers as mapped in THIS process (NULL at the ends of the slab chain).  `d_view` = the lattice
+ * part of a state vector ((nx_local + 2 halo) rows x pitch, 16-byte aligned).  `step` = exchange
+ * number, 1, 2, 3, ... the same on all ranks.  Both calls only enqueue one small kernel on
+ * `stream`: push = remote stores of the first / last `halo` owned rows + release of the
+ * neighbours' flag words; wait_copy = acquire of this rank's flag words, then staged rows ->
+ * halo rows. */
+int64_t pde_halo_stage_doubles(int64_t halo, int64_t pitch);
+int pde_halo_push(const double *d_view, int64_t nx_local, int64_t halo, int64_t pitch,
+                  double *my_stage, double *peer_lo_stage, double *peer_hi_stage, uint64_t step,
+                  void *stream);
+int pde_halo_wait_copy(double *d_view, int64_t nx_local, int64_t halo, int64_t pitch,
+                       const double *my_stage, int has_lo, int has_hi, uint64_t step,
+                       void *stream);
+
+/* ------------------------------------------------------------------------
  * EXTENSION (no counterpart in the reference): the convex envelope of convex_envelope.py:44-46
  * on a structured 2-D pairs grid by directional convex-hull sweeps.  The discrete solution is
  * the largest u <= g with a non-negative second difference for every pair (ddg.py:281) of every

@@ -1,10 +1,14 @@
-"""CPU baseline: the NumPy restatement of the reference operator timed on host cores.
+"""CPU baseline: the reference operator timed on host cores.
 
-TEST / BENCH INFRASTRUCTURE.  ``ddg_oracle.d2eigs`` is the faithful port of
-ddg.d2eigs (gathers + norms + segmented selection, recomputing the geometry on
-every call like ddg.py:274-292).  The reference is single-threaded; to use every
-core the sample is split into disjoint row chunks, one worker process each
-(valid because the reference groups pairs by centre point, ddg.py:283-292).
+TEST / BENCH INFRASTRUCTURE.  ``impl="reference"``: the UNMODIFIED ``pyellipticfd.ddg.d2eigs``
+(ddg.py:251-327), imported through ``oracle/refshim.py`` from /root/reference or from the
+byte-for-byte copy ``oracle/ref_install.py`` leaves in the git-ignored ``oracle/_ref/`` (that is
+what travels to the GPU box) -- the reference's operators accept any object with ``points``,
+``pairs``, ``num_interior``, ``num_points``.  ``impl="port"``: ``ddg_oracle.d2eigs``, the NumPy
+restatement (gathers + norms + segmented selection, recomputing the geometry on every call
+like ddg.py:274-292).  The reference is single-threaded; to use every core the sample is split
+into disjoint row chunks, one worker process each (valid because the reference groups pairs by
+centre point, ddg.py:283-292).  No product code is imported here.
 """
 import multiprocessing as mp
 import os
@@ -39,24 +43,38 @@ def lattice_chunk(ny, r, table, scaling, b0, row_lo, nrows):
     return G
 
 
+def operator(impl):
+    """``d2eigs(G, u)`` of the chosen implementation ("reference" | "port")."""
+    if impl == "reference":
+        from . import refshim
+        return refshim.modules().ddg.d2eigs
+    return ddg_oracle.d2eigs
+
+
+def reference_available():
+    from . import refshim
+    return refshim.available()
+
+
 def _work(args):
-    ny, r, table, scaling, b0, row_lo, nrows, reps, seed = args
+    ny, r, table, scaling, b0, row_lo, nrows, reps, seed, impl = args
+    d2eigs = operator(impl)
     G = lattice_chunk(ny, r, np.asarray(table), np.asarray(scaling), np.asarray(b0), row_lo, nrows)
     u = np.random.default_rng(seed).standard_normal(G.num_points)
-    ddg_oracle.d2eigs(G, u)                       # warm-up (page faults, imports)
+    d2eigs(G, u)                                  # warm-up (page faults, imports)
     t = time.perf_counter()
     for _ in range(reps):
-        ddg_oracle.d2eigs(G, u)
+        d2eigs(G, u)
     dt = (time.perf_counter() - t) / reps
     return G.num_interior, len(G.pairs), dt
 
 
-def time_d2eigs(ny, r, table, scaling, b0, rows_per_worker=24, workers=None, reps=2):
+def time_d2eigs(ny, r, table, scaling, b0, rows_per_worker=24, workers=None, reps=2, impl="port"):
     """Returns dict(points_per_s, pairs_per_s, cores, sample, seconds)."""
     workers = workers or os.cpu_count() or 1
     H = int(np.abs(np.asarray(table)).max())
     args = [(ny, r, np.asarray(table), tuple(scaling), tuple(b0),
-             r + H + w * rows_per_worker, rows_per_worker, reps, w) for w in range(workers)]
+             r + H + w * rows_per_worker, rows_per_worker, reps, w, impl) for w in range(workers)]
     if workers == 1:
         res = [_work(args[0])]
     else:
@@ -65,9 +83,12 @@ def time_d2eigs(ny, r, table, scaling, b0, rows_per_worker=24, workers=None, rep
     pts = sum(x[0] for x in res)
     prs = sum(x[1] for x in res)
     wall = max(x[2] for x in res)
+    what = ("the unmodified reference's ddg.d2eigs" if impl == "reference"
+            else "NumPy port of ddg.d2eigs")
     return dict(points_per_s=pts / wall, pairs_per_s=prs / wall, cores=workers, seconds=wall,
-                sample="%d workers x %d deep rows x %d cols (%d pairs), NumPy port of ddg.d2eigs"
-                       % (workers, rows_per_worker, ny - 2 * r, prs))
+                kind=impl,
+                sample="%d workers x %d deep rows x %d cols (%d pairs), %s"
+                       % (workers, rows_per_worker, ny - 2 * r, prs, what))
 
 
 def time_ddi_cached(idx, w, u, nds):
@@ -104,19 +125,31 @@ def time_ddi_cached(idx, w, u, nds):
 
 
 def main(argv=None):
-    """``python -m oracle.cpu_baseline NY R ROWS_PER_WORKER WORKERS REPS`` on a unit-square
-    dyadic lattice; prints one JSON line.  bench.py runs this in a fresh (CUDA-free)
-    process so that the worker pool can fork safely."""
+    """``python -m oracle.cpu_baseline NY R ROWS_PER_WORKER WORKERS REPS [IMPL]`` on a unit-square
+    dyadic lattice; prints one JSON line.  IMPL = reference | port | auto (reference when the
+    tree or its copy under oracle/_ref is there).  bench.py runs this in a fresh (CUDA-free)
+    process so that the worker pool can fork safely.  The direction table comes from
+    oracle/grid_oracle.py: no product module (and no product .so) is loaded."""
     import json
     import sys
-    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    from . import grid_oracle
     a = (argv or sys.argv[1:])
     ny, r, rows, workers, reps = int(a[0]), int(a[1]), int(a[2]), int(a[3]), int(a[4])
-    small = FDRegularGrid([4 * r + 3, 4 * r + 3], np.array([[0.0, 1.0], [0.0, 1.0]]).T * 1.0, r,
-                          interpolation=False)
+    impl = a[5] if len(a) > 5 else "auto"
+    ratio = impl.endswith("+ratio")            # also time port and reference on one core
+    impl = impl.replace("+ratio", "")
+    if impl == "auto":
+        impl = "reference" if reference_available() else "port"
+    table = grid_oracle.stencil_table(r)
     h = 1.0 / (ny + 1)
-    out = time_d2eigs(ny, r, small.stencil_pairs, (h, h), (0.0, 0.0), rows, workers, reps)
-    out["D"] = int(small.stencil_pairs.shape[0])
+    out = time_d2eigs(ny, r, table, (h, h), (0.0, 0.0), rows, workers, reps, impl)
+    out["D"] = int(table.shape[0])
+    if impl == "reference" and ratio:
+        # the port on ONE worker's sample beside it: per-core ratio of the two CPU arms
+        one_ref = time_d2eigs(ny, r, table, (h, h), (0.0, 0.0), rows, 1, 1, "reference")
+        one_port = time_d2eigs(ny, r, table, (h, h), (0.0, 0.0), rows, 1, 1, "port")
+        out["port_over_reference_per_core"] = one_port["pairs_per_s"] / one_ref["pairs_per_s"]
+        out["reference_pairs_per_s_per_core"] = one_ref["pairs_per_s"]
     print(json.dumps(out))
 
 

@@ -30,14 +30,12 @@ from .cpu_baseline import lattice_chunk
 
 
 def main(argv=None):
-    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    from . import grid_oracle
     a = argv or sys.argv[1:]
     n, r = int(a[0]), int(a[1])
     rows = int(a[2]) if len(a) > 2 else 48
     kits = int(a[3]) if len(a) > 3 else 4
-    small = FDRegularGrid([4 * r + 3] * 2, np.array([[0.0, 1.0], [0.0, 1.0]]).T, r,
-                          interpolation=False)
-    table = np.asarray(small.stencil_pairs)
+    table = grid_oracle.stencil_table(r)       # no product code in the CPU arm
     D = table.shape[0]
     H = int(np.abs(table).max())
     h = 1.0 / (n + 1)

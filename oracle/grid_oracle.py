@@ -90,3 +90,18 @@ def build(shape, bounds, r):
         pair_rows += [(i, int(kc[x]), int(kc[y])) for x, y in zip(a, b)]
     return dict(points=points, num_interior=N, neighbours=np.array(nb_rows, dtype=np.int64),
                 pairs=np.array(pair_rows, dtype=np.int64))
+
+
+def stencil_table(r):
+    """(D, 4) integer offsets (a0, b0, a1, b1) of the antipodal pairs of a deep-interior point of a
+    2-D lattice with stencil radius r: the pairs `build` gives the centre point of a small square
+    grid (so the colinear-tolerance pruning of pointclasses.py:37-103 is included: radius 6 yields
+    the 36 pairs of radius 5).  Used by the CPU baseline so that it needs no product code."""
+    n = 4 * r + 3
+    bounds = np.array([[0.0, 1.0], [0.0, 1.0]]).T
+    b = build([n, n], bounds, r)
+    P, _ = unscaled_points([n, n], bounds, r)
+    c = (n // 2) * n + n // 2
+    rows = b["pairs"][b["pairs"][:, 0] == c]
+    return np.concatenate([np.rint(P[rows[:, 1]] - P[c]), np.rint(P[rows[:, 2]] - P[c])],
+                          axis=1).astype(np.int64)

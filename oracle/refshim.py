@@ -4,8 +4,9 @@ This module makes the read-only tree at /root/reference importable as the
 package ``pyellipticfd`` inside THIS container so that
 ``oracle/make_golden.py`` can generate golden vectors from the real reference
 and so that the numpy/C restatements under ``oracle/`` can be pinned against it.
-It is never imported by the product package, by ``bench.py`` or by the ``-m
-gpu`` tests: /root/reference does not exist on the GPU box.
+It is never imported by the product package or by the ``-m gpu`` tests.  On the GPU box
+/root/reference does not exist; ``bench.py --impl reference`` (the CPU reference arm) imports
+the byte-for-byte copy under the git-ignored ``oracle/_ref/`` instead (oracle/ref_install.py).
 
 The four mechanical patches paper over API drift between
 the reference's 2018-era NumPy/SciPy and the versions installed here; none of
@@ -25,7 +26,18 @@ import warnings
 import numpy as np
 import scipy.sparse.linalg as sla
 
-REFERENCE_ROOT = os.environ.get("PYELLIPTICFD_REFERENCE", "/root/reference")
+def _root():
+    """/root/reference in the build container; on the GPU box the byte-for-byte copy that
+    oracle/ref_install.py left in the git-ignored oracle/_ref/ (it travels with the snapshot)."""
+    env = os.environ.get("PYELLIPTICFD_REFERENCE")
+    if env:
+        return env
+    if os.path.exists("/root/reference/ddg.py"):
+        return "/root/reference"
+    return os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "pyellipticfd")
+
+
+REFERENCE_ROOT = _root()
 
 _installed = False
 

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpde_b200.so")
 SOURCES = ["grid_ctx.cu", "ddg_kernels.cu", "bicgstab.cu", "misc.cu", "ell.cu", "band_builder.cu",
-           "cloud_builder.cu", "first_deriv.cu", "ce_sweep.cu"]
+           "cloud_builder.cu", "first_deriv.cu", "ce_sweep.cu", "halo_push.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

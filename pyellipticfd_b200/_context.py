@@ -305,13 +305,16 @@ class GridContext(object):
         return lmin, lmax, pmin, pmax
 
     def d2eigs_host(self, u_host, want_min=True, want_max=True, mode=0, chunk_rows=256,
-                    linear=None):
+                    linear=None, halo_hook=None, out=None):
         """ddg.d2eigs values for a field in PINNED host memory, results in pinned host
         memory: the H2D copy, the stencil kernels and the D2H copy are pipelined over
         chunks of rows on three streams (PCIe is full duplex).  ``linear=False``: the layout
         conversion is done by the 2-D DMA copies themselves; ``linear=True``: the PCIe copies
         are plain linear copies to / from flat device staging buffers and the conversion is
-        a device-side 2-D copy (default: ``HOST_COPY_LINEAR``)."""
+        a device-side 2-D copy (default: ``HOST_COPY_LINEAR``).
+        ``halo_hook(S)`` (slab contexts, multigpu.ShardedGrid.d2eigs_host): the slab's first /
+        last rows are uploaded first and the hook -- the halo exchange -- runs on the compute
+        stream before the first chunk.  ``out``: (pinned lmin, pinned lmax) to reuse."""
         linear = HOST_COPY_LINEAR if linear is None else linear
         nloc, ny, H = self.nx_local, self.ny, max(self.radius, 1)
         if not hasattr(self, "_stage"):
@@ -323,26 +326,48 @@ class GridContext(object):
                                 torch.empty(nloc * ny, dtype=torch.float64, device=self.device),
                                 torch.empty(nloc * ny, dtype=torch.float64, device=self.device))
         main = torch.cuda.current_stream()
-        out_min = torch.empty(nloc * ny, dtype=torch.float64, pin_memory=True) if want_min else None
-        out_max = torch.empty(nloc * ny, dtype=torch.float64, pin_memory=True) if want_max else None
+        out_min, out_max = out if out is not None else (None, None)
+        if want_min and out_min is None:
+            out_min = torch.empty(nloc * ny, dtype=torch.float64, pin_memory=True)
+        if want_max and out_max is None:
+            out_max = torch.empty(nloc * ny, dtype=torch.float64, pin_memory=True)
         edges = list(range(0, nloc, chunk_rows)) + [nloc]
         nchunk = len(edges) - 1
         ev_in = [torch.cuda.Event() for _ in range(nchunk)]
         s_in.wait_stream(main)
         s_out.wait_stream(main)
+
+        def upload(lo, hi, wall):
+            src = u_host
+            if linear:
+                fin = self._stage_flat[0]
+                fin[lo * ny:hi * ny].copy_(u_host[lo * ny:hi * ny], non_blocking=True)
+                if wall and self.nb:
+                    fin[nloc * ny:].copy_(u_host[nloc * ny:], non_blocking=True)
+                src = fin
+            check(self.lib.pde_grid_h2d_rows(self.h, vp(src.data_ptr()), _ptr(S), lo, hi,
+                                             int(wall), _stream()))
+
         with torch.cuda.stream(s_in):
+            first = 0
+            if halo_hook is not None and self.halo_rows and nloc >= 2 * self.halo_rows:
+                # the rows the neighbours need go first; chunk 0 then starts after them
+                hr = self.halo_rows
+                upload(0, hr, True)
+                upload(nloc - hr, nloc, False)
+                ev_edge = torch.cuda.Event()
+                ev_edge.record()
+            else:
+                ev_edge = None
             for k in range(nchunk):
-                lo, hi = edges[k], edges[k + 1]
-                src = u_host
-                if linear:
-                    fin = self._stage_flat[0]
-                    fin[lo * ny:hi * ny].copy_(u_host[lo * ny:hi * ny], non_blocking=True)
-                    if k == 0 and self.nb:
-                        fin[nloc * ny:].copy_(u_host[nloc * ny:], non_blocking=True)
-                    src = fin
-                check(self.lib.pde_grid_h2d_rows(self.h, vp(src.data_ptr()), _ptr(S), lo, hi,
-                                                 int(k == 0), _stream()))
+                upload(edges[k], edges[k + 1], k == 0 and ev_edge is None)
                 ev_in[k].record()
+        if halo_hook is not None:
+            if ev_edge is not None:
+                main.wait_event(ev_edge)
+            else:
+                main.wait_event(ev_in[-1])
+            halo_hook(S)
         outs = (Lmin if want_min else None, Lmax if want_max else None, None, None)
         try:
             for k in range(nchunk):
@@ -356,7 +381,7 @@ class GridContext(object):
                 s_out.wait_event(ev)
                 with torch.cuda.stream(s_out):
                     for q, (L, o) in enumerate(((Lmin, out_min), (Lmax, out_max))):
-                        if o is None:
+                        if o is None or not (want_min, want_max)[q]:
                             continue
                         dst = self._stage_flat[1 + q] if linear else o
                         check(self.lib.pde_grid_d2h_rows(self.h, _ptr(L), vp(dst.data_ptr()),

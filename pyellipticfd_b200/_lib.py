@@ -85,6 +85,9 @@ SIGNATURES = {
     "pde_band_build": (c_int, [c_i64, c_i64, c_int, c_dbl, c_dbl, c_dbl, c_dbl, c_i64, vp,
                                c_i64, vp, c_dbl, C.POINTER(vp), C.POINTER(vp), C.POINTER(c_dbl),
                                C.POINTER(vp), C.POINTER(vp)]),
+    "pde_halo_stage_doubles": (c_i64, [c_i64, c_i64]),
+    "pde_halo_push": (c_int, [vp, c_i64, c_i64, c_i64, vp, vp, vp, C.c_uint64, vp]),
+    "pde_halo_wait_copy": (c_int, [vp, c_i64, c_i64, c_i64, vp, c_int, c_int, C.c_uint64, vp]),
     "pde_ce_sweep_work_bytes": (c_i64, [c_i64, c_i64, c_int, vp, c_i64]),
     "pde_ce_sweep_setup": (c_int, [c_int, c_i64, c_i64, c_i64, c_i64, c_int, c_int, vp, vp, vp, c_i64,
                                    vp, vp]),

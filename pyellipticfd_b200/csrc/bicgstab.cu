@@ -240,10 +240,12 @@ static int launch_tiled_h(pde_grid *g, const Op &op, double *partials, const Bic
     if (rc) return rc;
     constexpr int smem = k_jac_tiled_smem_bytes<H, P>();
     auto kern = k_jac_tiled<Op, H, P>;
-    static bool attr_set = false;   // per template instantiation
-    if (!attr_set) {
+    // the opt-in is per device: one bit per device, per template instantiation
+    static unsigned long long attr_set = 0ull;
+    const unsigned long long dev_bit = 1ull << (g->device & 63);
+    if (!(attr_set & dev_bit)) {
         PDE_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_set |= dev_bit;
     }
     int ntiles = geo.tiles_x * geo.tiles_y;
     int grid = std::min(ntiles, g->num_sms * 3);
@@ -302,8 +304,14 @@ static int launch_rows(pde_grid *g, const Op &op, double *partials, const BicgSc
     return 0;
 }
 
+// U_new = U + d, max|U - U_new|, <F, J d>, <d, d> (solvers.py:188-197).  Fixed-order sums: per
+// thread over a grid-stride sequence, shuffle tree per warp, warps in order per block, and the
+// last block to finish adds the block partials in block order -- the same bits on every run.
 __global__ void k_newton_update(int64_t n, const double *U, const double *d, const double *F,
-                                const double *Jd, double *Unew, double *out) {
+                                const double *Jd, double *Unew, double *out /* 3 */,
+                                double *partials /* 3 x gridDim */, unsigned *counter) {
+    __shared__ double sh[3][32];
+    __shared__ bool last;
     double mx = 0.0, a = 0.0, b = 0.0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
          i += (int64_t)gridDim.x * blockDim.x) {
@@ -317,10 +325,36 @@ __global__ void k_newton_update(int64_t n, const double *U, const double *d, con
     mx = warp_max(mx);
     a = warp_sum(a);
     b = warp_sum(b);
-    if ((threadIdx.x & 31) == 0) {
-        atomic_max_nonneg(&out[0], mx);
-        atomicAdd(&out[1], a);
-        atomicAdd(&out[2], b);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    if (lane == 0) {
+        sh[0][wid] = mx;
+        sh[1][wid] = a;
+        sh[2][wid] = b;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < nw; ++w) {
+            mx = fmax(mx, sh[0][w]);
+            a += sh[1][w];
+            b += sh[2][w];
+        }
+        partials[3 * blockIdx.x] = mx;
+        partials[3 * blockIdx.x + 1] = a;
+        partials[3 * blockIdx.x + 2] = b;
+        __threadfence();
+        last = atomicAdd(counter, 1u) == gridDim.x - 1;
+        if (last) {
+            __threadfence();
+            mx = a = b = 0.0;
+            for (unsigned k = 0; k < gridDim.x; ++k) {
+                mx = fmax(mx, partials[3 * k]);
+                a += partials[3 * k + 1];
+                b += partials[3 * k + 2];
+            }
+            out[0] = mx;
+            out[1] = a;
+            out[2] = b;
+        }
     }
 }
 
@@ -489,10 +523,13 @@ int pde_vec_newton_update(pde_grid *g, const double *d_U, const double *d_d, con
 namespace pde {
 int newton_update_launch(int64_t n, int num_sms, const double *U, const double *d, const double *F,
                          const double *Jd, double *Unew, double *h_out, cudaStream_t st) {
-    double *out = nullptr;
-    PDE_CHECK(cudaMallocAsync((void **)&out, 3 * sizeof(double), st));
-    PDE_CHECK(cudaMemsetAsync(out, 0, 3 * sizeof(double), st));
-    k_newton_update<<<elem_grid(n, num_sms), 256, 0, st>>>(n, U, d, F, Jd, Unew, out);
+    const unsigned grid = (unsigned)elem_grid(n, num_sms);
+    double *out = nullptr;                       // [3 results | counter word | 3 x grid partials]
+    const size_t bytes = (4 + 3 * (size_t)grid) * sizeof(double);
+    PDE_CHECK(cudaMallocAsync((void **)&out, bytes, st));
+    PDE_CHECK(cudaMemsetAsync(out, 0, 4 * sizeof(double), st));
+    k_newton_update<<<grid, 256, 0, st>>>(n, U, d, F, Jd, Unew, out, out + 4,
+                                          reinterpret_cast<unsigned *>(out + 3));
     pde::count_launch();
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(h_out, out, 3 * sizeof(double), cudaMemcpyDeviceToHost, st);

@@ -135,10 +135,12 @@ static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *
     if (rc) return rc;
     constexpr int smem = k_deep_smem_bytes<H, P>();
     auto kern = k_deep<Eval, H, P, MODE, Epi, MINB, ICMP>;
-    static bool attr_set = false;   // per template instantiation
-    if (!attr_set) {
+    // the opt-in is per device: one bit per device, per template instantiation
+    static unsigned long long attr_set = 0ull;
+    const unsigned long long dev_bit = 1ull << (g->device & 63);
+    if (!(attr_set & dev_bit)) {
         PDE_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-        attr_set = true;
+        attr_set |= dev_bit;
     }
     int ntiles = geo.tiles_x * geo.tiles_y;
     int grid = std::min(ntiles, g->num_sms * MINB);

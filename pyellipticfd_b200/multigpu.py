@@ -5,9 +5,13 @@ grids that do not fit, or are too slow on, one GPU.  The lattice is cut into
 contiguous slabs of rows (x is the slow axis, rows of ``ny`` values are contiguous:
 pointclasses.py:513-515).  Every rank owns one slab plus ``r`` halo rows on each
 side in its state buffer; before an operator application the halo rows are
-refreshed from the neighbouring ranks (NCCL send/recv over NVLink, one message of
-``r * pitch`` doubles per neighbour).  Wall points are replicated on every rank.
-Infinity-norm / dot-product reductions of the solvers are small all-reduces.
+refreshed from the two neighbouring ranks.  On GPUs that is a PUSH over NVLink peer
+memory (:class:`HaloChannel`, ``csrc/halo_push.cu``): each rank stores its edge rows
+straight into the neighbours' staging buffers and raises a flag, two small kernels on
+the rank's own stream, no collective.  (Fallback when peer memory cannot be mapped: one
+NCCL all-gather of the edge rows; CPU tensors: gloo send/recv.)  Wall points are
+replicated on every rank.  Infinity-norm / dot-product reductions of the solvers are
+small NCCL all-reduces.
 """
 import os
 
@@ -59,6 +63,67 @@ def halo_exchange(view, nx_local, halo, rank, world, group=None, method="auto"):
         req.wait()
 
 
+def bind_to_gpu_numa_node(device_index):
+    """Pin this process (one per GPU) to the CPUs of the NUMA node its GPU hangs off, so that the
+    pinned host buffers it allocates afterwards are node-local (first touch) and the ranks do not
+    all stream through node 0.  Best effort: returns the node number or None."""
+    try:
+        prop = torch.cuda.get_device_properties(device_index)
+        bdf = "%04x:%02x:%02x.0" % (prop.pci_domain_id, prop.pci_bus_id, prop.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.extend(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
+class HaloChannel(object):
+    """Neighbour-only halo exchange through peer-mapped staging buffers (torch symmetric
+    memory supplies the mapping; the copies and flags are ``pde_halo_push`` /
+    ``pde_halo_wait_copy``).  One instance per (rank, halo, pitch)."""
+
+    def __init__(self, halo, pitch, rank, world, device, group=None):
+        import torch.distributed._symmetric_memory as symm
+        from . import _lib
+        self.lib, self.rank, self.world = _lib.lib(), rank, world
+        self.halo, self.pitch = int(halo), int(pitch)
+        n = int(self.lib.pde_halo_stage_doubles(self.halo, self.pitch))
+        self.stage = symm.empty(n, dtype=torch.float64, device=device)
+        self.hdl = symm.rendezvous(self.stage, group if group is not None else dist.group.WORLD)
+        self.stage.zero_()
+        torch.cuda.synchronize(device)
+        dist.barrier()                       # nobody pushes before every flag word is zero
+        ptrs = self.hdl.buffer_ptrs
+        self.lo = int(ptrs[rank - 1]) if rank > 0 else None
+        self.hi = int(ptrs[rank + 1]) if rank < world - 1 else None
+        self.step = 0
+
+    def exchange(self, view, nx_local):
+        """Refresh the halo rows of ``view`` ((nx_local + 2*halo) x pitch); enqueues two kernels
+        on the current stream.  Every rank must call it for the same sequence of vectors."""
+        from ._lib import check, vp
+        if view.stride(0) != self.pitch or view.shape[0] != nx_local + 2 * self.halo:
+            raise ValueError("halo channel: unexpected view layout")
+        self.step += 1
+        st = vp(torch.cuda.current_stream().cuda_stream)
+        check(self.lib.pde_halo_push(vp(view.data_ptr()), int(nx_local), self.halo, self.pitch,
+                                     vp(self.stage.data_ptr()), vp(self.lo), vp(self.hi),
+                                     self.step, st))
+        check(self.lib.pde_halo_wait_copy(vp(view.data_ptr()), int(nx_local), self.halo, self.pitch,
+                                          vp(self.stage.data_ptr()), int(self.lo is not None),
+                                          int(self.hi is not None), self.step, st))
+
+
 class ShardedGrid(object):
     """One rank's slab of a global FDRegularGrid."""
 
@@ -82,22 +147,44 @@ class ShardedGrid(object):
         if world > 1 and os.environ.get("PDE_DYNAMIC_SCHEDULE", "0") == "1":
             from ._lib import check
             check(self.ctx.lib.pde_grid_set_dynamic_schedule(self.ctx.h, 1))
+        # neighbour-only halo push over NVLink peer memory; PDE_HALO=nccl keeps the all-gather
+        self.channel = None
+        if (world > 1 and self.ctx.device.type == "cuda" and dist.is_initialized()
+                and os.environ.get("PDE_HALO", "push") != "nccl"):
+            try:
+                self.channel = HaloChannel(halo, self.ctx.pitch, rank, world, self.ctx.device)
+            except Exception as e:                      # peer mapping unavailable on this system
+                import warnings
+                warnings.warn("NVLink halo push unavailable (%s); using the NCCL all-gather" % e)
+            ok = torch.tensor([1.0 if self.channel is not None else 0.0], device=self.ctx.device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)   # all ranks take the same path
+            if float(ok) == 0.0:
+                self.channel = None
 
     def lattice_view(self, S):
         c = self.ctx
         return S[:c.rows * c.pitch].view(c.rows, c.pitch)
 
     def exchange_halo(self, S):
+        if self.channel is not None:
+            self.channel.exchange(self.lattice_view(S), self.ctx.nx_local)
+            return
         halo_exchange(self.lattice_view(S), self.ctx.nx_local, self.slab.halo, self.rank,
                       self.world)
 
     def overlapped(self, S, launch):
-        """Run ``launch()`` (stencil launches that read the state ``S``) with the halo
-        exchange of ``S`` hidden behind the rows that do not need it: the exchange goes to a
-        communication stream, the interior rows [r, nx_local - r) are computed meanwhile on
-        the current stream, the 2*r edge rows afterwards (both strips in one launch group)."""
+        """Run ``launch()`` (stencil launches that read the state ``S``) after refreshing the
+        halo rows of ``S``.  With the NVLink push channel that is simply exchange + launch on
+        one stream.  NCCL fallback: the all-gather goes to a communication stream, the interior
+        rows [r, nx_local - r) are computed meanwhile on the current stream, the 2*r edge rows
+        afterwards (both strips in one launch group)."""
         c, H = self.ctx, self.slab.halo
         if self.world == 1 or H == 0:
+            return launch()
+        if self.channel is not None:
+            # push + wait-copy are two small kernels in stream order; the neighbours push at the
+            # same point of their streams, so the wait is only the ranks' skew: one launch group
+            self.exchange_halo(S)
             return launch()
         if c.nx_local <= 4 * H:
             self.exchange_halo(S)
@@ -124,6 +211,16 @@ class ShardedGrid(object):
         return self.overlapped(S, lambda: self.ctx.d2eigs(S, want_min=out[0] is not None or out[2] is not None,
                                                            want_max=out[1] is not None or out[3] is not None,
                                                            out=out, **kw))
+
+    def d2eigs_host(self, u_host, want_min=True, want_max=True, out=None, chunk_rows=256):
+        """Slab-parallel ``ddg.d2eigs`` VALUES for this rank's flat vector (owned rows, then all
+        wall points) in pinned host memory, results in pinned host memory.  The slab's edge rows
+        are uploaded first and pushed to the neighbours, then H2D copy, stencil kernels and D2H
+        copy are pipelined over row chunks (``GridContext.d2eigs_host``).  Returns
+        (lambda_min, lambda_max) pinned host tensors over the owned rows (None if not wanted)."""
+        hook = self.exchange_halo if self.world > 1 and self.slab.halo else None
+        return self.ctx.d2eigs_host(u_host, want_min=want_min, want_max=want_max,
+                                    chunk_rows=chunk_rows, halo_hook=hook, out=out)
 
     def local_flat(self, fn):
         """Evaluate ``fn(points (n,2) tensor) -> values`` on this rank's points:
@@ -237,6 +334,13 @@ class ShardedGrid(object):
             if ok:
                 self.exchange_halo(D)
                 JD = Jac.matvec_state(D)
+                # the norms of the decrease test are over OWNED rows: the halo rows of D hold the
+                # neighbours' values (they were only needed for J d) and would be counted twice
+                H = self.slab.halo
+                if H:
+                    v = self.lattice_view(D)
+                    v[:H].zero_()
+                    v[H + c.nx_local:].zero_()
                 Un, dmax, gtd, dd = c.newton_update(U, D, F, JD)
                 t = torch.tensor([gtd, dd], dtype=torch.float64, device=c.device)
                 self._allreduce(t)

@@ -21,7 +21,9 @@ def test_defaults_follow_the_contract(monkeypatch):
     monkeypatch.setattr(sys, "argv", ["bench.py"])
     a = b.parse()
     assert a.gpus == 1 and a.impl == "b200" and a.warmup >= 3 and a.steps > 0
-    assert a.n == 4095 and a.radius == 4            # BASELINE configs[1]: 4097^2 lattice, r = 4
+    # 0 = "by GPU count": 4095 (BASELINE configs[1], 4097^2 lattice) on one GPU; on N > 1 GPUs one
+    # 4096 x 32766 slab each (N = 8: the 32768^2 lattice of configs[4]) -- resolved in main()
+    assert a.n == 0 and a.cols == 0 and a.radius == 4
     monkeypatch.setattr(sys, "argv", ["bench.py", "--gpus", "8", "--rows", "4096", "--cols", "32766",
                                       "--steps", "7", "--warmup", "3", "--impl", "reference"])
     a = b.parse()
