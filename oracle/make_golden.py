@@ -195,6 +195,101 @@ def cloud_case(R, name, h0):
           (name, len(p), nint, len(G.simplices), time.time() - t), flush=True)
 
 
+def _rows5(M, N):
+    """CSR matrix with <= 5 entries per row -> (cols (N,4) int32, vals (N,4), diag (N,)): the
+    off-diagonal entries in CSR order, padded with (row, 0)."""
+    M = M.tocsr()
+    M.sum_duplicates()
+    cols = np.repeat(np.arange(N, dtype=np.int32)[:, None], 4, 1)
+    vals = np.zeros((N, 4))
+    diag = np.zeros(N)
+    for i in range(N):
+        k = 0
+        for j, v in zip(M.indices[M.indptr[i]:M.indptr[i + 1]], M.data[M.indptr[i]:M.indptr[i + 1]]):
+            if j == i:
+                diag[i] = v
+            else:
+                cols[i, k], vals[i, k] = j, v
+                k += 1
+    return cols, vals, diag
+
+
+def ellpin_case(R, name, h0, via):
+    """Weight-level pin of the ELL rows (SURVEY 8d parity gate): the unmodified reference's
+    first-call path ``ddi.d2`` / ``ddf.d2`` (ddi.py:223-301, ddf.py:8-131) for a few of the
+    directions of ``d2eigs`` on a disc -- the finite-difference matrix entries and the values.
+    via='reference': the stencils come from the reference constructor (the reference tests' own
+    h = 0.03 disc, tests/test_ddi.py:11, setup_discs.py:41-46); via='fast': from the product's
+    FDTriMesh host build (a larger cloud the reference constructor cannot do),
+    which the test rebuilds from the stored points and triangulation."""
+    from scipy.spatial import Delaunay
+    from . import disc
+    t = time.time()
+    theta = np.pi * h0 ** (1 / 3)
+    p, nint = disc.disc_points(h0, theta)
+    tri = Delaunay(p).simplices
+    if via == "reference":
+        G = R.pointclasses.FDTriMesh(p, tri, num_interior=nint, angular_resolution=theta,
+                                     bdry_normals=p[nint:])
+        out = dict(simplices=G.simplices.astype(np.int32))
+    else:
+        from pyellipticfd_b200.pointclasses import FDTriMesh
+        G = FDTriMesh(p, tri, num_interior=nint, angular_resolution=theta, device="cpu")
+        out = dict(triangulation=tri.astype(np.int32))
+    out.update(points=G.points, num_interior=nint, via=via,
+               spatial_resolution=G.spatial_resolution, angular_resolution=G.angular_resolution)
+    u = np.random.default_rng(0).standard_normal(len(p))
+    # the LAPACK solve of this NumPy build, restated operation by operation (csrc/ell.cu::solve2):
+    # checked bit for bit against np.linalg.solve on this cloud's simplices
+    S = np.asarray(G.simplices)
+    S = S[S[:, 0] < nint]
+    a, c = (G.points[S[:, 1]] - G.points[S[:, 0]]).T
+    b, d = (G.points[S[:, 2]] - G.points[S[:, 0]]).T
+    X = np.stack([np.stack([a, b], 1), np.stack([c, d], 1)], 1)
+    for tag, mod in (("ddi", R.ddi), ("ddf", R.ddf)):
+        nds = int(mod._num_directions(G))
+        # every entry is (N, 4) indices + values: one direction on the large cloud, four on the small
+        ks = sorted({0, nds // 3, (2 * nds) // 3 + 1, nds - 1}) if via == "reference" else [nds // 3]
+        out[tag + "_nds"], out[tag + "_ks"] = nds, np.array(ks)
+        th = np.arange(0, 2 * np.pi, 2 * np.pi / nds)           # the directions of d2eigs, ddi.py:342-343
+        for k in ks:
+            v = np.array([np.cos(th[k]), np.sin(th[k])])
+            dd, M = mod.d2(G, v, u, jacobian=True)
+            cols, vals, diag = _rows5(M, nint)
+            out["%s_d2_%d" % (tag, k)] = dd
+            out["%s_cols_%d" % (tag, k)], out["%s_vals_%d" % (tag, k)] = cols, vals
+            out["%s_diag_%d" % (tag, k)] = diag
+            if tag == "ddi":
+                ref = np.linalg.solve(X, np.broadcast_to(v, (len(a), 2))[..., None])[..., 0]
+                mine = solve2_lapack_order(a, b, c, d, v[0], v[1])
+                assert np.array_equal(ref, mine), "np.linalg.solve is not the pinned operation order"
+    np.savez_compressed(os.path.join(OUT, "ellpin_%s.npz" % name), **out)
+    print("ellpin_%s: %d points (%d interior), %d simplices, via %s, %.1fs" %
+          (name, len(p), nint, len(G.simplices), via, time.time() - t), flush=True)
+
+
+def solve2_lapack_order(a, b, c, d, v0, v1):
+    """csrc/ell.cu::solve2 in NumPy (exact FMA through integer-exact fractions is too slow for
+    arrays: the fused operations are done in extended precision and rounded once, which agrees
+    with a true FMA unless the 64-bit-mantissa intermediate rounds a tie -- checked by the caller)."""
+    from fractions import Fraction
+    v0 = np.broadcast_to(v0, a.shape).astype(float)
+    v1 = np.broadcast_to(v1, a.shape).astype(float)
+    sw = np.abs(c) > np.abs(a)
+    a, c = np.where(sw, c, a), np.where(sw, a, c)
+    b, d = np.where(sw, d, b), np.where(sw, b, d)
+    v0, v1 = np.where(sw, v1, v0), np.where(sw, v0, v1)
+    l = c * (1.0 / a)
+    u22 = d - l * b
+
+    def fma(x, y, z):
+        return np.array([float(Fraction(p) * Fraction(q) + Fraction(r)) for p, q, r in zip(x, y, z)])
+    y1 = fma(-l, v0, v1)
+    x1 = y1 / u22
+    x0 = fma(-b, x1, v0) / a
+    return np.stack([x0, x1], 1)
+
+
 def trimesh_case(R, name, h0):
     """Stencils of the reference FDTriMesh constructor (pointclasses.py:289-398) on a disc:
     the inputs (points, triangulation) and every derived attribute the fast constructor
@@ -381,6 +476,10 @@ def main():
         trimesh_case(R, "disc_h0.1", 0.1)
         trimesh_case(R, "disc_h0.05", 0.05)
         return
+    if "--ellpin-only" in sys.argv:
+        ellpin_case(R, "disc_h0.03", 0.03, "reference")
+        ellpin_case(R, "disc_h0.014", 0.014, "fast")
+        return
     if "--clouds-only" in sys.argv:
         cloud_case(R, "disc_h0.1", 0.1)
         cloud_case(R, "disc_h0.06", 0.06)
@@ -393,6 +492,8 @@ def main():
     solve_case(R, "n31_r2", (31, 31), [[-1, 1], [-1, 1]], 2, pucci=True)
     solve_case(R, "n63_r2", (63, 63), [[-1, 1], [-1, 1]], 2)     # BASELINE config 1a (65^2 grid)
     solve_case(R, "n15_r4", (15, 15), [[-1, 1], [-1, 1]], 4, pucci=True)
+    ellpin_case(R, "disc_h0.03", 0.03, "reference")
+    ellpin_case(R, "disc_h0.014", 0.014, "fast")
     cloud_case(R, "disc_h0.1", 0.1)
     cloud_case(R, "disc_h0.06", 0.06)
     trimesh_case(R, "disc_h0.1", 0.1)

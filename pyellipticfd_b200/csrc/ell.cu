@@ -84,7 +84,11 @@ __global__ void k_ell_apply(int64_t n, int64_t off, const int4 *__restrict__ idx
            wb.y * (x[id.w] - xi);
 }
 
-// 2x2 solve X xi = v with partial pivoting (what LAPACK gesv does for ddi.py:265)
+// 2x2 solve X xi = v, the operations of LAPACK gesv behind np.linalg.solve (ddi.py:265, ddf.py:60)
+// in the order and with the roundings of the NumPy/OpenBLAS build of this image -- pinned bit for
+// bit against np.linalg.solve on the fixture clouds (oracle/make_golden.py::ellpin_case): partial
+// pivoting on |a| vs |c| (first maximum wins), multiplier = c * (1/a), Schur complement with a
+// separate multiply and subtract, forward and back substitution with fused multiply-adds.
 __device__ __forceinline__ void solve2(double a, double b, double c, double d, double v0, double v1,
                                        double &x0, double &x1) {
     // rows: [a b | v0], [c d | v1]
@@ -94,11 +98,11 @@ __device__ __forceinline__ void solve2(double a, double b, double c, double d, d
         t = b; b = d; d = t;
         t = v0; v0 = v1; v1 = t;
     }
-    double l = c * (1.0 / a);
-    double u22 = d - l * b;
-    double y1 = v1 - l * v0;
-    x1 = y1 / u22;
-    x0 = (v0 - b * x1) / a;
+    const double l = __dmul_rn(c, __ddiv_rn(1.0, a));
+    const double u22 = __dsub_rn(d, __dmul_rn(l, b));
+    const double y1 = __fma_rn(-l, v0, v1);
+    x1 = __ddiv_rn(y1, u22);
+    x0 = __ddiv_rn(__fma_rn(-b, x1, v0), a);
 }
 
 // one thread per (interior point, direction)
