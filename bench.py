@@ -62,9 +62,9 @@ def parse():
     ap.add_argument("--radius", type=int, default=4)
     ap.add_argument("--e2e-steps", type=int, default=10)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cloud-h0", type=float, default=0.003,
-                    help="spacing of the unit-disc point cloud of the ddi line (0.003 -> 0.4 M "
-                         "points; 0.00135 -> the 2 M points of BASELINE configs[3])")
+    ap.add_argument("--cloud-h0", type=float, default=0.00135,
+                    help="spacing of the unit-disc point cloud of the ddi line: 0.00135 -> the 2 M "
+                         "points / 164 directions of BASELINE configs[3] (0.003 -> 0.4 M points)")
     ap.add_argument("--solve", type=int, default=255,
                     help="also time convex_envelope.solve on the 65^2 lattice of BASELINE "
                          "configs[0] (Euler and Newton) and Newton on an S^2 interior grid; 0 = skip")
@@ -469,9 +469,13 @@ def pucci_full_size(args):
     Newton with matrix-free BiCGStab): device time of the two kernels a Newton iteration is made
     of -- the fused residual + policy pass (pucci.py:45-58,127-141) and one Jacobi-BiCGStab
     iteration on the two-policy Jacobian A0*M_max + A1*M_min (pucci.py:50-54, solvers.py:179-181).
-    A converged solve is not timed at this size: with wide stencils the reference's Newton loop
-    cycles between policies (the CPU oracle needs 101 iterations without converging at 63^2, r=4;
-    tools/pucci_scaling.py), so its 100-iteration cap would be what is measured."""
+    A converged solve is not timed at this size because the reference's algorithm has none to
+    offer: with wide stencils its Newton loop does not settle -- the CPU oracle (pinned against the
+    unmodified reference) ends on the 100-iteration cap with a residual of order 1 on a 65^2
+    lattice at r = 4 and r = 6 (tests/test_pucci_evidence.py), the same loop on the GPU at 257^2,
+    r = 6 (profiles/r02_pucci_newton_scaling.jsonl: 101 iterations, 45 k BiCGStab iterations,
+    residual 3.0), and a 1025^2, r = 6 run was still iterating after 10 minutes.  With r = 2 the
+    same code converges in 9-12 Newton iterations to the exact solution (1e-15)."""
     import numpy as np
     import torch
     from pyellipticfd_b200.pointclasses import FDRegularGrid
@@ -829,6 +833,7 @@ def main():
         except Exception as e:
             fp64["probe"] = {"error": str(e)[:200]}
         extra = secondary_kernels(args, ctx, S, lmin, n_local, D, pk, dev)
+        both = extra.get("ddg.d2eigs_mode0") if extra else None
         if args.solve:
             import warnings
             from pyellipticfd_b200 import convex_envelope
@@ -960,6 +965,14 @@ def main():
             line["pucci_8193"] = pucci_full
         if world == 1 and extra:
             line["other_kernels"] = extra
+            if both:
+                # SURVEY 8d defines metric 1 on the call the reference always makes: both extremes
+                line["d2eigs_both_extremes"] = {
+                    "value": n_local * D / (both["ms"] * 1e-3) / 1e9, "unit": UNIT,
+                    "ms_per_step": both["ms"], "algorithmic_bytes": both["algorithmic_bytes"],
+                    "roofline_frac": both["hbm_frac"],
+                    "note": "ddg.d2eigs (lambda_min AND lambda_max, 24 B/point) -- what the CPU "
+                            "reference arm computes per step; the headline step is d2min only"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
