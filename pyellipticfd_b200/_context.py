@@ -84,6 +84,11 @@ def pair_weights(PI, PJ0, PJ1):
     return np.ascontiguousarray(w), np.ascontiguousarray(X0)
 
 
+# FDRegularGrid(weights="auto"): lattices with inexact coordinates larger than this many interior
+# points run the structured kernel with nominal per-direction weights
+NOMINAL_ABOVE = 1 << 20
+
+
 class Slab(object):
     """Rows [x_offset, x_offset + nx_local) of the lattice plus ``halo`` rows each side."""
 
@@ -99,12 +104,20 @@ class GridContext(object):
         self.device = require_cuda(device)
         self.G = G
         structured = hasattr(G, "stencil_pairs") and hasattr(G, "band_pairs")
-        if structured and G.uniform_weights():
+        exact = structured and G.uniform_weights()
+        # lattices with inexact coordinates (FDRegularGrid(weights=...)): one weight triple per
+        # direction ("nominal", within the documented tolerance) or explicit per-pair rows
+        mode = getattr(G, "weights", "auto")
+        nominal = structured and not exact and (
+            mode == "nominal" or (mode == "auto" and (G.num_interior > NOMINAL_ABOVE or slab is not None)))
+        if exact or nominal:
             self._init_structured(G, slab)
+            self.weights = "exact" if exact else "nominal"
         else:
             if slab is not None:
-                raise _lib.PdeError("slab decomposition needs a structured, uniformly weighted grid")
+                raise _lib.PdeError("slab decomposition needs a structured grid")
             self._init_generic(G)
+            self.weights = "exact"
         self.pitch = int(self.lib.pde_grid_pitch(self.h))
         self.rows = int(self.lib.pde_grid_rows(self.h))
         self.n_state = int(self.lib.pde_grid_state_len(self.h))

@@ -63,8 +63,11 @@ int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double b
         std::vector<std::pair<double, int64_t>> tmp;
         for (int64_t i = 0; i < nb; ++i) {
             double x = wall[2 * i], y = wall[2 * i + 1];
-            bool on = (L.axis == 0 ? x : y) == L.val;
-            if (L.axis == 1 && (x == 0.0 || x == (double)(nx + 1))) on = false;   // corners once
+            // unscaled wall coordinates carry the rounding of pointclasses.py:538
+            // (4000.9999999999995 for 4001): compare with a tolerance far below the 1/r spacing
+            bool on = std::fabs((L.axis == 0 ? x : y) - L.val) < 1e-6;
+            if (L.axis == 1 && (std::fabs(x) < 1e-6 || std::fabs(x - (double)(nx + 1)) < 1e-6))
+                on = false;                                                        // corners once
             if (on) tmp.emplace_back(L.axis == 0 ? y : x, i);
         }
         std::stable_sort(tmp.begin(), tmp.end(),

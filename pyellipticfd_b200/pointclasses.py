@@ -412,7 +412,20 @@ class FDRegularGrid(FDPointCloud):
                 "and angular resolution {0.angular_resolution:.3g}").format(self)
 
     def __init__(self, interior_shape, bounds, stencil_radius, interpolation=True,
-                 native=True):
+                 native=True, weights="auto"):
+        """``weights`` (extension) chooses the deep-interior arithmetic on lattices whose
+        coordinates are NOT exactly representable (any spacing that is not a power of two), where
+        the reference's per-pair lengths ``h = |x_J - x_I|`` differ by an ulp from point to point:
+        "exact": explicit pair rows with the reference's per-pair weights (bit-exact; needs
+        ~10 GB of host memory per 400 M pair rows and 60x the kernel traffic); "nominal": the
+        structured stencil kernel with ONE weight triple per direction, taken at a deep point
+        (values within 1e-12 * max(|d|, w0 (|du0| w_0 + |du1| w_1)) of the reference, SURVEY
+        7.3-B; band points stay per-pair exact; slab sharding available); "auto" (default):
+        "nominal" above 2^20 interior points, "exact" below.  Exactly representable lattices
+        always run the structured kernel bit-exactly."""
+        if weights not in ("auto", "exact", "nominal"):
+            raise ValueError("weights must be 'auto', 'exact' or 'nominal'")
+        self.weights = weights
         self._native_band = native
         if interpolation:
             raise NotImplementedError(
@@ -714,9 +727,10 @@ class FDRegularGrid(FDPointCloud):
         lists = []
         for axis, val, excl in ((0, 0.0, False), (0, nx + 1.0, False),
                                 (1, 0.0, True), (1, ny + 1.0, True)):
-            m = W[:, axis] == val
+            # unscaled wall coordinates carry the rounding of :538 (4000.9999999999995 for 4001)
+            m = np.abs(W[:, axis] - val) < 1e-6
             if excl:
-                m &= ~((W[:, 0] == 0) | (W[:, 0] == nx + 1))
+                m &= ~((np.abs(W[:, 0]) < 1e-6) | (np.abs(W[:, 0] - (nx + 1)) < 1e-6))
             ids = wid[m]
             t = W[ids, 1 - axis]
             o = np.argsort(t, kind="stable")

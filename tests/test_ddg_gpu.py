@@ -270,3 +270,59 @@ def test_3d_pairs_grid_bitexact():
             assert vmin.shape == (G.num_interior, 3)
     lam, _, _ = ddg.d2min(G, X ** 2 - Y ** 2 + 2 * Z ** 2)
     assert np.abs(lam[np.abs(z["lmin_quad"] + 2) < 1e-9] + 2).max() < 1e-9
+
+
+@pytest.mark.parametrize("n,weights", [(1500, "nominal"), (4000, "auto")])
+def test_inexact_lattice_runs_the_structured_kernel_within_tolerance(n, weights):
+    """[0,1]^2 with n interior points per side, r = 4: the spacing 1/(n+1) is not a power of two,
+    so the reference's per-pair lengths differ by an ulp from point to point.  With
+    FDRegularGrid(weights='nominal') (the default above 2^20 points) the structured kernel K1
+    runs with one weight triple per direction -- no pair rows are materialised -- and agrees with
+    the NumPy restatement of ddg.d2eigs (per-pair weights, ddg.py:274-281) on sampled rows within
+    c * max(|d_ref|, w0 (|du0| w_0 + |du1| w_1)), c = max(1e-12, 8 eps max|x| / h): the size of the
+    coordinate rounding the reference's own weights carry."""
+    import torch
+    from oracle import ddg_oracle
+    from oracle.cpu_baseline import lattice_chunk
+    from pyellipticfd_b200 import ddg
+    from pyellipticfd_b200._context import GridContext
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    r = 4
+    G = FDRegularGrid([n, n], np.array([[0.0, 1.0], [0.0, 1.0]]).T, r, interpolation=False,
+                      weights=weights)
+    assert not G.uniform_weights()
+    ctx = GridContext.get(G)
+    assert ctx.structured and ctx.weights == "nominal" and G._pairs is None
+    x = torch.arange(1, n + 1, device="cuda", dtype=torch.float64) * G.scaling[0]
+    rng = torch.Generator(device="cuda").manual_seed(0)
+    U = torch.empty(G.num_points, dtype=torch.float64, device="cuda")
+    U[:n * n] = (torch.sin(3 * x)[:, None] * torch.cos(2 * x)[None, :]
+                 + 0.1 * torch.randn(n, n, generator=rng, dtype=torch.float64, device="cuda")).reshape(-1)
+    wp = torch.from_numpy(G.bdry_points).cuda()
+    U[n * n:] = torch.sin(3 * wp[:, 0]) * torch.cos(2 * wp[:, 1])
+    (lmin, Mmin, _), (lmax, _, _) = ddg.d2eigs(G, U, jacobian=True)
+    assert G._pairs is None                                    # still not materialised
+    assert float((Mmin.dot(U) - lmin).abs().max()) == 0.0      # rows == operator, bit for bit
+    table = np.asarray(G.stencil_pairs)
+    H = int(np.abs(table).max())
+    u = U[:n * n].view(n, n)
+    c = max(1e-12, 8 * np.finfo(float).eps * 1.0 / G.scaling.min())
+    worst = 0.0
+    for row in (r + H, n // 2, n - r - H - 3):
+        Gc = lattice_chunk(n, r, table, G.scaling, (0.0, 0.0), row, 3)
+        win = u[row - H:row + 3 + H].cpu().numpy()
+        ix, iy = np.meshgrid(np.arange(0, 3 + 2 * H), np.arange(n), indexing="ij")
+        deep = (ix >= H) & (ix < H + 3) & (iy >= r) & (iy < n - r)
+        order = np.concatenate([np.flatnonzero(deep.ravel()), np.flatnonzero(~deep.ravel())])
+        uu = win.ravel()[order]
+        (omin, _, _), (omax, _, _) = ddg_oracle.d2eigs(Gc, uu)
+        I, J = Gc.pairs[:, 0], Gc.pairs[:, 1:]
+        hh = np.linalg.norm(Gc.points[J] - Gc.points[I, None], axis=2)
+        term = (2 / hh.sum(1) * (np.abs(uu[J] - uu[I, None]) / hh).sum(1)).reshape(-1, len(table)).max(1)
+        mine_min = lmin[:n * n].view(n, n)[row:row + 3, r:n - r].cpu().numpy().ravel()
+        mine_max = lmax[:n * n].view(n, n)[row:row + 3, r:n - r].cpu().numpy().ravel()
+        for mine, ref in ((mine_min, omin), (mine_max, omax)):
+            worst = max(worst, (np.abs(mine - ref) / (c * np.maximum(np.abs(ref), term))).max())
+    print("n = %d: max |d - d_ref| / tolerance = %.3f (c = %.2e)" % (n, worst, c))
+    assert worst < 1.0
+    GridContext.drop(G)

@@ -58,3 +58,32 @@ def test_grid_invariants(n, r):
     # deep-interior table: antipodal offsets, each direction once
     sp = G.stencil_pairs
     assert np.array_equal(sp[:, :2], -sp[:, 2:]) and len({tuple(x) for x in sp[:, :2]}) == len(sp)
+
+
+import pytest
+
+
+@pytest.mark.parametrize("nx,ny,r,bounds", [
+    (12, 13, 1, [[0, 0], [0.37 * 13 / 8, 0.61 * 14 / 8]]),     # wall coordinate 13.999999999999998
+    (7, 13, 1, [[0, 0], [1.0, 0.61 * 14 / 8]]),
+    (40, 40, 2, [[0, 0], [1, 1]]),
+    (23, 31, 3, [[0.1, -0.3], [1.3, 0.77]])])
+def test_rounded_wall_coordinates_against_the_brute_force_restatement(nx, ny, r, bounds):
+    """Lattices whose unscaled wall coordinates carry rounding (pointclasses.py:538 gives
+    4000.9999999999995 for 4001 on [0,1]^2 with n = 4000): the wall lists of the fast constructor
+    must still find those points -- pair sets equal to oracle/grid_oracle.py (pinned against the
+    reference constructor), native builder and NumPy specification alike."""
+    from oracle import grid_oracle
+    b = np.array(bounds, dtype=float)
+    ref = grid_oracle.build([nx, ny], b, r)
+
+    def canon(P):
+        return sorted((int(a),) + tuple(sorted((int(x), int(y)))) for a, x, y in P)
+    for native in (True, False):
+        G = FDRegularGrid([nx, ny], b, r, interpolation=False, native=native)
+        assert canon(G.pairs) == canon(ref["pairs"])
+
+
+def test_large_inexact_lattice_builds():
+    G = FDRegularGrid([4000, 4000], np.array([[0.0, 1.0], [0.0, 1.0]]).T, 4, interpolation=False)
+    assert not G.uniform_weights() and G._pairs is None and G.band_pairs.shape[0] > 2_000_000
