@@ -290,6 +290,46 @@ def solve2_lapack_order(a, b, c, d, v0, v1):
     return np.stack([x0, x1], 1)
 
 
+def helpers_case(R):
+    """The public module-level helpers of pointclasses.py (:12-121) and stencils.stern_brocot
+    (stencils.py:6-23): inputs (a neighbour list) and the reference's outputs."""
+    from scipy.spatial import Delaunay
+    from . import disc
+    h0 = 0.12
+    th = np.pi * h0 ** (1 / 3)
+    p, nint = disc.disc_points(h0, th)
+    Gr = R.pointclasses.FDTriMesh(p, Delaunay(p).simplices, num_interior=nint, angular_resolution=th)
+    D = np.linalg.norm(p[:, None] - p[None], axis=2)
+    i, j = np.nonzero((D <= 0.8 * Gr.max_radius) & (D > 0))
+    allnb = np.stack([i, j], 1)
+    out = dict(points=p, num_interior=nint, angular_resolution=th, neighbours_in=allnb.astype(np.int32),
+               spatial_resolution=Gr.spatial_resolution, bdry_resolution=Gr.bdry_resolution,
+               dist_to_bdry=Gr.dist_to_bdry, min_dist_to_bdry=Gr.min_dist_to_bdry,
+               maximum_bdry_res=Gr.maximum_bdry_res)
+    O = R.pointclasses.FDPointCloud(p, angular_resolution=th, num_interior=nint,
+                                    spatial_resolution=Gr.spatial_resolution)
+    for prefer in ("min", "max"):
+        O.neighbours = allnb
+        R.pointclasses.remove_colinear_neighbours(O, 1 - np.cos(th / 8), prefer=prefer)
+        out["neighbours_" + prefer] = O.neighbours.astype(np.int32)
+    R.pointclasses.compute_simplices(O)                       # on the prefer="max" list
+    out["simplices_max"] = O.simplices.astype(np.int32)
+    out["adjacency_nnz"] = O.adjacency.nnz
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    G = FDRegularGrid([7, 8], np.array([[0, 0], [1.0, 1.3]]), 2, interpolation=False)
+    nb = np.asarray(G.neighbours)
+    nb = nb[np.lexsort((nb[:, 1], nb[:, 0]))]
+    Q = R.pointclasses.FDPointCloud(G.points, num_interior=G.num_interior)
+    Q.neighbours = nb
+    R.pointclasses.compute_pairs(Q, 1e-3)
+    out.update(grid_points=G.points, grid_num_interior=G.num_interior, grid_neighbours=nb.astype(np.int32),
+               grid_pairs=Q.pairs.astype(np.int32))
+    for N in (1, 2, 4):
+        out["stern_brocot_%d" % N] = R.stencils.stern_brocot(N)
+    np.savez_compressed(os.path.join(OUT, "helpers.npz"), **out)
+    print("helpers: %d points, %d candidate neighbours" % (len(p), len(allnb)), flush=True)
+
+
 def trimesh_case(R, name, h0):
     """Stencils of the reference FDTriMesh constructor (pointclasses.py:289-398) on a disc:
     the inputs (points, triangulation) and every derived attribute the fast constructor
@@ -476,6 +516,9 @@ def main():
         trimesh_case(R, "disc_h0.1", 0.1)
         trimesh_case(R, "disc_h0.05", 0.05)
         return
+    if "--helpers-only" in sys.argv:
+        helpers_case(R)
+        return
     if "--ellpin-only" in sys.argv:
         ellpin_case(R, "disc_h0.03", 0.03, "reference")
         ellpin_case(R, "disc_h0.014", 0.014, "fast")
@@ -499,6 +542,7 @@ def main():
     trimesh_case(R, "disc_h0.1", 0.1)
     trimesh_case(R, "disc_h0.05", 0.05)
     d1_case(R)
+    helpers_case(R)
     ddg3d_case(R)
     grid3d_case(R, "n4x5x6_r2", (4, 5, 6), [[0, 1], [0, 1], [0, 1]], 2, solve=False)
     grid3d_case(R, "n6_r2", (6, 6, 6), [[-1, 1], [-1, 1], [-1, 1]], 2)

@@ -90,6 +90,25 @@ class EllTable(object):
         except Exception:
             pass
 
+    # ---- the pieces of GridContext the solvers use (solvers.NewtonEulerLS, newton_state,
+    # euler_state): point clouds work on the reference's flat vectors, so pack / unpack only
+    # move the vector to the device
+    def n_flat(self):
+        return self.n_points
+
+    def pack(self, u):
+        return to_device(u, self.device).to(torch.float64).clone()
+
+    def unpack(self, S):
+        return S
+
+    def newton_update(self, U, D, F, JD):
+        Unew = torch.empty_like(U)
+        out = (C.c_double * 3)()
+        check(self.lib.pde_ell_newton_update(self.h, _ptr(U), _ptr(D), _ptr(F), _ptr(JD),
+                                             _ptr(Unew), out, _stream()))
+        return Unew, float(out[0]), float(out[1]), float(out[2])
+
     def d2eigs(self, u, want_k=False):
         N, dev = self.N, self.device
         lmin = torch.empty(N, dtype=torch.float64, device=dev)
@@ -305,19 +324,7 @@ class EllJacobian(object):
 
 
 def _problem_table(G, module_name, nds, froese):
-    table = cached_table(G, module_name, nds, froese)
-    # duck-type the pieces of GridContext that solvers.newton_state / euler_state use
-    if not hasattr(table, "n_flat"):
-        table.n_flat = lambda: table.n_points
-
-        def newton_update(U, D, F, JD):
-            Unew = torch.empty_like(U)
-            out = (C.c_double * 3)()
-            check(table.lib.pde_ell_newton_update(table.h, _ptr(U), _ptr(D), _ptr(F), _ptr(JD),
-                                                  _ptr(Unew), out, _stream()))
-            return Unew, float(out[0]), float(out[1]), float(out[2])
-        table.newton_update = newton_update
-    return table
+    return cached_table(G, module_name, nds, froese)
 
 
 def residual(table, W, g, mode, A=(0.0, 0.0), policy=True):
@@ -361,8 +368,7 @@ def ce_solve(G, g, U0, solver, module_name, nds, froese, stats=None, **kwargs):
         Us, diff, iters = solvers.euler_state(table, Us, euler_res, dt, sol, opt,
                                               kwargs.get("max_iters"), kwargs.get("timeout"))
         return like_input(proto, Us), diff, iters, time.time() - t0
-    for k in ("plotter", "max_euler_iters"):
-        kwargs.pop(k, None)
+    solvers.drop_unsupported(kwargs)
 
     def res(U, jacobian):
         F, kmin, _, red = residual(table, U, gs, 0, policy=jacobian)
@@ -445,8 +451,7 @@ def pucci_solve(G, f, g, A, U0, solver, module_name, nds, froese, stats=None, **
         Us, diff, iters = solvers.euler_state(table, Us, euler_res, dt, sol, opt,
                                               kwargs.get("max_iters"), kwargs.get("timeout"))
         return like_input(proto, Us), diff, iters, time.time() - t0
-    for k in ("plotter", "max_euler_iters"):
-        kwargs.pop(k, None)
+    solvers.drop_unsupported(kwargs)
 
     def fallback(U, timeout):
         U, diff, _ = solvers.euler_state(table, U, euler_res, dt, sol, opt, 10 * n, timeout)

@@ -85,8 +85,7 @@ def _solve_grid(Grid, g, U0, solver, stats=None, **kwargs):
         return solvers.euler(U0f, G, **kwargs)
 
     elif solver == "newton":
-        for k in ("plotter", "max_euler_iters"):
-            kwargs.pop(k, None)
+        solvers.drop_unsupported(kwargs)
 
         def residual(U, jacobian):
             F, P, red = ctx.ce_residual(U, gs, policy=jacobian)

@@ -38,6 +38,83 @@ from . import stencils
 COLINEAR_TOL = 1e-3          # pointclasses.py:577
 
 
+def _rows_by_centre(I):
+    """CSR pointer of a neighbour list grouped by ascending centre index."""
+    I = np.asarray(I)
+    if (np.diff(I) < 0).any():
+        raise ValueError("the neighbour list must be grouped by ascending centre point")
+    return I
+
+
+def compute_pairs(PointCloud, colinear_tol):
+    """Antipodal pairs of every interior point's stencil (pointclasses.py:12-35): neighbour
+    pairs (k < l in list order) whose unit vectors have cos < -1 + colinear_tol.  Sets
+    ``PointCloud.pairs`` (rows ``(i, J_k, J_l)``); TypeError "Point i has no pairs"."""
+    I, J, Vs = _rows_by_centre(PointCloud._I), PointCloud._J, PointCloud._Vs
+    out = []
+    for i in PointCloud.interior:
+        lo, hi = np.searchsorted(I, [i, i + 1])
+        vs, nb = Vs[lo:hi], J[lo:hi]
+        k, l = np.nonzero(np.triu(vs.dot(vs.T) < -1 + colinear_tol))
+        if k.size == 0:
+            raise TypeError("Point {0} has no pairs".format(i))
+        out.append(np.column_stack([np.full(k.size, i), nb[k], nb[l]]))
+    PointCloud.pairs = np.concatenate(out)
+
+
+def remove_colinear_neighbours(PointCloud, colinear_tol, prefer="min"):
+    """Strip colinear neighbours from every stencil (pointclasses.py:37-103): of two neighbours
+    whose cosine distance is below ``colinear_tol`` the farther one goes (``prefer='min'``; the
+    nearer one with ``prefer='max'``; the first of the two on a tie); a boundary neighbour is
+    re-admitted unless it lost against an interior one.  Sets ``PointCloud.neighbours``."""
+    if prefer not in ("min", "max"):
+        raise ValueError("prefer must be 'min' or 'max'")
+    I, J = _rows_by_centre(PointCloud._I), PointCloud._J
+    V = PointCloud._V
+    D = np.linalg.norm(V, axis=1)
+    N = PointCloud.num_interior
+    out = []
+    for i in range(PointCloud.num_points):
+        lo, hi = np.searchsorted(I, [i, i + 1])
+        nb, v, d = J[lo:hi], V[lo:hi], D[lo:hi]
+        nv = nb.size
+        keep = np.ones(nv, bool)
+        if nv > 1:
+            c = v.dot(v.T) / np.outer(d, d)
+            k, l = np.nonzero(np.triu(1 - c < colinear_tol, 1))
+            if k.size:
+                first_loses = d[k] >= d[l] if prefer == "min" else d[k] <= d[l]
+                loser = np.where(first_loses, k, l)
+                keep[loser] = False
+                isb = nb >= N
+                mixed = isb[k] != isb[l]
+                lost_mixed = np.zeros(nv, bool)
+                lost_mixed[loser[mixed]] = True
+                keep |= isb & ~lost_mixed
+        out.append(np.column_stack([np.full(int(keep.sum()), i), nb[keep]]))
+    PointCloud.neighbours = np.concatenate(out)
+
+
+def compute_simplices(PointCloud):
+    """Simplices for the interpolating finite differences (pointclasses.py:105-121): the facets of
+    the convex hull of every stencil's unit vectors.  In 2-D every unit vector is a hull vertex,
+    so the facets are the consecutive neighbours in angular order; in higher dimension Qhull
+    (``ConvexHull(vs, qhull_options="QJ")`` like the reference).  Sets ``PointCloud.simplices``."""
+    I, J, Vs = _rows_by_centre(PointCloud._I), PointCloud._J, PointCloud._Vs
+    out = []
+    for i in range(PointCloud.num_points):
+        lo, hi = np.searchsorted(I, [i, i + 1])
+        nb, vs = J[lo:hi], Vs[lo:hi]
+        if PointCloud.dim == 2:
+            ring = nb[np.argsort(np.arctan2(vs[:, 1], vs[:, 0]), kind="stable")]
+            facets = np.stack([ring, np.roll(ring, -1)], 1)
+        else:
+            from scipy.spatial import ConvexHull
+            facets = nb[ConvexHull(vs, qhull_options="QJ").simplices]
+        out.append(np.column_stack([np.full(facets.shape[0], i), facets]))
+    PointCloud.simplices = np.concatenate(out)
+
+
 class FDPointCloud(object):
     """Base container (pointclasses.py:123-285): interior points first."""
 
@@ -118,6 +195,48 @@ class FDPointCloud(object):
     def min_radius(self):
         h, th = self.spatial_resolution, self.angular_resolution
         return h * (-1 + self.Cd / np.sin(th / 2))
+
+    @property
+    def min_dist_to_bdry(self):
+        """Smallest admissible distance of interior points to the boundary (:272-275)."""
+        d1 = self.Cd * self.bdry_resolution / np.tan(self.angular_resolution / 2)
+        return np.min([self.min_radius, d1])
+
+    @property
+    def maximum_bdry_res(self):
+        """Maximum allowable boundary resolution, given the angular resolution (:277-280)."""
+        return self.dist_to_bdry * np.tan(self.angular_resolution / 2) / self.Cd
+
+    @property
+    def adjacency(self):
+        """Adjacency matrix of each point and its neighbours (:239-244)."""
+        from scipy.sparse import coo_matrix
+        nb = np.asarray(self.neighbours)
+        n = self.num_points
+        return coo_matrix((np.ones(nb.shape[0], dtype=np.intp), (nb[:, 0], nb[:, 1])),
+                          shape=(n, n), dtype=np.intp).tocsr()
+
+    # the reference keeps the neighbour list as private vectors (:215-237); the module-level
+    # helpers below (compute_pairs, remove_colinear_neighbours, compute_simplices) read them
+    @property
+    def _I(self):
+        return np.asarray(self.neighbours)[:, 0]
+
+    @property
+    def _J(self):
+        return np.asarray(self.neighbours)[:, 1]
+
+    @property
+    def _V(self):
+        return self.points[self._J] - self.points[self._I]
+
+    @property
+    def _VDist(self):
+        return np.linalg.norm(self._V, axis=1)
+
+    @property
+    def _Vs(self):
+        return self._V / self._VDist[:, None]
 
     @property
     def min_interior_nb_dist(self):
@@ -224,24 +343,6 @@ class FDTriMesh(FDPointCloud):
         self.graph_depth = max(depth, 1)
         self.colinear_tol = 1 - np.cos(angular_resolution / 8)               # :395
         self._build_stencils(device)
-
-    @property
-    def min_dist_to_bdry(self):
-        d1 = self.Cd * self.bdry_resolution / np.tan(self.angular_resolution / 2)
-        return np.min([self.min_radius, d1])
-
-    @property
-    def maximum_bdry_res(self):
-        return self.dist_to_bdry * np.tan(self.angular_resolution / 2) / self.Cd
-
-    @property
-    def adjacency(self):
-        """Adjacency matrix of each point and its (current) neighbours (:239-244)."""
-        from scipy.sparse import coo_matrix
-        nb = self.neighbours
-        n = self.num_points
-        return coo_matrix((np.ones(nb.shape[0], dtype=np.intp), (nb[:, 0], nb[:, 1])),
-                          shape=(n, n), dtype=np.intp).tocsr()
 
     # -- the native stencil search -------------------------------------------------------------
     def _build_stencils(self, device=None):

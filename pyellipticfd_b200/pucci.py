@@ -132,8 +132,7 @@ def _solve_grid(Grid, f, g, A, U0, solver, stats=None, **kwargs):
                                               kwargs.get("max_iters"), kwargs.get("timeout"))
         return like_input(proto, ctx.unpack(Us)), diff, iters, time.time() - t0
     elif solver == "newton":
-        for k in ("plotter", "max_euler_iters"):
-            kwargs.pop(k, None)
+        solvers.drop_unsupported(kwargs)
 
         def euler_fallback(U, timeout):
             U, diff, _ = solvers.euler_state(ctx, U, euler_residual, dt, sol, opt,

@@ -108,9 +108,12 @@ def NewtonEulerLS(U, operator, solution_tol=1e-6, operator_tol=1e-6, max_iters=1
         try:
             tstart = time.time()
             Gu, Jac, _ = operator(U, jacobian=True)
-            if not isinstance(Jac, PolicyJacobian):
-                raise TypeError("NewtonEulerLS needs a device PolicyJacobian from the operator; "
-                                "pyellipticfd_b200 has no CPU linear solver")
+            # any device Jacobian of this package: regular grids (linop.PolicyJacobian, state
+            # layout) or point clouds (_ell.EllJacobian, the reference's flat vectors)
+            if not (hasattr(Jac, "bicgstab_state") and hasattr(Jac, "matvec_state")
+                    and hasattr(getattr(Jac, "ctx", None), "newton_update")):
+                raise TypeError("NewtonEulerLS needs a device Jacobian (PolicyJacobian / EllJacobian) "
+                                "from the operator; pyellipticfd_b200 has no CPU linear solver")
             ctx = Jac.ctx
             B = ctx.pack(Gu)
             B.neg_()
@@ -150,6 +153,17 @@ def NewtonEulerLS(U, operator, solution_tol=1e-6, operator_tol=1e-6, max_iters=1
         elif i >= max_iters:
             warn("Maximum iterations reached")
             return U, diff, i + 1, time.time() - t0
+
+
+def drop_unsupported(kwargs, names=("plotter", "max_euler_iters", "zeromean", "zeromax")):
+    """Solver keywords of the reference that the device-resident loops of ``*.solve`` do not
+    implement are dropped LOUDLY (``plotter`` needs the host copy of every iterate,
+    ``max_euler_iters`` is overridden by the reference itself, solvers.py:166; ``zeromean`` /
+    ``zeromax`` exist in solvers.euler only)."""
+    for k in names:
+        if kwargs.pop(k, None):
+            warn("solver keyword %r is not supported by the device-resident loop and is ignored; "
+                 "use solvers.NewtonEulerLS / solvers.euler with an operator closure for it" % k)
 
 
 class _Fallback(Exception):

@@ -13,6 +13,18 @@ import math
 import numpy as np
 
 
+def stern_brocot(N):
+    """Stern-Brocot tree of depth N (stencils.py:6-23): rows (p, q) from (1, 0) to (0, 1), every
+    level inserting the mediant between neighbours."""
+    sb = np.array([[1, 0], [1, 1], [0, 1]], dtype=np.intp)
+    for _ in range(1, N):
+        new = np.empty((2 * sb.shape[0] - 1, 2), dtype=np.intp)
+        new[0::2] = sb
+        new[1::2] = sb[:-1] + sb[1:]
+        sb = new
+    return sb
+
+
 def create_nd(r, n):
     if r < 1:
         raise ValueError('r must be positive')

@@ -126,3 +126,33 @@ def test_first_derivative_errors():
     c3 = FDPointCloud(np.zeros((4, 3)), num_interior=2)
     with pytest.raises(NotImplementedError):             # ddi.py:157-158
         ddi.d1grad(c3, np.zeros(4))
+
+
+def test_public_helpers_match_the_reference():
+    """pointclasses.compute_pairs / remove_colinear_neighbours / compute_simplices (:12-121),
+    the FDPointCloud properties adjacency / min_dist_to_bdry / maximum_bdry_res (:239-280) and
+    stencils.stern_brocot (stencils.py:6-23) against outputs of the unmodified reference
+    (tests/golden/helpers.npz, oracle/make_golden.py::helpers_case)."""
+    import os
+    from pyellipticfd_b200 import pointclasses as PC, stencils
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "helpers.npz"))
+    for N in (1, 2, 4):
+        assert np.array_equal(stencils.stern_brocot(N), z["stern_brocot_%d" % N])
+    th = float(z["angular_resolution"])
+    O = PC.FDPointCloud(z["points"], angular_resolution=th, num_interior=int(z["num_interior"]),
+                        spatial_resolution=float(z["spatial_resolution"]),
+                        bdry_resolution=float(z["bdry_resolution"]), dist_to_bdry=float(z["dist_to_bdry"]))
+    assert O.min_dist_to_bdry == float(z["min_dist_to_bdry"])
+    assert O.maximum_bdry_res == float(z["maximum_bdry_res"])
+    for prefer in ("min", "max"):
+        O.neighbours = z["neighbours_in"].astype(np.int64)
+        PC.remove_colinear_neighbours(O, 1 - np.cos(th / 8), prefer=prefer)
+        assert np.array_equal(O.neighbours, z["neighbours_" + prefer])
+    assert O.adjacency.nnz == int(z["adjacency_nnz"]) and O.adjacency.shape == (O.num_points,) * 2
+    PC.compute_simplices(O)
+    canon = lambda S: sorted((int(a),) + tuple(sorted((int(b), int(c)))) for a, b, c in S)
+    assert canon(O.simplices) == canon(z["simplices_max"])       # facet orientation is Qhull's own
+    Q = PC.FDPointCloud(z["grid_points"], num_interior=int(z["grid_num_interior"]))
+    Q.neighbours = z["grid_neighbours"].astype(np.int64)
+    PC.compute_pairs(Q, 1e-3)
+    assert np.array_equal(Q.pairs, z["grid_pairs"])

@@ -313,3 +313,23 @@ def test_ell_weights_against_the_reference_matrices(path, tag):
         assert worst_w <= 1e-12
     else:                                   # see GATE_C: Froese's formula amplifies libm ulps
         assert worst_w <= 1e-11 and above <= 0.005 * max(entries, 1) + 4 * N * len(ks) * 0.005
+
+
+@pytest.mark.parametrize("fd", ["interpolate", "froese"])
+def test_public_newton_with_a_cloud_operator(fd):
+    """The reference workflow solvers.NewtonEulerLS(U0, G) with a user-built operator closure
+    (convex_envelope.py:107,120-123) on a point cloud: the operator returns an EllJacobian."""
+    from pyellipticfd_b200 import convex_envelope, solvers
+    from oracle.make_golden import two_cones
+    z = np.load(CLOUD[0])
+    G = cloud_of(z)
+    g = two_cones(G.points)
+    dt = convex_envelope.cfl_dt(G)
+
+    def op(W, jacobian=True):
+        F, J = convex_envelope.operator(G, W, g, jacobian=jacobian, fdmethod=fd)
+        return F, J, dt
+    U, diff, it, _ = solvers.NewtonEulerLS(g.copy(), op, solution_tol=1e-10)
+    tag = "ddi" if fd == "interpolate" else "ddf"
+    assert isinstance(U, np.ndarray) and abs(it - int(z[tag + "_ce_iters"])) <= 2
+    assert np.abs(U - z[tag + "_ce_U"]).max() < 1e-8
