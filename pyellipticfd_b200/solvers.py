@@ -202,12 +202,18 @@ def euler_state(ctx, U, residual, dt, solution_tol=1e-6, operator_tol=1e-6, max_
 
 def newton_state(ctx, U, residual, euler_fallback, solution_tol=1e-6, operator_tol=1e-6,
                  max_iters=1e2, euler_ratio=1, verbose=False, force_euler=False, stats=None,
-                 bicgstab_check_every=32, krylov_rtol=None, trace=None):
+                 bicgstab_check_every=32, krylov_rtol=None, krylov_restarts=0, trace=None):
     """NewtonEulerLS (solvers.py:168-233) on state tensors.
 
     ``residual(U, jacobian) -> (F_state, PolicyJacobian|None, max|F|)``;
     ``euler_fallback(U, timeout) -> (U, diff)`` runs Euler steps for at most
-    ``timeout`` seconds.  ``stats`` (dict) collects iteration counts."""
+    ``timeout`` seconds.  ``stats`` (dict) collects iteration counts.
+
+    Extensions (defaults = the reference's behaviour): ``krylov_rtol`` replaces the reference's
+    ``min(operator_tol, solution_tol)`` as the relative tolerance of the linear solves;
+    ``krylov_restarts = k`` restarts BiCGStab up to k times on the current residual when it
+    leaves on a breakdown (SciPy's info -10 / -11, which the reference accepts as a solve,
+    solvers.py:186-187: it only tests ``info > 0``) before its tolerance is met."""
     if euler_ratio <= 0:
         raise ValueError('euler_ratio must be positive')
     rho, p = 0.5, 2
@@ -224,11 +230,26 @@ def newton_state(ctx, U, residual, euler_fallback, solution_tol=1e-6, operator_t
         B = -F
         # reference: tol = min(operator_tol, solution_tol) (solvers.py:181); `krylov_rtol`
         # is an extension for fine grids where a 1e-6 linear solve lets the active set chatter
-        D, info, kit = Jac.bicgstab_state(
-            B, rtol=min(operator_tol, solution_tol) if krylov_rtol is None else krylov_rtol,
-            check_every=bicgstab_check_every)
+        rtol = min(operator_tol, solution_tol) if krylov_rtol is None else krylov_rtol
+        D, info, kit = Jac.bicgstab_state(B, rtol=rtol, check_every=bicgstab_check_every)
         krylov_total += kit
-        if trace is not None:
+        if krylov_restarts and info < 0:
+            target = rtol * float(torch.linalg.vector_norm(B))
+            for _ in range(int(krylov_restarts)):
+                R = B - Jac.matvec_state(D)
+                if float(torch.linalg.vector_norm(R)) <= target:
+                    info = 0
+                    break
+                dD, info, k2 = Jac.bicgstab_state(R, rtol=0.0, atol=target,
+                                                  check_every=bicgstab_check_every)
+                D += dD
+                krylov_total += k2
+                kit += k2
+                if info == 0:
+                    break
+        if callable(trace):
+            trace(i, float(fmax), kit, info)
+        elif trace is not None:
             trace.append((i, float(fmax), kit, info))
         newtontime = time.time() - tstart
         timeout = euler_ratio * newtontime

@@ -136,3 +136,31 @@ def test_generic_solver_api():
     assert np.abs(U - z["newton_U"]).max() < 1e-6
     with pytest.raises(ValueError):
         solvers.NewtonEulerLS(np.copy(g), op, euler_ratio=0)
+
+
+def test_policy_iteration_with_tight_restarted_linear_solves():
+    """Why the reference's policy iteration stops converging on fine grids, and the opt-in
+    remedy: with the reference's linear-solve tolerance min(tols) = 1e-6 the number of Newton
+    iterations grows with the lattice (the 513^2 lattice does not finish within the reference's
+    cap of 100) and BiCGStab often leaves on a breakdown that the reference accepts
+    (solvers.py:186-187 only tests info > 0).  With ``krylov_rtol=1e-10`` and
+    ``krylov_restarts`` the same loop converges well inside the cap (1025^2: 120 iterations,
+    profiles/r02_policy_iteration.md)."""
+    import warnings
+    from pyellipticfd_b200 import convex_envelope
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    from oracle.make_golden import two_cones
+    G = FDRegularGrid([511, 511], np.array([[-1.0, 1.0], [-1.0, 1.0]]).T, 4, interpolation=False)
+    g = two_cones(G.points)
+    st = {}
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        U0, d0, it0, _ = convex_envelope.solve(G, g, fdmethod="grid", solver="newton")
+    assert it0 == 101 and any("Maximum iterations" in str(x.message) for x in w)
+    U, diff, it, _ = convex_envelope.solve(G, g, fdmethod="grid", solver="newton", stats=st,
+                                           krylov_rtol=1e-10, krylov_restarts=30)
+    assert it < 80 and diff < 1e-6 and st["residual"] < 1e-6
+    F = convex_envelope.operator(G, U, g, jacobian=False, fdmethod="grid")[0]
+    assert np.abs(F).max() < 1e-6
+    Us, _, _, _ = convex_envelope.solve(G, g, fdmethod="grid", solver="sweep")
+    assert np.abs(U - Us).max() < 1e-6            # the sweep solver ends on the same solution

@@ -10,6 +10,8 @@ r = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 KW = {}
 if os.environ.get("KRYLOV_RTOL"):
     KW["krylov_rtol"] = float(os.environ["KRYLOV_RTOL"])
+if os.environ.get("KRYLOV_RESTARTS"):
+    KW["krylov_restarts"] = int(os.environ["KRYLOV_RESTARTS"])
 if os.environ.get("MAX_ITERS"):          # the reference's cap is 100 (solvers.py:100)
     KW["max_iters"] = int(os.environ["MAX_ITERS"])
 sizes = [int(s) for s in sys.argv[2:]] or [63, 127, 255, 511]
@@ -22,8 +24,12 @@ for n in sizes:
     torch.cuda.synchronize()
     t = time.time()
     tr = []
+    if os.environ.get("TRACE") == "live":
+        t00 = time.time()
+        tr = lambda i, fmax, kit, info: print("  it %d  max|F| %.3e  krylov %d  info %d  t %.1fs"
+                                              % (i, fmax, kit, info, time.time() - t00), flush=True)
     U, diff, it, _ = convex_envelope._solve_grid(G, g, None, "newton", stats=st, trace=tr, **KW)
-    if os.environ.get("TRACE"):
+    if os.environ.get("TRACE") and not callable(tr):
         print([(a, "%.2e" % b, c, d) for a, b, c, d in tr][:60])
     torch.cuda.synchronize()
     dt = time.time() - t
