@@ -821,7 +821,7 @@ def main():
         try:
             probe = {}
             for kind, name in ((1, "dadd_per_s"), (2, "dmul_per_s"), (3, "cmpsel_per_s"),
-                               (4, "exact_pairs_per_s")):
+                               (4, "exact_pairs_per_s"), (5, "dsetp_independent_per_s")):
                 _lib.check(_lib.lib().pde_fp64_probe(local, kind, ctypes.byref(v)))
                 probe[name] = v.value
             fp64["probe"] = probe

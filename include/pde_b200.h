@@ -434,7 +434,8 @@ int pde_fp64_peak(int device, double *h_dfma_per_s);
  * 256 threads per SM): kind 1 DADD, 2 DMUL, 3 compare-select (DSETP + 2 FSEL) -- units/s = thread
  * instructions per second; kind 4 = the exact pair formula of ddg.py:281 plus the min update on
  * register operands (units/s = pairs per second): the speed of light of the reference's
- * operation order, which K1 is compared against in bench.py. */
+ * operation order, which K1 is compared against in bench.py; kind 5 = independent DSETP (the
+ * predicate feeds an integer select + add: no fp64 select, no dependency between compares). */
 int pde_fp64_probe(int device, int kind, double *h_units_per_s);
 
 #ifdef __cplusplus

@@ -61,9 +61,13 @@ __global__ void k_dfma_chain(double *out, int iters) {
 //           instructions per pair) on register operands perturbed by one integer op each,
 //           i.e. K1's inner loop without shared-memory traffic: the arithmetic speed of
 //           light of the reference's operation order.
+//   kind 5: INDEPENDENT fp64 compares: DSETP on two register operands (one perturbed by an
+//           integer op), the predicate consumed by an integer select + add -- no fp64 select,
+//           no dependency between compares: the issue rate of DSETP alone.
 template <int KIND>
 __global__ void k_fp64_probe(double *out, int iters) {
     double a[8], m[8];
+    int cnt[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int p = 0; p < 8; ++p) {
         a[p] = 1.0 + threadIdx.x * 1e-6 + p * 1e-3;
@@ -79,6 +83,13 @@ __global__ void k_fp64_probe(double *out, int iters) {
                 double d = __hiloint2double(__double2hiint(a[p]), __double2loint(a[p]) ^ i);
                 m[p] = d <= m[p] ? d : m[p];
             }
+            if (KIND == 5) {
+                double d = __hiloint2double(__double2hiint(a[p]), __double2loint(a[p]) ^ i);
+                int q;
+                asm volatile("{ .reg .pred t; setp.lt.f64 t, %1, %2; selp.s32 %0, 1, 0, t; }"
+                             : "=r"(q) : "d"(d), "d"(a[(p + 1) & 7]));
+                cnt[p] += q;
+            }
             if (KIND == 4) {
                 int hi = __double2hiint(a[p]), lo = __double2loint(a[p]);
                 double u0 = __hiloint2double(hi, lo ^ i), u1 = __hiloint2double(hi, lo + i);
@@ -89,7 +100,7 @@ __global__ void k_fp64_probe(double *out, int iters) {
     }
     double s = 0;
 #pragma unroll
-    for (int p = 0; p < 8; ++p) s += a[p] + m[p];
+    for (int p = 0; p < 8; ++p) s += a[p] + m[p] + cnt[p];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
@@ -147,7 +158,7 @@ int pde_fp64_peak(int device, double *h_dfma_per_s) {
 }
 
 int pde_fp64_probe(int device, int kind, double *h_units_per_s) {
-    PDE_REQUIRE(h_units_per_s && kind >= 1 && kind <= 4, "bad argument");
+    PDE_REQUIRE(h_units_per_s && kind >= 1 && kind <= 5, "bad argument");
     DeviceGuard guard(device);
     cudaDeviceProp prop;
     PDE_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -164,6 +175,7 @@ int pde_fp64_probe(int device, int kind, double *h_units_per_s) {
             case 1: k_fp64_probe<1><<<blocks, threads>>>(out, iters); break;
             case 2: k_fp64_probe<2><<<blocks, threads>>>(out, iters); break;
             case 3: k_fp64_probe<3><<<blocks, threads>>>(out, iters); break;
+            case 5: k_fp64_probe<5><<<blocks, threads>>>(out, iters); break;
             default: k_fp64_probe<4><<<blocks, threads>>>(out, iters); break;
         }
         pde::count_launch();
