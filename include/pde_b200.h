@@ -74,6 +74,18 @@ int pde_grid_create(pde_grid **out, int device,
                     const int64_t *h_band_j /* P x 2 : state offsets of J0, J1 */,
                     const double *h_band_w /* P x 3 : w_0, w_1, w0 */,
                     const double *h_band_X /* P x 2 : points[J0]-points[I] */);
+/* 3-D regular pairs grid (the 3-D stencils of stencils.py:46-61 behind the dimension-agnostic
+ * ddg.d2eigs, ddg.py:251-292): lattice [nx][ny][nz] = h_shape, stored as nx*ny state-layout rows
+ * of nz columns, so every other entry point (pack/unpack, d2eigs, residuals, Euler, Jacobian
+ * rows, BiCGStab) applies unchanged.  Deep points: D antipodal offset pairs
+ * (a0,b0,c0,a1,b1,c1) with per-direction weights, evaluated by the 3-D TMA kernel (stencil
+ * halo 1 or 2, D <= PDE_MAX_DIRS); band points: explicit rows as in pde_grid_create. */
+int pde_grid_create_nd(pde_grid **out, int device, int dim /* 3 */,
+                       const int64_t *h_shape /* dim */, int64_t nb, int stencil_radius,
+                       int D, const int32_t *h_stencil_pairs /* D x 2*dim */,
+                       const double *h_stencil_w /* D x 3 */,
+                       int64_t n_band, const int64_t *h_band_center, const int64_t *h_band_ptr,
+                       const int64_t *h_band_j /* P x 2 */, const double *h_band_w /* P x 3 */);
 int pde_grid_destroy(pde_grid *g);
 /* Restrict the following stencil launches (pde_ddg_d2eigs, pde_ce_residual,
  * pde_ce_euler_step, pde_pucci_residual) to owned rows [row_lo, row_hi); wall entries

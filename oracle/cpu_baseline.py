@@ -91,6 +91,54 @@ def time_d2eigs(ny, r, table, scaling, b0, rows_per_worker=24, workers=None, rep
                        % (workers, rows_per_worker, ny - 2 * r, prs, what))
 
 
+def _work_steps(args):
+    """One worker of ``time_d2eigs_steps``: builds its row chunk once, then times every one of the
+    ``nsteps`` calls of d2eigs on it."""
+    ny, r, table, scaling, b0, row_lo, nrows, nsteps, seed, impl = args
+    d2eigs = operator(impl)
+    G = lattice_chunk(ny, r, np.asarray(table), np.asarray(scaling), np.asarray(b0), row_lo, nrows)
+    u = np.random.default_rng(seed).standard_normal(G.num_points)
+    d2eigs(G, u)                                  # page faults, imports
+    dts = []
+    for _ in range(nsteps):
+        t = time.perf_counter()
+        d2eigs(G, u)
+        dts.append(time.perf_counter() - t)
+    return G.num_interior, len(G.pairs), dts
+
+
+def time_d2eigs_steps(ny, r, table, scaling, b0, workers, steps, warmup, impl, budget_s=150.0,
+                      max_rows=32):
+    """``warmup + steps`` timed steps for ``bench.py --impl reference``: every step is one call of
+    d2eigs per worker process on that worker's chunk of deep rows (all workers at once, one per
+    core).  The chunk height is chosen from a calibration call so that the whole run takes about
+    ``budget_s`` seconds (2..max_rows rows per worker).  Step time = the slowest worker's."""
+    table = np.asarray(table)
+    H = int(np.abs(table).max())
+    cal = time_d2eigs(ny, r, table, scaling, b0, 4, workers, 1, impl)      # 4 rows per worker
+    per_row = cal["seconds"] / 4.0
+    rows = int(budget_s / max(steps + warmup, 1) / per_row)
+    rows = max(2, min(max_rows, rows))
+    args = [(ny, r, table, tuple(scaling), tuple(b0), r + H + w * rows, rows, warmup + steps, w, impl)
+            for w in range(workers)]
+    if workers == 1:
+        res = [_work_steps(args[0])]
+    else:
+        with mp.get_context("fork").Pool(workers) as pool:
+            res = pool.map(_work_steps, args)
+    pts = sum(x[0] for x in res)
+    prs = sum(x[1] for x in res)
+    step_s = [max(x[2][k] for x in res) for k in range(warmup, warmup + steps)]
+    what = ("the unmodified reference's ddg.d2eigs" if impl == "reference"
+            else "NumPy port of ddg.d2eigs")
+    mean = sum(step_s) / len(step_s)
+    return dict(points_per_s=pts / mean, pairs_per_s=prs / mean, cores=workers, seconds=mean,
+                step_seconds_min=min(step_s), step_seconds_max=max(step_s), steps=steps,
+                warmup=warmup, kind=impl,
+                sample="%d workers x %d deep rows x %d cols (%d pairs) per step, %s"
+                       % (workers, rows, ny - 2 * r, prs, what))
+
+
 def time_ddi_cached(idx, w, u, nds):
     """The reference's cached ddi.d2eigs path (ddi.py:358-367): Nds SciPy CSR mat-vecs
     (5 nnz per row) followed by an argsort of the (N, Nds) array.  ``idx``/``w`` hold the
@@ -125,7 +173,7 @@ def time_ddi_cached(idx, w, u, nds):
 
 
 def main(argv=None):
-    """``python -m oracle.cpu_baseline NY R ROWS_PER_WORKER WORKERS REPS [IMPL]`` on a unit-square
+    """``python -m oracle.cpu_baseline NY R ROWS_PER_WORKER WORKERS REPS [IMPL [STEPS WARMUP]]`` on a unit-square
     dyadic lattice; prints one JSON line.  IMPL = reference | port | auto (reference when the
     tree or its copy under oracle/_ref is there).  bench.py runs this in a fresh (CUDA-free)
     process so that the worker pool can fork safely.  The direction table comes from
@@ -142,7 +190,11 @@ def main(argv=None):
         impl = "reference" if reference_available() else "port"
     table = grid_oracle.stencil_table(r)
     h = 1.0 / (ny + 1)
-    out = time_d2eigs(ny, r, table, (h, h), (0.0, 0.0), rows, workers, reps, impl)
+    if len(a) > 7:                             # ... STEPS WARMUP: the --impl reference arm
+        out = time_d2eigs_steps(ny, r, table, (h, h), (0.0, 0.0), workers, int(a[6]), int(a[7]),
+                                impl, max_rows=rows)
+    else:
+        out = time_d2eigs(ny, r, table, (h, h), (0.0, 0.0), rows, workers, reps, impl)
     out["D"] = int(table.shape[0])
     if impl == "reference" and ratio:
         # the port on ONE worker's sample beside it: per-core ratio of the two CPU arms

@@ -87,6 +87,10 @@ def pair_weights(PI, PJ0, PJ1):
 # FDRegularGrid(weights="auto"): lattices with inexact coordinates larger than this many interior
 # points run the structured kernel with nominal per-direction weights
 NOMINAL_ABOVE = 1 << 20
+# 3-D lattices run the structured 3-D kernel (False: explicit pair rows for every point, the
+# round-1 path; kept for tests that compare the two)
+ND_STRUCTURED = True
+MAX_DIRS = 64                 # PDE_MAX_DIRS of include/pde_b200.h
 
 
 class Slab(object):
@@ -104,13 +108,23 @@ class GridContext(object):
         self.device = require_cuda(device)
         self.G = G
         structured = hasattr(G, "stencil_pairs") and hasattr(G, "band_pairs")
+        # 3-D lattices: table-driven kernel when the table fits (halo <= 2, D <= 64)
+        structured_nd = (ND_STRUCTURED and slab is None and hasattr(G, "stencil_pairs_nd")
+                         and hasattr(G, "band_pairs") and getattr(G, "dim", 2) == 3
+                         and 1 <= G.halo <= 2 and len(G.stencil_pairs_nd) <= MAX_DIRS
+                         and G.num_deep > 0)
+        structured = structured or structured_nd
         exact = structured and G.uniform_weights()
         # lattices with inexact coordinates (FDRegularGrid(weights=...)): one weight triple per
         # direction ("nominal", within the documented tolerance) or explicit per-pair rows
         mode = getattr(G, "weights", "auto")
         nominal = structured and not exact and (
             mode == "nominal" or (mode == "auto" and (G.num_interior > NOMINAL_ABOVE or slab is not None)))
-        if exact or nominal:
+        self.nd = False
+        if (exact or nominal) and structured_nd:
+            self._init_structured_nd(G)
+            self.weights = "exact" if exact else "nominal"
+        elif exact or nominal:
             self._init_structured(G, slab)
             self.weights = "exact" if exact else "nominal"
         else:
@@ -195,6 +209,75 @@ class GridContext(object):
                      bw, bX)
         self.band_pairs = bp
         self.structured = True
+
+    def _init_structured_nd(self, G):
+        """3-D lattice [nx][ny][nz] as nx*ny state-layout rows of nz columns
+        (``pde_grid_create_nd``): deep points through the 3-D table kernel, band points as
+        explicit rows.  Point ids, policies and the flat vectors are the reference's."""
+        nx, ny, nz = G.interior_shape
+        dim, r, N = 3, G.stencil_radius, G.num_interior
+        pitch = (nz + 15) // 16 * 16
+        rows = nx * ny
+        sp = np.ascontiguousarray(G.stencil_pairs_nd, dtype=np.int32)
+        c = np.full((1, dim), r + 1.0)
+        w, X0 = pair_weights(np.repeat(G._scaled(c), len(sp), 0), G._scaled(c + sp[:, :dim]),
+                             G._scaled(c + sp[:, dim:]))
+        self.stencil_X_nd = X0                      # (D, 3) physical vector of the first neighbour
+        bi = np.asarray(G.band_index, dtype=np.int64)
+        bp = np.asarray(G.band_pairs, dtype=np.int64)
+
+        def offs(ids):
+            ids = np.asarray(ids, dtype=np.int64)
+            return np.where(ids < N, (ids // nz) * pitch + ids % nz, rows * pitch + (ids - N))
+
+        bw, bX = pair_weights(G.coords(bp[:, 0]), G.coords(bp[:, 1]), G.coords(bp[:, 2]))
+        self.band_X_full = bX
+        shape = np.array([nx, ny, nz], dtype=np.int64)
+        band_center = np.ascontiguousarray(offs(bi))
+        band_ptr = np.ascontiguousarray(G.band_ptr, dtype=np.int64)
+        band_j = np.ascontiguousarray(np.stack([offs(bp[:, 1]), offs(bp[:, 2])], 1)
+                                      if len(bp) else np.zeros((0, 2), np.int64))
+        w = np.ascontiguousarray(w)
+        h = vp()
+        check(self.lib.pde_grid_create_nd(
+            C.byref(h), self.device.index, dim, _np_ptr(shape), G.num_bdry, r, sp.shape[0],
+            _np_ptr(sp), _np_ptr(w), bi.shape[0], _np_ptr(band_center), _np_ptr(band_ptr),
+            _np_ptr(band_j), _np_ptr(bw)))
+        self.h = h
+        self.slab = Slab(0, rows, 0)
+        self.nx_global, self.ny, self.nb = rows, int(nz), int(G.num_bdry)
+        self.x_offset, self.nx_local, self.halo_rows = 0, rows, 0
+        self.radius = int(r)
+        self.n_interior_local = N
+        self.stencil_pairs = sp
+        self.band_ptr = band_ptr
+        self.n_band = bi.shape[0]
+        self.band_pairs = bp
+        self.band_global = bi
+        self.band_sel = np.arange(bi.shape[0])
+        self.structured = True
+        self.nd = True
+
+    def deep_pair_weights(self):
+        """(w_0, w_1, w0) of every row of the deep table, at a generic deep point."""
+        G, sp = self.G, self.stencil_pairs
+        dim = sp.shape[1] // 2
+        c = np.full((1, dim), self.radius + 1.0)
+        w, _ = pair_weights(np.repeat(G._scaled(c), len(sp), 0), G._scaled(c + sp[:, :dim]),
+                            G._scaled(c + sp[:, dim:]))
+        return w
+
+    def deep_neighbours(self, deep_ids, rows):
+        """Global point ids (J0, J1) of table rows ``rows`` applied at the deep points
+        ``deep_ids`` (flat interior ids of this context's lattice)."""
+        sp = self.stencil_pairs[rows].astype(np.int64)
+        if self.nd:
+            nx, ny, nz = self.G.interior_shape
+            stride = np.array([ny * nz, nz, 1], dtype=np.int64)
+            return (deep_ids + (sp[:, :3] * stride).sum(1), deep_ids + (sp[:, 3:] * stride).sum(1))
+        ny = self.ny
+        di, dj = deep_ids // ny, deep_ids % ny
+        return ((di + sp[:, 0]) * ny + dj + sp[:, 1], (di + sp[:, 2]) * ny + dj + sp[:, 3])
 
     def _init_generic(self, G):
         """Any object with ``pairs``, ``points``, ``num_interior`` (e.g. a grid built
@@ -481,7 +564,7 @@ class GridContext(object):
         ``g``) towards the convex-envelope solution until one sweep changes no value by ``tol``
         or more.  ``relax_every``: direction passes between band relaxations (0: once per
         sweep).  Returns (U, last change, sweeps)."""
-        if not self.structured or self.halo_rows or self.nx_local != self.nx_global:
+        if not self.structured or self.nd or self.halo_rows or self.nx_local != self.nx_global:
             raise _lib.PdeError("the sweep solver needs a structured, unsharded 2-D pairs grid")
         if not hasattr(self, "_sweep"):
             from . import _sweep
@@ -568,15 +651,8 @@ class GridContext(object):
             isband[self.band_global - self.x_offset * ny] = True
             deep = np.flatnonzero(~isband)
             gid = deep + self.x_offset * ny
-            sp = self.stencil_pairs[pol[deep]]
-            di, dj = gid // ny, gid % ny
-            J0[deep] = (di + sp[:, 0]) * ny + dj + sp[:, 1]
-            J1[deep] = (di + sp[:, 2]) * ny + dj + sp[:, 3]
-            c = np.array([[self.radius + 1.0] * 2])
-            w, _ = pair_weights(np.repeat(G._scaled(c), len(self.stencil_pairs), 0),
-                                G._scaled(c + self.stencil_pairs[:, 0:2]),
-                                G._scaled(c + self.stencil_pairs[:, 2:4]))
-            W[deep] = w[pol[deep]]
+            J0[deep], J1[deep] = self.deep_neighbours(gid, pol[deep])
+            W[deep] = self.deep_pair_weights()[pol[deep]]
             bl = self.band_global - self.x_offset * ny
             rows = self.band_ptr[:-1] + pol[bl]
             bp = self.band_pairs[rows]

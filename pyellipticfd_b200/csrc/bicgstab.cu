@@ -37,8 +37,7 @@ k_rows(const GridDev G, const __grid_constant__ DeepTable tab, Op op, double *pa
             int64_t lr = br - G.halo_rows;
             if (lr >= 0 && lr < G.nx_local) {
                 int64_t gx = lr + G.x_offset;
-                bool deep_row = gx >= G.radius && gx < G.nx_global - G.radius;
-                if (deep_row) {
+                if (deep_row(G, gx)) {
                     const int64_t base = br * G.pitch;
                     const int c1 = (int)G.ny - G.radius;
                     for (int c = G.radius + threadIdx.x; c < c1; c += PASS_THREADS)
@@ -279,7 +278,7 @@ static int launch_rows(pde_grid *g, const Op &op, double *partials, const BicgSc
                        cudaStream_t st, int *nblocks_out = nullptr) {
     GridDev G = grid_dev(g);
     if constexpr (Op::kTiled) {
-        if (g->tab.D > 0 && g->tab.H >= 1 && g->tab.H <= 6 && jac_tiled_enabled() &&
+        if (g->tab.D > 0 && g->nmid == 0 && g->tab.H >= 1 && g->tab.H <= 6 && jac_tiled_enabled() &&
             (reinterpret_cast<uintptr_t>(op.source()) & 15) == 0) {      // TMA: 16-byte aligned base
             // deep-interior points: TMA-tiled kernel; band points and wall entries: the tail
             // blocks of the plain kernel, their partial sums appended after the tiled CTAs'

@@ -67,6 +67,11 @@ struct pde_grid {
     int radius;                  // stencil radius r: deep = [r, n-r) on both axes
     pde::DeepTable tab;
     int ct_id;                   // index of the matching compile-time table, or -1
+    // 3-D lattices (pde_grid_create_nd): [nx3][nmid][ny] stored as nx3*nmid rows; the table's
+    // row offsets a0/a1 are flattened (a*nmid + b), nd_abc keeps the (a,b,c | a',b',c') triples
+    int64_t nmid, nx3;           // 0, 0 for 2-D lattices
+    int ct3_id;                  // matching compile-time 3-D table, or -1
+    int nd_abc[PDE_MAX_DIRS][6];
     double stencil_X[PDE_MAX_DIRS][2];  // physical vector of (a0,b0)
     // band (CSR over band points owned by this context)
     int64_t n_band, n_band_pairs;

@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <type_traits>
 #include "stencil_deep.cuh"
+#include "stencil_deep3.cuh"
 #include "tiles.cuh"
 
 using namespace pde;
@@ -150,10 +151,74 @@ static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *
     return 0;
 }
 
+// ---- 3-D lattices: bricks staged by 3-D TMA loads (stencil_deep3.cuh) -----------------------
+template <class Eval, int H, int MODE, class Epi>
+static int launch_deep3_h(pde_grid *g, const double *S, const Epi &epi, double *red,
+                          const unsigned long long *done, cudaStream_t st) {
+    constexpr int P = 8;
+    using T = Deep3Tile<H, P>;
+    const int r = g->radius;
+    Deep3Geom geo;
+    geo.pitch = g->pitch;
+    geo.ny = (int)g->nmid;
+    geo.x0 = geo.y0 = geo.z0 = r;
+    geo.nxd = (int)g->nx3 - 2 * r;
+    geo.nyd = (int)g->nmid - 2 * r;
+    geo.nzd = (int)g->ny - 2 * r;
+    if (geo.nxd <= 0 || geo.nyd <= 0 || geo.nzd <= 0) return 0;
+    PDE_REQUIRE(g->win_lo == 0 && g->win_hi == g->nx_local, "row windows are not available in 3-D");
+    geo.tiles_x = (geo.nxd + T::TX - 1) / T::TX;
+    geo.tiles_y = (geo.nyd + K3_TY - 1) / K3_TY;
+    geo.tiles_z = (geo.nzd + K3_TZ - 1) / K3_TZ;
+    Deep3Offsets offs;
+    for (int k = 0; k < g->tab.D; ++k) {
+        const int *q = g->nd_abc[k];
+        offs.off0[k] = q[0] * T::SX + q[1] * T::SY + q[2];
+        offs.off1[k] = q[3] * T::SX + q[4] * T::SY + q[5];
+    }
+    PDE_REQUIRE((reinterpret_cast<uintptr_t>(S) & 15) == 0, "state buffer must be 16-byte aligned");
+    CUtensorMap tmap;
+    cuuint64_t gdim[3] = {(cuuint64_t)g->ny, (cuuint64_t)g->nmid, (cuuint64_t)g->nx3};
+    cuuint64_t gstr[2] = {(cuuint64_t)g->pitch * 8, (cuuint64_t)g->nmid * g->pitch * 8};
+    cuuint32_t box[3] = {(cuuint32_t)T::TZH, (cuuint32_t)T::TYH, (cuuint32_t)T::TXH};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult cr = g->encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double *>(S), gdim,
+                            gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (cr != CUDA_SUCCESS) return pde::fail("cuTensorMapEncodeTiled (3-D) failed", __FILE__, __LINE__);
+    auto kern = k_deep3<Eval, H, P, MODE, Epi>;
+    static unsigned long long attr_set = 0ull;
+    const unsigned long long dev_bit = 1ull << (g->device & 63);
+    if (!(attr_set & dev_bit)) {
+        PDE_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, T::SMEM));
+        attr_set |= dev_bit;
+    }
+    int ntiles = geo.tiles_x * geo.tiles_y * geo.tiles_z;
+    int grid = std::min(ntiles, g->num_sms * 2);
+    kern<<<grid, K3_THREADS, T::SMEM, st>>>(tmap, g->tab, offs, geo, epi, red, done);
+    PDE_LAUNCH_CHECK();
+    return 0;
+}
+
+template <int MODE, class Epi>
+static int launch_deep3(pde_grid *g, const double *S, const Epi &epi, double *red,
+                        const unsigned long long *done, cudaStream_t st) {
+    static const bool force_rt = getenv("PDE_K3_RUNTIME") && atoi(getenv("PDE_K3_RUNTIME")) != 0;
+    if (!force_rt) {
+        if (g->ct3_id == 0) return launch_deep3_h<EvalCt3<0>, 1, MODE, Epi>(g, S, epi, red, done, st);
+        if (g->ct3_id == 1) return launch_deep3_h<EvalCt3<1>, 2, MODE, Epi>(g, S, epi, red, done, st);
+    }
+    if (g->tab.H == 1) return launch_deep3_h<EvalRuntime3, 1, MODE, Epi>(g, S, epi, red, done, st);
+    if (g->tab.H == 2) return launch_deep3_h<EvalRuntime3, 2, MODE, Epi>(g, S, epi, red, done, st);
+    return pde::fail("unsupported 3-D stencil halo", __FILE__, __LINE__);
+}
+
 template <int MODE, class Epi>
 static int launch_deep(pde_grid *g, const double *S, const Epi &epi, double *red,
                        const unsigned long long *done, cudaStream_t st) {
     if (g->tab.D == 0) return 0;
+    if (g->nmid > 0) return launch_deep3<MODE, Epi>(g, S, epi, red, done, st);
     if constexpr (std::is_same<Epi, EpiEigs<true, false, false>>::value && MODE == 0) {
         // tuning switch for the benchmark kernel (r = 4, d2min values): PDE_K1_VARIANT
         static const int variant = getenv("PDE_K1_VARIANT") ? atoi(getenv("PDE_K1_VARIANT")) : 0;

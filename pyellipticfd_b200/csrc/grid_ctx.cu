@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "stencil_ct.cuh"
+#include "stencil_ct3.cuh"
 
 namespace pde {
 
@@ -139,6 +140,7 @@ int pde_grid_create(pde_grid **out, int device, int64_t nx_global, int64_t ny, i
     }
     g->tab.H = H;
     g->ct_id = -1;
+    g->ct3_id = -1;
     for (int t = 0; t < pde::CT_NUM_TABLES && g->ct_id < 0; ++t) {
         if (pde::CT_TABLE_D[t] != D) continue;
         bool same = true;
@@ -193,6 +195,53 @@ int pde_grid_create(pde_grid **out, int device, int64_t nx_global, int64_t ny, i
     }
     g->encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(fn);
     *out = g;
+    return 0;
+}
+
+// 3-D lattice [nx][ny][nz] (stencils.py:46-61): stored as nx*ny state-layout rows of nz
+// columns, so that every per-point array, the band rows and the Krylov passes are those of the
+// 2-D case; deep points are served by the 3-D TMA kernel (stencil_deep3.cuh).
+int pde_grid_create_nd(pde_grid **out, int device, int dim, const int64_t *h_shape, int64_t nb,
+                       int stencil_radius, int D, const int32_t *h_stencil_pairs /* D x 6 */,
+                       const double *h_stencil_w, int64_t n_band, const int64_t *h_band_center,
+                       const int64_t *h_band_ptr, const int64_t *h_band_j, const double *h_band_w) {
+    PDE_REQUIRE(out && h_shape, "null argument");
+    PDE_REQUIRE(dim == 3, "structured n-D lattices: dim = 3 only");
+    PDE_REQUIRE(D >= 1 && D <= PDE_MAX_DIRS, "D out of range");
+    const int64_t nx = h_shape[0], ny = h_shape[1], nz = h_shape[2];
+    PDE_REQUIRE(nx > 0 && ny > 0 && nz > 0 && nx * ny < (1ll << 31), "bad lattice shape");
+    int H = 0;
+    for (int k = 0; k < 6 * D; ++k) H = max(H, abs(h_stencil_pairs[k]));
+    PDE_REQUIRE(H >= 1 && H <= 2 && H <= stencil_radius, "3-D stencil halo must be 1 or 2");
+    // band rows carry 2-D control vectors in the 2-D ABI; none in 3-D (host side, ddg.py)
+    std::vector<double> zeroX((size_t)(n_band ? h_band_ptr[n_band] : 0) * 2 + 2, 0.0);
+    int rc = pde_grid_create(out, device, nx * ny, nz, nb, stencil_radius, 0, nx * ny, 0, 0, nullptr,
+                             nullptr, nullptr, n_band, h_band_center, h_band_ptr, h_band_j, h_band_w,
+                             zeroX.data());
+    if (rc) return rc;
+    pde_grid *g = *out;
+    g->nmid = ny;
+    g->nx3 = nx;
+    g->tab.D = D;
+    g->tab.H = H;
+    for (int k = 0; k < D; ++k) {
+        const int32_t *q = h_stencil_pairs + 6 * k;
+        for (int j = 0; j < 6; ++j) g->nd_abc[k][j] = q[j];
+        g->tab.a0[k] = q[0] * (int)ny + q[1];      // row offset in the flattened (x, y) index
+        g->tab.b0[k] = q[2];
+        g->tab.a1[k] = q[3] * (int)ny + q[4];
+        g->tab.b1[k] = q[5];
+        g->tab.w_0[k] = h_stencil_w[3 * k + 0];
+        g->tab.w_1[k] = h_stencil_w[3 * k + 1];
+        g->tab.w0[k] = h_stencil_w[3 * k + 2];
+    }
+    for (int t = 0; t < pde::CT3_NUM_TABLES && g->ct3_id < 0; ++t) {
+        if (pde::CT3_TABLE_D[t] != D) continue;
+        bool same = true;
+        for (int k = 0; k < D && same; ++k)
+            for (int j = 0; j < 6; ++j) same = same && pde::CT3_TABLES[t][k][j] == h_stencil_pairs[6 * k + j];
+        if (same) g->ct3_id = t;
+    }
     return 0;
 }
 

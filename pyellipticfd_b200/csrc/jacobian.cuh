@@ -23,6 +23,7 @@ struct GridDev {
     int64_t pitch, rows, ny, nb;
     int64_t halo_rows, x_offset, nx_global, nx_local;
     int radius;
+    int64_t nmid, nx3;          // 3-D lattices: rows = nx3 * nmid (0, 0 in 2-D)
     int64_t n_band;
     const int64_t *band_center, *band_ptr, *band_j;
     const double *band_w;
@@ -39,6 +40,8 @@ inline GridDev grid_dev(const pde_grid *g) {
     d.nx_global = g->nx_global;
     d.nx_local = g->nx_local;
     d.radius = g->radius;
+    d.nmid = g->nmid;
+    d.nx3 = g->nx3;
     d.n_band = g->n_band;
     d.band_center = g->d_band_center;
     d.band_ptr = g->d_band_ptr;
@@ -67,15 +70,14 @@ __device__ __forceinline__ void row_entries(double w_0, double w_1, double w0, d
     Ac = __dmul_rn(w0, __dadd_rn(-w_0, -w_1));
 }
 
-// classify a lattice entry (buffer row br, column c): 0 = not owned / padding,
-// 1 = deep interior, 2 = band
-__device__ __forceinline__ int classify(const GridDev &G, int64_t br, int64_t c) {
-    int64_t lr = br - G.halo_rows;
-    if (c >= G.ny || lr < 0 || lr >= G.nx_local) return 0;
-    int64_t gx = lr + G.x_offset;
-    bool deep = gx >= G.radius && gx < G.nx_global - G.radius && c >= G.radius &&
-                c < G.ny - G.radius;
-    return deep ? 1 : 2;
+// is global lattice row gx a row of deep-interior points (columns [radius, ny - radius))?
+// 2-D: rows [r, nx - r); 3-D: row = ix * nmid + iy with both ix and iy r away from the walls
+__device__ __forceinline__ bool deep_row(const GridDev &G, int64_t gx) {
+    if (G.nmid > 0) {
+        int64_t ix = gx / G.nmid, iy = gx - ix * G.nmid;
+        return ix >= G.radius && ix < G.nx3 - G.radius && iy >= G.radius && iy < G.nmid - G.radius;
+    }
+    return gx >= G.radius && gx < G.nx_global - G.radius;
 }
 
 // (J x)_o for a deep-interior point

@@ -17,7 +17,7 @@ __global__ void k_control(const GridDev G, const __grid_constant__ DeepTable tab
         int64_t lr = br - G.halo_rows;
         if (lr < 0 || lr >= G.nx_local) return;
         int64_t gx = lr + G.x_offset;
-        if (!(gx >= G.radius && gx < G.nx_global - G.radius)) return;
+        if (!deep_row(G, gx)) return;
         for (int64_t c = threadIdx.x; c < G.ny; c += blockDim.x) {
             if (c < G.radius || c >= G.ny - G.radius) continue;
             int64_t o = br * G.pitch + c;
@@ -111,6 +111,7 @@ extern "C" {
 int pde_ddg_control(pde_grid *g, const uint16_t *d_pmin, const uint16_t *d_pmax, double *d_vmin,
                     double *d_vmax, void *stream) {
     PDE_REQUIRE(g && d_pmin && d_pmax && d_vmin && d_vmax, "null argument");
+    PDE_REQUIRE(g->nmid == 0, "pde_ddg_control serves 2-D lattices");
     DeviceGuard guard(g->device);
     cudaStream_t st = (cudaStream_t)stream;
     double *sX = nullptr;

@@ -29,7 +29,8 @@ def _pinned_host(u):
 
 def _require_pairs(G):
     # structured grids answer without touching `pairs` (a lazily materialised property there)
-    if not hasattr(G, "stencil_pairs") and getattr(G, "pairs", None) is None:
+    if (not hasattr(G, "stencil_pairs") and not hasattr(G, "stencil_pairs_nd")
+            and getattr(G, "pairs", None) is None):
         raise TypeError('The grid was has no finite difference pairs. '
                         'Construct the grid with "interpolation=False"')
 
@@ -45,7 +46,7 @@ def d2eigs(G, u, jacobian=False, control=False):
     _require_pairs(G)
     ctx = GridContext.get(G)
     need_policy = jacobian or control
-    if _pinned_host(u) and not need_policy and ctx.structured and ctx.nx_local >= 1024:
+    if _pinned_host(u) and not need_policy and ctx.structured and not ctx.nd and ctx.nx_local >= 1024:
         lo, hi = ctx.d2eigs_host(u, mode=ARITHMETIC_MODE)      # pipelined over row chunks
         return (lo, None, None), (hi, None, None)
     S = ctx.pack(u)
@@ -70,12 +71,17 @@ def _control_nd(ctx, pmin, pmax):
     (ddg.py:297-300, quirk Q1 replicated), gathered on the host from the selected rows."""
     kmin = ctx.unpad_policy(pmin).cpu().numpy().astype(np.int64)
     kmax = ctx.unpad_policy(pmax).cpu().numpy().astype(np.int64)
-    rows_min, rows_max = ctx.band_ptr[:-1] + kmin, ctx.band_ptr[:-1] + kmax
     X = ctx.band_X_full
-    h = np.linalg.norm(X[rows_min], axis=1)
+    if ctx.nd:       # structured 3-D: deep points index the direction table, band points their rows
+        bl = ctx.band_global
+        Xmin, Xmax = ctx.stencil_X_nd[kmin % len(ctx.stencil_X_nd)], ctx.stencil_X_nd[kmax % len(ctx.stencil_X_nd)]
+        Xmin[bl], Xmax[bl] = X[ctx.band_ptr[:-1] + kmin[bl]], X[ctx.band_ptr[:-1] + kmax[bl]]
+    else:
+        Xmin, Xmax = X[ctx.band_ptr[:-1] + kmin], X[ctx.band_ptr[:-1] + kmax]
+    h = np.linalg.norm(Xmin, axis=1)
     w = (1 / h)[:, None]
     dev = ctx.device
-    return torch.from_numpy(X[rows_min] * w).to(dev), torch.from_numpy(X[rows_max] * w).to(dev)
+    return torch.from_numpy(Xmin * w).to(dev), torch.from_numpy(Xmax * w).to(dev)
 
 
 def _one_extreme(G, u, which, jacobian=False, control=False):
@@ -85,7 +91,7 @@ def _one_extreme(G, u, which, jacobian=False, control=False):
         return d2eigs(G, u, jacobian=jacobian, control=True)[which]
     _require_pairs(G)
     ctx = GridContext.get(G)
-    if _pinned_host(u) and not jacobian and ctx.structured and ctx.nx_local >= 1024:
+    if _pinned_host(u) and not jacobian and ctx.structured and not ctx.nd and ctx.nx_local >= 1024:
         lo, hi = ctx.d2eigs_host(u, want_min=(which == 0), want_max=(which == 1),
                                  mode=ARITHMETIC_MODE)
         return (lo if which == 0 else hi), None, None
@@ -128,9 +134,10 @@ def _aligned_policy(G, ctx, v):
         isband[ctx.band_global] = True
         deep = np.flatnonzero(~isband)
         sp = ctx.stencil_pairs
-        c = np.array([[ctx.radius + 1.0] * 2])
-        X0 = G._scaled(c + sp[:, 0:2]) - G._scaled(c)
-        X1 = G._scaled(c + sp[:, 2:4]) - G._scaled(c)
+        dim = sp.shape[1] // 2
+        c = np.array([[ctx.radius + 1.0] * dim])
+        X0 = G._scaled(c + sp[:, :dim]) - G._scaled(c)
+        X1 = G._scaled(c + sp[:, dim:]) - G._scaled(c)
         s = score(X0[None], X1[None], v[deep][:, None, :])
         pol[deep] = np.argmax(s, axis=1)
         bp = ctx.band_pairs

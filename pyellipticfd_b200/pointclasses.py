@@ -504,6 +504,31 @@ def _prune_and_pair(V, valid, is_bdry, tol=COLINEAR_TOL):
     return keep, pair
 
 
+def _deep_table_nd(dim, r, scaling, bounds0):
+    """Translation-invariant pair table of the deep points of a ``dim``-dimensional lattice:
+    (stencil_offsets (K, dim), stencil_pairs (D, 2*dim) int32).  Canonical row order (this
+    module's own; it only matters for exact ties): every pair is oriented so that the last
+    non-zero component of its first vector is positive, and the rows are sorted by the reversed
+    component tuple -- pairs that share the offsets along all axes but the first are adjacent,
+    which lets the structured kernels evaluate them from one register window."""
+    offs = np.stack(np.meshgrid(*[np.arange(-r, r + 1)] * dim, indexing="ij"), -1).reshape(-1, dim)
+    offs = offs[(offs != 0).any(axis=1)]
+    c = np.full(dim, r + 1.0)
+    V = (c + offs) * scaling + bounds0 - (c * scaling + bounds0)
+    keep, pair = _prune_and_pair(V[None], np.ones((1, len(offs)), bool),
+                                 np.zeros((1, len(offs)), bool))
+    k, l = np.nonzero(pair[0])
+    sp = np.concatenate([offs[k], offs[l]], axis=1).astype(np.int32)
+    first = sp[:, :dim]
+    # sign of the last non-zero component of the first vector
+    nz = first != 0
+    last = dim - 1 - np.argmax(nz[:, ::-1], axis=1)
+    flip = first[np.arange(len(sp)), last] < 0
+    sp[flip] = np.concatenate([sp[flip][:, dim:], sp[flip][:, :dim]], axis=1)
+    order = np.lexsort(tuple(sp[:, d] for d in range(dim)))
+    return offs[keep[0]], np.ascontiguousarray(sp[order])
+
+
 class FDRegularGrid(FDPointCloud):
     """Fast drop-in for pointclasses.FDRegularGrid (pointclasses.py:473-622)."""
 
@@ -718,36 +743,55 @@ class FDRegularGrid(FDPointCloud):
             for q in (ptr, pairs, nptr, nbl):
                 L.pde_free(q)
         min_nb = mn.value if n else np.inf
-        # deep points: one translation-invariant table
-        offs = np.stack(np.meshgrid(*[np.arange(-r, r + 1)] * dim, indexing="ij"), -1).reshape(-1, dim)
-        offs = offs[(offs != 0).any(axis=1)]
-        c = np.full(dim, r + 1.0)
-        V = self._scaled(c + offs) - self._scaled(c)
-        keep, pair = _prune_and_pair(V[None], np.ones((1, len(offs)), bool),
-                                     np.zeros((1, len(offs)), bool))
-        k, l = np.nonzero(pair[0])
-        self.stencil_offsets = offs[keep[0]]
-        self.stencil_pairs_nd = np.concatenate([offs[k], offs[l]], axis=1).astype(np.int32)
-        rows, nbrows = [band_pairs], [np.stack([np.repeat(band_index, np.diff(bnptr)), band_nb], 1)]
+        self.band_ptr, self.band_pairs = bptr, band_pairs
+        self.band_nb_ptr, self.band_nb = bnptr, band_nb
+        # deep points: one translation-invariant table; rows, neighbours and points are
+        # materialised only when asked for (`pairs`, `neighbours`, `points`)
+        self.stencil_offsets, self.stencil_pairs_nd = _deep_table_nd(dim, r, self.scaling,
+                                                                     self.bounds[0])
+        self.halo = int(np.abs(self.stencil_pairs_nd).max()) if len(self.stencil_pairs_nd) else 0
         if deep.size:
-            stride = np.array([int(np.prod(shape[d + 1:])) for d in range(dim)], dtype=np.int64)
+            offs_k = self.stencil_offsets * self.scaling
+            min_nb = min(min_nb, np.sqrt((offs_k ** 2).sum(1)).min())
+        self._neighbours = None
+        self._min_interior_nb_dist = float(min_nb)
+
+    def _deep_ids(self):
+        isband = np.zeros(self.num_interior, bool)
+        isband[self.band_index] = True
+        return np.flatnonzero(~isband).astype(np.int64)
+
+    def _strides(self):
+        shape = self.interior_shape
+        return np.array([int(np.prod(shape[d + 1:])) for d in range(len(shape))], dtype=np.int64)
+
+    def _materialise_pairs_nd(self, max_rows=2 ** 31):
+        if self.num_pairs > max_rows:
+            raise MemoryError("refusing to materialise %d pair rows" % self.num_pairs)
+        dim = self.dim
+        deep, stride = self._deep_ids(), self._strides()
+        rows = [self.band_pairs]
+        if deep.size:
             sp = self.stencil_pairs_nd.astype(np.int64)
             J0 = deep[:, None] + (sp[:, :dim] * stride).sum(1)[None, :]
             J1 = deep[:, None] + (sp[:, dim:] * stride).sum(1)[None, :]
             I = np.broadcast_to(deep[:, None], J0.shape)
             rows.append(np.stack([I.ravel(), J0.ravel(), J1.ravel()], axis=1))
+        allrows = np.concatenate(rows)
+        return allrows[np.argsort(allrows[:, 0], kind="stable")]
+
+    def _materialise_neighbours_nd(self):
+        deep, stride = self._deep_ids(), self._strides()
+        K = self.stencil_offsets.shape[0]
+        if deep.size * K + self.band_nb.size > 2 ** 28:
+            raise MemoryError("refusing to materialise %d neighbour rows"
+                              % (deep.size * K + self.band_nb.size))
+        nbrows = [np.stack([np.repeat(self.band_index, np.diff(self.band_nb_ptr)), self.band_nb], 1)]
+        if deep.size:
             Jn = deep[:, None] + (self.stencil_offsets.astype(np.int64) * stride).sum(1)[None, :]
             nbrows.append(np.stack([np.broadcast_to(deep[:, None], Jn.shape).ravel(), Jn.ravel()], 1))
-            offs_k = self.stencil_offsets * self.scaling
-            min_nb = min(min_nb, np.sqrt((offs_k ** 2).sum(1)).min())
-        allrows = np.concatenate(rows)
-        self._pairs = allrows[np.argsort(allrows[:, 0], kind="stable")]
         nbrows = np.concatenate(nbrows)
-        self._neighbours = nbrows[np.argsort(nbrows[:, 0], kind="stable")]
-        self._min_interior_nb_dist = float(min_nb)
-        grids = np.meshgrid(*[np.arange(1, m + 1) for m in shape], indexing="ij")
-        Xint = np.stack([g.ravel() for g in grids], axis=1)
-        self._points = np.concatenate([Xint, self._wall_unscaled]) * self.scaling + self.bounds[0]
+        return nbrows[np.argsort(nbrows[:, 0], kind="stable")]
 
     def coords(self, ids):
         """Physical coordinates of the given point ids, with the arithmetic of
@@ -931,9 +975,8 @@ class FDRegularGrid(FDPointCloud):
         """(num_points, 2) physical coordinates, interior first in C order with
         y fastest (:513-515, :540, :551).  Materialised on first access."""
         if self._points is None:
-            nx, ny = self.interior_shape
-            ix, iy = np.meshgrid(np.arange(1, nx + 1), np.arange(1, ny + 1), indexing="ij")
-            Xint = np.stack([ix.ravel(), iy.ravel()], axis=1)
+            grids = np.meshgrid(*[np.arange(1, m + 1) for m in self.interior_shape], indexing="ij")
+            Xint = np.stack([g.ravel() for g in grids], axis=1)
             P = np.concatenate([Xint, self._wall_unscaled])
             self._points = P * self.scaling + self.bounds[0]
         return self._points
@@ -956,6 +999,8 @@ class FDRegularGrid(FDPointCloud):
         grouped by ascending I (pointclasses.py:576-578; the reference also lists the
         neighbours of the wall points, which only ``d1n`` reads -- not built here).
         Materialised on demand."""
+        if getattr(self, "_neighbours", None) is None and hasattr(self, "band_nb") and self.dim != 2:
+            self._neighbours = self._materialise_neighbours_nd()
         if getattr(self, "_neighbours", None) is None and hasattr(self, "band_nb"):
             nx, ny = self.interior_shape
             K = self.stencil_offsets.shape[0]
@@ -985,7 +1030,7 @@ class FDRegularGrid(FDPointCloud):
     @property
     def num_pairs(self):
         if self.dim != 2:
-            return int(self._pairs.shape[0])
+            return self.num_deep * self.stencil_pairs_nd.shape[0] + self.band_pairs.shape[0]
         return self.num_deep * self.stencil_pairs.shape[0] + self.band_pairs.shape[0]
 
     @property
@@ -994,7 +1039,7 @@ class FDRegularGrid(FDPointCloud):
         the reference operators consume (pointclasses.py:35).  Materialised on
         demand -- ~24 bytes per pair, so only sensible up to a few 1000^2."""
         if self._pairs is None:
-            self._pairs = self._materialise_pairs()
+            self._pairs = self._materialise_pairs() if self.dim == 2 else self._materialise_pairs_nd()
         return self._pairs
 
     @pairs.setter
@@ -1042,11 +1087,9 @@ class FDRegularGrid(FDPointCloud):
         bit-identical length wherever it is applied.  Then 1/h and 2/(h0+h1)
         are per-direction constants and the structured kernel is bit-exact
         against the per-pair arithmetic of the reference (ddg.py:276-281)."""
-        nx, ny = self.interior_shape
         r = self.halo
         ok = True
-        for n, s, b in ((nx, self.scaling[0], self.bounds[0][0]),
-                        (ny, self.scaling[1], self.bounds[0][1])):
+        for n, s, b in zip(self.interior_shape, self.scaling, self.bounds[0]):
             c = np.arange(1, n + 1) * s + b
             for a in range(1, r + 1):
                 if n - a <= 0:

@@ -68,3 +68,111 @@ def test_33cubed_against_the_numpy_restatement():
     assert np.abs(lam + 2).max() < 1e-9                        # d2/dy2 of -y^2, exact for quadratics
     lam = ddg.d2max(G, X ** 2 - Y ** 2 + 2 * Z ** 2)[0]
     assert np.abs(lam - 4).max() < 1e-9
+
+
+# ---- the structured 3-D kernel (stencil_deep3.cuh): bricks staged by 3-D TMA loads -------------
+def _dyadic_box(shape, cell=(1 / 8.0, 1 / 8.0, 1 / 8.0), origin=(0.0, -1.0, 0.5)):
+    return np.array([[o, o + c * (n + 1)] for n, c, o in zip(shape, cell, origin)]).T
+
+
+def _fields(G, seed=0):
+    rng = np.random.default_rng(seed)
+    X, Y, Z = G.points.T
+    return (("random", rng.standard_normal(G.num_points)),
+            ("saddle", X * Y - Z * X),                          # exact ties among the pairs
+            ("ints", rng.integers(-3, 4, G.num_points).astype(float)),   # heavy exact ties
+            ("zero", np.zeros(G.num_points)))
+
+
+@pytest.mark.parametrize("shape,cell,r", [
+    ((9, 8, 11), (1 / 8.0,) * 3, 1),            # compile-time table, r = 1
+    ((9, 8, 11), (1 / 8.0,) * 3, 2),            # compile-time table, r = 2 (49 pairs)
+    ((13, 7, 70), (1 / 16.0,) * 3, 2),          # two bricks along z, partial bricks everywhere
+    ((21, 14, 9), (1 / 8.0, 1 / 4.0, 1 / 16.0), 2),   # anisotropic cells: run-time table
+    ((6, 9, 7), (1 / 2.0, 1 / 8.0, 1 / 8.0), 1),
+])
+def test_structured_3d_kernel_bitexact(shape, cell, r):
+    """Values, selected pairs (tie rule included: explicit matrices and control vectors) of the
+    3-D table kernel against the NumPy restatement of ddg.d2eigs on the grid's pair rows, and
+    against the explicit-row kernel every 3-D grid ran through before."""
+    from pyellipticfd_b200 import ddg, _context
+    from pyellipticfd_b200._context import GridContext
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    G = FDRegularGrid(list(shape), _dyadic_box(shape, cell), r, interpolation=False)
+    assert G.uniform_weights()
+    ctx = GridContext.get(G)
+    assert ctx.nd and ctx.structured and ctx.weights == "exact"
+    G2 = FDRegularGrid(list(shape), _dyadic_box(shape, cell), r, interpolation=False)
+    _context.ND_STRUCTURED = False
+    try:
+        assert not GridContext.get(G2).structured
+    finally:
+        _context.ND_STRUCTURED = True
+    for name, u in _fields(G):
+        (lmin, Mmin, vmin), (lmax, Mmax, vmax) = ddg.d2eigs(G, u, jacobian=True, control=True)
+        (omin, OMmin, ovmin), (omax, OMmax, ovmax) = O.d2eigs(G, u, True, True)
+        assert np.array_equal(lmin, omin) and np.array_equal(lmax, omax), name
+        assert np.array_equal(vmin, ovmin) and np.array_equal(vmax, ovmax), name
+        assert (Mmin.tocsr() != OMmin).nnz == 0 and (Mmax.tocsr() != OMmax).nnz == 0, name
+        (gmin, _, gvmin), (gmax, _, gvmax) = ddg.d2eigs(G2, u, control=True)
+        assert np.array_equal(lmin, gmin) and np.array_equal(lmax, gmax)
+        assert np.array_equal(vmin, gvmin) and np.array_equal(vmax, gvmax)
+        assert np.array_equal(ddg.d2min(G, u)[0], omin) and np.array_equal(ddg.d2max(G, u)[0], omax)
+        assert np.array_equal(Mmin.dot(u), lmin) and np.array_equal(Mmax.dot(u), lmax)
+        w = np.random.default_rng(5).standard_normal(G.num_interior)
+        assert np.abs(Mmin.transpose().dot(w) - OMmin.T.dot(w)).max() < 1e-10 * np.abs(w).max() / G.scaling.min() ** 2
+
+
+def test_structured_3d_solves_equal_explicit_rows():
+    """convex_envelope on a 3-D lattice: the Euler iteration through the table kernel is
+    bit-identical to the explicit-row path (same values -> same iterates), Newton (policy
+    Jacobian rows of deep points from the table) agrees to solver tolerance."""
+    from pyellipticfd_b200 import convex_envelope, _context
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    shape = (15, 15, 15)
+    mk = lambda: FDRegularGrid(list(shape), np.array([[-1.0, 1.0]] * 3).T, 2, interpolation=False)
+    G, G2 = mk(), mk()
+    X = G.points
+    g = np.minimum(np.linalg.norm(X - np.array([0.4, 0.0, 0.1]), axis=1),
+                   np.linalg.norm(X + np.array([0.4, 0.1, 0.0]), axis=1)) - 0.3
+    U, diff, it, _ = convex_envelope.solve(G, g, fdmethod="grid", solver="euler")
+    Un, diffn, itn, _ = convex_envelope.solve(G, g, fdmethod="grid", solver="newton")
+    _context.ND_STRUCTURED = False
+    try:
+        U2, diff2, it2, _ = convex_envelope.solve(G2, g, fdmethod="grid", solver="euler")
+        Un2, _, itn2, _ = convex_envelope.solve(G2, g, fdmethod="grid", solver="newton")
+    finally:
+        _context.ND_STRUCTURED = True
+    assert _context.GridContext.get(G).nd and not _context.GridContext.get(G2).structured
+    assert it == it2 and diff == diff2 and np.array_equal(U, U2)
+    assert abs(itn - itn2) <= 2 and np.abs(Un - Un2).max() < 2e-6
+    assert np.abs(Un - U).max() < 1e-3
+
+
+def test_structured_3d_129cubed_properties():
+    """2.1 M interior points, r = 2: no pair rows are materialised for the deep points; the
+    kernel's values against the C oracle formula on a sample of deep points, exact answers for
+    a quadratic, and translation invariance."""
+    from pyellipticfd_b200 import ddg
+    from pyellipticfd_b200._context import GridContext
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    n = 129
+    G = FDRegularGrid([n, n, n], np.array([[0.0, (n + 1) / 128.0]] * 3).T, 2, interpolation=False)
+    ctx = GridContext.get(G)
+    assert ctx.nd and G._pairs is None
+    rng = np.random.default_rng(3)
+    u = rng.standard_normal(G.num_points)
+    lmin, lmax = ddg.d2min(G, u)[0], ddg.d2max(G, u)[0]
+    assert G._pairs is None
+    # sample of deep points against the reference formula (ddg.py:276-292) row by row
+    sp = G.stencil_pairs_nd.astype(np.int64)
+    stride = np.array([n * n, n, 1])
+    w = ctx.deep_pair_weights()
+    ids = rng.choice(G._deep_ids(), 4000, replace=False)
+    J0 = ids[:, None] + (sp[:, :3] * stride).sum(1)[None]
+    J1 = ids[:, None] + (sp[:, 3:] * stride).sum(1)[None]
+    d = w[None, :, 2] * ((u[J0] - u[ids, None]) * w[None, :, 0] + (u[J1] - u[ids, None]) * w[None, :, 1])
+    assert np.array_equal(d.min(1), lmin[ids]) and np.array_equal(d.max(1), lmax[ids])
+    X, Y, Z = G.points.T
+    q = X ** 2 - Y ** 2 + 2 * Z ** 2
+    assert np.abs(ddg.d2min(G, q)[0] + 2).max() < 1e-8 and np.abs(ddg.d2max(G, q)[0] - 4).max() < 1e-8
