@@ -426,11 +426,118 @@ def gather_rows(local, sizes, group=None):
     return torch.cat([got[r * m:r * m + sizes[r]] for r in range(world)])
 
 
+def bicgstab_replicated(matvec, b, dinv, rtol, atol=0.0, maxiter=None):
+    """Jacobi-preconditioned BiCGStab with SciPy's statements (scipy/sparse/linalg/_isolve/
+    iterative.py::bicgstab, the call of solvers.py:179-181; same order as csrc/krylov.cuh) on
+    vectors that are REPLICATED on every rank: only ``matvec`` is distributed (every rank applies
+    its rows and the slices are re-assembled by an all-gather), the vector algebra and the dot
+    products are repeated on identical data, so all ranks take identical decisions without a
+    reduction.  Meant for point clouds, whose vectors are small next to the per-rank ELL table.
+    Returns ``(x, info, iterations)``."""
+    n = b.numel()
+    maxiter = 10 * n if not maxiter else int(maxiter)
+    rhotol = float(np.finfo(np.float64).eps) ** 2
+    bnrm2 = float(torch.linalg.vector_norm(b))
+    x = torch.zeros_like(b)
+    if bnrm2 == 0.0:
+        return x, 0, 0
+    atol = max(float(atol), float(rtol) * bnrm2)
+    r = b.clone()
+    rtilde = r.clone()
+    p = v = None
+    rho_prev = omega = alpha = 1.0
+    for it in range(maxiter):
+        if float(torch.linalg.vector_norm(r)) < atol:
+            return x, 0, it
+        rho = float(torch.dot(rtilde, r))
+        if abs(rho) < rhotol:
+            return x, -10, it
+        if it > 0:
+            if abs(omega) < rhotol:
+                return x, -11, it
+            beta = (rho / rho_prev) * (alpha / omega)
+            p = p - omega * v          # iterative.py: p -= omega*v; p *= beta; p += r
+            p = p * beta
+            p = p + r
+        else:
+            p = r.clone()
+        phat = dinv * p
+        v = matvec(phat)
+        rv = float(torch.dot(rtilde, v))
+        if rv == 0.0:
+            return x, -11, it
+        alpha = rho / rv
+        r = r - alpha * v              # this is s
+        if float(torch.linalg.vector_norm(r)) < atol:
+            x = x + alpha * phat
+            return x, 0, it + 1
+        shat = dinv * r
+        t = matvec(shat)
+        omega = float(torch.dot(t, r)) / float(torch.dot(t, t))
+        x = x + alpha * phat
+        x = x + omega * shat
+        r = r - omega * t
+        rho_prev = rho
+    return x, maxiter, maxiter
+
+
+class _ShardedEllJacobian(object):
+    """Rows [lo, hi) of the point-cloud policy Jacobian (convex_envelope.py:48-54,
+    pucci.py:136-139) on this rank; vectors replicated; ``matvec_state`` re-assembles the rows
+    of all ranks (boundary rows are the identity)."""
+
+    def __init__(self, cloud, kmin, kmax=None, cmin=1.0, cmax=0.0):
+        self.cloud, self.ctx = cloud, cloud
+        self.kmin, self.kmax, self.cmin, self.cmax = kmin, kmax, float(cmin), float(cmax)
+        self.active = kmin >= 0
+        self.k0 = torch.where(self.active, kmin, torch.zeros_like(kmin))
+
+    def _rows(self, X):
+        c = self.cloud
+        y = self.cmin * c.table.apply(self.k0, X)
+        if self.kmax is not None:
+            y = y + self.cmax * c.table.apply(self.kmax, X)
+        return torch.where(self.active, y, X[c.lo:c.hi])
+
+    def matvec_state(self, X, out=None):
+        c = self.cloud
+        Y = torch.cat([c.gather(self._rows(X)), X[c.n_interior:]])
+        if out is not None:
+            out.copy_(Y)
+            return out
+        return Y
+
+    def diagonal(self):
+        c = self.cloud
+        t = c.table
+
+        def dg(k):      # -(sum of the four weights), the centre entry of the row (ell.cu::ell_diag)
+            w = t.w[k.long(), torch.arange(t.N, device=t.device)]
+            return -(w[:, 0] + w[:, 1] + w[:, 2] + w[:, 3])
+
+        d = self.cmin * dg(self.k0)
+        if self.kmax is not None:
+            d = d + self.cmax * dg(self.kmax)
+        d = torch.where(self.active, d, torch.ones_like(d))
+        return torch.cat([c.gather(d), torch.ones(c.n_points - c.n_interior, dtype=d.dtype,
+                                                  device=d.device)])
+
+    def bicgstab_state(self, B, rtol, atol=0.0, maxiter=0, check_every=32):
+        return bicgstab_replicated(self.matvec_state, B, 1.0 / self.diagonal(), rtol, atol, maxiter)
+
+
 class ShardedCloud(object):
     """One rank's share of the ``ddi`` / ``ddf`` operator on a point cloud: the ELL table of
     the interior points ``[lo, hi)`` only (``Nds * 48`` bytes per point stay local), the
     function values ``u`` replicated (16 MB at 2 M points) and re-assembled after an update
-    by one all-gather of the ranks' slices."""
+    by one all-gather of the ranks' slices.
+
+    ``ce_solve`` / ``pucci_solve`` (round 2) run ``convex_envelope.solve`` / ``pucci.solve`` with
+    ``fdmethod='interpolate'|'froese'`` (convex_envelope.py:35-40, pucci.py:60-160) on the
+    sharded table: the residual -- all ``Nds`` rows of every point, the expensive part -- is
+    evaluated on the rank's points only, the policy Jacobian applies the rank's rows, and the
+    Newton / Euler loops are those of the single-GPU path (``solvers.newton_state``) on
+    replicated vectors."""
 
     def __init__(self, G, rank, world, device, scheme="ddi"):
         from . import ddi, ddf, _ell
@@ -443,6 +550,9 @@ class ShardedCloud(object):
         self.V = _ell.directions(self.nds)
         self.table = _ell.EllTable(G, self.V, scheme == "ddf", device=device,
                                    rows=(self.lo, self.hi))
+        self.device = self.table.device
+        self.n_interior = int(G.num_interior)
+        self.n_points = self.table.n_points
 
     def d2eigs(self, u, want_k=False):
         """(lmin, lmax, kmin, kmax) of this rank's points; ``u``: values on ALL points."""
@@ -455,3 +565,114 @@ class ShardedCloud(object):
     def d2eigs_all(self, u):
         lmin, lmax, _, _ = self.d2eigs(u)
         return self.gather(lmin), self.gather(lmax)
+
+    # ---- what solvers.newton_state / euler_state ask of a context ------------------------------
+    def n_flat(self):
+        return self.n_points
+
+    def newton_update(self, U, D, F, JD):
+        """solvers.py:188-197 on replicated vectors (identical on every rank)."""
+        Un = U + D
+        return (Un, float((U - Un).abs().max()), float(torch.dot(F, JD)), float(torch.dot(D, D)))
+
+    def residual(self, W, g, mode, A=(0.0, 0.0), policy=True):
+        """Sharded ``pde_ell_residual``: mode 0 convex envelope (convex_envelope.py:44-46), mode 1
+        Pucci (pucci.py:48,128,141).  Same row arithmetic and tie rules as the single-GPU kernel
+        (the rows come from the same ``k_ell_d2eigs``).  Returns (F, kmin, kmax, max|F|)."""
+        N, lo, hi = self.n_interior, self.lo, self.hi
+        lmin, lmax, kmin, kmax = self.table.d2eigs(W, want_k=policy)
+        f = W[lo:hi] - g[lo:hi]
+        if mode == 0:
+            nl = -lmin
+            active = nl > f
+            f = torch.where(active, nl, f)
+            if policy:
+                kmin = torch.where(active, kmin, torch.full_like(kmin, -1))
+            kmax = None
+        else:
+            f = (A[0] * lmax + A[1] * lmin) - g[lo:hi]
+        F = torch.cat([self.gather(f), W[N:] - g[N:]])
+        return F, kmin, kmax, F.abs().max()
+
+    def ce_solve(self, g, U0=None, solver="newton", stats=None, **kwargs):
+        """convex_envelope.solve(G, g, U0, fdmethod, solver) on the sharded cloud
+        (convex_envelope.py:100-123).  Returns (U on all points [device tensor], diff, iterations,
+        seconds), identical on every rank."""
+        import time
+        from . import solvers
+        from ._context import to_device
+        G, dev = self.G, self.device
+        t0 = time.time()
+        gs = to_device(g, dev)
+        Us = gs.clone() if U0 is None else to_device(U0, dev).clone()
+        dt = 1 / 2 * np.max([G.min_interior_nb_dist, G.min_radius]) ** 2      # convex_envelope.py:110
+        sol, opt = kwargs.get("solution_tol", 1e-6), kwargs.get("operator_tol", 1e-6)
+
+        def euler_res(U):
+            F, _, _, fmax = self.residual(U, gs, 0, policy=False)
+            return F, fmax
+
+        if solver == "euler":
+            Us, diff, iters = solvers.euler_state(self, Us, euler_res, dt, sol, opt,
+                                                  kwargs.get("max_iters"), kwargs.get("timeout"))
+            return Us, diff, iters, time.time() - t0
+        solvers.drop_unsupported(kwargs)
+
+        def res(U, jacobian):
+            F, kmin, _, fmax = self.residual(U, gs, 0, policy=jacobian)
+            return F, (_ShardedEllJacobian(self, kmin, None, cmin=-1.0) if jacobian else None), fmax
+
+        def fallback(U, timeout):
+            # a wall-clock budget would let the ranks take different numbers of steps: the
+            # fallback runs a fixed number of Euler steps instead (solvers.py:166's cap / 100)
+            U, diff, _ = solvers.euler_state(self, U, euler_res, dt, sol, opt,
+                                             max(self.n_points // 10, 100), None)
+            return U, diff
+
+        Us, diff, iters = solvers.newton_state(self, Us, res, fallback, stats=stats, **kwargs)
+        return Us, diff, iters, time.time() - t0
+
+    def pucci_solve(self, f, g, A, U0=None, solver="newton", stats=None, **kwargs):
+        """pucci.solve on the sharded cloud (pucci.py:105-160), scalar coefficients A."""
+        import time
+        from . import solvers
+        from ._context import to_device
+        G, dev, N, n = self.G, self.device, self.n_interior, self.n_points
+        t0 = time.time()
+        Fv = torch.zeros(n, dtype=torch.float64, device=dev)
+        Fv[:N] = to_device(f, dev) if not np.isscalar(f) else float(f)
+        if g is not None:
+            Fv[N:] = to_device(g, dev) if not np.isscalar(g) else float(g)
+        dt = 1 / 2 * np.max([G.min_radius, G.min_interior_nb_dist]) ** 2
+        if U0 is None:
+            Us = torch.ones(n, dtype=torch.float64, device=dev)
+            if g is not None:
+                Us[N:] = Fv[N:]
+        else:
+            Us = to_device(U0, dev).clone()
+        sol, opt = kwargs.get("solution_tol", 1e-6), kwargs.get("operator_tol", 1e-6)
+
+        def res(U, jacobian):
+            R, kmin, kmax, fmax = self.residual(U, Fv, 1, A, policy=jacobian)
+            Jac = (_ShardedEllJacobian(self, kmin, kmax, cmin=float(A[1]), cmax=float(A[0]))
+                   if jacobian else None)
+            return R, Jac, fmax
+
+        def euler_res(U):
+            R, _, _, fmax = self.residual(U, Fv, 1, A, policy=False)
+            R[:N].neg_()                      # stable sign for explicit Euler (SURVEY Q3)
+            return R, fmax
+
+        if solver == "euler":
+            Us, diff, iters = solvers.euler_state(self, Us, euler_res, dt, sol, opt,
+                                                  kwargs.get("max_iters"), kwargs.get("timeout"))
+            return Us, diff, iters, time.time() - t0
+        solvers.drop_unsupported(kwargs)
+
+        def fallback(U, timeout):
+            U, diff, _ = solvers.euler_state(self, U, euler_res, dt, sol, opt,
+                                             max(n // 10, 100), None)
+            return U, diff
+
+        Us, diff, iters = solvers.newton_state(self, Us, res, fallback, stats=stats, **kwargs)
+        return Us, diff, iters, time.time() - t0

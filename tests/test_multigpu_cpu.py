@@ -108,3 +108,65 @@ def test_point_range_gather_gloo(world, n):
         assert p.exitcode == 0
     res = dict(q.get(timeout=5) for _ in range(world))
     assert all(res.values()) and len(res) == world
+
+
+def _krylov_worker(rank, world, port, n, q):
+    """bicgstab_replicated with a row-sharded matrix (every rank applies its rows, one padded
+    all-gather re-assembles the product) against SciPy's bicgstab on the whole matrix."""
+    import scipy.sparse as sp
+    from scipy.sparse.linalg import bicgstab
+    from pyellipticfd_b200.multigpu import bicgstab_replicated, gather_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        rng = np.random.default_rng(0)                       # same matrix on every rank
+        # an M-matrix like the policy Jacobians: identity rows + weighted second differences
+        rows, cols, vals = [], [], []
+        for i in range(n):
+            if i % 5 == 0 or i in (0, n - 1):
+                rows.append(i); cols.append(i); vals.append(1.0)
+            else:
+                a, b = rng.uniform(0.5, 2.0, 2)
+                j0, j1 = max(i - rng.integers(1, 4), 0), min(i + rng.integers(1, 4), n - 1)
+                rows += [i, i, i]; cols += [j0, j1, i]; vals += [-a, -b, a + b]
+        A = sp.coo_matrix((vals, (rows, cols)), shape=(n, n)).tocsr()
+        b = rng.standard_normal(n)
+        parts = slab_partition(n, world)
+        lo, hi = parts[rank]
+        sizes = [h - l for l, h in parts]
+        Aloc = torch.from_numpy(A[lo:hi].toarray())
+
+        def matvec(x):
+            return gather_rows(Aloc @ x, sizes)
+
+        dinv = torch.from_numpy(1.0 / A.diagonal())
+        x, info, its = bicgstab_replicated(matvec, torch.from_numpy(b), dinv, 1e-10)
+        calls = [0]
+        xs, infos = bicgstab(A, b, rtol=1e-10, atol=0.0, M=sp.diags(1.0 / A.diagonal()),
+                             callback=lambda xk: calls.__setitem__(0, calls[0] + 1))
+        ok = info == 0 and infos == 0 and abs(its - calls[0]) <= 2
+        ok &= bool(np.abs(x.numpy() - xs).max() < 1e-8 * np.abs(xs).max())
+        ok &= bool(np.abs(A.dot(x.numpy()) - b).max() < 1e-8)
+        # zero right-hand side, and the breakdown exit of a singular system stays finite
+        x0, info0, its0 = bicgstab_replicated(matvec, torch.zeros(n, dtype=torch.float64), dinv, 1e-10)
+        ok &= info0 == 0 and its0 == 0 and float(x0.abs().max()) == 0.0
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n", [(2, 60), (3, 47)])
+@pytest.mark.timeout(120)
+def test_replicated_bicgstab_gloo(world, n):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_krylov_worker, args=(r, world, port, n, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(100)
+        assert p.exitcode == 0
+    res = dict(q.get(timeout=5) for _ in range(world))
+    assert all(res.values()) and len(res) == world

@@ -96,5 +96,49 @@ for name, mod in (("ddi", ddi), ("ddf", ddf)):
     report("%s.d2eigs on %d points, %d point ranges (bit-exact vs 1 GPU)" % (name, len(p), world),
            bool(torch.equal(lo_all, rmin)) and bool(torch.equal(hi_all, rmax))
            and lo_all.shape[0] == nint)
+# sharded point-cloud SOLVES (round 2): convex envelope of the two cones of
+# examples/convex_envelope.py:8-18 and a Pucci problem on the disc, policy iteration + Euler on
+# the sharded table against the single-GPU solve
+from pyellipticfd_b200 import convex_envelope, pucci
+import time
+P = torch.from_numpy(p).to(dev)
+cen = 3 / 7 * np.array([[np.cos(np.pi / 5), np.sin(np.pi / 5)], [-np.cos(np.pi / 5), -np.sin(np.pi / 5)]])
+gc = torch.minimum(((P - torch.tensor(cen[0], device=dev)) ** 2).sum(1).sqrt(),
+                   ((P - torch.tensor(cen[1], device=dev)) ** 2).sum(1).sqrt())
+sc = ShardedCloud(Gc, rank, world, dev, scheme="ddi")
+for solver, kw in (("newton", dict(solution_tol=1e-10)), ("euler", dict(max_iters=300))):
+    st = {}
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t = time.time()
+        Us, diff, it, _ = sc.ce_solve(gc, solver=solver, stats=st, **kw)
+        torch.cuda.synchronize()
+        ts = time.time() - t
+        Gc._d2cache = None
+        t = time.time()
+        U1, diff1, it1, _ = convex_envelope.solve(Gc, gc, fdmethod="interpolate", solver=solver, **kw)
+        torch.cuda.synchronize()
+        t1 = time.time() - t
+    err = float((Us - U1).abs().max())
+    # identical on every rank: replicated vectors, no reduction
+    chk = torch.tensor([float(Us.sum()), float(it)], device=dev, dtype=torch.float64)
+    lo_, hi_ = chk.clone(), chk.clone()
+    dist.all_reduce(lo_, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi_, op=dist.ReduceOp.MAX)
+    report("sharded cloud convex_envelope.solve(%s): %d its (1 GPU: %d), |U - U_1gpu| = %.2e, "
+           "%.2f s vs %.2f s" % (solver, it, it1, err, ts, t1),
+           err < (1e-8 if solver == "newton" else 1e-12) and abs(it - it1) <= 2
+           and bool(torch.equal(lo_, hi_)))
+fP = 2.0 * torch.ones(nint, device=dev, dtype=torch.float64)
+gP = (P[nint:] ** 2).sum(1)
+with warnings.catch_warnings():
+    warnings.simplefilter("ignore")
+    Us, diff, it, _ = sc.pucci_solve(fP, gP, (1.0, 1.0), solver="newton")
+    Gc._d2cache = None
+    U1, diff1, it1, _ = pucci.solve(Gc, fP, gP, (1.0, 1.0), fdmethod="interpolate", solver="newton")
+err = float((Us - U1).abs().max())
+report("sharded cloud pucci.solve(newton): %d its (1 GPU: %d), |U - U_1gpu| = %.2e" % (it, it1, err),
+       err < 1e-6 and abs(it - it1) <= 2)
 dist.destroy_process_group()
 sys.exit(0 if ok_all else 1)
