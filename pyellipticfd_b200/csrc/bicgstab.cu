@@ -25,7 +25,8 @@ namespace pde {
 template <class Op>
 __global__ void __launch_bounds__(PASS_THREADS)
 k_rows(const GridDev G, const __grid_constant__ DeepTable tab, Op op, double *partials,
-       const BicgScal *scal, const int nrb /* row blocks; the rest are tail blocks */) {
+       BicgScal *scal, const int nrb /* row blocks; the rest are tail blocks */,
+       const double *partials_base, const StageArgs sa) {
     double acc[Op::NRED > 0 ? Op::NRED : 1] = {0.0};
     bool skip = scal && (scal->done || (Op::kSkipOnHalf && scal->half));
     if (!skip) {
@@ -52,7 +53,10 @@ k_rows(const GridDev G, const __grid_constant__ DeepTable tab, Op op, double *pa
                 op.wall(G.rows * G.pitch + (i - G.n_band), acc);
         }
     }
-    if (Op::NRED > 0) block_store_partials(acc, partials);
+    // `partials`: first slot of THIS launch; `partials_base`: first slot of the pass (the tiled
+    // launch that may precede this one on the stream has stored its sums there already)
+    if constexpr (Op::NRED > 0)
+        pass_finish(acc, partials + (int64_t)blockIdx.x * Op::NRED, partials_base, scal, sa);
 }
 
 // ---- J x ------------------------------------------------------------------------------
@@ -217,7 +221,7 @@ struct OpAt {
 
 // deep-interior rows through the TMA-tiled kernel (jac_tiled.cuh); *nblocks = CTAs launched
 template <class Op, int H>
-static int launch_tiled_h(pde_grid *g, const Op &op, double *partials, const BicgScal *scal,
+static int launch_tiled_h(pde_grid *g, const Op &op, double *partials, BicgScal *scal,
                           cudaStream_t st, int *nblocks) {
     constexpr int P = 8, TX = 2 * P;
     DeepRegion dr = deep_region(g, 0, g->nx_local);
@@ -255,7 +259,7 @@ static int launch_tiled_h(pde_grid *g, const Op &op, double *partials, const Bic
 }
 
 template <class Op>
-static int launch_tiled(pde_grid *g, const Op &op, double *partials, const BicgScal *scal,
+static int launch_tiled(pde_grid *g, const Op &op, double *partials, BicgScal *scal,
                         cudaStream_t st, int *nblocks) {
     switch (g->tab.H) {
         case 1: return launch_tiled_h<Op, 1>(g, op, partials, scal, st, nblocks);
@@ -274,30 +278,33 @@ static bool jac_tiled_enabled() {
 }
 
 template <class Op>
-static int launch_rows(pde_grid *g, const Op &op, double *partials, const BicgScal *scal,
-                       cudaStream_t st, int *nblocks_out = nullptr) {
+static int launch_rows(pde_grid *g, const Op &op, double *partials, BicgScal *scal,
+                       cudaStream_t st, int *nblocks_out = nullptr,
+                       StageArgs sa = StageArgs{ST_NONE, 0, 0.0, 0.0}) {
     GridDev G = grid_dev(g);
     if constexpr (Op::kTiled) {
+        int64_t tb = tail_blocks(g->n_band, g->nb);
         if (g->tab.D > 0 && g->nmid == 0 && g->tab.H >= 1 && g->tab.H <= 6 && jac_tiled_enabled() &&
-            (reinterpret_cast<uintptr_t>(op.source()) & 15) == 0) {      // TMA: 16-byte aligned base
+            tb > 0 && (reinterpret_cast<uintptr_t>(op.source()) & 15) == 0) {      // TMA: 16-byte aligned base
             // deep-interior points: TMA-tiled kernel; band points and wall entries: the tail
-            // blocks of the plain kernel, their partial sums appended after the tiled CTAs'
+            // blocks of the plain kernel, their partial sums appended after the tiled CTAs';
+            // the last tail block performs the pass's scalar stage
             int nd = 0;
             int rc = launch_tiled(g, op, partials, scal, st, &nd);
             if (rc) return rc;
-            int64_t tb = tail_blocks(g->n_band, g->nb);
-            if (tb > 0) {
-                k_rows<Op><<<(unsigned)tb, PASS_THREADS, 0, st>>>(
-                    G, g->tab, op, partials ? partials + (int64_t)nd * Op::NRED : nullptr, scal, 0);
-                PDE_LAUNCH_CHECK();
-            }
+            sa.total = nd + (int)tb;
+            k_rows<Op><<<(unsigned)tb, PASS_THREADS, 0, st>>>(
+                G, g->tab, op, partials ? partials + (int64_t)nd * Op::NRED : nullptr, scal, 0,
+                partials, sa);
+            PDE_LAUNCH_CHECK();
             if (nblocks_out) *nblocks_out = nd + (int)tb;
             return 0;
         }
     }
     int nrb = (int)g->rows;
     int64_t nblk = nrb + tail_blocks(g->n_band, g->nb);
-    k_rows<Op><<<(unsigned)nblk, PASS_THREADS, 0, st>>>(G, g->tab, op, partials, scal, nrb);
+    sa.total = (int)nblk;
+    k_rows<Op><<<(unsigned)nblk, PASS_THREADS, 0, st>>>(G, g->tab, op, partials, scal, nrb, partials, sa);
     PDE_LAUNCH_CHECK();
     if (nblocks_out) *nblocks_out = (int)nblk;
     return 0;
@@ -404,12 +411,12 @@ int pde_bicgstab(pde_grid *g, const pde_jac *J, const double *d_b, double *d_x, 
         int num_sms() const { return g->num_sms; }
         int dinv(double *out, cudaStream_t st) { return launch_rows(g, OpDiag{J, out, 1}, nullptr, nullptr, st); }
         int Av(const double *src, const double *rtilde, double *dst, double *partials,
-               const BicgScal *scal, cudaStream_t st, int *nb) {
-            return launch_rows(g, OpAv{J, src, rtilde, dst}, partials, scal, st, nb);
+               BicgScal *scal, cudaStream_t st, int *nb, const StageArgs &sa) {
+            return launch_rows(g, OpAv{J, src, rtilde, dst}, partials, scal, st, nb, sa);
         }
         int At(const double *src, const double *s, double *dst, double *partials,
-               const BicgScal *scal, cudaStream_t st, int *nb) {
-            return launch_rows(g, OpAt{J, src, s, dst}, partials, scal, st, nb);
+               BicgScal *scal, cudaStream_t st, int *nb, const StageArgs &sa) {
+            return launch_rows(g, OpAt{J, src, s, dst}, partials, scal, st, nb, sa);
         }
     } backend{g, jac_dev(J)};
     return bicgstab_run(backend, d_b, d_x, rtol, atol, maxiter, check_every, d_work, h_info,
@@ -442,10 +449,12 @@ int pde_bicgstab_dist_step(pde_grid *g, const pde_jac *J, int step, const double
     auto reduce = [&](int stage, int nred) {
         if (nred == 1) k_stage<1><<<1, PASS_THREADS, 0, st>>>(stage, d_partials, nb, scal, rtol, atol, d_sums, 1);
         else k_stage<2><<<1, PASS_THREADS, 0, st>>>(stage, d_partials, nb, scal, rtol, atol, d_sums, 1);
+        pde::count_launch();
     };
     auto finalize = [&](int stage, int nred) {
         if (nred == 1) k_stage<1><<<1, PASS_THREADS, 0, st>>>(stage, d_partials, 0, scal, rtol, atol, d_sums, 2);
         else k_stage<2><<<1, PASS_THREADS, 0, st>>>(stage, d_partials, 0, scal, rtol, atol, d_sums, 2);
+        pde::count_launch();
     };
     switch (step) {
         case 0: {   // setup + init pass

@@ -16,6 +16,11 @@ void set_error(const std::string &msg);
 int fail(const char *what, const char *file, int line);
 int fail_cuda(cudaError_t e, const char *what, const char *file, int line);
 void count_launch(int n = 1);
+int64_t launch_count();
+// keep the stream-ordered allocator's memory across synchronisations (the default release
+// threshold of 0 hands every freed block back to the driver at the next sync, which made each
+// cudaMallocAsync of the solver loops a real allocation: 12 ms per Newton update, measured)
+void keep_async_pool(int device);
 
 #define PDE_CHECK(call)                                                        \
     do {                                                                       \

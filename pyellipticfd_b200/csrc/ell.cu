@@ -219,6 +219,7 @@ int pde_ell_create(pde_ell **out, int device, int64_t n_interior, int64_t n_poin
     cudaDeviceProp prop;
     PDE_CHECK(cudaGetDeviceProperties(&prop, device));
     PDE_REQUIRE(prop.major == 10, "pde_b200 requires an sm_100-class (Blackwell) device");
+    pde::keep_async_pool(device);
     pde_ell *e = new pde_ell();
     e->device = device;
     e->n_interior = n_interior;
@@ -332,7 +333,8 @@ template <int MODE, int NRED>
 __global__ void __launch_bounds__(PASS_THREADS)
 k_ell_rows(int64_t n, int64_t npts, const int4 *__restrict__ idx, const double2 *__restrict__ w,
            EllJacDev J, const double *__restrict__ x, const double *__restrict__ aux,
-           double *__restrict__ y, int invert, double *partials, const BicgScal *scal) {
+           double *__restrict__ y, int invert, double *partials, BicgScal *scal,
+           const StageArgs sa) {
     double acc[NRED > 0 ? NRED : 1] = {0.0};
     bool skip = scal && (scal->done || (MODE == 3 && scal->half));
     if (!skip) {
@@ -357,7 +359,8 @@ k_ell_rows(int64_t n, int64_t npts, const int4 *__restrict__ idx, const double2 
             }
         }
     }
-    if (NRED > 0) block_store_partials(acc, partials);
+    if constexpr (NRED > 0)
+        pass_finish(acc, partials + (int64_t)blockIdx.x * NRED, partials, scal, sa);
 }
 
 // residuals: mode 0 convex envelope, mode 1 Pucci
@@ -430,13 +433,15 @@ static pde::EllJacDev ell_jac_dev(const pde_ell_jac *J) {
 
 template <int MODE, int NRED>
 static int ell_rows(pde_ell *e, const pde::EllJacDev &J, const double *x, const double *aux,
-                    double *y, int invert, double *partials, const pde::BicgScal *scal,
-                    cudaStream_t st, int *nb) {
+                    double *y, int invert, double *partials, pde::BicgScal *scal,
+                    cudaStream_t st, int *nb,
+                    pde::StageArgs sa = pde::StageArgs{pde::ST_NONE, 0, 0.0, 0.0}) {
     PDE_REQUIRE(e->row_offset == 0, "the point-cloud Jacobian needs the full table (row_offset 0)");
     int nblk = pde::elem_grid(e->n_points, e->num_sms);
+    sa.total = nblk;
     pde::k_ell_rows<MODE, NRED><<<nblk, pde::PASS_THREADS, 0, st>>>(
         e->n_interior, e->n_points, reinterpret_cast<const int4 *>(e->idx),
-        reinterpret_cast<const double2 *>(e->w), J, x, aux, y, invert, partials, scal);
+        reinterpret_cast<const double2 *>(e->w), J, x, aux, y, invert, partials, scal, sa);
     PDE_LAUNCH_CHECK();
     if (nb) *nb = nblk;
     return 0;
@@ -475,12 +480,12 @@ int pde_ell_bicgstab(pde_ell *e, const pde_ell_jac *J, const double *d_b, double
             return ell_rows<1, 0>(e, J, nullptr, nullptr, out, 1, nullptr, nullptr, st, nullptr);
         }
         int Av(const double *src, const double *rtilde, double *dst, double *partials,
-               const pde::BicgScal *scal, cudaStream_t st, int *nb) {
-            return ell_rows<2, 1>(e, J, src, rtilde, dst, 0, partials, scal, st, nb);
+               pde::BicgScal *scal, cudaStream_t st, int *nb, const pde::StageArgs &sa) {
+            return ell_rows<2, 1>(e, J, src, rtilde, dst, 0, partials, scal, st, nb, sa);
         }
         int At(const double *src, const double *s, double *dst, double *partials,
-               const pde::BicgScal *scal, cudaStream_t st, int *nb) {
-            return ell_rows<3, 2>(e, J, src, s, dst, 0, partials, scal, st, nb);
+               pde::BicgScal *scal, cudaStream_t st, int *nb, const pde::StageArgs &sa) {
+            return ell_rows<3, 2>(e, J, src, s, dst, 0, partials, scal, st, nb, sa);
         }
     } backend{e, ell_jac_dev(J)};
     return pde::bicgstab_run(backend, d_b, d_x, rtol, atol, maxiter, check_every, d_work, h_info,

@@ -15,6 +15,20 @@ static std::atomic<int64_t> g_launches{0};
 
 void set_error(const std::string &msg) { g_last_error = msg; }
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(); }
+
+void keep_async_pool(int device) {
+    static std::atomic<unsigned long long> done{0ull};
+    const unsigned long long bit = 1ull << (device & 63);
+    if (done.load() & bit) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    done.fetch_or(bit);
+}
 
 int fail(const char *what, const char *file, int line) {
     char buf[512];
@@ -111,6 +125,7 @@ int pde_grid_create(pde_grid **out, int device, int64_t nx_global, int64_t ny, i
     PDE_CHECK(cudaGetDeviceCount(&ndev));
     PDE_REQUIRE(device >= 0 && device < ndev, "no such CUDA device");
     DeviceGuard guard(device);
+    pde::keep_async_pool(device);
 
     pde_grid *g = new pde_grid();
     memset(g, 0, sizeof(*g));

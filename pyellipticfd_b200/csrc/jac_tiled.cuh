@@ -130,7 +130,7 @@ k_jac_tiled(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ De
             __syncthreads();     // everyone is done with this slot before it is refilled
         }
     }
-    if (Op::NRED > 0) block_store_partials(acc, partials);
+    if constexpr (Op::NRED > 0) block_store_partials(acc, partials + (int64_t)blockIdx.x * Op::NRED);
 }
 
 template <int H, int P>

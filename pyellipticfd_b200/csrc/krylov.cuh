@@ -23,11 +23,13 @@ struct BicgScal {
     double bnrm2, atol, rho, rho_prev, alpha, omega, beta, rv, ss, ts, tt, rr, rtr;
     double sums[MAX_RED];
     long long iter, info, maxiter;
-    int done, half, first, pad;
+    int done, half, first;
+    unsigned counter;     // blocks of the pass in flight that have stored their partial sums
 };
 
 template <int NRED>
-__device__ __forceinline__ void block_store_partials(double (&acc)[NRED], double *partials) {
+__device__ __forceinline__ void block_store_partials(double (&acc)[NRED], double *mine) {
+    // `mine`: this block's NRED slots of the pass's partial sums
     __shared__ double sh[NRED][PASS_THREADS / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
@@ -40,14 +42,181 @@ __device__ __forceinline__ void block_store_partials(double (&acc)[NRED], double
         double s = 0.0;
 #pragma unroll
         for (int w = 0; w < PASS_THREADS / 32; ++w) s += sh[threadIdx.x][w];
-        partials[(int64_t)blockIdx.x * NRED + threadIdx.x] = s;
+        mine[threadIdx.x] = s;
     }
+}
+
+// ---- scalar stages ------------------------------------------------------------------------
+enum Stage { ST_NONE = -1, ST_INIT = 0, ST_V = 1, ST_S = 2, ST_T = 3, ST_X = 4 };
+
+__device__ inline void top_of_loop(BicgScal *s) {
+    // iterative.py: loop head of `for iteration in range(maxiter)`
+    const double rhotol = 4.930380657631324e-32;      // eps**2 (iterative.py: rhotol)
+    if (s->iter >= s->maxiter) {
+        s->done = 1;
+        s->info = s->maxiter;
+        return;
+    }
+    if (sqrt(s->rr) < s->atol) {
+        s->done = 1;
+        s->info = 0;
+        return;
+    }
+    double rho = s->rtr;
+    if (fabs(rho) < rhotol) {
+        s->done = 1;
+        s->info = -10;
+        return;
+    }
+    if (s->iter > 0) {
+        if (fabs(s->omega) < rhotol) {
+            s->done = 1;
+            s->info = -11;
+            return;
+        }
+        s->beta = (rho / s->rho_prev) * (s->alpha / s->omega);
+    }
+    s->rho = rho;
+}
+
+// the scalar update that follows the reduction of one pass (one thread)
+__device__ inline void stage_update(int stage, BicgScal *s, double s0, double s1, double rtol,
+                                    double atol) {
+    switch (stage) {
+        case ST_INIT:
+            s->bnrm2 = sqrt(s0);
+            s->atol = fmax(atol, rtol * s->bnrm2);
+            s->rr = s0;
+            s->rtr = s0;
+            s->iter = 0;
+            s->first = 1;
+            s->half = 0;
+            if (s->bnrm2 == 0.0) {
+                s->done = 1;
+                s->info = 0;
+                return;
+            }
+            top_of_loop(s);
+            break;
+        case ST_V:
+            s->rv = s0;
+            if (s0 == 0.0) {
+                s->done = 1;
+                s->info = -11;
+                return;
+            }
+            s->alpha = s->rho / s0;
+            break;
+        case ST_S:
+            s->ss = s0;
+            if (sqrt(s0) < s->atol) s->half = 1;
+            break;
+        case ST_T:
+            s->ts = s0;
+            s->tt = s1;
+            s->omega = s0 / s1;
+            break;
+        case ST_X:
+            if (s->half) {
+                s->done = 1;
+                s->info = 0;
+                return;
+            }
+            s->rr = s0;
+            s->rtr = s1;
+            s->rho_prev = s->rho;
+            s->iter += 1;
+            s->first = 0;
+            top_of_loop(s);
+            break;
+    }
+}
+
+// fixed-order sum of the per-block partials by one block of PASS_THREADS threads: thread t adds
+// blocks t, t + PASS_THREADS, ..., then a binary tree -- the same bits whoever runs it
+template <int NRED>
+__device__ __forceinline__ void reduce_partials(const double *partials, int nblocks, double &s0,
+                                                double &s1) {
+    __shared__ double shr[NRED][PASS_THREADS];
+    double acc[NRED];
+#pragma unroll
+    for (int j = 0; j < NRED; ++j) acc[j] = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += PASS_THREADS)
+#pragma unroll
+        for (int j = 0; j < NRED; ++j) acc[j] += partials[(int64_t)b * NRED + j];
+#pragma unroll
+    for (int j = 0; j < NRED; ++j) shr[j][threadIdx.x] = acc[j];
+    __syncthreads();
+    for (int o = PASS_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o)
+#pragma unroll
+            for (int j = 0; j < NRED; ++j) shr[j][threadIdx.x] += shr[j][threadIdx.x + o];
+        __syncthreads();
+    }
+    s0 = shr[0][0];
+    s1 = NRED > 1 ? shr[NRED > 1 ? 1 : 0][0] : 0.0;
+}
+
+// What the LAST block of a pass does after storing its partial sums: reduce all `total`
+// partials (a pass may consist of two launches on one stream; `base` points at the first
+// partial of the pass, and only the second launch carries a stage) and update the scalars --
+// this replaces a one-block launch after every pass.
+struct StageArgs {
+    int stage;            // ST_NONE: no in-kernel stage (multi-GPU: an all-reduce sits in between)
+    int total;            // partial sums of the whole pass
+    double rtol, atol;
+};
+
+template <int NRED>
+__device__ __forceinline__ void pass_finish(double (&acc)[NRED], double *mine, const double *base,
+                                            BicgScal *scal, const StageArgs &sa) {
+    block_store_partials(acc, mine);
+    if (sa.stage == ST_NONE || scal == nullptr) return;
+    __shared__ bool last;
+    __syncthreads();                       // the partial sums of this block are stored
+    if (threadIdx.x == 0) {
+        __threadfence();
+        last = atomicAdd(&scal->counter, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    double s0, s1;
+    reduce_partials<NRED>(base, sa.total, s0, s1);
+    if (threadIdx.x == 0) {
+        scal->counter = 0u;
+        if (!scal->done && !(sa.stage == ST_T && scal->half))
+            stage_update(sa.stage, scal, s0, s1, sa.rtol, sa.atol);
+    }
+}
+
+// One-block stage kernel, kept for the slab-parallel path (an all-reduce of the local sums sits
+// between the two phases):
+//   phase 1: reduce only, local sums -> sums_io        phase 2: update the scalars from sums_io
+template <int NRED>
+__global__ void k_stage(int stage, const double *partials, int nblocks, BicgScal *s, double rtol,
+                        double atol, double *sums_io, int phase) {
+    if (s->done) return;
+    if (stage == ST_T && s->half) return;
+    double s0 = 0.0, s1 = 0.0;
+    if (phase == 1) {
+        reduce_partials<NRED>(partials, nblocks, s0, s1);
+        if (threadIdx.x == 0) {
+            sums_io[0] = s0;
+            if (NRED > 1) sums_io[1] = s1;
+        }
+        return;
+    }
+    if (threadIdx.x != 0) return;
+    s0 = sums_io[0];
+    if (NRED > 1) s1 = sums_io[1];
+    stage_update(stage, s, s0, s1, rtol, atol);
 }
 
 // elementwise passes over a whole vector (padding entries stay zero)
 template <class Op>
 __global__ void __launch_bounds__(PASS_THREADS)
-k_elem(int64_t n, Op op, double *partials, const BicgScal *scal) {
+k_elem(int64_t n, Op op, double *partials, BicgScal *scal, const StageArgs sa) {
     double acc[Op::NRED > 0 ? Op::NRED : 1] = {0.0};
     if (!(scal && scal->done)) {
         op.prepare(scal);
@@ -55,7 +224,8 @@ k_elem(int64_t n, Op op, double *partials, const BicgScal *scal) {
              i += (int64_t)gridDim.x * PASS_THREADS)
             op.at(i, acc);
     }
-    if (Op::NRED > 0) block_store_partials(acc, partials);
+    if constexpr (Op::NRED > 0)
+        pass_finish(acc, partials + (int64_t)blockIdx.x * Op::NRED, partials, scal, sa);
 }
 
 // r = b (x0 = 0), rtilde = r, x = 0; partial <b,b>
@@ -141,137 +311,19 @@ struct OpX {
     }
 };
 
-// ---- scalar stages ------------------------------------------------------------------------
-enum Stage { ST_INIT = 0, ST_V = 1, ST_S = 2, ST_T = 3, ST_X = 4 };
-
-__device__ inline void top_of_loop(BicgScal *s) {
-    // iterative.py: loop head of `for iteration in range(maxiter)`
-    const double rhotol = 4.930380657631324e-32;      // eps**2 (iterative.py: rhotol)
-    if (s->iter >= s->maxiter) {
-        s->done = 1;
-        s->info = s->maxiter;
-        return;
-    }
-    if (sqrt(s->rr) < s->atol) {
-        s->done = 1;
-        s->info = 0;
-        return;
-    }
-    double rho = s->rtr;
-    if (fabs(rho) < rhotol) {
-        s->done = 1;
-        s->info = -10;
-        return;
-    }
-    if (s->iter > 0) {
-        if (fabs(s->omega) < rhotol) {
-            s->done = 1;
-            s->info = -11;
-            return;
-        }
-        s->beta = (rho / s->rho_prev) * (s->alpha / s->omega);
-    }
-    s->rho = rho;
-}
-
-template <int NRED>
-__global__ void k_stage(int stage, const double *partials, int nblocks, BicgScal *s, double rtol,
-                        double atol, double *sums_io = nullptr, int phase = 0) {
-    // phase 0: reduce the per-block partials and update the scalars (single GPU)
-    // phase 1: reduce only, local sums -> sums_io   } multi-GPU: an all-reduce of sums_io
-    // phase 2: update the scalars from sums_io       } sits between the two
-    __shared__ double sh[NRED][PASS_THREADS];
-    if (s->done) return;
-    if (stage == ST_T && s->half) return;
-    if (phase == 2) {
-        if (threadIdx.x == 0) sh[0][0] = sums_io[0];
-        if (threadIdx.x == 0 && NRED > 1) sh[NRED > 1 ? 1 : 0][0] = sums_io[1];
-    }
-    double acc[NRED];
-#pragma unroll
-    for (int j = 0; j < NRED; ++j) acc[j] = 0.0;
-    if (phase != 2) {
-        for (int b = threadIdx.x; b < nblocks; b += PASS_THREADS)
-#pragma unroll
-            for (int j = 0; j < NRED; ++j) acc[j] += partials[(int64_t)b * NRED + j];
-#pragma unroll
-        for (int j = 0; j < NRED; ++j) sh[j][threadIdx.x] = acc[j];
-        __syncthreads();
-        for (int o = PASS_THREADS / 2; o > 0; o >>= 1) {
-            if (threadIdx.x < o)
-#pragma unroll
-                for (int j = 0; j < NRED; ++j) sh[j][threadIdx.x] += sh[j][threadIdx.x + o];
-            __syncthreads();
-        }
-    }
-    if (threadIdx.x != 0) return;
-    double s0 = sh[0][0], s1 = NRED > 1 ? sh[NRED > 1 ? 1 : 0][0] : 0.0;
-    if (phase == 1) {
-        sums_io[0] = s0;
-        if (NRED > 1) sums_io[1] = s1;
-        return;
-    }
-    switch (stage) {
-        case ST_INIT:
-            s->bnrm2 = sqrt(s0);
-            s->atol = fmax(atol, rtol * s->bnrm2);
-            s->rr = s0;
-            s->rtr = s0;
-            s->iter = 0;
-            s->first = 1;
-            s->half = 0;
-            if (s->bnrm2 == 0.0) {
-                s->done = 1;
-                s->info = 0;
-                return;
-            }
-            top_of_loop(s);
-            break;
-        case ST_V:
-            s->rv = s0;
-            if (s0 == 0.0) {
-                s->done = 1;
-                s->info = -11;
-                return;
-            }
-            s->alpha = s->rho / s0;
-            break;
-        case ST_S:
-            s->ss = s0;
-            if (sqrt(s0) < s->atol) s->half = 1;
-            break;
-        case ST_T:
-            s->ts = s0;
-            s->tt = s1;
-            s->omega = s0 / s1;
-            break;
-        case ST_X:
-            if (s->half) {
-                s->done = 1;
-                s->info = 0;
-                return;
-            }
-            s->rr = s0;
-            s->rtr = s1;
-            s->rho_prev = s->rho;
-            s->iter += 1;
-            s->first = 0;
-            top_of_loop(s);
-            break;
-    }
-}
-
 static inline int elem_grid(int64_t n, int num_sms) {
     int64_t b = (n + PASS_THREADS * 4 - 1) / (PASS_THREADS * 4);
     int64_t cap = (int64_t)num_sms * 8;
     return (int)(b < 1 ? 1 : (b > cap ? cap : b));
 }
 
+// stage: the scalar stage the last block of the pass performs (ST_NONE: none)
 template <class Op>
-static int launch_elem(int64_t n, int num_sms, const Op &op, double *partials,
-                       const BicgScal *scal, cudaStream_t st, int *nblocks_out = nullptr) {
+static int launch_elem(int64_t n, int num_sms, const Op &op, double *partials, BicgScal *scal,
+                       cudaStream_t st, int *nblocks_out = nullptr, int stage = ST_NONE,
+                       double rtol = 0.0, double atol = 0.0) {
     int nblk = elem_grid(n, num_sms);
-    k_elem<Op><<<nblk, PASS_THREADS, 0, st>>>(n, op, partials, scal);
+    k_elem<Op><<<nblk, PASS_THREADS, 0, st>>>(n, op, partials, scal, StageArgs{stage, nblk, rtol, atol});
     PDE_LAUNCH_CHECK();
     if (nblocks_out) *nblocks_out = nblk;
     return 0;
@@ -285,8 +337,9 @@ int newton_update_launch(int64_t n, int num_sms, const double *U, const double *
 // Backend concept:
 //   int64_t n() / unknowns() / max_row_blocks(); int num_sms();
 //   int dinv(double *out, cudaStream_t);                       out = 1/diag(J), 0 on padding
-//   int Av(src, rtilde, dst, partials, scal, st, &nblocks);    dst = J src, partial <rtilde,dst>
-//   int At(src, s, dst, partials, scal, st, &nblocks);         dst = J src, partial <dst,s>,<dst,dst>
+//   int Av(src, rtilde, dst, partials, scal, st, &nblocks, sa);   dst = J src, partial <rtilde,dst>
+//   int At(src, s, dst, partials, scal, st, &nblocks, sa);        dst = J src, partial <dst,s>,<dst,dst>
+//   (sa: StageArgs; the last block of the pass's LAST launch performs stage sa.stage)
 template <class Backend>
 static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol, double atol,
                         int64_t maxiter, int64_t check_every, double *d_work, int64_t *h_info,
@@ -324,33 +377,29 @@ static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol,
     PDE_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * n, st));
     PDE_CHECK(cudaMemsetAsync(t, 0, sizeof(double) * n, st));
     PDE_CHECK(cudaMemsetAsync(p, 0, sizeof(double) * n, st));
-    if ((rc = launch_elem(n, sms, OpInit{d_b, d_x, r, rtilde}, partials, nullptr, st, &nb))) return rc;
-    k_stage<1><<<1, PASS_THREADS, 0, st>>>(ST_INIT, partials, nb, scal, rtol, atol);
-    PDE_LAUNCH_CHECK();
+    if ((rc = launch_elem(n, sms, OpInit{d_b, d_x, r, rtilde}, partials, scal, st, &nb, ST_INIT, rtol,
+                          atol)))
+        return rc;
 
     struct {
         long long iter, info, maxiter;
-        int done, half, first, pad;
+        int done, half, first;
+        unsigned counter;
     } h_tail;
     const size_t tail_off = offsetof(BicgScal, iter);
-    // one BiCGStab iteration = 9 launches whose arguments never change within a solve
+    // one BiCGStab iteration = 5 passes (7 launches on grids: the two operator passes are a
+    // tiled launch + a tail launch) whose arguments never change within a solve; the last block
+    // of every pass reduces the partial sums and updates the scalars
     auto iteration = [&]() -> int {
         int rc2;
         if ((rc2 = launch_elem(n, sms, OpP{r, v, dinv, p, phat, 0, 0, 0}, nullptr, scal, st))) return rc2;
-        if ((rc2 = B.Av(phat, rtilde, v, partials, scal, st, &nb))) return rc2;
-        k_stage<1><<<1, PASS_THREADS, 0, st>>>(ST_V, partials, nb, scal, rtol, atol);
-        PDE_LAUNCH_CHECK();
-        if ((rc2 = launch_elem(n, sms, OpS{v, dinv, r, shat, 0}, partials, scal, st, &nb))) return rc2;
-        k_stage<1><<<1, PASS_THREADS, 0, st>>>(ST_S, partials, nb, scal, rtol, atol);
-        PDE_LAUNCH_CHECK();
-        if ((rc2 = B.At(shat, r, t, partials, scal, st, &nb))) return rc2;
-        k_stage<2><<<1, PASS_THREADS, 0, st>>>(ST_T, partials, nb, scal, rtol, atol);
-        PDE_LAUNCH_CHECK();
-        if ((rc2 = launch_elem(n, sms, OpX{phat, shat, t, rtilde, d_x, r, 0, 0, 0}, partials, scal, st,
-                               &nb)))
+        if ((rc2 = B.Av(phat, rtilde, v, partials, scal, st, &nb, StageArgs{ST_V, 0, rtol, atol}))) return rc2;
+        if ((rc2 = launch_elem(n, sms, OpS{v, dinv, r, shat, 0}, partials, scal, st, &nb, ST_S, rtol, atol)))
             return rc2;
-        k_stage<2><<<1, PASS_THREADS, 0, st>>>(ST_X, partials, nb, scal, rtol, atol);
-        PDE_LAUNCH_CHECK();
+        if ((rc2 = B.At(shat, r, t, partials, scal, st, &nb, StageArgs{ST_T, 0, rtol, atol}))) return rc2;
+        if ((rc2 = launch_elem(n, sms, OpX{phat, shat, t, rtilde, d_x, r, 0, 0, 0}, partials, scal, st,
+                               &nb, ST_X, rtol, atol)))
+            return rc2;
         return 0;
     };
     // Small and medium grids are launch bound (9 launches of a few microseconds each per
@@ -358,12 +407,15 @@ static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol,
     // a whole batch cost ~30 ms, measured) and replay it; the device-side `done` flag turns
     // surplus replays into no-ops.  Large grids gain nothing and skip the capture.
     cudaGraphExec_t exec = nullptr;
+    int launches_per_iteration = 0;
     if (B.unknowns() < (int64_t)4 << 20 &&
         cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int64_t l0 = pde::launch_count();
         int rcc = iteration();
+        launches_per_iteration = (int)(pde::launch_count() - l0);
         cudaGraph_t graph = nullptr;
         cudaError_t e = cudaStreamEndCapture(st, &graph);
-        pde::count_launch(-9);                                 // captured, not executed
+        pde::count_launch(-launches_per_iteration);            // captured, not executed
         if (rcc == 0 && e == cudaSuccess && graph) {
             if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
         }
@@ -382,7 +434,7 @@ static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol,
     while (true) {
         if (exec) {
             for (int64_t k = 0; k < check_every; ++k, ++launched) PDE_CHECK(cudaGraphLaunch(exec, st));
-            pde::count_launch((int)(9 * check_every));
+            pde::count_launch((int)(launches_per_iteration * check_every));
         } else {
             for (int64_t k = 0; k < check_every; ++k, ++launched)
                 if ((rc = iteration())) return rc;
