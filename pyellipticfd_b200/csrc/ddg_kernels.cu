@@ -195,7 +195,8 @@ static int launch_deep3_h(pde_grid *g, const double *S, const Epi &epi, double *
         attr_set |= dev_bit;
     }
     int ntiles = geo.tiles_x * geo.tiles_y * geo.tiles_z;
-    int grid = std::min(ntiles, g->num_sms * 2);
+    static const int ctas = getenv("PDE_K3_CTAS") ? std::max(1, atoi(getenv("PDE_K3_CTAS"))) : 2;
+    int grid = std::min(ntiles, g->num_sms * ctas);
     kern<<<grid, K3_THREADS, T::SMEM, st>>>(tmap, g->tab, offs, geo, epi, red, done);
     PDE_LAUNCH_CHECK();
     return 0;

@@ -322,7 +322,20 @@ template <class Op>
 static int launch_elem(int64_t n, int num_sms, const Op &op, double *partials, BicgScal *scal,
                        cudaStream_t st, int *nblocks_out = nullptr, int stage = ST_NONE,
                        double rtol = 0.0, double atol = 0.0) {
-    int nblk = elem_grid(n, num_sms);
+    // one wave: no more blocks than are resident at once (the 40-register OpX fits 6 blocks per
+    // SM; 8 per SM left a second, mostly empty wave -- 57 % achieved occupancy in round 1)
+    static int resident = 0;
+    if (resident == 0) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_elem<Op>, PASS_THREADS, 0) != cudaSuccess ||
+            occ < 1)
+            occ = 4;
+        cudaGetLastError();
+        resident = occ > 8 ? 8 : occ;
+    }
+    int64_t b = (n + PASS_THREADS * 4 - 1) / (PASS_THREADS * 4);
+    int64_t cap = (int64_t)num_sms * resident;
+    int nblk = (int)(b < 1 ? 1 : (b > cap ? cap : b));
     k_elem<Op><<<nblk, PASS_THREADS, 0, st>>>(n, op, partials, scal, StageArgs{stage, nblk, rtol, atol});
     PDE_LAUNCH_CHECK();
     if (nblocks_out) *nblocks_out = nblk;
