@@ -155,7 +155,7 @@ def run_reference(args):
     git-ignored oracle/_ref/ (oracle/ref_install.py; falls back to the NumPy port pinned against it
     if that copy is missing), on all host cores (one worker process per core over disjoint row
     chunks; the reference itself is single-threaded), on this arm's lattice.  Each of the
-    --warmup + --steps steps evaluates a bounded sample of deep rows (2..32 per worker, calibrated
+    --warmup + --steps steps evaluates a bounded sample of deep rows (1..32 per worker, calibrated
     so that the whole run takes about 150 s); the value is the sample's throughput over the timed
     steps, ms_per_step the mean measured wall time of one step's sample.  Both
     extremes are computed, as the reference always does (ddg.py:329-339)."""

@@ -112,13 +112,13 @@ def time_d2eigs_steps(ny, r, table, scaling, b0, workers, steps, warmup, impl, b
     """``warmup + steps`` timed steps for ``bench.py --impl reference``: every step is one call of
     d2eigs per worker process on that worker's chunk of deep rows (all workers at once, one per
     core).  The chunk height is chosen from a calibration call so that the whole run takes about
-    ``budget_s`` seconds (2..max_rows rows per worker).  Step time = the slowest worker's."""
+    ``budget_s`` seconds (1..max_rows rows per worker).  Step time = the slowest worker's."""
     table = np.asarray(table)
     H = int(np.abs(table).max())
     cal = time_d2eigs(ny, r, table, scaling, b0, 4, workers, 1, impl)      # 4 rows per worker
     per_row = cal["seconds"] / 4.0
     rows = int(budget_s / max(steps + warmup, 1) / per_row)
-    rows = max(2, min(max_rows, rows))
+    rows = max(1, min(max_rows, rows))
     args = [(ny, r, table, tuple(scaling), tuple(b0), r + H + w * rows, rows, warmup + steps, w, impl)
             for w in range(workers)]
     if workers == 1:
