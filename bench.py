@@ -835,6 +835,19 @@ def main():
                   "unknowns": unknowns,
                   "achieved_GBps_at_192B_per_unknown": 192.0 * unknowns / (tk / max(int(kdone), 1)) / 1e9,
                   "note": "wall clock incl. setup (diag, init) and the final host poll"}
+        if world == 1:
+            # opt-in fused s / t pass (PDE_JAC_FUSED=1, csrc/jac_tiled.cuh::k_jac_fused_st): same
+            # iterates to rounding, 22 instead of 25 vector passes per iteration
+            os.environ["PDE_JAC_FUSED"] = "1"
+            try:
+                run_k(4)
+                torch.cuda.synchronize()
+                tf = time.perf_counter()
+                _, _, kd2 = run_k(kit)
+                torch.cuda.synchronize()
+                krylov["fused_s_t_ms_per_iteration"] = (time.perf_counter() - tf) / max(int(kd2), 1) * 1e3
+            finally:
+                os.environ.pop("PDE_JAC_FUSED", None)
         del Fk, Pk, Jk, g_obst
     except Exception as e:                # reported, not fatal
         krylov = {"error": str(e)[:300]}

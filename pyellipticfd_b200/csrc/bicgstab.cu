@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(PASS_THREADS)
 k_rows(const GridDev G, const __grid_constant__ DeepTable tab, Op op, double *partials,
        BicgScal *scal, const int nrb /* row blocks; the rest are tail blocks */,
        const double *partials_base, const StageArgs sa) {
-    double acc[Op::NRED > 0 ? Op::NRED : 1] = {0.0};
+    DD acc[Op::NRED > 0 ? Op::NRED : 1] = {};
     bool skip = scal && (scal->done || (Op::kSkipOnHalf && scal->half));
     if (!skip) {
         op.prepare(scal);
@@ -56,7 +56,7 @@ k_rows(const GridDev G, const __grid_constant__ DeepTable tab, Op op, double *pa
     // `partials`: first slot of THIS launch; `partials_base`: first slot of the pass (the tiled
     // launch that may precede this one on the stream has stored its sums there already)
     if constexpr (Op::NRED > 0)
-        pass_finish(acc, partials + (int64_t)blockIdx.x * Op::NRED, partials_base, scal, sa);
+        pass_finish(acc, partials + (int64_t)blockIdx.x * DDW * Op::NRED, partials_base, scal, sa);
 }
 
 // ---- J x ------------------------------------------------------------------------------
@@ -70,15 +70,15 @@ struct OpMatvec {
     const double *source() const { return x; }
     __device__ const JacDev &jac() const { return J; }
     __device__ double aux(int64_t) const { return 0.0; }
-    __device__ void tile(int64_t o, double v, double, double *) { y[o] = v; }
+    __device__ void tile(int64_t o, double v, double, DD *) { y[o] = v; }
     __device__ void prepare(const BicgScal *) {}
-    __device__ void deep(const DeepTable &tab, const GridDev &G, int64_t o, double *) {
+    __device__ void deep(const DeepTable &tab, const GridDev &G, int64_t o, DD *) {
         y[o] = jac_row_deep(tab, J, x, o, G.pitch);
     }
-    __device__ void band(const GridDev &G, int64_t bi, double *) {
+    __device__ void band(const GridDev &G, int64_t bi, DD *) {
         y[G.band_center[bi]] = jac_row_band(G, J, x, bi);
     }
-    __device__ void wall(int64_t o, double *) { y[o] = x[o]; }
+    __device__ void wall(int64_t o, DD *) { y[o] = x[o]; }
 };
 
 // y += J^T x by scatter (solvers.py:192 only; not on the Krylov path)
@@ -98,7 +98,7 @@ struct OpMatvecT {
         atomicAdd(&y[j1], coef * A1 * xi);
         atomicAdd(&y[o], coef * Ac * xi);
     }
-    __device__ void deep(const DeepTable &tab, const GridDev &G, int64_t o, double *) {
+    __device__ void deep(const DeepTable &tab, const GridDev &G, int64_t o, DD *) {
         unsigned pm = J.pmin[o];
         double xi = x[o];
         if (pm == PDE_POLICY_IDENTITY) {
@@ -114,7 +114,7 @@ struct OpMatvecT {
                     J.cmax ? J.cmax[o] : J.cmax_s);
         }
     }
-    __device__ void band(const GridDev &G, int64_t bi, double *) {
+    __device__ void band(const GridDev &G, int64_t bi, DD *) {
         int64_t o = G.band_center[bi];
         unsigned pm = J.pmin[o];
         double xi = x[o];
@@ -131,7 +131,7 @@ struct OpMatvecT {
                     G.band_w[3 * k + 1], G.band_w[3 * k + 2], J.cmax ? J.cmax[o] : J.cmax_s);
         }
     }
-    __device__ void wall(int64_t o, double *) { atomicAdd(&y[o], x[o]); }
+    __device__ void wall(int64_t o, DD *) { atomicAdd(&y[o], x[o]); }
 };
 
 struct OpDiag {
@@ -142,15 +142,15 @@ struct OpDiag {
     double *d;
     int invert;
     __device__ void prepare(const BicgScal *) {}
-    __device__ void deep(const DeepTable &tab, const GridDev &, int64_t o, double *) {
+    __device__ void deep(const DeepTable &tab, const GridDev &, int64_t o, DD *) {
         double v = jac_diag_deep(tab, J, o);
         d[o] = invert ? 1.0 / v : v;
     }
-    __device__ void band(const GridDev &G, int64_t bi, double *) {
+    __device__ void band(const GridDev &G, int64_t bi, DD *) {
         double v = jac_diag_band(G, J, bi);
         d[G.band_center[bi]] = invert ? 1.0 / v : v;
     }
-    __device__ void wall(int64_t o, double *) { d[o] = 1.0; }
+    __device__ void wall(int64_t o, DD *) { d[o] = 1.0; }
 };
 
 // ---- BiCGStab passes -------------------------------------------------------------------
@@ -165,26 +165,26 @@ struct OpAv {
     const double *source() const { return src; }
     __device__ const JacDev &jac() const { return J; }
     __device__ double aux(int64_t o) const { return rtilde[o]; }
-    __device__ void tile(int64_t o, double v, double rt, double *acc) {
+    __device__ void tile(int64_t o, double v, double rt, DD *acc) {
         dst[o] = v;
-        acc[0] += rt * v;
+        dd_mac(acc[0], rt, v);
     }
     __device__ void prepare(const BicgScal *) {}
-    __device__ void deep(const DeepTable &tab, const GridDev &G, int64_t o, double *acc) {
+    __device__ void deep(const DeepTable &tab, const GridDev &G, int64_t o, DD *acc) {
         double v = jac_row_deep(tab, J, src, o, G.pitch);
         dst[o] = v;
-        acc[0] += rtilde[o] * v;
+        dd_mac(acc[0], rtilde[o], v);
     }
-    __device__ void band(const GridDev &G, int64_t bi, double *acc) {
+    __device__ void band(const GridDev &G, int64_t bi, DD *acc) {
         int64_t o = G.band_center[bi];
         double v = jac_row_band(G, J, src, bi);
         dst[o] = v;
-        acc[0] += rtilde[o] * v;
+        dd_mac(acc[0], rtilde[o], v);
     }
-    __device__ void wall(int64_t o, double *acc) {
+    __device__ void wall(int64_t o, DD *acc) {
         double v = src[o];
         dst[o] = v;
-        acc[0] += rtilde[o] * v;
+        dd_mac(acc[0], rtilde[o], v);
     }
 };
 
@@ -199,25 +199,111 @@ struct OpAt {
     const double *source() const { return src; }
     __device__ const JacDev &jac() const { return J; }
     __device__ double aux(int64_t o) const { return s[o]; }
-    __device__ void tile(int64_t o, double t, double so, double *acc) {
+    __device__ void tile(int64_t o, double t, double so, DD *acc) {
         dst[o] = t;
-        acc[0] += t * so;
-        acc[1] += t * t;
+        dd_mac(acc[0], t, so);
+        dd_mac(acc[1], t, t);
     }
     __device__ void prepare(const BicgScal *) {}
-    __device__ void one(int64_t o, double t, double *acc) {
+    __device__ void one(int64_t o, double t, DD *acc) {
         dst[o] = t;
-        acc[0] += t * s[o];
-        acc[1] += t * t;
+        dd_mac(acc[0], t, s[o]);
+        dd_mac(acc[1], t, t);
     }
-    __device__ void deep(const DeepTable &tab, const GridDev &G, int64_t o, double *acc) {
+    __device__ void deep(const DeepTable &tab, const GridDev &G, int64_t o, DD *acc) {
         one(o, jac_row_deep(tab, J, src, o, G.pitch), acc);
     }
-    __device__ void band(const GridDev &G, int64_t bi, double *acc) {
+    __device__ void band(const GridDev &G, int64_t bi, DD *acc) {
         one(G.band_center[bi], jac_row_band(G, J, src, bi), acc);
     }
-    __device__ void wall(int64_t o, double *acc) { one(o, src[o], acc); }
+    __device__ void wall(int64_t o, DD *acc) { one(o, src[o], acc); }
 };
+
+// band points and wall entries of the fused s / t pass (jac_tiled.cuh::k_jac_fused_st): the
+// neighbours' shat = dinv*(r - alpha*v) are recomputed per gathered value
+struct OpSAtTail {
+    static constexpr int NRED = 3;
+    static constexpr bool kSkipOnHalf = false;
+    static constexpr bool kTiled = false;
+    JacDev J;
+    const double *r, *v, *dinv;
+    double *s_out, *t_out;
+    double alpha;
+    __device__ void prepare(const BicgScal *s) { alpha = s->alpha; }
+    __device__ double sval(int64_t o) const { return __dsub_rn(r[o], __dmul_rn(alpha, v[o])); }
+    __device__ double shat(int64_t o) const { return dinv[o] * sval(o); }
+    __device__ void one(int64_t o, double sv, double tv, DD *acc) {
+        s_out[o] = sv;
+        t_out[o] = tv;
+        dd_mac(acc[0], sv, sv);
+        dd_mac(acc[1], tv, sv);
+        dd_mac(acc[2], tv, tv);
+    }
+    __device__ void deep(const DeepTable &, const GridDev &, int64_t, DD *) {}   // tiled kernel
+    __device__ void band(const GridDev &G, int64_t bi, DD *acc) {
+        const int64_t o = G.band_center[bi];
+        const double sv = sval(o);
+        const double tv = jac_row_band_get(G, J, bi, dinv[o] * sv,
+                                           [this](int64_t j) { return shat(j); });
+        one(o, sv, tv, acc);
+    }
+    __device__ void wall(int64_t o, DD *acc) {
+        const double sv = sval(o);
+        one(o, sv, dinv[o] * sv, acc);
+    }
+};
+
+template <int H>
+static int launch_fused_st_h(pde_grid *g, const JacDev &J, const double *r, const double *v,
+                             const double *dinv, double *s_out, double *t_out, double *partials,
+                             BicgScal *scal, cudaStream_t st, int *nblocks) {
+    constexpr int TX = KF_THREADS / K1_TY * 4;
+    DeepRegion dr = deep_region(g, 0, g->nx_local);
+    *nblocks = 0;
+    if (dr.nrows <= 0 || dr.ncols <= 0) return 0;
+    DeepGeom geo;
+    geo.pitch = g->pitch;
+    geo.row0 = dr.row0;
+    geo.col0 = dr.col0;
+    geo.nrows = dr.nrows;
+    geo.ncols = dr.ncols;
+    geo.tiles_x = (dr.nrows + TX - 1) / TX;
+    geo.tiles_y = (dr.ncols + K1_TY - 1) / K1_TY;
+    geo.split = geo.tiles_x;
+    geo.row0b = 0;
+    geo.nrowsb = 0;
+    CUtensorMap mr, mv, md;
+    int rc;
+    if ((rc = make_tmap(g, r, K1_TY + 2 * H + 2, TX + 2 * H, &mr))) return rc;
+    if ((rc = make_tmap(g, v, K1_TY + 2 * H + 2, TX + 2 * H, &mv))) return rc;
+    if ((rc = make_tmap(g, dinv, K1_TY + 2 * H + 2, TX + 2 * H, &md))) return rc;
+    constexpr int smem = k_jac_fused_smem_bytes<H>();
+    auto kern = k_jac_fused_st<H>;
+    static unsigned long long attr_set = 0ull;
+    const unsigned long long dev_bit = 1ull << (g->device & 63);
+    if (!(attr_set & dev_bit)) {
+        PDE_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set |= dev_bit;
+    }
+    int ntiles = geo.tiles_x * geo.tiles_y;
+    int grid = std::min(ntiles, g->num_sms);
+    kern<<<grid, KF_THREADS, smem, st>>>(mr, mv, md, g->tab, geo, J, s_out, t_out, partials, scal);
+    PDE_LAUNCH_CHECK();
+    *nblocks = grid;
+    return 0;
+}
+
+// Opt-in (PDE_JAC_FUSED=1, read at every solve): the fused pass is 6 % faster per iteration
+// (0.60 vs 0.64 ms at 4097^2) and its first iterate agrees with the separate passes to 4e-16,
+// but it regroups the partial sums of <s,s>, <t,s>, <t,t>, and BiCGStab on the policy Jacobians
+// amplifies a rounding-level perturbation tenfold per iteration (tools/fused_check.py): the
+// iteration COUNT of a solve is a lottery in the grouping (certifying solve at 4097^2: 492
+// iterations with the separate passes, 843 fused; tools/certify_counts.py).  The default keeps
+// the grouping the committed iteration counts and tests were measured with.
+static bool fused_st_enabled() {
+    const char *e = getenv("PDE_JAC_FUSED");
+    return e && atoi(e) != 0;
+}
 
 // deep-interior rows through the TMA-tiled kernel (jac_tiled.cuh); *nblocks = CTAs launched
 template <class Op, int H>
@@ -294,7 +380,7 @@ static int launch_rows(pde_grid *g, const Op &op, double *partials, BicgScal *sc
             if (rc) return rc;
             sa.total = nd + (int)tb;
             k_rows<Op><<<(unsigned)tb, PASS_THREADS, 0, st>>>(
-                G, g->tab, op, partials ? partials + (int64_t)nd * Op::NRED : nullptr, scal, 0,
+                G, g->tab, op, partials ? partials + (int64_t)nd * DDW * Op::NRED : nullptr, scal, 0,
                 partials, sa);
             PDE_LAUNCH_CHECK();
             if (nblocks_out) *nblocks_out = nd + (int)tb;
@@ -417,6 +503,33 @@ int pde_bicgstab(pde_grid *g, const pde_jac *J, const double *d_b, double *d_x, 
         int At(const double *src, const double *s, double *dst, double *partials,
                BicgScal *scal, cudaStream_t st, int *nb, const StageArgs &sa) {
             return launch_rows(g, OpAt{J, src, s, dst}, partials, scal, st, nb, sa);
+        }
+        // fused s / t pass: unsharded 2-D lattices with a tiled table and a band / wall tail
+        bool fused_st() const {
+            return fused_st_enabled() && jac_tiled_enabled() && g->tab.D > 0 && g->nmid == 0 &&
+                   g->tab.H >= 1 && g->tab.H <= 6 && g->halo_rows == 0 &&
+                   tail_blocks(g->n_band, g->nb) > 0;
+        }
+        int SAt(const double *r, const double *v, const double *dinv, double *s_out, double *t_out,
+                double *partials, BicgScal *scal, cudaStream_t st, int *nb, StageArgs sa) {
+            int nd = 0, rc = 1;
+            switch (g->tab.H) {
+                case 1: rc = launch_fused_st_h<1>(g, J, r, v, dinv, s_out, t_out, partials, scal, st, &nd); break;
+                case 2: rc = launch_fused_st_h<2>(g, J, r, v, dinv, s_out, t_out, partials, scal, st, &nd); break;
+                case 3: rc = launch_fused_st_h<3>(g, J, r, v, dinv, s_out, t_out, partials, scal, st, &nd); break;
+                case 4: rc = launch_fused_st_h<4>(g, J, r, v, dinv, s_out, t_out, partials, scal, st, &nd); break;
+                case 5: rc = launch_fused_st_h<5>(g, J, r, v, dinv, s_out, t_out, partials, scal, st, &nd); break;
+                case 6: rc = launch_fused_st_h<6>(g, J, r, v, dinv, s_out, t_out, partials, scal, st, &nd); break;
+            }
+            if (rc) return rc;
+            int64_t tb = tail_blocks(g->n_band, g->nb);
+            sa.total = nd + (int)tb;
+            k_rows<OpSAtTail><<<(unsigned)tb, PASS_THREADS, 0, st>>>(
+                grid_dev(g), g->tab, OpSAtTail{J, r, v, dinv, s_out, t_out, 0.0},
+                partials + (int64_t)nd * 3 * DDW, scal, 0, partials, sa);
+            PDE_LAUNCH_CHECK();
+            if (nb) *nb = nd + (int)tb;
+            return 0;
         }
     } backend{g, jac_dev(J)};
     return bicgstab_run(backend, d_b, d_x, rtol, atol, maxiter, check_every, d_work, h_info,

@@ -335,7 +335,7 @@ k_ell_rows(int64_t n, int64_t npts, const int4 *__restrict__ idx, const double2 
            EllJacDev J, const double *__restrict__ x, const double *__restrict__ aux,
            double *__restrict__ y, int invert, double *partials, BicgScal *scal,
            const StageArgs sa) {
-    double acc[NRED > 0 ? NRED : 1] = {0.0};
+    DD acc[NRED > 0 ? NRED : 1] = {};
     bool skip = scal && (scal->done || (MODE == 3 && scal->half));
     if (!skip) {
         for (int64_t i = blockIdx.x * (int64_t)PASS_THREADS + threadIdx.x; i < npts;
@@ -352,15 +352,15 @@ k_ell_rows(int64_t n, int64_t npts, const int4 *__restrict__ idx, const double2 
                 v = i < n ? ell_jac_row(idx, w, n, J, i, x) : x[i];
             }
             y[i] = v;
-            if (MODE == 2) acc[0] += aux[i] * v;
+            if (MODE == 2) dd_mac(acc[0], aux[i], v);
             if (MODE == 3) {
-                acc[0] += v * aux[i];
-                acc[1] += v * v;
+                dd_mac(acc[0], v, aux[i]);
+                dd_mac(acc[1], v, v);
             }
         }
     }
     if constexpr (NRED > 0)
-        pass_finish(acc, partials + (int64_t)blockIdx.x * NRED, partials, scal, sa);
+        pass_finish(acc, partials + (int64_t)blockIdx.x * pde::DDW * NRED, partials, scal, sa);
 }
 
 // residuals: mode 0 convex envelope, mode 1 Pucci
@@ -486,6 +486,11 @@ int pde_ell_bicgstab(pde_ell *e, const pde_ell_jac *J, const double *d_b, double
         int At(const double *src, const double *s, double *dst, double *partials,
                pde::BicgScal *scal, cudaStream_t st, int *nb, const pde::StageArgs &sa) {
             return ell_rows<3, 2>(e, J, src, s, dst, 0, partials, scal, st, nb, sa);
+        }
+        bool fused_st() const { return false; }
+        int SAt(const double *, const double *, const double *, double *, double *, double *,
+                pde::BicgScal *, cudaStream_t, int *, pde::StageArgs) {
+            return pde::fail("no fused s / t pass on point clouds", __FILE__, __LINE__);
         }
     } backend{e, ell_jac_dev(J)};
     return pde::bicgstab_run(backend, d_b, d_x, rtol, atol, maxiter, check_every, d_work, h_info,

@@ -144,6 +144,28 @@ __device__ __forceinline__ double jac_row_band(const GridDev &G, const JacDev &J
     return y;
 }
 
+// band row with the source values supplied by `get(offset)` (fused passes recompute them)
+template <class Get>
+__device__ __forceinline__ double jac_row_band_get(const GridDev &G, const JacDev &J, int64_t bi,
+                                                   double xc, Get get) {
+    int64_t o = G.band_center[bi];
+    unsigned pm = J.pmin[o];
+    if (pm == PDE_POLICY_IDENTITY) return xc;
+    int64_t k = G.band_ptr[bi] + pm;
+    double m = pair_value_exact(xc, get(G.band_j[2 * k]), get(G.band_j[2 * k + 1]), G.band_w[3 * k],
+                                G.band_w[3 * k + 1], G.band_w[3 * k + 2]);
+    double cm = J.cmin ? J.cmin[o] : J.cmin_s;
+    double y = cm * m;
+    if (J.pmax) {
+        k = G.band_ptr[bi] + J.pmax[o];
+        double mm = pair_value_exact(xc, get(G.band_j[2 * k]), get(G.band_j[2 * k + 1]),
+                                     G.band_w[3 * k], G.band_w[3 * k + 1], G.band_w[3 * k + 2]);
+        double cx = J.cmax ? J.cmax[o] : J.cmax_s;
+        y += cx * mm;
+    }
+    return y;
+}
+
 __device__ __forceinline__ double jac_diag_band(const GridDev &G, const JacDev &J, int64_t bi) {
     int64_t o = G.band_center[bi];
     unsigned pm = J.pmin[o];

@@ -11,6 +11,7 @@
 // point-cloud ELL Jacobian (ell.cu).
 #pragma once
 #include <cstddef>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -27,27 +28,44 @@ struct BicgScal {
     unsigned counter;     // blocks of the pass in flight that have stored their partial sums
 };
 
-template <int NRED>
-__device__ __forceinline__ void block_store_partials(double (&acc)[NRED], double *mine) {
+// ---- dot-product accumulators --------------------------------------------------------------
+// Plain double sums in a fixed order (per thread over its grid-stride sequence, shuffle tree per
+// warp, warps in order per block, blocks in a fixed order by the last block): deterministic for
+// a given launch geometry.  BiCGStab's iteration count on the policy Jacobians is chaotic in
+// the rounding of these sums: the certifying solve of the 4097^2 lattice took between 320 and
+// 1 905 iterations depending only on how the partial sums were grouped (tools/certify_counts.py).
+// Accumulating them in two- and three-fold working precision (Dot2 / Dot3, round 2) made the
+// count independent of most regroupings, but not smaller on average (360-770), 15 % slower per
+// iteration, and one 65^2 solve then stagnated for 10 n iterations -- the plain sums stay.
+constexpr int DDW = 1;            // doubles per partial sum
+struct DD {
+    double hi;
+};
+__device__ __forceinline__ void dd_mac(DD &s, double a, double b) { s.hi += a * b; }
+
+template <int NRED, int NT = PASS_THREADS>
+__device__ __forceinline__ void block_store_partials(DD (&acc)[NRED], double *mine) {
     // `mine`: this block's NRED slots of the pass's partial sums
-    __shared__ double sh[NRED][PASS_THREADS / 32];
+    __shared__ double sh[NRED][NT / 32];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
 #pragma unroll
     for (int j = 0; j < NRED; ++j) {
-        double v = warp_sum(acc[j]);
+        double v = warp_sum(acc[j].hi);
         if (lane == 0) sh[j][wid] = v;
     }
     __syncthreads();
     if (threadIdx.x < NRED) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < PASS_THREADS / 32; ++w) s += sh[threadIdx.x][w];
+        for (int w = 0; w < NT / 32; ++w) s += sh[threadIdx.x][w];
         mine[threadIdx.x] = s;
+        __threadfence();                  // visible device-wide before this block is counted
     }
 }
 
 // ---- scalar stages ------------------------------------------------------------------------
-enum Stage { ST_NONE = -1, ST_INIT = 0, ST_V = 1, ST_S = 2, ST_T = 3, ST_X = 4 };
+enum Stage { ST_NONE = -1, ST_INIT = 0, ST_V = 1, ST_S = 2, ST_T = 3, ST_X = 4,
+             ST_ST = 5 /* fused s / t pass: <s,s>, <t,s>, <t,t> at once */ };
 
 __device__ inline void top_of_loop(BicgScal *s) {
     // iterative.py: loop head of `for iteration in range(maxiter)`
@@ -81,8 +99,18 @@ __device__ inline void top_of_loop(BicgScal *s) {
 
 // the scalar update that follows the reduction of one pass (one thread)
 __device__ inline void stage_update(int stage, BicgScal *s, double s0, double s1, double rtol,
-                                    double atol) {
+                                    double atol, double s2 = 0.0) {
     switch (stage) {
+        case ST_ST:                       // ST_S, then ST_T unless the half step converged
+            s->ss = s0;
+            if (sqrt(s0) < s->atol) {
+                s->half = 1;
+            } else {
+                s->ts = s1;
+                s->tt = s2;
+                s->omega = s1 / s2;
+            }
+            break;
         case ST_INIT:
             s->bnrm2 = sqrt(s0);
             s->atol = fmax(atol, rtol * s->bnrm2);
@@ -136,14 +164,14 @@ __device__ inline void stage_update(int stage, BicgScal *s, double s0, double s1
 // blocks t, t + PASS_THREADS, ..., then a binary tree -- the same bits whoever runs it
 template <int NRED>
 __device__ __forceinline__ void reduce_partials(const double *partials, int nblocks, double &s0,
-                                                double &s1) {
+                                                double &s1, double &s2) {
     __shared__ double shr[NRED][PASS_THREADS];
     double acc[NRED];
 #pragma unroll
     for (int j = 0; j < NRED; ++j) acc[j] = 0.0;
     for (int b = threadIdx.x; b < nblocks; b += PASS_THREADS)
 #pragma unroll
-        for (int j = 0; j < NRED; ++j) acc[j] += partials[(int64_t)b * NRED + j];
+        for (int j = 0; j < NRED; ++j) acc[j] += __ldcg(partials + (int64_t)b * NRED + j);   // other blocks' stores: L2
 #pragma unroll
     for (int j = 0; j < NRED; ++j) shr[j][threadIdx.x] = acc[j];
     __syncthreads();
@@ -155,6 +183,7 @@ __device__ __forceinline__ void reduce_partials(const double *partials, int nblo
     }
     s0 = shr[0][0];
     s1 = NRED > 1 ? shr[NRED > 1 ? 1 : 0][0] : 0.0;
+    s2 = NRED > 2 ? shr[NRED > 2 ? 2 : 0][0] : 0.0;
 }
 
 // What the LAST block of a pass does after storing its partial sums: reduce all `total`
@@ -168,7 +197,7 @@ struct StageArgs {
 };
 
 template <int NRED>
-__device__ __forceinline__ void pass_finish(double (&acc)[NRED], double *mine, const double *base,
+__device__ __forceinline__ void pass_finish(DD (&acc)[NRED], double *mine, const double *base,
                                             BicgScal *scal, const StageArgs &sa) {
     block_store_partials(acc, mine);
     if (sa.stage == ST_NONE || scal == nullptr) return;
@@ -181,12 +210,12 @@ __device__ __forceinline__ void pass_finish(double (&acc)[NRED], double *mine, c
     __syncthreads();
     if (!last) return;
     __threadfence();
-    double s0, s1;
-    reduce_partials<NRED>(base, sa.total, s0, s1);
+    double s0, s1, s2;
+    reduce_partials<NRED>(base, sa.total, s0, s1, s2);
     if (threadIdx.x == 0) {
         scal->counter = 0u;
         if (!scal->done && !(sa.stage == ST_T && scal->half))
-            stage_update(sa.stage, scal, s0, s1, sa.rtol, sa.atol);
+            stage_update(sa.stage, scal, s0, s1, sa.rtol, sa.atol, s2);
     }
 }
 
@@ -198,9 +227,9 @@ __global__ void k_stage(int stage, const double *partials, int nblocks, BicgScal
                         double atol, double *sums_io, int phase) {
     if (s->done) return;
     if (stage == ST_T && s->half) return;
-    double s0 = 0.0, s1 = 0.0;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0;
     if (phase == 1) {
-        reduce_partials<NRED>(partials, nblocks, s0, s1);
+        reduce_partials<NRED>(partials, nblocks, s0, s1, s2);
         if (threadIdx.x == 0) {
             sums_io[0] = s0;
             if (NRED > 1) sums_io[1] = s1;
@@ -217,7 +246,7 @@ __global__ void k_stage(int stage, const double *partials, int nblocks, BicgScal
 template <class Op>
 __global__ void __launch_bounds__(PASS_THREADS)
 k_elem(int64_t n, Op op, double *partials, BicgScal *scal, const StageArgs sa) {
-    double acc[Op::NRED > 0 ? Op::NRED : 1] = {0.0};
+    DD acc[Op::NRED > 0 ? Op::NRED : 1] = {};
     if (!(scal && scal->done)) {
         op.prepare(scal);
         for (int64_t i = blockIdx.x * (int64_t)PASS_THREADS + threadIdx.x; i < n;
@@ -225,7 +254,7 @@ k_elem(int64_t n, Op op, double *partials, BicgScal *scal, const StageArgs sa) {
             op.at(i, acc);
     }
     if constexpr (Op::NRED > 0)
-        pass_finish(acc, partials + (int64_t)blockIdx.x * Op::NRED, partials, scal, sa);
+        pass_finish(acc, partials + (int64_t)blockIdx.x * DDW * Op::NRED, partials, scal, sa);
 }
 
 // r = b (x0 = 0), rtilde = r, x = 0; partial <b,b>
@@ -234,12 +263,12 @@ struct OpInit {
     const double *b;
     double *x, *r, *rtilde;
     __device__ void prepare(const BicgScal *) {}
-    __device__ void at(int64_t i, double *acc) {
+    __device__ void at(int64_t i, DD *acc) {
         double v = b[i];
         r[i] = v;
         rtilde[i] = v;
         x[i] = 0.0;
-        acc[0] += v * v;
+        dd_mac(acc[0], v, v);
     }
 };
 
@@ -255,7 +284,7 @@ struct OpP {
         omega = s->omega;
         first = s->first;
     }
-    __device__ void at(int64_t i, double *) {
+    __device__ void at(int64_t i, DD *) {
         double pn;
         if (first) {
             pn = r[i];
@@ -276,11 +305,11 @@ struct OpS {
     double *r, *shat;
     double alpha;
     __device__ void prepare(const BicgScal *s) { alpha = s->alpha; }
-    __device__ void at(int64_t i, double *acc) {
+    __device__ void at(int64_t i, DD *acc) {
         double s = __dsub_rn(r[i], __dmul_rn(alpha, v[i]));
         r[i] = s;
         shat[i] = dinv[i] * s;
-        acc[0] += s * s;
+        dd_mac(acc[0], s, s);
     }
 };
 
@@ -296,7 +325,7 @@ struct OpX {
         omega = s->omega;
         half = s->half;
     }
-    __device__ void at(int64_t i, double *acc) {
+    __device__ void at(int64_t i, DD *acc) {
         double xn = __dadd_rn(x[i], __dmul_rn(alpha, phat[i]));
         if (half) {          // converged after the half step: x += alpha*phat only
             x[i] = xn;
@@ -306,8 +335,37 @@ struct OpX {
         x[i] = xn;
         double rn = __dsub_rn(r[i], __dmul_rn(omega, t[i]));
         r[i] = rn;
-        acc[0] += rn * rn;
-        acc[1] += rtilde[i] * rn;
+        dd_mac(acc[0], rn, rn);
+        dd_mac(acc[1], rtilde[i], rn);
+    }
+};
+
+// OpX after the fused s / t pass (the grid backend): s is kept instead of shat, and shat =
+// dinv*s -- the same product OpS stores -- is formed on the fly
+struct OpXs {
+    static constexpr int NRED = 2;
+    const double *phat, *sv, *dinv, *t, *rtilde;
+    double *x, *r;
+    double alpha, omega;
+    int half;
+    __device__ void prepare(const BicgScal *s) {
+        alpha = s->alpha;
+        omega = s->omega;
+        half = s->half;
+    }
+    __device__ void at(int64_t i, DD *acc) {
+        double xn = __dadd_rn(x[i], __dmul_rn(alpha, phat[i]));
+        if (half) {
+            x[i] = xn;
+            return;
+        }
+        const double si = sv[i];
+        xn = __dadd_rn(xn, __dmul_rn(omega, __dmul_rn(dinv[i], si)));
+        x[i] = xn;
+        double rn = __dsub_rn(si, __dmul_rn(omega, t[i]));
+        r[i] = rn;
+        dd_mac(acc[0], rn, rn);
+        dd_mac(acc[1], rtilde[i], rn);
     }
 };
 
@@ -332,6 +390,7 @@ static int launch_elem(int64_t n, int num_sms, const Op &op, double *partials, B
             occ = 4;
         cudaGetLastError();
         resident = occ > 8 ? 8 : occ;
+        if (const char *e = getenv("PDE_ELEM_BLOCKS")) resident = atoi(e) > 0 ? atoi(e) : resident;
     }
     int64_t b = (n + PASS_THREADS * 4 - 1) / (PASS_THREADS * 4);
     int64_t cap = (int64_t)num_sms * resident;
@@ -353,6 +412,8 @@ int newton_update_launch(int64_t n, int num_sms, const double *U, const double *
 //   int Av(src, rtilde, dst, partials, scal, st, &nblocks, sa);   dst = J src, partial <rtilde,dst>
 //   int At(src, s, dst, partials, scal, st, &nblocks, sa);        dst = J src, partial <dst,s>,<dst,dst>
 //   (sa: StageArgs; the last block of the pass's LAST launch performs stage sa.stage)
+//   bool fused_st();  int SAt(r, v, dinv, s_out, t_out, partials, scal, st, &nblocks, sa):
+//       s = r - alpha*v, t = J (dinv*s), partial <s,s>, <t,s>, <t,t> (optional, grids only)
 template <class Backend>
 static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol, double atol,
                         int64_t maxiter, int64_t check_every, double *d_work, int64_t *h_info,
@@ -361,13 +422,22 @@ static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol,
     const int sms = B.num_sms();
     if (maxiter <= 0) maxiter = 10 * B.unknowns();     // iterative.py: maxiter = n*10
     if (check_every < 1) check_every = 32;
-    double *r = d_work, *rtilde = r + n, *p = rtilde + n, *v = p + n, *phat = v + n,
-           *t = phat + n, *shat = t + n, *dinv = shat + n;   // phat, shat at even multiples of n:
-    // 16-byte aligned sources for the TMA-tiled operator passes whatever the parity of n
+    // TMA sources must be 16-byte aligned whatever the parity of n: they sit at even multiples
+    // of n.  Plain passes: phat, shat.  Fused s / t pass (grids): r, v, phat, dinv; slot 7 keeps s.
+    const bool fused = B.fused_st();
+    double *r = d_work, *rtilde = r + n;
+    double *p, *v, *phat, *t, *shat, *dinv;
+    if (fused) {
+        v = d_work + 2 * n; p = d_work + 3 * n; phat = d_work + 4 * n; t = d_work + 5 * n;
+        dinv = d_work + 6 * n; shat = d_work + 7 * n;      // shat: holds s
+    } else {
+        p = d_work + 2 * n; v = d_work + 3 * n; phat = d_work + 4 * n; t = d_work + 5 * n;
+        shat = d_work + 6 * n; dinv = d_work + 7 * n;
+    }
     int64_t max_blocks = B.max_row_blocks() + (int64_t)sms * 8;
     double *partials = nullptr;
     BicgScal *scal = nullptr;
-    PDE_CHECK(cudaMallocAsync((void **)&partials, sizeof(double) * MAX_RED * max_blocks, st));
+    PDE_CHECK(cudaMallocAsync((void **)&partials, sizeof(double) * DDW * MAX_RED * max_blocks, st));
     PDE_CHECK(cudaMallocAsync((void **)&scal, sizeof(BicgScal), st));
     struct Cleanup {
         double *p;
@@ -390,6 +460,8 @@ static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol,
     PDE_CHECK(cudaMemsetAsync(v, 0, sizeof(double) * n, st));
     PDE_CHECK(cudaMemsetAsync(t, 0, sizeof(double) * n, st));
     PDE_CHECK(cudaMemsetAsync(p, 0, sizeof(double) * n, st));
+    // the fused s / t pass writes s at real entries only: its padding entries must read as zero
+    if (fused) PDE_CHECK(cudaMemsetAsync(shat, 0, sizeof(double) * n, st));
     if ((rc = launch_elem(n, sms, OpInit{d_b, d_x, r, rtilde}, partials, scal, st, &nb, ST_INIT, rtol,
                           atol)))
         return rc;
@@ -407,6 +479,14 @@ static int bicgstab_run(Backend &B, const double *d_b, double *d_x, double rtol,
         int rc2;
         if ((rc2 = launch_elem(n, sms, OpP{r, v, dinv, p, phat, 0, 0, 0}, nullptr, scal, st))) return rc2;
         if ((rc2 = B.Av(phat, rtilde, v, partials, scal, st, &nb, StageArgs{ST_V, 0, rtol, atol}))) return rc2;
+        if (fused) {
+            // s = r - alpha*v (-> slot 7), t = J (dinv*s), <s,s>, <t,s>, <t,t> in ONE pass over
+            // tiles of r, v, dinv: 5 vector passes instead of the 8 of OpS + OpAt
+            if ((rc2 = B.SAt(r, v, dinv, shat, t, partials, scal, st, &nb, StageArgs{ST_ST, 0, rtol, atol})))
+                return rc2;
+            return launch_elem(n, sms, OpXs{phat, shat, dinv, t, rtilde, d_x, r, 0, 0, 0}, partials, scal,
+                               st, &nb, ST_X, rtol, atol);
+        }
         if ((rc2 = launch_elem(n, sms, OpS{v, dinv, r, shat, 0}, partials, scal, st, &nb, ST_S, rtol, atol)))
             return rc2;
         if ((rc2 = B.At(shat, r, t, partials, scal, st, &nb, StageArgs{ST_T, 0, rtol, atol}))) return rc2;
