@@ -418,6 +418,10 @@ def solve_full_size(args, obstacle):
                 first = {"sweep_seconds": t_sw, "certify_seconds": t_nw, "seconds": t_sw + t_nw}
         out["first_call"] = first
         out["seconds"] = t_sw + t_nw
+        # everything a cold caller pays: grid constructor, the sweep solver's one-off tables, and
+        # the first (cold) sweep + certification
+        out["seconds_incl_setup_first_call"] = (out["grid_build_s"] + out["sweep_tables_s"]
+                                                + first["seconds"])
         out["converged"] = bool(sw_ok and nw_ok)
         if args.solve_policy_from_g:
             st = {}

@@ -152,6 +152,22 @@ static int launch_deep_hp(pde_grid *g, const double *S, const Epi &epi, double *
 }
 
 // ---- 3-D lattices: bricks staged by 3-D TMA loads (stencil_deep3.cuh) -----------------------
+static bool band3_fused(const pde_grid *g, int ntiles) {
+    // opt-in (PDE_K3_FUSE_BAND=1, read per call: a test compares both paths).  Measured SLOWER
+    // than the separate band launch -- 259^3: 1.27 vs 0.92 ms, 131^3: 0.30 vs 0.19 ms: at 16 warps
+    // per SM the dependent loads of a band point (centre -> row pointer -> offsets -> values) are
+    // latency bound and a brick's share of band points takes longer than the brick itself.
+    const char *e = getenv("PDE_K3_FUSE_BAND");
+    const bool on = e && atoi(e) != 0;
+    return on && g->nmid > 0 && g->n_band > 0 && ntiles >= 2 * g->num_sms;
+}
+static int deep3_tiles(const pde_grid *g) {
+    const int r = g->radius, P = 8;
+    int nxd = (int)g->nx3 - 2 * r, nyd = (int)g->nmid - 2 * r, nzd = (int)g->ny - 2 * r;
+    if (nxd <= 0 || nyd <= 0 || nzd <= 0) return 0;
+    return ((nxd + P - 1) / P) * ((nyd + K3_TY - 1) / K3_TY) * ((nzd + K3_TZ - 1) / K3_TZ);
+}
+
 template <class Eval, int H, int MODE, class Epi>
 static int launch_deep3_h(pde_grid *g, const double *S, const Epi &epi, double *red,
                           const unsigned long long *done, cudaStream_t st) {
@@ -197,7 +213,11 @@ static int launch_deep3_h(pde_grid *g, const double *S, const Epi &epi, double *
     int ntiles = geo.tiles_x * geo.tiles_y * geo.tiles_z;
     static const int ctas = getenv("PDE_K3_CTAS") ? std::max(1, atoi(getenv("PDE_K3_CTAS"))) : 2;
     int grid = std::min(ntiles, g->num_sms * ctas);
-    kern<<<grid, K3_THREADS, T::SMEM, st>>>(tmap, g->tab, offs, geo, epi, red, done);
+    // band points ride along in the brick loop on request (PDE_K3_FUSE_BAND=1) when the lattice
+    // has enough bricks to spread them over
+    Band3 band{0, g->d_band_center, g->d_band_ptr, g->d_band_j, g->d_band_w};
+    if (band3_fused(g, ntiles)) band.n = g->n_band;
+    kern<<<grid, K3_THREADS, T::SMEM, st>>>(tmap, g->tab, offs, geo, epi, red, done, band, S);
     PDE_LAUNCH_CHECK();
     return 0;
 }
@@ -289,6 +309,11 @@ static int launch_both(pde_grid *g, const double *S, const Epi &epi, int mode, d
     // forked onto the context's side stream so that it shares the SMs with the fp64-bound
     // deep kernel instead of running after it; the two write disjoint points.
     int rc;
+    if (g->nmid > 0 && g->tab.D > 0 && band3_fused(g, deep3_tiles(g))) {
+        // 3-D: the band points are evaluated inside the brick loop of the deep kernel
+        if (mode == 0) return launch_deep<0, Epi>(g, S, epi, red, done, st);
+        return launch_deep<1, Epi>(g, S, epi, red, done, st);
+    }
     const bool fork = g->n_band > 0 && g->tab.D > 0 && g->win_hi - g->win_lo > 64;
     cudaStream_t sb = fork ? g->side : st;
     if (fork) {

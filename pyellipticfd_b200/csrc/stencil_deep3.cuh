@@ -95,11 +95,69 @@ struct Deep3Tile {
     static constexpr int SMEM = 2 * TILE_STRIDE + 64;
 };
 
+// Band points handled inside the brick loop: after every brick a CTA evaluates its share of the
+// band points (one warp per point over its explicit pair rows, as k_band).  In 3-D the band is a
+// surface layer two cells thick -- as much work as all deep points at 259^3 -- and a separate
+// band kernel cannot overlap with this one (two 125-register CTAs fill the register file); here
+// the memory-bound band rows of one CTA can overlap with the fp64-bound brick of its neighbour.
+// Opt-in: measured slower than the separate launch (see ddg_kernels.cu::band3_fused).
+struct Band3 {
+    int64_t n;                       // 0: band points are served by a separate launch
+    const int64_t *center, *ptr, *jj;
+    const double *ww;
+};
+
+template <int MODE, class Epi>
+__device__ __forceinline__ void band_point_warp(const Band3 &B, int64_t i, const double *__restrict__ S,
+                                                const Epi &epi, BlockMax2 &red) {
+    const int lane = threadIdx.x & 31;
+    const int64_t o = B.center[i];
+    const double uc = S[o];
+    double mn = __longlong_as_double(0x7ff0000000000000LL);
+    double mx = __longlong_as_double(0xfff0000000000000LL);
+    int kmn = -1, kmx = 0x7fffffff;
+    const int64_t b = B.ptr[i], e = B.ptr[i + 1];
+    for (int64_t k = b + lane; k < e; k += 32) {
+        double u0 = S[B.jj[2 * k]], u1 = S[B.jj[2 * k + 1]];
+        double w_0 = B.ww[3 * k], w_1 = B.ww[3 * k + 1], w0 = B.ww[3 * k + 2];
+        double d;
+        if (MODE == 0)
+            d = pair_value_exact(uc, u0, u1, w_0, w_1, w0);
+        else
+            d = (fma(w_1, u1 - uc, w_0 * (u0 - uc))) * w0;
+        if (Epi::kMin && d <= mn) {        // rows ascend within a lane: keeps the last
+            mn = d;
+            kmn = (int)(k - b);
+        }
+        if (Epi::kMax && d > mx) {         // keeps the first
+            mx = d;
+            kmx = (int)(k - b);
+        }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {     // tie rule across lanes: min -> highest row, max -> lowest
+        double omn = __shfl_xor_sync(0xffffffffu, mn, s);
+        int okn = __shfl_xor_sync(0xffffffffu, kmn, s);
+        double omx = __shfl_xor_sync(0xffffffffu, mx, s);
+        int okx = __shfl_xor_sync(0xffffffffu, kmx, s);
+        if (Epi::kMin && (omn < mn || (omn == mn && okn > kmn))) {
+            mn = omn;
+            kmn = okn;
+        }
+        if (Epi::kMax && (omx > mx || (omx == mx && okx < kmx))) {
+            mx = omx;
+            kmx = okx;
+        }
+    }
+    if (lane == 0) epi(o, uc, mn, mx, kmn, kmx, Epi::kPre ? epi.pre(o) : 0.0, red);
+}
+
 template <class Eval, int H, int P, int MODE, class Epi>
 __global__ void __launch_bounds__(K3_THREADS, 2)
 k_deep3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTable tab,
         const __grid_constant__ Deep3Offsets offs, const Deep3Geom geo, const Epi epi,
-        double *red_out, const unsigned long long *done_flag) {
+        double *red_out, const unsigned long long *done_flag, const Band3 band,
+        const double *__restrict__ S) {
     using T = Deep3Tile<H, P>;
     if (done_flag && *done_flag) return;
 
@@ -175,6 +233,11 @@ k_deep3(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ DeepTa
                     epi(o0 + p * ox, uc[p], mn[p], mx[p], kmn[p], kmx[p], pre[Epi::kPre ? p : 0], red);
         }
         __syncthreads();
+        if (band.n > 0) {     // this brick's share of the band points, one warp per point
+            const int64_t q0 = band.n * tile / ntiles, q1 = band.n * (int64_t)(tile + 1) / ntiles;
+            for (int64_t i = q0 + (tid >> 5); i < q1; i += K3_THREADS / 32)
+                band_point_warp<MODE>(band, i, S, epi, red);
+        }
     }
 
     if (Epi::kRed) {

@@ -176,3 +176,41 @@ def test_structured_3d_129cubed_properties():
     X, Y, Z = G.points.T
     q = X ** 2 - Y ** 2 + 2 * Z ** 2
     assert np.abs(ddg.d2min(G, q)[0] + 2).max() < 1e-8 and np.abs(ddg.d2max(G, q)[0] - 4).max() < 1e-8
+
+
+def test_band_points_inside_the_brick_loop_equal_the_band_kernel(monkeypatch):
+    """Opt-in (PDE_K3_FUSE_BAND=1): lattices with at least two bricks per CTA can evaluate their
+    band points inside the brick loop of the 3-D kernel (stencil_deep3.cuh::band_point_warp)
+    instead of a separate band launch: values, policies and the fused residual / Euler epilogues
+    are bit-identical either way (the separate launch is faster and stays the default)."""
+    import torch
+    from pyellipticfd_b200._context import GridContext
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    n = 97
+    G = FDRegularGrid([n, n - 8, n + 5], _dyadic_box((n, n - 8, n + 5), (1 / 128.0,) * 3), 2,
+                      interpolation=False)
+    ctx = GridContext.get(G)
+    assert ctx.nd
+    rng = np.random.default_rng(11)
+    S = ctx.pack(torch.from_numpy(rng.integers(-4, 5, G.num_points).astype(float)).cuda())   # ties
+    g = ctx.pack(torch.from_numpy(rng.standard_normal(G.num_points)).cuda())
+    res = {}
+    for fuse in ("1", "0"):
+        monkeypatch.setenv("PDE_K3_FUSE_BAND", fuse)
+        lmin, lmax, pmin, pmax = ctx.d2eigs(S, policy=True)
+        F, P, red = ctx.ce_residual(S, g, policy=True)
+        Un, red2 = ctx.ce_euler_step(S, g, 1e-5)
+        torch.cuda.synchronize()
+        res[fuse] = [t.clone() for t in (lmin, lmax, ctx.unpad_policy(pmin), ctx.unpad_policy(pmax),
+                                         F, ctx.unpad_policy(P), red, Un, red2)]
+    for a, b in zip(res["1"], res["0"]):
+        assert torch.equal(a, b)
+    # and against the reference formula on the band points themselves (explicit rows, host)
+    u = ctx.unpack(S).cpu().numpy()
+    bp = np.asarray(G.band_pairs)
+    P0 = G.coords(bp[:, 0]); h0 = np.linalg.norm(G.coords(bp[:, 1]) - P0, axis=1)
+    h1 = np.linalg.norm(G.coords(bp[:, 2]) - P0, axis=1)
+    d = 2 / (h0 + h1) * ((u[bp[:, 1]] - u[bp[:, 0]]) * (1 / h0) + (u[bp[:, 2]] - u[bp[:, 0]]) * (1 / h1))
+    want = np.minimum.reduceat(d, G.band_ptr[:-1])
+    got = ctx.unpad(res["1"][0]).cpu().numpy()[G.band_index]
+    assert np.array_equal(got, want)
