@@ -166,6 +166,18 @@ int pde_jac_matvec(pde_grid *g, const pde_jac *J, const double *d_x, double *d_y
                    int transpose, void *stream);
 int pde_jac_diagonal(pde_grid *g, const pde_jac *J, double *d_diag, void *stream);
 
+/* ddg.d2eigs / d2min / d2max (ddg.py:251-339) for a field in PINNED host memory with the results
+ * in pinned host memory (the reference's arrays live on the host): H2D copy, stencil kernels and
+ * D2H copy pipelined over chunks of `chunk_rows` lattice rows on three streams, enqueued by one
+ * call.  h_u: the reference's flat vector (interior points row-major, then the wall points);
+ * h_lmin / h_lmax (either may be NULL): values over the interior points.  Staging: d_S, d_lmin,
+ * d_lmax state-layout vectors (pde_grid_state_len doubles), d_fin nx*ny + nb doubles,
+ * d_fout_* nx*ny doubles.  On return the work is enqueued; the results are complete once
+ * s_main is.  Unsharded 2-D lattices. */
+int pde_ddg_d2eigs_host(pde_grid *g, const double *h_u, double *h_lmin, double *h_lmax, int mode,
+                        int64_t chunk_rows, double *d_S, double *d_lmin, double *d_lmax,
+                        double *d_fin, double *d_fout_min, double *d_fout_max, void *s_main,
+                        void *s_in, void *s_out);
 /* ------------------------------------------------------------------------
  * Convex envelope, convex_envelope.py:8-56 / :58-123.
  * residual: F = W-g everywhere; interior rows with -lambda_min > W-g are

@@ -18,7 +18,8 @@ from . import _lib
 from ._lib import pde_jac, check, vp
 
 POLICY_IDENTITY = 0xFFFF
-HOST_COPY_LINEAR = False      # see GridContext.d2eigs_host
+HOST_COPY_LINEAR = True       # see GridContext.d2eigs_host
+HOST_CHUNK_ROWS = 128
 
 
 def _ptr(t):
@@ -400,19 +401,28 @@ class GridContext(object):
                                       _ptr(pmax), int(mode), _stream()))
         return lmin, lmax, pmin, pmax
 
-    def d2eigs_host(self, u_host, want_min=True, want_max=True, mode=0, chunk_rows=256,
-                    linear=None, halo_hook=None, out=None):
+    def d2eigs_host(self, u_host, want_min=True, want_max=True, mode=0, chunk_rows=None,
+                    linear=None, halo_hook=None, out=None, native=False):
         """ddg.d2eigs values for a field in PINNED host memory, results in pinned host
         memory: the H2D copy, the stencil kernels and the D2H copy are pipelined over
         chunks of rows on three streams (PCIe is full duplex).  ``linear=False``: the layout
-        conversion is done by the 2-D DMA copies themselves; ``linear=True``: the PCIe copies
-        are plain linear copies to / from flat device staging buffers and the conversion is
-        a device-side 2-D copy (default: ``HOST_COPY_LINEAR``).
+        conversion is done by the 2-D DMA copies themselves; ``linear=True`` (default,
+        ``HOST_COPY_LINEAR``): the copy streams carry nothing but back-to-back linear PCIe copies
+        to / from flat device staging buffers and the conversions are device-side copies on the
+        compute stream (4097^2, 128-row chunks: 3.5 ms against 3.75 ms).  ``native=True``: the same
+        pipeline enqueued by ONE C call (``pde_ddg_d2eigs_host``, the C-ABI entry point for host
+        buffers; same results, 3.5 - 4.2 ms with a larger run-to-run spread).
         ``halo_hook(S)`` (slab contexts, multigpu.ShardedGrid.d2eigs_host): the slab's first /
         last rows are uploaded first and the hook -- the halo exchange -- runs on the compute
         stream before the first chunk.  ``out``: (pinned lmin, pinned lmax) to reuse."""
-        linear = HOST_COPY_LINEAR if linear is None else linear
         nloc, ny, H = self.nx_local, self.ny, max(self.radius, 1)
+        if chunk_rows is None:
+            chunk_rows = HOST_CHUNK_ROWS if halo_hook is None else 256
+        if native:
+            if halo_hook is not None or self.nd or self.halo_rows or not self.structured:
+                raise _lib.PdeError("pde_ddg_d2eigs_host serves unsharded 2-D lattices")
+            return self._d2eigs_host_native(u_host, want_min, want_max, mode, chunk_rows, out)
+        linear = HOST_COPY_LINEAR if linear is None else linear
         if not hasattr(self, "_stage"):
             self._stage = (self.zeros(), self.zeros(), self.zeros(),
                            torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
@@ -434,15 +444,22 @@ class GridContext(object):
         s_out.wait_stream(main)
 
         def upload(lo, hi, wall):
-            src = u_host
+            """Enqueue (on the current stream) the PCIe copy of rows [lo, hi) of the field."""
             if linear:
                 fin = self._stage_flat[0]
                 fin[lo * ny:hi * ny].copy_(u_host[lo * ny:hi * ny], non_blocking=True)
                 if wall and self.nb:
                     fin[nloc * ny:].copy_(u_host[nloc * ny:], non_blocking=True)
-                src = fin
-            check(self.lib.pde_grid_h2d_rows(self.h, vp(src.data_ptr()), _ptr(S), lo, hi,
+                return
+            check(self.lib.pde_grid_h2d_rows(self.h, vp(u_host.data_ptr()), _ptr(S), lo, hi,
                                              int(wall), _stream()))
+
+        def convert_in(lo, hi, wall):
+            """linear mode: flat staging -> state layout, a device-side 2-D copy on the COMPUTE
+            stream (the copy streams carry nothing but back-to-back linear PCIe copies)."""
+            if linear:
+                check(self.lib.pde_grid_h2d_rows(self.h, vp(self._stage_flat[0].data_ptr()), _ptr(S),
+                                                 lo, hi, int(wall), _stream()))
 
         with torch.cuda.stream(s_in):
             first = 0
@@ -461,17 +478,33 @@ class GridContext(object):
         if halo_hook is not None:
             if ev_edge is not None:
                 main.wait_event(ev_edge)
+                convert_in(0, self.halo_rows, True)
+                convert_in(nloc - self.halo_rows, nloc, False)
             else:
                 main.wait_event(ev_in[-1])
+                for k in range(nchunk):
+                    convert_in(edges[k], edges[k + 1], k == 0)
             halo_hook(S)
         outs = (Lmin if want_min else None, Lmax if want_max else None, None, None)
+        converted = nchunk if (linear and halo_hook is not None and ev_edge is None) else 0
         try:
             for k in range(nchunk):
                 lo, hi = edges[k], edges[k + 1]
                 # rows of chunk k read up to H rows of chunk k+1
-                main.wait_event(ev_in[min(k + 1, nchunk - 1)])
+                need = min(k + 1, nchunk - 1)
+                main.wait_event(ev_in[need])
+                while linear and converted <= need:
+                    convert_in(edges[converted], edges[converted + 1],
+                               converted == 0 and ev_edge is None)
+                    converted += 1
                 self.set_row_window(lo, hi)
                 self.d2eigs(S, want_min=want_min, want_max=want_max, mode=mode, out=outs)
+                if linear:      # state layout -> flat staging, still on the compute stream
+                    for q, L in enumerate((Lmin, Lmax)):
+                        if (want_min, want_max)[q]:
+                            check(self.lib.pde_grid_d2h_rows(
+                                self.h, _ptr(L), vp(self._stage_flat[1 + q].data_ptr()), lo, hi,
+                                _stream()))
                 ev = torch.cuda.Event()
                 ev.record(main)
                 s_out.wait_event(ev)
@@ -479,16 +512,42 @@ class GridContext(object):
                     for q, (L, o) in enumerate(((Lmin, out_min), (Lmax, out_max))):
                         if o is None or not (want_min, want_max)[q]:
                             continue
-                        dst = self._stage_flat[1 + q] if linear else o
-                        check(self.lib.pde_grid_d2h_rows(self.h, _ptr(L), vp(dst.data_ptr()),
-                                                         lo, hi, _stream()))
                         if linear:
-                            o[lo * ny:hi * ny].copy_(dst[lo * ny:hi * ny], non_blocking=True)
+                            o[lo * ny:hi * ny].copy_(self._stage_flat[1 + q][lo * ny:hi * ny],
+                                                     non_blocking=True)
+                        else:
+                            check(self.lib.pde_grid_d2h_rows(self.h, _ptr(L), vp(o.data_ptr()),
+                                                             lo, hi, _stream()))
         finally:
             self.set_row_window()
         main.wait_stream(s_out)
         s_out.synchronize()
         return out_min, out_max
+
+    def _d2eigs_host_native(self, u_host, want_min, want_max, mode, chunk_rows, out):
+        nloc, ny = self.nx_local, self.ny
+        if not hasattr(self, "_stage"):
+            self._stage = (self.zeros(), self.zeros(), self.zeros(),
+                           torch.cuda.Stream(device=self.device), torch.cuda.Stream(device=self.device))
+        if not hasattr(self, "_stage_flat"):
+            self._stage_flat = (torch.empty(self.n_flat(), dtype=torch.float64, device=self.device),
+                                torch.empty(nloc * ny, dtype=torch.float64, device=self.device),
+                                torch.empty(nloc * ny, dtype=torch.float64, device=self.device))
+        S, Lmin, Lmax, s_in, s_out = self._stage
+        fin, fmin, fmax = self._stage_flat
+        out_min, out_max = out if out is not None else (None, None)
+        if want_min and out_min is None:
+            out_min = torch.empty(nloc * ny, dtype=torch.float64, pin_memory=True)
+        if want_max and out_max is None:
+            out_max = torch.empty(nloc * ny, dtype=torch.float64, pin_memory=True)
+        main = torch.cuda.current_stream()
+        check(self.lib.pde_ddg_d2eigs_host(
+            self.h, vp(u_host.data_ptr()), _ptr(out_min if want_min else None),
+            _ptr(out_max if want_max else None), int(mode), int(chunk_rows), _ptr(S), _ptr(Lmin),
+            _ptr(Lmax), _ptr(fin), _ptr(fmin), _ptr(fmax), vp(main.cuda_stream),
+            vp(s_in.cuda_stream), vp(s_out.cuda_stream)))
+        main.synchronize()
+        return (out_min if want_min else None), (out_max if want_max else None)
 
     def apply_policy(self, policy, X):
         Y = self.zeros()

@@ -95,6 +95,8 @@ struct pde_grid {
     unsigned long long *d_ctrl;  // 16 words
     cudaStream_t side;           // band kernel runs here, concurrently with the deep kernel
     cudaEvent_t ev_fork, ev_join;
+    cudaEvent_t *ev_pool;        // events of the host-to-host pipeline (pde_ddg_d2eigs_host)
+    int n_ev_pool;
     PFN_cuTensorMapEncodeTiled_v12000 encode;
     int num_sms;
 };

@@ -392,6 +392,120 @@ int pde_ddg_d2eigs(pde_grid *g, const double *d_state, double *d_lmin, double *d
 #undef PDE_EIGS
 }
 
+// layout conversions of a row range on the SMs (the copy engines carry the PCIe traffic)
+__global__ void k_rows_in(const double *__restrict__ flat, double *__restrict__ state, int64_t lo,
+                          int64_t hi, int64_t ny, int64_t pitch) {
+    const int64_t total = (hi - lo) * ny;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ny, c = i - r * ny;
+        state[(lo + r) * pitch + c] = flat[(lo + r) * ny + c];
+    }
+}
+__global__ void k_rows_out(const double *__restrict__ state, double *__restrict__ flat, int64_t lo,
+                           int64_t hi, int64_t ny, int64_t pitch) {
+    const int64_t total = (hi - lo) * ny;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = i / ny, c = i - r * ny;
+        flat[(lo + r) * ny + c] = state[(lo + r) * pitch + c];
+    }
+}
+__global__ void k_copy(const double *__restrict__ src, double *__restrict__ dst, int64_t n) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = src[i];
+}
+
+// Host-to-host ddg.d2eigs: the whole H2D / stencil / D2H pipeline over row chunks enqueued by
+// ONE call (the Python loop spent ~65 us of host time per chunk, which capped the chunk count).
+// The PCIe copies are plain linear copies on their own streams (s_in, s_out) to / from flat
+// staging buffers; the layout conversions (flat <-> state rows) are device-side 2-D copies on the
+// compute stream, between the stencil launches.
+int pde_ddg_d2eigs_host(pde_grid *g, const double *h_u, double *h_lmin, double *h_lmax, int mode,
+                        int64_t chunk_rows, double *d_S, double *d_lmin, double *d_lmax,
+                        double *d_fin, double *d_fout_min, double *d_fout_max, void *s_main,
+                        void *s_in_, void *s_out_) {
+    PDE_REQUIRE(g && h_u && d_S && d_fin && (h_lmin || h_lmax), "null argument");
+    PDE_REQUIRE((!h_lmin || (d_lmin && d_fout_min)) && (!h_lmax || (d_lmax && d_fout_max)),
+                "missing staging buffer");
+    PDE_REQUIRE(g->halo_rows == 0 && g->nmid == 0, "host pipeline: unsharded 2-D lattices");
+    DeviceGuard guard(g->device);
+    cudaStream_t main = (cudaStream_t)s_main, s_in = (cudaStream_t)s_in_, s_out = (cudaStream_t)s_out_;
+    const int64_t nloc = g->nx_local, ny = g->ny;
+    if (chunk_rows < 16) chunk_rows = 16;
+    const int nch = (int)((nloc + chunk_rows - 1) / chunk_rows);
+    const int need_ev = 2 * nch + 2;
+    if (g->n_ev_pool < need_ev) {
+        cudaEvent_t *p = new cudaEvent_t[need_ev];
+        for (int i = 0; i < g->n_ev_pool; ++i) p[i] = g->ev_pool[i];
+        for (int i = g->n_ev_pool; i < need_ev; ++i)
+            PDE_CHECK(cudaEventCreateWithFlags(&p[i], cudaEventDisableTiming));
+        delete[] g->ev_pool;
+        g->ev_pool = p;
+        g->n_ev_pool = need_ev;
+    }
+    cudaEvent_t *ev_in = g->ev_pool, *ev_k = g->ev_pool + nch, ev_a = g->ev_pool[2 * nch],
+                ev_b = g->ev_pool[2 * nch + 1];
+    auto cgrid = [&](int64_t rows) {
+        return (unsigned)std::min<int64_t>((rows * ny + 1023) / 1024, (int64_t)g->num_sms * 4);
+    };
+    auto lo_of = [&](int k) { return (int64_t)k * chunk_rows; };
+    auto hi_of = [&](int k) { return std::min<int64_t>(nloc, (int64_t)(k + 1) * chunk_rows); };
+    PDE_CHECK(cudaEventRecord(ev_a, main));                  // earlier work on the compute stream
+    PDE_CHECK(cudaStreamWaitEvent(s_in, ev_a, 0));
+    PDE_CHECK(cudaStreamWaitEvent(s_out, ev_a, 0));
+    for (int k = 0; k < nch; ++k) {
+        const int64_t lo = lo_of(k), hi = hi_of(k);
+        PDE_CHECK(cudaMemcpyAsync(d_fin + lo * ny, h_u + lo * ny, (size_t)(hi - lo) * ny * 8,
+                                  cudaMemcpyHostToDevice, s_in));
+        if (k == 0 && g->nb > 0)
+            PDE_CHECK(cudaMemcpyAsync(d_fin + nloc * ny, h_u + nloc * ny, (size_t)g->nb * 8,
+                                      cudaMemcpyHostToDevice, s_in));
+        PDE_CHECK(cudaEventRecord(ev_in[k], s_in));
+    }
+    int converted = 0, rc = 0;
+    for (int k = 0; k < nch && !rc; ++k) {
+        const int64_t lo = lo_of(k), hi = hi_of(k);
+        const int need = std::min(k + 1, nch - 1);           // chunk k reads rows of chunk k + 1
+        PDE_CHECK(cudaStreamWaitEvent(main, ev_in[need], 0));
+        for (; converted <= need; ++converted) {
+            const int64_t clo = lo_of(converted), chi = hi_of(converted);
+            k_rows_in<<<cgrid(chi - clo), 256, 0, main>>>(d_fin, d_S, clo, chi, ny, g->pitch);
+            PDE_LAUNCH_CHECK();
+            if (converted == 0 && g->nb > 0) {
+                k_copy<<<64, 256, 0, main>>>(d_fin + nloc * ny, d_S + g->rows * g->pitch, g->nb);
+                PDE_LAUNCH_CHECK();
+            }
+        }
+        pde_grid_set_row_window(g, lo, hi);
+        rc = pde_ddg_d2eigs(g, d_S, h_lmin ? d_lmin : nullptr, h_lmax ? d_lmax : nullptr, nullptr,
+                            nullptr, mode, main);
+        if (rc) break;
+        if (h_lmin) {
+            k_rows_out<<<cgrid(hi - lo), 256, 0, main>>>(d_lmin, d_fout_min, lo, hi, ny, g->pitch);
+            PDE_LAUNCH_CHECK();
+        }
+        if (h_lmax) {
+            k_rows_out<<<cgrid(hi - lo), 256, 0, main>>>(d_lmax, d_fout_max, lo, hi, ny, g->pitch);
+            PDE_LAUNCH_CHECK();
+        }
+        PDE_CHECK(cudaEventRecord(ev_k[k], main));
+        PDE_CHECK(cudaStreamWaitEvent(s_out, ev_k[k], 0));
+        if (h_lmin)
+            PDE_CHECK(cudaMemcpyAsync(h_lmin + lo * ny, d_fout_min + lo * ny, (size_t)(hi - lo) * ny * 8,
+                                      cudaMemcpyDeviceToHost, s_out));
+        if (h_lmax)
+            PDE_CHECK(cudaMemcpyAsync(h_lmax + lo * ny, d_fout_max + lo * ny, (size_t)(hi - lo) * ny * 8,
+                                      cudaMemcpyDeviceToHost, s_out));
+    }
+    pde_grid_set_row_window(g, 0, nloc);
+    if (rc) return rc;
+    PDE_CHECK(cudaEventRecord(ev_b, s_out));
+    PDE_CHECK(cudaStreamWaitEvent(main, ev_b, 0));           // results are complete on `main`
+    return 0;
+}
+
 int pde_ce_residual(pde_grid *g, const double *d_W, const double *d_g, double *d_F,
                     uint16_t *d_policy, double *d_red, void *stream) {
     PDE_REQUIRE(g && d_W && d_g && d_F, "null argument");

@@ -271,6 +271,8 @@ int pde_grid_destroy(pde_grid *g) {
     cudaFree(g->d_red);
     cudaFree(g->d_ctrl);
     delete[] g->h_band_row;
+    for (int i = 0; i < g->n_ev_pool; ++i) cudaEventDestroy(g->ev_pool[i]);
+    delete[] g->ev_pool;
     if (g->side) cudaStreamDestroy(g->side);
     if (g->ev_fork) cudaEventDestroy(g->ev_fork);
     if (g->ev_join) cudaEventDestroy(g->ev_join);

@@ -122,6 +122,16 @@ def test_pinned_host_pipeline_bitexact():
     u2 = u[::-1].copy()
     o2 = c_oracle.pairs_d2eigs(G.points, G.pairs, u2, G.num_interior)[0]
     assert np.array_equal(ddg.d2min(G, torch.from_numpy(u2).pin_memory())[0].numpy(), o2)
+    # the three variants of the pipeline: linear PCIe copies + device-side conversion (default),
+    # 2-D DMA copies, and the single C-ABI call pde_ddg_d2eigs_host
+    from pyellipticfd_b200._context import GridContext
+    ctx = GridContext.get(G)
+    for kw in (dict(linear=True, chunk_rows=128), dict(linear=False, chunk_rows=256),
+               dict(native=True, chunk_rows=96), dict(native=True, chunk_rows=4096)):
+        lo, hi = ctx.d2eigs_host(host, **kw)
+        assert np.array_equal(lo.numpy(), omin) and np.array_equal(hi.numpy(), omax), kw
+        lo, hi = ctx.d2eigs_host(host, want_max=False, **kw)
+        assert hi is None and np.array_equal(lo.numpy(), omin), kw
 
 
 def test_full_size_4097_r4_bitexact_and_properties():
