@@ -414,6 +414,21 @@ def solve_full_size(args, obstacle):
                               "residual": nst.get("residual"), "converged": nw_ok,
                               "max_abs_U_sweep_minus_U_newton": float((Us - Un).abs().max()),
                               "warnings": sorted({str(w.message) for w in wl})}
+            # the reference's OTHER solver as a second certifier: solvers.euler stops at the first
+            # step whose change and residual are below the tolerances (solvers.py:84)
+            with warnings.catch_warnings(record=True) as wl:
+                warnings.simplefilter("always")
+                est = {}
+                torch.cuda.synchronize()
+                t = time.perf_counter()
+                Ue, ediff, eit, _ = convex_envelope.solve(Gs, g, U0=Us, fdmethod="grid",
+                                                          solver="euler", stats=est)
+                torch.cuda.synchronize()
+                out["certify_euler"] = {"seconds": time.perf_counter() - t, "iterations": int(eit),
+                                        "diff": float(ediff), "residual": est.get("residual"),
+                                        "converged": bool(eit == 1 and ediff < 1e-6
+                                                          and (est.get("residual") or 1.0) < 1e-6)}
+                del Ue
             if first is None:
                 first = {"sweep_seconds": t_sw, "certify_seconds": t_nw, "seconds": t_sw + t_nw}
         out["first_call"] = first
