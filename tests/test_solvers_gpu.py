@@ -168,3 +168,40 @@ def test_policy_iteration_with_tight_restarted_linear_solves():
     assert np.abs(F).max() < 1e-6
     Us, _, _, _ = convex_envelope.solve(G, g, fdmethod="grid", solver="sweep")
     assert np.abs(U - Us).max() < 1e-6            # the sweep solver ends on the same solution
+
+
+def test_fused_s_t_pass_matches_the_separate_passes(monkeypatch):
+    """Opt-in fused pass of BiCGStab (PDE_JAC_FUSED=1: s = r - alpha v, t = J (dinv s) and their
+    three inner products in one kernel over tiles of r, v, dinv): the first iterates agree with
+    the separate passes to rounding (the elementwise arithmetic is identical, only the grouping
+    of the partial sums differs), and a solve converges to the same solution."""
+    import torch
+    from pyellipticfd_b200._context import GridContext
+    from pyellipticfd_b200.linop import PolicyJacobian
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    n, m = 300, 337
+    G = FDRegularGrid([n, m], np.array([[0.0, (n + 1) / 512.0], [0.0, (m + 1) / 512.0]]).T, 4,
+                      interpolation=False)
+    ctx = GridContext.get(G)
+    assert ctx.structured and ctx.weights == "exact"
+    X = G.points
+    g = np.minimum(np.linalg.norm(X - 0.2, axis=1), np.linalg.norm(X - 0.45, axis=1))
+    U = ctx.pack(torch.from_numpy(g - 0.05 * np.exp(-40 * ((X - 0.3) ** 2).sum(1))).cuda())
+    F, P, _ = ctx.ce_residual(U, ctx.pack(torch.from_numpy(g).cuda()), policy=True)
+    J = PolicyJacobian(ctx, P, None, cmin=-1.0)
+    B = -F
+    res = {}
+    for fused in ("0", "1"):
+        monkeypatch.setenv("PDE_JAC_FUSED", fused)
+        its = {k: J.bicgstab_state(B, rtol=1e-30, maxiter=k, check_every=k)[0].clone() for k in (1, 2)}
+        x, info, nit = J.bicgstab_state(B, rtol=1e-9)
+        res[fused] = (its, x, info, nit)
+    for k, tol in ((1, 1e-14), (2, 1e-12)):
+        a, b = res["0"][0][k], res["1"][0][k]
+        assert float((a - b).abs().max()) <= tol * float(a.abs().max()), k
+    nb = float(torch.linalg.vector_norm(B))
+    for fused in ("0", "1"):
+        _, x, info, nit = res[fused]
+        assert info == 0 and nit > 10
+        assert float(torch.linalg.vector_norm(J.matvec_state(x) - B)) <= 1.001e-9 * nb
+    assert float((res["0"][1] - res["1"][1]).abs().max()) < 1e-6 * float(res["0"][1].abs().max())
