@@ -1168,6 +1168,7 @@ int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall
             }
             return cmax;
         };
+        const bool trace = getenv("PDE_SWEEP_TRACE") != nullptr;     // per-direction changes (host builds)
         while (sweeps < max_sweeps) {
             change = 0.0;
             for (int k = 0; k < ndir; ++k) {
@@ -1186,7 +1187,12 @@ int pde_ce_sweep(int device, int64_t nx, int64_t ny, int64_t pitch, int64_t wall
                     }
                 }
                 if (cmax > change) change = cmax;
-                if ((k + 1) % relax_every == 0 || k == ndir - 1) change = std::max(change, relax());
+                if (trace) fprintf(stderr, "sweep %lld dir %d (%d,%d) change %.3e\n", (long long)sweeps, k, a, b, cmax);
+                if ((k + 1) % relax_every == 0 || k == ndir - 1) {
+                    double rc_ = relax();
+                    if (trace) fprintf(stderr, "sweep %lld relax after dir %d change %.3e\n", (long long)sweeps, k, rc_);
+                    change = std::max(change, rc_);
+                }
             }
             ++sweeps;
             if (change < tol) break;
