@@ -2,6 +2,7 @@
 // stencil_deep.cuh) + CSR band kernel, with the convex-envelope / Pucci
 // epilogues fused in.  C ABI in include/pde_b200.h.
 #include <algorithm>
+#include <vector>
 #include <cstdlib>
 #include <type_traits>
 #include "stencil_deep.cuh"
@@ -455,6 +456,14 @@ int pde_ddg_d2eigs_host(pde_grid *g, const double *h_u, double *h_lmin, double *
     PDE_CHECK(cudaEventRecord(ev_a, main));                  // earlier work on the compute stream
     PDE_CHECK(cudaStreamWaitEvent(s_in, ev_a, 0));
     PDE_CHECK(cudaStreamWaitEvent(s_out, ev_a, 0));
+    // PDE_E2E_TRACE=1: per-chunk completion times of the three streams on stderr (synchronises)
+    const bool trace = getenv("PDE_E2E_TRACE") != nullptr;
+    std::vector<cudaEvent_t> tev;
+    if (trace) {
+        tev.resize(3 * (size_t)nch + 1);
+        for (auto &e : tev) PDE_CHECK(cudaEventCreate(&e));
+        PDE_CHECK(cudaEventRecord(tev[3 * nch], s_in));
+    }
     for (int k = 0; k < nch; ++k) {
         const int64_t lo = lo_of(k), hi = hi_of(k);
         PDE_CHECK(cudaMemcpyAsync(d_fin + lo * ny, h_u + lo * ny, (size_t)(hi - lo) * ny * 8,
@@ -463,6 +472,7 @@ int pde_ddg_d2eigs_host(pde_grid *g, const double *h_u, double *h_lmin, double *
             PDE_CHECK(cudaMemcpyAsync(d_fin + nloc * ny, h_u + nloc * ny, (size_t)g->nb * 8,
                                       cudaMemcpyHostToDevice, s_in));
         PDE_CHECK(cudaEventRecord(ev_in[k], s_in));
+        if (trace) PDE_CHECK(cudaEventRecord(tev[k], s_in));
     }
     int converted = 0, rc = 0;
     for (int k = 0; k < nch && !rc; ++k) {
@@ -491,6 +501,7 @@ int pde_ddg_d2eigs_host(pde_grid *g, const double *h_u, double *h_lmin, double *
             PDE_LAUNCH_CHECK();
         }
         PDE_CHECK(cudaEventRecord(ev_k[k], main));
+        if (trace) PDE_CHECK(cudaEventRecord(tev[nch + k], main));
         PDE_CHECK(cudaStreamWaitEvent(s_out, ev_k[k], 0));
         if (h_lmin)
             PDE_CHECK(cudaMemcpyAsync(h_lmin + lo * ny, d_fout_min + lo * ny, (size_t)(hi - lo) * ny * 8,
@@ -498,11 +509,24 @@ int pde_ddg_d2eigs_host(pde_grid *g, const double *h_u, double *h_lmin, double *
         if (h_lmax)
             PDE_CHECK(cudaMemcpyAsync(h_lmax + lo * ny, d_fout_max + lo * ny, (size_t)(hi - lo) * ny * 8,
                                       cudaMemcpyDeviceToHost, s_out));
+        if (trace) PDE_CHECK(cudaEventRecord(tev[2 * nch + k], s_out));
     }
     pde_grid_set_row_window(g, 0, nloc);
     if (rc) return rc;
     PDE_CHECK(cudaEventRecord(ev_b, s_out));
     PDE_CHECK(cudaStreamWaitEvent(main, ev_b, 0));           // results are complete on `main`
+    if (trace) {
+        PDE_CHECK(cudaStreamSynchronize(main));
+        fprintf(stderr, "chunk  h2d_done  kernels_done  d2h_done (ms)\n");
+        for (int k = 0; k < nch; ++k) {
+            float a = 0, b = 0, c = 0;
+            cudaEventElapsedTime(&a, tev[3 * nch], tev[k]);
+            cudaEventElapsedTime(&b, tev[3 * nch], tev[nch + k]);
+            cudaEventElapsedTime(&c, tev[3 * nch], tev[2 * nch + k]);
+            fprintf(stderr, "%3d  %8.3f  %8.3f  %8.3f\n", k, a, b, c);
+        }
+        for (auto &e : tev) cudaEventDestroy(e);
+    }
     return 0;
 }
 
