@@ -16,6 +16,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <vector>
+#include <unordered_map>
 #ifdef _OPENMP
 #include <omp.h>
 #endif
@@ -215,6 +216,12 @@ int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double b
     return 0;
 }
 
+struct ClassEntry {                  // result of the stencil rules for one translation class
+    std::vector<double> V;           // candidate vectors of the representative (K x dim)
+    std::vector<char> isb;           // candidate is a wall point
+    std::vector<int> kept, pk, pl;   // kept candidates; paired candidates (k < l)
+};
+
 // ---------------------------------------------------------------------------------------------
 // n-D (dim >= 2; used for 3-D) version of pde_band_build: the same three rules on lattices of any
 // dimension.  Wall points are bucketed by integer cell (floor of the unscaled coordinates) in a
@@ -239,6 +246,8 @@ int pde_band_build_nd(int dim, const int64_t *shape, int r, const double *scalin
         lstride[d] = lstride[d + 1] * shape[d + 1];
         cstride[d] = cstride[d + 1] * (shape[d + 1] + 2);
     }
+    double vscale = INFINITY;
+    for (int d = 0; d < dim; ++d) vscale = std::min(vscale, std::fabs(scaling[d]));
     // wall points sorted by cell key
     std::vector<std::pair<int64_t, int64_t>> cells(nb);
     for (int64_t i = 0; i < nb; ++i) {
@@ -263,6 +272,7 @@ int pde_band_build_nd(int dim, const int64_t *shape, int r, const double *scalin
         std::vector<double> V, D, S;      // K x dim, K, K x dim
         std::vector<int64_t> ID, wids;
         std::vector<char> isb, disc, discm, keep;
+        std::unordered_map<int64_t, ClassEntry> cache;       // translation classes, per thread
 #pragma omp for schedule(dynamic, 8)
         for (int64_t p = 0; p < n_band; ++p) {
             const int64_t id = band_ids[p];
@@ -340,47 +350,83 @@ int pde_band_build_nd(int dim, const int64_t *shape, int r, const double *scalin
                 isb.push_back(1);
             }
             const int K = (int)ID.size();
-            D.resize(K); S.resize((size_t)K * dim);
-            disc.assign(K, 0); discm.assign(K, 0); keep.assign(K, 0);
+            D.resize(K);
             for (int k = 0; k < K; ++k) {
                 double s = 0;
                 for (int d = 0; d < dim; ++d) s += V[(size_t)k * dim + d] * V[(size_t)k * dim + d];
                 D[k] = std::sqrt(s);
             }
-            for (int k = 0; k < K; ++k)
-                for (int l = k + 1; l < K; ++l) {
-                    double dot = 0;
-                    for (int d = 0; d < dim; ++d) dot += V[(size_t)k * dim + d] * V[(size_t)l * dim + d];
-                    double cosv = dot / (D[k] * D[l]);
-                    cosv = cosv < -1.0 ? -1.0 : (cosv > 1.0 ? 1.0 : cosv);
-                    if ((1.0 - cosv) < tol) {
-                        int loser = D[k] >= D[l] ? k : l;
-                        disc[loser] = 1;
-                        if (isb[k] != isb[l]) discm[loser] = 1;
+            // Translation classes: band points with the same distances to the walls (capped at
+            // r + 2 per side) see the same candidate vectors, hence the same pruning and pairing.
+            // The O(K^2) rules run once per class and thread; every other point of the class
+            // re-uses the kept / paired candidate NUMBERS after checking that its candidate
+            // vectors equal the class representative's to 1e-9 of the cell size (inexact
+            // lattices differ in the last bits; decisions have a tolerance of 1e-3).
+            int64_t sig = 0;
+            for (int d = 0; d < dim; ++d) {
+                const int64_t a = std::min<int64_t>(ci[d] - 1, r + 2);
+                const int64_t b = std::min<int64_t>(shape[d] - ci[d], r + 2);
+                sig = (sig * (r + 3) + a) * (r + 3) + b;
+            }
+            ClassEntry *ce = nullptr;
+            {
+                auto it = cache.find(sig);
+                if (it != cache.end() && (int)it->second.isb.size() == K) {
+                    ClassEntry &e = it->second;
+                    bool same = true;
+                    for (int k = 0; k < K && same; ++k) same = e.isb[k] == isb[k];
+                    for (size_t q = 0; q < (size_t)K * dim && same; ++q)
+                        same = std::fabs(e.V[q] - V[q]) <= 1e-9 * vscale;
+                    if (same) ce = &e;
+                }
+            }
+            if (!ce) {
+                S.resize((size_t)K * dim);
+                disc.assign(K, 0); discm.assign(K, 0); keep.assign(K, 0);
+                for (int k = 0; k < K; ++k)
+                    for (int l = k + 1; l < K; ++l) {
+                        double dot = 0;
+                        for (int d = 0; d < dim; ++d) dot += V[(size_t)k * dim + d] * V[(size_t)l * dim + d];
+                        double cosv = dot / (D[k] * D[l]);
+                        cosv = cosv < -1.0 ? -1.0 : (cosv > 1.0 ? 1.0 : cosv);
+                        if ((1.0 - cosv) < tol) {
+                            int loser = D[k] >= D[l] ? k : l;
+                            disc[loser] = 1;
+                            if (isb[k] != isb[l]) discm[loser] = 1;
+                        }
+                    }
+                ClassEntry e;
+                e.V = V;
+                e.isb = isb;
+                for (int k = 0; k < K; ++k) {
+                    keep[k] = !disc[k] || (isb[k] && !discm[k]);
+                    for (int d = 0; d < dim; ++d) S[(size_t)k * dim + d] = V[(size_t)k * dim + d] / D[k];
+                    if (keep[k]) e.kept.push_back(k);
+                }
+                for (int k = 0; k < K; ++k) {
+                    if (!keep[k]) continue;
+                    for (int l = k + 1; l < K; ++l) {
+                        if (!keep[l]) continue;
+                        double cs = 0;
+                        for (int d = 0; d < dim; ++d) cs += S[(size_t)k * dim + d] * S[(size_t)l * dim + d];
+                        if (cs < -1 + tol) {
+                            e.pk.push_back(k);
+                            e.pl.push_back(l);
+                        }
                     }
                 }
-            double mnb = INFINITY;
-            for (int k = 0; k < K; ++k) {
-                keep[k] = !disc[k] || (isb[k] && !discm[k]);
-                for (int d = 0; d < dim; ++d) S[(size_t)k * dim + d] = V[(size_t)k * dim + d] / D[k];
-                if (keep[k]) mnb = std::min(mnb, D[k]);
+                ce = &(cache[sig] = std::move(e));
             }
+            double mnb = INFINITY;
+            for (int k : ce->kept) mnb = std::min(mnb, D[k]);
             min_nb[p] = mnb;
             if (want_nb)
-                for (int k = 0; k < K; ++k)
-                    if (keep[k]) nbs[p].push_back(ID[k]);
+                for (int k : ce->kept) nbs[p].push_back(ID[k]);
             std::vector<int64_t> &out = rows[p];
-            for (int k = 0; k < K; ++k) {
-                if (!keep[k]) continue;
-                for (int l = k + 1; l < K; ++l) {
-                    if (!keep[l]) continue;
-                    double cs = 0;
-                    for (int d = 0; d < dim; ++d) cs += S[(size_t)k * dim + d] * S[(size_t)l * dim + d];
-                    if (cs < -1 + tol) {
-                        out.push_back(ID[k]);
-                        out.push_back(ID[l]);
-                    }
-                }
+            out.reserve(2 * ce->pk.size());
+            for (size_t q = 0; q < ce->pk.size(); ++q) {
+                out.push_back(ID[ce->pk[q]]);
+                out.push_back(ID[ce->pl[q]]);
             }
             if (out.empty()) {
 #pragma omp critical
