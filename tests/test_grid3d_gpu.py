@@ -214,3 +214,24 @@ def test_band_points_inside_the_brick_loop_equal_the_band_kernel(monkeypatch):
     want = np.minimum.reduceat(d, G.band_ptr[:-1])
     got = ctx.unpad(res["1"][0]).cpu().numpy()[G.band_index]
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("shape,r", [((9, 8, 7), 3), ((5, 4, 6, 5), 1)])
+def test_lattices_outside_the_structured_3d_kernel_use_explicit_rows(shape, r):
+    """3-D lattices with r >= 3 (145 pairs: more than the direction table holds) and 4-D lattices
+    keep the explicit-row path (rows materialised lazily from the offset table): bit-exact against
+    the NumPy restatement."""
+    from pyellipticfd_b200 import ddg
+    from pyellipticfd_b200._context import GridContext
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    dim = len(shape)
+    G = FDRegularGrid(list(shape), np.array([[0.0, (n + 1) / 16.0] for n in shape]).T, r,
+                      interpolation=False)
+    ctx = GridContext.get(G)
+    assert not ctx.nd and not ctx.structured
+    u = np.random.default_rng(2).standard_normal(G.num_points)
+    (lmin, M, _), (lmax, _, _) = ddg.d2eigs(G, u, jacobian=True)
+    (omin, OM, _), (omax, _, _) = O.d2eigs(G, u, True, False)
+    assert np.array_equal(lmin, omin) and np.array_equal(lmax, omax)
+    assert (M.tocsr() != OM).nnz == 0
+    assert G.points.shape[1] == dim
