@@ -235,3 +235,36 @@ def test_lattices_outside_the_structured_3d_kernel_use_explicit_rows(shape, r):
     assert np.array_equal(lmin, omin) and np.array_equal(lmax, omax)
     assert (M.tocsr() != OM).nnz == 0
     assert G.points.shape[1] == dim
+
+
+def test_inexact_3d_lattice_nominal_weights_within_tolerance():
+    """[-1,1]^3 with 31 interior points per axis (h = 1/16 exactly would be dyadic: use 29 ->
+    h = 2/30, not a power of two): with weights='nominal' the 3-D kernel runs with one weight
+    triple per direction; values agree with the NumPy restatement (per-pair weights) within
+    c * max(|d_ref|, w0 (|du0| w_0 + |du1| w_1)), c = max(1e-12, 8 eps max|x| / h) -- the 2-D
+    statement of test_ddg_gpu.py; band points stay per-pair exact."""
+    from pyellipticfd_b200 import ddg
+    from pyellipticfd_b200._context import GridContext
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    n = 29
+    G = FDRegularGrid([n, n - 3, n + 2], np.array([[-1.0, 1.0]] * 3).T, 2, interpolation=False,
+                      weights="nominal")
+    assert not G.uniform_weights()
+    ctx = GridContext.get(G)
+    assert ctx.nd and ctx.weights == "nominal"
+    rng = np.random.default_rng(4)
+    X, Y, Z = G.points.T
+    u = np.sin(2 * X) * np.cos(3 * Y) + Z * X + 0.1 * rng.standard_normal(G.num_points)
+    (lmin, _, _), (lmax, _, _) = ddg.d2eigs(G, u)
+    (omin, _, _), (omax, _, _) = O.d2eigs(G, u)
+    P = G.pairs
+    I, J = P[:, 0], P[:, 1:]
+    hh = np.linalg.norm(G.points[J] - G.points[I, None], axis=2)
+    term_rows = 2 / hh.sum(1) * (np.abs(u[J] - u[I, None]) / hh).sum(1)
+    term = np.maximum.reduceat(term_rows, np.flatnonzero(np.r_[True, np.diff(I) != 0]))
+    c = max(1e-12, 8 * np.finfo(float).eps * 1.0 / G.scaling.min())
+    for mine, ref in ((lmin, omin), (lmax, omax)):
+        assert (np.abs(mine - ref) <= c * np.maximum(np.abs(ref), term)).all()
+    band = np.zeros(G.num_interior, bool)
+    band[G.band_index] = True
+    assert np.array_equal(lmin[band], omin[band]) and np.array_equal(lmax[band], omax[band])
