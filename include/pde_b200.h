@@ -86,6 +86,18 @@ int pde_grid_create_nd(pde_grid **out, int device, int dim /* 3 */,
                        const double *h_stencil_w /* D x 3 */,
                        int64_t n_band, const int64_t *h_band_center, const int64_t *h_band_ptr,
                        const int64_t *h_band_j /* P x 2 */, const double *h_band_w /* P x 3 */);
+/* Optional compact form of the band rows for the operator kernels (3-D lattices, where the band
+ * is a surface layer as expensive as the deep points): band points with the same distances to
+ * the walls share their rows up to translation.  Class c owns rows [h_cls_ptr[c], h_cls_ptr[c+1]);
+ * a row is two references -- (state-offset delta << 1) for a lattice neighbour, (q << 1 | 1) for
+ * the q-th entry of the band point's own wall list h_wl[h_wl_ptr[i] ..] (state offsets) -- and the
+ * weights (w_0, w_1, w0), in the order of the explicit rows (policies keep their meaning).  The
+ * explicit rows given to pde_grid_create* stay in use for the Jacobian rows. */
+int pde_grid_set_band_classes(pde_grid *g, int n_cls, const int32_t *h_cls_ptr,
+                              const int32_t *h_cls_ref /* rows x 2 */,
+                              const double *h_cls_w /* rows x 3 */,
+                              const uint16_t *h_cls_id /* n_band */,
+                              const int32_t *h_wl_ptr /* n_band + 1 */, const int32_t *h_wl);
 int pde_grid_destroy(pde_grid *g);
 /* Restrict the following stencil launches (pde_ddg_d2eigs, pde_ce_residual,
  * pde_ce_euler_step, pde_pucci_residual) to owned rows [row_lo, row_hi); wall entries

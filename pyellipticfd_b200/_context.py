@@ -91,6 +91,7 @@ NOMINAL_ABOVE = 1 << 20
 # 3-D lattices run the structured 3-D kernel (False: explicit pair rows for every point, the
 # round-1 path; kept for tests that compare the two)
 ND_STRUCTURED = True
+BAND_CLASSES = True           # 3-D lattices: band rows as translation classes for the operator kernels
 MAX_DIRS = 64                 # PDE_MAX_DIRS of include/pde_b200.h
 
 
@@ -258,6 +259,88 @@ class GridContext(object):
         self.band_sel = np.arange(bi.shape[0])
         self.structured = True
         self.nd = True
+        # compact band rows for the operator kernels (exact lattices: weights are per class)
+        self.band_classes = 0
+        if BAND_CLASSES and self.weights_exact_hint(G):
+            t = self._band_classes(G, bi, bp, bw, band_ptr, pitch, rows)
+            if t is not None:
+                check(self.lib.pde_grid_set_band_classes(
+                    self.h, t["n_cls"], _np_ptr(t["cls_ptr"]), _np_ptr(t["cls_ref"]),
+                    _np_ptr(t["cls_w"]), _np_ptr(t["cls_id"]), _np_ptr(t["wl_ptr"]), _np_ptr(t["wl"])))
+                self.band_classes = t["n_cls"]
+
+    @staticmethod
+    def weights_exact_hint(G):
+        return bool(G.uniform_weights())
+
+    def _band_classes(self, G, bi, bp, bw, band_ptr, pitch, rows):
+        """Translation classes of the band rows of a 3-D lattice for ``pde_grid_set_band_classes``:
+        band points with the same distances to the six walls (capped at r + 2) have the same rows
+        up to translation.  The rows of every class are taken from its first member and EVERY
+        member is checked against them (row count, lattice offsets, wall-list positions, weights
+        bit for bit); any mismatch -> None, the explicit rows stay in charge."""
+        nx, ny, nz = G.interior_shape
+        r, N = G.stencil_radius, G.num_interior
+        nB, P = bi.shape[0], bp.shape[0]
+        if nB == 0 or P == 0 or P >= 2 ** 31:
+            return None
+        counts = np.diff(band_ptr)
+        pt = np.repeat(np.arange(nB), counts)                 # band point number of every row
+        kin = np.arange(P) - band_ptr[:-1][pt]                # row number within its point
+
+        def soff(ids):                                        # lattice ids -> state offsets
+            return (ids // nz) * pitch + ids % nz
+
+        ctr = soff(bp[:, 0])
+        J = bp[:, 1:3]
+        lat = J < N
+        delta = np.where(lat, soff(np.where(lat, J, 0)) - ctr[:, None], 0)
+        # the wall points a band point refers to, in order of first appearance in its rows
+        flatJ, flatpt, flatlat = J.ravel(), np.repeat(pt, 2), lat.ravel()
+        wsel = np.flatnonzero(~flatlat)
+        nbw = int(G.num_bdry)
+        key = flatpt[wsel] * nbw + (flatJ[wsel] - N)
+        ukey, first = np.unique(key, return_index=True)
+        order = np.argsort(first, kind="stable")              # by point, then by first appearance
+        upt = ukey[order] // nbw
+        wl_counts = np.bincount(upt, minlength=nB)
+        wl_ptr = np.concatenate([[0], np.cumsum(wl_counts)])
+        pos_sorted = np.arange(order.size) - wl_ptr[:-1][upt]
+        pos_of_ukey = np.empty(order.size, np.int64)
+        pos_of_ukey[order] = pos_sorted
+        wl = rows * pitch + (ukey[order] % nbw)               # state offsets of the wall points
+        wpos = np.zeros(2 * P, np.int64)
+        wpos[wsel] = pos_of_ukey[np.searchsorted(ukey, key)]
+        ref = np.where(flatlat, delta.ravel() * 2, wpos * 2 + 1).reshape(P, 2)
+        if np.abs(ref).max() >= 2 ** 31 or wl.max(initial=0) >= 2 ** 31:
+            return None
+        # classes by wall distances
+        idx = np.stack(np.unravel_index(bi, (nx, ny, nz)), 1) + 1
+        sig = np.zeros(nB, np.int64)
+        for d, n in enumerate((nx, ny, nz)):
+            a = np.minimum(idx[:, d] - 1, r + 2)
+            b = np.minimum(n - idx[:, d], r + 2)
+            sig = (sig * (r + 3) + a) * (r + 3) + b
+        _, rep, cls = np.unique(sig, return_index=True, return_inverse=True)
+        n_cls = rep.shape[0]
+        if n_cls >= 65535:
+            return None
+        cls_counts = counts[rep]
+        cls_ptr = np.concatenate([[0], np.cumsum(cls_counts)])
+        if (counts != cls_counts[cls]).any():
+            return None
+        take = (np.repeat(band_ptr[:-1][rep], cls_counts)
+                + np.arange(cls_ptr[-1]) - np.repeat(cls_ptr[:-1], cls_counts))
+        cls_ref, cls_w = ref[take], bw[take]
+        mine = cls_ptr[:-1][cls[pt]] + kin                    # class row every explicit row maps to
+        if not (np.array_equal(ref, cls_ref[mine]) and np.array_equal(bw, cls_w[mine])):
+            return None
+        return dict(n_cls=int(n_cls), cls_ptr=np.ascontiguousarray(cls_ptr, dtype=np.int32),
+                    cls_ref=np.ascontiguousarray(cls_ref, dtype=np.int32),
+                    cls_w=np.ascontiguousarray(cls_w, dtype=np.float64),
+                    cls_id=np.ascontiguousarray(cls, dtype=np.uint16),
+                    wl_ptr=np.ascontiguousarray(wl_ptr, dtype=np.int32),
+                    wl=np.ascontiguousarray(wl if wl.size else np.zeros(1), dtype=np.int32))
 
     def deep_pair_weights(self):
         """(w_0, w_1, w0) of every row of the deep table, at a generic deep point."""

@@ -37,6 +37,7 @@ SIGNATURES = {
                                 c_i64, vp, vp, vp, vp, vp]),
     "pde_grid_create_nd": (c_int, [C.POINTER(vp), c_int, c_int, vp, c_i64, c_int, c_int, vp, vp,
                                    c_i64, vp, vp, vp, vp]),
+    "pde_grid_set_band_classes": (c_int, [vp, c_int, vp, vp, vp, vp, vp, vp]),
     "pde_grid_destroy": (c_int, [vp]),
     "pde_ddg_d2eigs_host": (c_int, [vp, vp, vp, vp, c_int, c_i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "pde_grid_set_row_window": (c_int, [vp, c_i64, c_i64]),

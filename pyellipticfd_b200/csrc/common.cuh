@@ -97,6 +97,16 @@ struct pde_grid {
     cudaEvent_t ev_fork, ev_join;
     cudaEvent_t *ev_pool;        // events of the host-to-host pipeline (pde_ddg_d2eigs_host)
     int n_ev_pool;
+    // band translation classes (pde_grid_set_band_classes): the rows of a band point as a class
+    // table (relative lattice offsets / positions in the point's wall list + weights) instead of
+    // 40-byte explicit rows, for the operator kernels of 3-D lattices
+    int n_cls;
+    int32_t *d_cls_ptr;          // n_cls + 1
+    int32_t *d_cls_ref;          // rows x 2: (delta << 1) lattice | (position << 1 | 1) wall list
+    double *d_cls_w;             // rows x 3
+    uint16_t *d_cls_id;          // n_band
+    int32_t *d_wl_ptr;           // n_band + 1
+    int32_t *d_wl;               // state offsets of the wall points a band point refers to
     PFN_cuTensorMapEncodeTiled_v12000 encode;
     int num_sms;
 };

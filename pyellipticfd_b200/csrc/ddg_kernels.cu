@@ -79,6 +79,76 @@ k_band(int64_t n_band, const int64_t *__restrict__ center, const int64_t *__rest
     }
 }
 
+// ---- band kernel on translation classes (3-D lattices) ------------------------------------------
+// Same evaluation, row order and tie rule as k_band, but the rows of a band point come from its
+// class table (pde_grid_set_band_classes): a neighbour is either a lattice point at a fixed state
+// offset from the centre or the q-th entry of the point's own list of wall points; the weights
+// are the class's.  ~0.2 kB per band point (class number + wall list) instead of ~2.2 kB of rows.
+template <int MODE, class Epi>
+__global__ void __launch_bounds__(128)
+k_band_cls(int64_t n_band, const int64_t *__restrict__ center, const uint16_t *__restrict__ cls_id,
+           const int32_t *__restrict__ cls_ptr, const int32_t *__restrict__ cls_ref,
+           const double *__restrict__ cls_w, const int32_t *__restrict__ wl_ptr,
+           const int32_t *__restrict__ wl, const double *__restrict__ S, const Epi epi,
+           double *red_out, const unsigned long long *done_flag) {
+    if (done_flag && *done_flag) return;
+    BlockMax2 red{0.0, 0.0};
+    const int lane = threadIdx.x & 31;
+    int64_t i = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    if (i < n_band) {
+        const int64_t o = center[i];
+        const double uc = S[o];
+        const int c = cls_id[i];
+        const int b = cls_ptr[c], e = cls_ptr[c + 1];
+        const int32_t *mywl = wl + wl_ptr[i];
+        double mn = __longlong_as_double(0x7ff0000000000000LL);
+        double mx = __longlong_as_double(0xfff0000000000000LL);
+        int kmn = -1, kmx = 0x7fffffff;
+        for (int k = b + lane; k < e; k += 32) {
+            const int r0 = cls_ref[2 * k], r1 = cls_ref[2 * k + 1];
+            const double u0 = (r0 & 1) ? S[mywl[r0 >> 1]] : S[o + (r0 >> 1)];
+            const double u1 = (r1 & 1) ? S[mywl[r1 >> 1]] : S[o + (r1 >> 1)];
+            const double w_0 = cls_w[3 * k], w_1 = cls_w[3 * k + 1], w0 = cls_w[3 * k + 2];
+            double d;
+            if (MODE == 0)
+                d = pair_value_exact(uc, u0, u1, w_0, w_1, w0);
+            else
+                d = (fma(w_1, u1 - uc, w_0 * (u0 - uc))) * w0;
+            if (Epi::kMin && d <= mn) {
+                mn = d;
+                kmn = k - b;
+            }
+            if (Epi::kMax && d > mx) {
+                mx = d;
+                kmx = k - b;
+            }
+        }
+#pragma unroll
+        for (int s = 16; s > 0; s >>= 1) {
+            double omn = __shfl_xor_sync(0xffffffffu, mn, s);
+            int okn = __shfl_xor_sync(0xffffffffu, kmn, s);
+            double omx = __shfl_xor_sync(0xffffffffu, mx, s);
+            int okx = __shfl_xor_sync(0xffffffffu, kmx, s);
+            if (Epi::kMin && (omn < mn || (omn == mn && okn > kmn))) {
+                mn = omn;
+                kmn = okn;
+            }
+            if (Epi::kMax && (omx > mx || (omx == mx && okx < kmx))) {
+                mx = omx;
+                kmx = okx;
+            }
+        }
+        if (lane == 0) epi(o, uc, mn, mx, kmn, kmx, Epi::kPre ? epi.pre(o) : 0.0, red);
+    }
+    if (Epi::kRed) {
+        double a = warp_max(red.a), bb = warp_max(red.b);
+        if (lane == 0) {
+            atomic_max_nonneg(&red_out[0], a);
+            atomic_max_nonneg(&red_out[1], bb);
+        }
+    }
+}
+
 // ---- wall rows of the residual / Euler step -------------------------------------------
 // mode 0: F = W - g  (convex_envelope.py:44; pucci.py:130,141), red[0] = max|F|
 // mode 1: Unew = U - dt*(U - g), red[0] = max|F|, red[1] = max|U-Unew|
@@ -287,6 +357,17 @@ template <int MODE, class Epi>
 static int launch_band(pde_grid *g, const double *S, const Epi &epi, double *red,
                        const unsigned long long *done, cudaStream_t st) {
     if (g->n_band == 0) return 0;
+    if (g->n_cls > 0 && g->win_lo == 0 && g->win_hi == g->nx_local && g->win2_hi == g->win2_lo) {
+        const char *e = getenv("PDE_BAND_CLASSES");       // read per call: a test compares both
+        if (!(e && atoi(e) == 0)) {
+            int grid = (int)((g->n_band + 3) / 4);        // one warp per band point
+            k_band_cls<MODE, Epi><<<grid, 128, 0, st>>>(g->n_band, g->d_band_center, g->d_cls_id,
+                                                         g->d_cls_ptr, g->d_cls_ref, g->d_cls_w,
+                                                         g->d_wl_ptr, g->d_wl, S, epi, red, done);
+            PDE_LAUNCH_CHECK();
+            return 0;
+        }
+    }
     // band points of the active row windows (band points are sorted by row)
     const int64_t *rb = g->h_band_row, *re = g->h_band_row + g->n_band;
     const int64_t wins[2][2] = {{g->win_lo, g->win_hi}, {g->win2_lo, g->win2_hi}};

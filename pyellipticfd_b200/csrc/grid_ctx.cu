@@ -260,9 +260,37 @@ int pde_grid_create_nd(pde_grid **out, int device, int dim, const int64_t *h_sha
     return 0;
 }
 
+int pde_grid_set_band_classes(pde_grid *g, int n_cls, const int32_t *h_cls_ptr,
+                              const int32_t *h_cls_ref, const double *h_cls_w,
+                              const uint16_t *h_cls_id, const int32_t *h_wl_ptr,
+                              const int32_t *h_wl) {
+    PDE_REQUIRE(g && n_cls >= 1 && n_cls < 65536 && h_cls_ptr && h_cls_ref && h_cls_w && h_cls_id &&
+                    h_wl_ptr && h_wl,
+                "bad band-class tables");
+    PDE_REQUIRE(g->n_cls == 0, "band classes already set");
+    DeviceGuard guard(g->device);
+    const size_t rows = (size_t)h_cls_ptr[n_cls], nw = (size_t)h_wl_ptr[g->n_band];
+    int rc = 0;
+    rc |= upload(&g->d_cls_ptr, h_cls_ptr, (size_t)n_cls + 1);
+    rc |= upload(&g->d_cls_ref, h_cls_ref, rows * 2);
+    rc |= upload(&g->d_cls_w, h_cls_w, rows * 3);
+    rc |= upload(&g->d_cls_id, h_cls_id, (size_t)g->n_band);
+    rc |= upload(&g->d_wl_ptr, h_wl_ptr, (size_t)g->n_band + 1);
+    rc |= upload(&g->d_wl, h_wl, nw);
+    if (rc) return rc;
+    g->n_cls = n_cls;
+    return 0;
+}
+
 int pde_grid_destroy(pde_grid *g) {
     if (!g) return 0;
     DeviceGuard guard(g->device);
+    cudaFree(g->d_cls_ptr);
+    cudaFree(g->d_cls_ref);
+    cudaFree(g->d_cls_w);
+    cudaFree(g->d_cls_id);
+    cudaFree(g->d_wl_ptr);
+    cudaFree(g->d_wl);
     cudaFree(g->d_band_center);
     cudaFree(g->d_band_ptr);
     cudaFree(g->d_band_j);

@@ -268,3 +268,30 @@ def test_inexact_3d_lattice_nominal_weights_within_tolerance():
     band = np.zeros(G.num_interior, bool)
     band[G.band_index] = True
     assert np.array_equal(lmin[band], omin[band]) and np.array_equal(lmax[band], omax[band])
+
+
+def test_band_translation_classes_equal_the_explicit_rows(monkeypatch):
+    """3-D lattices with exact weights evaluate their band points from translation-class tables
+    (pde_grid_set_band_classes, k_band_cls) instead of 40-byte explicit rows: values, policies,
+    residual and Euler epilogues bit-identical to the explicit band kernel."""
+    import torch
+    from pyellipticfd_b200._context import GridContext
+    from pyellipticfd_b200.pointclasses import FDRegularGrid
+    shape = (23, 17, 70)
+    G = FDRegularGrid(list(shape), _dyadic_box(shape, (1 / 64.0,) * 3), 2, interpolation=False)
+    ctx = GridContext.get(G)
+    assert ctx.nd and ctx.band_classes > 100
+    rng = np.random.default_rng(12)
+    S = ctx.pack(torch.from_numpy(rng.integers(-4, 5, G.num_points).astype(float)).cuda())   # ties
+    g = ctx.pack(torch.from_numpy(rng.standard_normal(G.num_points)).cuda())
+    res = {}
+    for on in ("1", "0"):
+        monkeypatch.setenv("PDE_BAND_CLASSES", on)
+        lmin, lmax, pmin, pmax = ctx.d2eigs(S, policy=True)
+        F, P, red = ctx.ce_residual(S, g, policy=True)
+        Un, red2 = ctx.ce_euler_step(S, g, 1e-5)
+        torch.cuda.synchronize()
+        res[on] = [t.clone() for t in (lmin, lmax, ctx.unpad_policy(pmin), ctx.unpad_policy(pmax),
+                                       F, ctx.unpad_policy(P), red, Un, red2)]
+    for a, b in zip(res["1"], res["0"]):
+        assert torch.equal(a, b)
