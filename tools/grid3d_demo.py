@@ -19,7 +19,7 @@ r = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 t = time.time()
 G = FDRegularGrid([n] * 3, np.array([[-1.0, 1.0]] * 3).T, r, interpolation=False)
 out = {"lattice": "%d^3" % (n + 2), "radius": r, "interior_points": G.num_interior,
-       "wall_points": G.num_bdry, "pair_rows": int(len(G.pairs)), "grid_build_s": time.time() - t}
+       "wall_points": G.num_bdry, "pair_rows": int(G.num_pairs), "grid_build_s": time.time() - t}
 C = 3 / 7 * np.array([[np.cos(np.pi / 5), np.sin(np.pi / 5), 0.3],
                       [-np.cos(np.pi / 5), -np.sin(np.pi / 5), -0.3]])
 g = np.min([np.sqrt(((G.points + c) ** 2).sum(1)) for c in C], axis=0)
@@ -31,7 +31,7 @@ for _ in range(10):
     ddg.d2min(G, gd)
 torch.cuda.synchronize()
 out["d2min_ms"] = (time.time() - t) / 10 * 1e3
-out["d2min_Gpair_per_s"] = len(G.pairs) / out["d2min_ms"] / 1e6
+out["d2min_Gpair_per_s"] = G.num_pairs / out["d2min_ms"] / 1e6
 for solver in ("euler", "newton"):
     import warnings
     with warnings.catch_warnings(record=True) as w:
