@@ -56,15 +56,33 @@ def tables(G, pitch, rows):
         return np.where(ids < N, (ids // ny) * pitch + ids % ny, rows * pitch + (ids - N))
 
     bp = np.asarray(G.band_pairs, dtype=np.int64)
-    PI, P0, P1 = ucoord(bp[:, 0]), ucoord(bp[:, 1]), ucoord(bp[:, 2])
-    V0, V1 = P0 - PI, P1 - PI
-    exact = ((np.abs(V0 - np.round(V0)) < 1e-9).all(axis=1) & (np.abs(V1 + V0) < 1e-9).all(axis=1)
-             & (np.abs(V0) <= r + 1e-9).all(axis=1))
+    # rows whose two neighbours are lattice points: integer arithmetic on the ids; only the rows
+    # that touch a wall point need the (float) unscaled wall coordinates
+    P = bp.shape[0]
+    Vi = np.zeros((P, 2), dtype=np.int64)
+    exact = np.zeros(P, dtype=bool)
+    both = (bp[:, 1] < N) & (bp[:, 2] < N)
+    if both.any():
+        b = bp[both]
+        ci, cj = b[:, 0] // ny, b[:, 0] % ny
+        v0 = np.stack([b[:, 1] // ny - ci, b[:, 1] % ny - cj], 1)
+        v1 = np.stack([b[:, 2] // ny - ci, b[:, 2] % ny - cj], 1)
+        ok = (v1 == -v0).all(axis=1) & (np.abs(v0) <= r).all(axis=1)
+        exact[both] = ok
+        Vi[both] = np.where(ok[:, None], v0, 0)
+    mixed = np.flatnonzero(~both)
+    if mixed.size:
+        b = bp[mixed]
+        PI, P0, P1 = ucoord(b[:, 0]), ucoord(b[:, 1]), ucoord(b[:, 2])
+        V0, V1 = P0 - PI, P1 - PI
+        ok = ((np.abs(V0 - np.round(V0)) < 1e-9).all(axis=1) & (np.abs(V1 + V0) < 1e-9).all(axis=1)
+              & (np.abs(V0) <= r + 1e-9).all(axis=1))
+        exact[mixed] = ok
+        Vi[mixed] = np.where(ok[:, None], np.round(V0), 0).astype(np.int64)
     lut = np.full((2 * r + 1, 2 * r + 1), -1, dtype=np.int64)
     k = np.arange(D)
     lut[dirs[:, 0] + r, dirs[:, 1] + r] = k
     lut[-dirs[:, 0] + r, -dirs[:, 1] + r] = k
-    Vi = np.where(exact[:, None], np.round(V0), 0).astype(np.int64)
     kk = np.where(exact, lut[Vi[:, 0] + r, Vi[:, 1] + r], -1)
     line = kk >= 0
     flags = np.zeros(band_slots(nx, ny, r), dtype=np.uint64)
