@@ -464,7 +464,7 @@ def solve_full_size(args, obstacle):
             cores = os.cpu_count() or 1
             k = 2
             t = time.perf_counter()
-            _, _, done = _sweep.host_sweep(Gs, g_host, tol=0.0, max_sweeps=k, relax_every=4)
+            _, _, done = _sweep.host_sweep(Gs, g_host, tol=0.0, max_sweeps=k, relax_every=2)
             t_host = (time.perf_counter() - t) / max(done, 1)
             cb = {"kind": "port (host/OpenMP build of the same sweep, pde_ce_sweep device=-1)",
                   "cores": cores, "seconds_per_sweep": t_host,

@@ -120,7 +120,9 @@ def _solve_grid(Grid, g, U0, solver, stats=None, **kwargs):
         mi = int(kwargs.get("max_iters") or 1000)
         chunk = int(kwargs.get("check_every", 8))
         timeout = kwargs.get("timeout")            # seconds, like solvers.euler's (solvers.py:58-61)
-        relax_every = int(kwargs.get("relax_every", 4))
+        # band relaxation after every 2nd direction pass: fewer sweeps than after every 4th
+        # (4097^2: 48 vs 53; host build at 1025^2: 33 with 1, 39 with 4) for 8 more tiny launches
+        relax_every = int(kwargs.get("relax_every", 2))
         if U0 is not None:
             # sweeps only lower values, so they must start on or above the solution: from g
             warnings.warn("solver='sweep' starts from the obstacle; U0 is ignored")
