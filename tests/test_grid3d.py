@@ -169,3 +169,43 @@ def test_3d_error_behaviour_follows_the_reference():
         ddi.d2eigs(G, u)                                   # ddi.py:330-331
     with pytest.raises(NotImplementedError):
         ddi.d1grad(G, u)                                   # ddi.py:157-158
+
+
+@pytest.mark.parametrize("shape,cell", [((9, 8, 11), 1 / 8.0), ((12, 21, 10), 1 / 32.0)])
+def test_band_translation_classes_decode_to_the_explicit_rows(shape, cell):
+    """Host logic of pde_grid_set_band_classes (CPU): the class tables built by
+    GridContext._band_classes reproduce every explicit band row -- lattice neighbours as
+    state-offset deltas from the centre, wall neighbours as positions in the band point's wall
+    list -- and the weights, for every band point."""
+    from pyellipticfd_b200._context import GridContext, pair_weights
+    G = FDRegularGrid(list(shape), np.array([[0.0, (n + 1) * cell] for n in shape]).T, 2,
+                      interpolation=False)
+    nx, ny, nz = shape
+    pitch, rows, N = (nz + 15) // 16 * 16, nx * ny, G.num_interior
+    bi, bp, ptr = np.asarray(G.band_index), np.asarray(G.band_pairs), np.asarray(G.band_ptr)
+    bw, _ = pair_weights(G.coords(bp[:, 0]), G.coords(bp[:, 1]), G.coords(bp[:, 2]))
+    t = GridContext._band_classes(None, G, bi, bp, bw, ptr, pitch, rows)
+    assert t is not None and 100 < t["n_cls"] < 65535
+    assert t["cls_id"].shape == (len(bi),) and t["wl_ptr"][-1] == t["wl"].shape[0]
+
+    def soff(ids):
+        return (ids // nz) * pitch + ids % nz
+
+    cls = t["cls_id"].astype(np.int64)
+    counts = np.diff(ptr)
+    assert np.array_equal(counts, np.diff(t["cls_ptr"])[cls])
+    pt = np.repeat(np.arange(len(bi)), counts)
+    krow = t["cls_ptr"][:-1][cls[pt]] + (np.arange(len(bp)) - ptr[:-1][pt])
+    assert np.array_equal(t["cls_w"][krow], bw)
+    ctr = soff(bp[:, 0])
+    for q in (0, 1):
+        ref = t["cls_ref"][krow, q].astype(np.int64)
+        J = bp[:, 1 + q]
+        wall = (ref & 1) == 1
+        assert np.array_equal(wall, J >= N)
+        assert np.array_equal(ctr[~wall] + (ref[~wall] >> 1), soff(J[~wall]))
+        got = t["wl"][t["wl_ptr"][:-1][pt[wall]] + (ref[wall] >> 1)]
+        assert np.array_equal(got, rows * pitch + (J[wall] - N))
+    # a lattice whose weights are not per-class constants is refused by the caller
+    Gi = FDRegularGrid([9, 8, 11], np.array([[-1.0, 1.0]] * 3).T, 2, interpolation=False)
+    assert not GridContext.weights_exact_hint(Gi)
