@@ -124,7 +124,7 @@ class GridContext(object):
             mode == "nominal" or (mode == "auto" and (G.num_interior > NOMINAL_ABOVE or slab is not None)))
         self.nd = False
         if (exact or nominal) and structured_nd:
-            self._init_structured_nd(G)
+            self._init_structured_nd(G, exact)
             self.weights = "exact" if exact else "nominal"
         elif exact or nominal:
             self._init_structured(G, slab)
@@ -212,7 +212,7 @@ class GridContext(object):
         self.band_pairs = bp
         self.structured = True
 
-    def _init_structured_nd(self, G):
+    def _init_structured_nd(self, G, exact=True):
         """3-D lattice [nx][ny][nz] as nx*ny state-layout rows of nz columns
         (``pde_grid_create_nd``): deep points through the 3-D table kernel, band points as
         explicit rows.  Point ids, policies and the flat vectors are the reference's."""
@@ -261,7 +261,7 @@ class GridContext(object):
         self.nd = True
         # compact band rows for the operator kernels (exact lattices: weights are per class)
         self.band_classes = 0
-        if BAND_CLASSES and self.weights_exact_hint(G):
+        if BAND_CLASSES and exact:
             t = self._band_classes(G, bi, bp, bw, band_ptr, pitch, rows)
             if t is not None:
                 check(self.lib.pde_grid_set_band_classes(
@@ -270,10 +270,7 @@ class GridContext(object):
                 self.band_classes = t["n_cls"]
 
     @staticmethod
-    def weights_exact_hint(G):
-        return bool(G.uniform_weights())
-
-    def _band_classes(self, G, bi, bp, bw, band_ptr, pitch, rows):
+    def _band_classes(G, bi, bp, bw, band_ptr, pitch, rows):
         """Translation classes of the band rows of a 3-D lattice for ``pde_grid_set_band_classes``:
         band points with the same distances to the six walls (capped at r + 2) have the same rows
         up to translation.  The rows of every class are taken from its first member and EVERY

@@ -184,7 +184,7 @@ def test_band_translation_classes_decode_to_the_explicit_rows(shape, cell):
     pitch, rows, N = (nz + 15) // 16 * 16, nx * ny, G.num_interior
     bi, bp, ptr = np.asarray(G.band_index), np.asarray(G.band_pairs), np.asarray(G.band_ptr)
     bw, _ = pair_weights(G.coords(bp[:, 0]), G.coords(bp[:, 1]), G.coords(bp[:, 2]))
-    t = GridContext._band_classes(None, G, bi, bp, bw, ptr, pitch, rows)
+    t = GridContext._band_classes(G, bi, bp, bw, ptr, pitch, rows)
     assert t is not None and 100 < t["n_cls"] < 65535
     assert t["cls_id"].shape == (len(bi),) and t["wl_ptr"][-1] == t["wl"].shape[0]
 
@@ -206,6 +206,10 @@ def test_band_translation_classes_decode_to_the_explicit_rows(shape, cell):
         assert np.array_equal(ctr[~wall] + (ref[~wall] >> 1), soff(J[~wall]))
         got = t["wl"][t["wl_ptr"][:-1][pt[wall]] + (ref[wall] >> 1)]
         assert np.array_equal(got, rows * pitch + (J[wall] - N))
-    # a lattice whose weights are not per-class constants is refused by the caller
+    # on a lattice with inexact coordinates the weights are not per-class constants: refused
     Gi = FDRegularGrid([9, 8, 11], np.array([[-1.0, 1.0]] * 3).T, 2, interpolation=False)
-    assert not GridContext.weights_exact_hint(Gi)
+    assert not Gi.uniform_weights()
+    bpi = np.asarray(Gi.band_pairs)
+    bwi, _ = pair_weights(Gi.coords(bpi[:, 0]), Gi.coords(bpi[:, 1]), Gi.coords(bpi[:, 2]))
+    assert GridContext._band_classes(Gi, np.asarray(Gi.band_index), bpi, bwi,
+                                     np.asarray(Gi.band_ptr), 16, 72) is None
