@@ -34,6 +34,12 @@ struct WallList {
 
 }  // namespace
 
+struct ClassEntry {                  // result of the stencil rules for one translation class
+    std::vector<double> V;           // candidate vectors of the representative (K x dim)
+    std::vector<char> isb;           // candidate is a wall point
+    std::vector<int> kept, pk, pl;   // kept candidates; paired candidates (k < l)
+};
+
 extern "C" {
 
 void pde_free(void *p) { free(p); }
@@ -92,6 +98,8 @@ int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double b
         std::vector<double> PX, PY, VX, VY, D, SX, SY;
         std::vector<int64_t> ID;
         std::vector<char> isb, disc, discm, keep;
+        std::unordered_map<int64_t, ClassEntry> cache;       // translation classes, per thread
+        const double vscale = std::min(std::fabs(sx), std::fabs(sy));
 #pragma omp for schedule(dynamic, 16)
         for (int64_t p = 0; p < n_band; ++p) {
             const int64_t id = band_ids[p];
@@ -125,47 +133,80 @@ int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double b
                 }
             }
             const int K = (int)PX.size();
-            VX.resize(K); VY.resize(K); D.resize(K); SX.resize(K); SY.resize(K);
-            disc.assign(K, 0); discm.assign(K, 0); keep.assign(K, 0);
+            VX.resize(K); VY.resize(K); D.resize(K);
             const double pcx = cx * sx + bx, pcy = cy * sy + by;
             for (int k = 0; k < K; ++k) {
                 VX[k] = (PX[k] * sx + bx) - pcx;
                 VY[k] = (PY[k] * sy + by) - pcy;
                 D[k] = std::sqrt(VX[k] * VX[k] + VY[k] * VY[k]);
             }
-            for (int k = 0; k < K; ++k)
-                for (int l = k + 1; l < K; ++l) {
-                    double dot = VX[k] * VX[l] + VY[k] * VY[l];
-                    double cosv = dot / (D[k] * D[l]);
-                    cosv = cosv < -1.0 ? -1.0 : (cosv > 1.0 ? 1.0 : cosv);
-                    if ((1.0 - cosv) < tol) {
-                        int loser = D[k] >= D[l] ? k : l;
-                        disc[loser] = 1;
-                        if (isb[k] != isb[l]) discm[loser] = 1;
+            // translation classes (see pde_band_build_nd): same wall distances, same candidate
+            // vectors -> the kept / paired candidate numbers of the class representative
+            const int64_t i1 = id / ny + 1, j1 = id % ny + 1;
+            int64_t sig = std::min<int64_t>(i1 - 1, r + 2);
+            sig = sig * (r + 3) + std::min<int64_t>(nx - i1, r + 2);
+            sig = sig * (r + 3) + std::min<int64_t>(j1 - 1, r + 2);
+            sig = sig * (r + 3) + std::min<int64_t>(ny - j1, r + 2);
+            ClassEntry *ce = nullptr;
+            {
+                auto it = cache.find(sig);
+                if (it != cache.end() && (int)it->second.isb.size() == K) {
+                    ClassEntry &e = it->second;
+                    bool same = true;
+                    for (int k = 0; k < K && same; ++k)
+                        same = e.isb[k] == isb[k] && std::fabs(e.V[2 * k] - VX[k]) <= 1e-9 * vscale &&
+                               std::fabs(e.V[2 * k + 1] - VY[k]) <= 1e-9 * vscale;
+                    if (same) ce = &e;
+                }
+            }
+            if (!ce) {
+                SX.resize(K); SY.resize(K);
+                disc.assign(K, 0); discm.assign(K, 0); keep.assign(K, 0);
+                for (int k = 0; k < K; ++k)
+                    for (int l = k + 1; l < K; ++l) {
+                        double dot = VX[k] * VX[l] + VY[k] * VY[l];
+                        double cosv = dot / (D[k] * D[l]);
+                        cosv = cosv < -1.0 ? -1.0 : (cosv > 1.0 ? 1.0 : cosv);
+                        if ((1.0 - cosv) < tol) {
+                            int loser = D[k] >= D[l] ? k : l;
+                            disc[loser] = 1;
+                            if (isb[k] != isb[l]) discm[loser] = 1;
+                        }
+                    }
+                ClassEntry e;
+                e.V.resize((size_t)2 * K);
+                e.isb = isb;
+                for (int k = 0; k < K; ++k) {
+                    e.V[2 * k] = VX[k];
+                    e.V[2 * k + 1] = VY[k];
+                    keep[k] = !disc[k] || (isb[k] && !discm[k]);
+                    SX[k] = VX[k] / D[k];
+                    SY[k] = VY[k] / D[k];
+                    if (keep[k]) e.kept.push_back(k);
+                }
+                for (int k = 0; k < K; ++k) {
+                    if (!keep[k]) continue;
+                    for (int l = k + 1; l < K; ++l) {
+                        if (!keep[l]) continue;
+                        double cs = SX[k] * SX[l] + SY[k] * SY[l];
+                        if (cs < -1 + tol) {
+                            e.pk.push_back(k);
+                            e.pl.push_back(l);
+                        }
                     }
                 }
-            double mnb = INFINITY;
-            for (int k = 0; k < K; ++k) {
-                keep[k] = !disc[k] || (isb[k] && !discm[k]);
-                SX[k] = VX[k] / D[k];
-                SY[k] = VY[k] / D[k];
-                if (keep[k]) mnb = std::min(mnb, D[k]);
+                ce = &(cache[sig] = std::move(e));
             }
+            double mnb = INFINITY;
+            for (int k : ce->kept) mnb = std::min(mnb, D[k]);
             min_nb[p] = mnb;
             if (want_nb)
-                for (int k = 0; k < K; ++k)
-                    if (keep[k]) nbs[p].push_back(ID[k]);
+                for (int k : ce->kept) nbs[p].push_back(ID[k]);
             std::vector<int64_t> &out = rows[p];
-            for (int k = 0; k < K; ++k) {
-                if (!keep[k]) continue;
-                for (int l = k + 1; l < K; ++l) {
-                    if (!keep[l]) continue;
-                    double cs = SX[k] * SX[l] + SY[k] * SY[l];
-                    if (cs < -1 + tol) {
-                        out.push_back(ID[k]);
-                        out.push_back(ID[l]);
-                    }
-                }
+            out.reserve(2 * ce->pk.size());
+            for (size_t q = 0; q < ce->pk.size(); ++q) {
+                out.push_back(ID[ce->pk[q]]);
+                out.push_back(ID[ce->pl[q]]);
             }
             if (out.empty()) {
 #pragma omp critical
@@ -216,11 +257,6 @@ int pde_band_build(int64_t nx, int64_t ny, int r, double sx, double sy, double b
     return 0;
 }
 
-struct ClassEntry {                  // result of the stencil rules for one translation class
-    std::vector<double> V;           // candidate vectors of the representative (K x dim)
-    std::vector<char> isb;           // candidate is a wall point
-    std::vector<int> kept, pk, pl;   // kept candidates; paired candidates (k < l)
-};
 
 // ---------------------------------------------------------------------------------------------
 // n-D (dim >= 2; used for 3-D) version of pde_band_build: the same three rules on lattices of any
